@@ -1,0 +1,330 @@
+"""fast-image-recognition_b200 — B200-native matching engine for the qt_cpp recognizer hot path.
+
+Python face of the C-ABI in include/fir_b200.h (libfir_b200.so, hand-written sm_100a CUDA).  The
+classes mirror the reference's C++ entry points for this path:
+
+    Gallery            ~ std::vector<ImageInfo> dbImages            (qt_cpp/db_features.h:14-29)
+    Gallery.search     ~ BruteForce::recognize / recognize_image_bf looped by testSetRecognition
+                                                                     (qt_cpp/ann.cpp:94-126, db_features.cpp:319-335)
+    Gallery.distances  ~ ImageInfo::distance / feature_distance      (qt_cpp/db_features.cpp:22-42)
+    Classifier         ~ KNNClassifier / PNNClassifier::predict_bf   (qt_cpp/classification.cpp:116-226)
+    Dem                ~ DirectedEnumeration                         (qt_cpp/ann.cpp:270-507)
+
+Arguments may be numpy arrays (host memory: copies happen inside the call, which synchronises) or
+CUDA torch tensors (device memory: asynchronous on the gallery's stream).  There is no CPU
+fallback: if the CUDA library is missing or no device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfir_b200.so")
+
+L2, CHI2, KL = 0, 1, 2
+METRICS = {"l2": L2, "chi2": CHI2, "kl": KL}
+HOST, DEVICE = 0, 1
+PATH_AUTO, PATH_EXACT, PATH_TENSOR = 0, 1, 2
+
+EXPORTS = [
+    "fir_last_error_string", "fir_version", "fir_device_count", "fir_set_device",
+    "fir_gallery_create", "fir_gallery_destroy", "fir_gallery_set_stream", "fir_gallery_info",
+    "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
+    "fir_class_min", "fir_pnn_scores", "fir_merge_topk",
+    "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn",
+    "fir_dem_build", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
+    "fir_dem_get_min_other", "fir_dem_search",
+]
+
+
+class FirError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("fir_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("path_used", C.c_int32), ("n_fallback", C.c_int32), ("n_candidates", C.c_int32),
+                ("gpu_launches", C.c_int32), ("approx_err_bound", C.c_float), ("reserved", C.c_float)]
+
+
+class DemParams(C.Structure):
+    _fields_ = [("pivot0", C.c_int32), ("seed", C.c_uint32), ("false_accept_rate", C.c_float),
+                ("threshold", C.c_float), ("max_chain", C.c_int32), ("max_pivots", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libfir_b200.so (built in-tree by build.sh / __graft_entry__.build()). Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FirError(-1, "CUDA extension %s is missing; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.fir_last_error_string.restype = C.c_char_p
+    vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.fir_gallery_create.argtypes = [vp, vp, i64, i32, i32, i32, i64, C.POINTER(vp)]
+    L.fir_gallery_destroy.argtypes = [vp]
+    L.fir_gallery_set_stream.argtypes = [vp, vp]
+    L.fir_gallery_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.fir_normalize_rows.argtypes = [vp, i64, i32, i32, i32, vp]
+    L.fir_search_topk.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, vp]
+    L.fir_search_last_stats.argtypes = [vp, C.POINTER(SearchStats)]
+    L.fir_pair_distances.argtypes = [vp, vp, i64, vp, i32, i32, i32, vp]
+    L.fir_class_min.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.fir_pnn_scores.argtypes = [vp, vp, i64, f64, i64, i32, vp, vp]
+    L.fir_merge_topk.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
+    L.fir_classifier_create.argtypes = [vp, vp, i64, i32, i32, vp, C.POINTER(vp)]
+    L.fir_classifier_destroy.argtypes = [vp]
+    L.fir_classifier_knn.argtypes = [vp, vp, i64, i32, vp]
+    L.fir_classifier_pnn.argtypes = [vp, vp, i64, vp, vp]
+    L.fir_dem_build.argtypes = [vp, C.POINTER(DemParams), C.POINTER(vp)]
+    L.fir_dem_destroy.argtypes = [vp]
+    L.fir_dem_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float)]
+    L.fir_dem_get_pivots.argtypes = [vp, vp]
+    L.fir_dem_get_pivot_matrix.argtypes = [vp, vp]
+    L.fir_dem_get_min_other.argtypes = [vp, vp]
+    L.fir_dem_search.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _check(code):
+    if code != 0:
+        raise FirError(code, lib().fir_last_error_string().decode(errors="replace"))
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+def _prep(a, dtype_np, dtype_name):
+    """Returns (array, memspace). numpy → contiguous host array; torch CUDA tensor → contiguous device tensor."""
+    if _is_torch(a):
+        import torch
+        want = getattr(torch, dtype_name)
+        if not a.is_cuda:
+            return np.ascontiguousarray(a.numpy(), dtype=dtype_np), HOST
+        if a.dtype != want:
+            a = a.to(want)
+        return a.contiguous(), DEVICE
+    return np.ascontiguousarray(a, dtype=dtype_np), HOST
+
+
+def _out(shape, dtype_np, dtype_name, like_device, device=None):
+    if like_device:
+        import torch
+        return torch.empty(shape, dtype=getattr(torch, dtype_name), device=device)
+    return np.empty(shape, dtype=dtype_np)
+
+
+def device_count():
+    n = C.c_int(0)
+    _check(lib().fir_device_count(C.byref(n)))
+    return n.value
+
+
+def normalize_rows(rows, metric="l2", stream=None):
+    """Loader normalisation of db_features.cpp:79-101, in place (numpy array or CUDA tensor)."""
+    m = METRICS[metric] if isinstance(metric, str) else metric
+    if _is_torch(rows) and rows.is_cuda:
+        assert rows.is_contiguous() and rows.dtype.is_floating_point and rows.element_size() == 4
+        _check(lib().fir_normalize_rows(_ptr(rows), rows.shape[0], rows.shape[1], m, DEVICE, stream))
+        return rows
+    assert rows.dtype == np.float32 and rows.flags["C_CONTIGUOUS"]
+    _check(lib().fir_normalize_rows(_ptr(rows), rows.shape[0], rows.shape[1], m, HOST, stream))
+    return rows
+
+
+class Gallery:
+    def __init__(self, rows, labels=None, metric="l2", index_offset=0, stream=None):
+        self.metric_name = metric if isinstance(metric, str) else {v: k for k, v in METRICS.items()}[metric]
+        m = METRICS[metric] if isinstance(metric, str) else metric
+        rows, space = _prep(rows, np.float32, "float32")
+        lab = None
+        if labels is not None:
+            lab, lspace = _prep(labels, np.int32, "int32")
+            if lspace != space:
+                raise ValueError("rows and labels must live in the same memory space")
+        self.n, self.d = int(rows.shape[0]), int(rows.shape[1])
+        self.index_offset = int(index_offset)
+        self._device = rows.device if space == DEVICE else None
+        h = C.c_void_p(None)
+        _check(lib().fir_gallery_create(_ptr(rows), _ptr(lab), self.n, self.d, m, space, self.index_offset, C.byref(h)))
+        self._h = h
+        nc = C.c_int32(0)
+        _check(lib().fir_gallery_info(self._h, None, None, None, C.byref(nc)))
+        self.n_classes = nc.value
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, stream):
+        _check(lib().fir_gallery_set_stream(self._h, C.c_void_p(int(stream))))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fir_gallery_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search(self, queries, k=1, max_features=0, path=PATH_AUTO):
+        """k smallest (feature_distance, index) per query; k=1 is BruteForce::recognize."""
+        q, space = _prep(queries, np.float32, "float32")
+        nq = int(q.shape[0])
+        idx = _out((nq, k), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
+        dist = _out((nq, k), np.float32, "float32", space == DEVICE, getattr(q, "device", None))
+        _check(lib().fir_search_topk(self._h, _ptr(q), nq, k, max_features, path, space, _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def stats(self):
+        s = SearchStats()
+        _check(lib().fir_search_last_stats(self._h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in SearchStats._fields_}
+
+    def distances(self, queries, cand_idx, gallery_is_lhs=False):
+        q, space = _prep(queries, np.float32, "float32")
+        c, cspace = _prep(cand_idx, np.int32, "int32")
+        if cspace != space:
+            raise ValueError("queries and cand_idx must live in the same memory space")
+        nq, r = int(c.shape[0]), int(c.shape[1])
+        out = _out((nq, r), np.float32, "float32", space == DEVICE, getattr(q, "device", None))
+        _check(lib().fir_pair_distances(self._h, _ptr(q), nq, _ptr(c), r, int(gallery_is_lhs), space, _ptr(out)))
+        return out
+
+    def class_min(self, queries):
+        q, space = _prep(queries, np.float32, "float32")
+        nq = int(q.shape[0])
+        mn = _out((nq, self.n_classes), np.float32, "float32", space == DEVICE, getattr(q, "device", None))
+        arg = _out((nq, self.n_classes), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
+        _check(lib().fir_class_min(self._h, _ptr(q), nq, space, _ptr(mn), _ptr(arg)))
+        return mn, arg
+
+    def pnn_scores(self, queries, var, n_total=0):
+        q, space = _prep(queries, np.float32, "float32")
+        nq = int(q.shape[0])
+        sc = _out((nq, self.n_classes), np.float64, "float64", space == DEVICE, getattr(q, "device", None))
+        lab = _out((nq,), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
+        _check(lib().fir_pnn_scores(self._h, _ptr(q), nq, float(var), int(n_total), space, _ptr(sc), _ptr(lab)))
+        return sc, lab
+
+
+def merge_topk(parts_dist, parts_idx, stream=None):
+    """k-way (dist, idx) merge of per-shard lists: CUDA tensors [n_parts, nq, k] → ([nq,k], [nq,k])."""
+    import torch
+    assert parts_dist.is_cuda and parts_idx.is_cuda
+    pd, pi = parts_dist.contiguous(), parts_idx.contiguous()
+    n_parts, nq, k = pd.shape
+    od = torch.empty((nq, k), dtype=torch.float32, device=pd.device)
+    oi = torch.empty((nq, k), dtype=torch.int32, device=pd.device)
+    s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    _check(lib().fir_merge_topk(_ptr(pd), _ptr(pi), n_parts, nq, k, _ptr(od), _ptr(oi), C.c_void_p(int(s))))
+    return oi, od
+
+
+class Classifier:
+    """fp64 kNN / PNN of classification.cpp over a class-major training set."""
+
+    def __init__(self, train_rows, train_labels, n_classes, avg):
+        tr = np.ascontiguousarray(train_rows, dtype=np.float64)
+        tl = np.ascontiguousarray(train_labels, dtype=np.int32)
+        av = np.ascontiguousarray(avg, dtype=np.float64)
+        self.n, self.d, self.n_classes = int(tr.shape[0]), int(tr.shape[1]), int(n_classes)
+        h = C.c_void_p(None)
+        _check(lib().fir_classifier_create(_ptr(tr), _ptr(tl), self.n, self.d, self.n_classes, _ptr(av), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fir_classifier_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def knn(self, queries, K):
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        lab = np.empty(q.shape[0], np.int32)
+        _check(lib().fir_classifier_knn(self._h, _ptr(q), q.shape[0], int(K), _ptr(lab)))
+        return lab
+
+    def pnn(self, queries, scores=True):
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        lab = np.empty(q.shape[0], np.int32)
+        sc = np.empty((q.shape[0], self.n_classes), np.float64) if scores else None
+        _check(lib().fir_classifier_pnn(self._h, _ptr(q), q.shape[0], _ptr(sc), _ptr(lab)))
+        return lab, sc
+
+
+class Dem:
+    """DirectedEnumeration over a Gallery (kept alive by this object)."""
+
+    def __init__(self, gallery, pivot0=-1, seed=0, false_accept_rate=0.01, threshold=0.0, max_chain=0, max_pivots=0):
+        self.gallery = gallery
+        p = DemParams(int(pivot0), int(seed), float(false_accept_rate), float(threshold), int(max_chain), int(max_pivots))
+        h = C.c_void_p(None)
+        _check(lib().fir_dem_build(gallery._h, C.byref(p), C.byref(h)))
+        self._h = h
+        a, b, t = C.c_int32(0), C.c_int32(0), C.c_float(0)
+        _check(lib().fir_dem_info(self._h, C.byref(a), C.byref(b), C.byref(t)))
+        self.n_pivots, self.chain_rows, self.threshold = a.value, b.value, np.float32(t.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fir_dem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def pivots(self):
+        out = np.empty(self.n_pivots, np.int32)
+        _check(lib().fir_dem_get_pivots(self._h, _ptr(out)))
+        return out
+
+    @property
+    def P(self):
+        out = np.empty((self.n_pivots, self.gallery.n), np.float32)
+        _check(lib().fir_dem_get_pivot_matrix(self._h, _ptr(out)))
+        return out
+
+    @property
+    def min_other(self):
+        out = np.empty(self.chain_rows, np.float32)
+        _check(lib().fir_dem_get_min_other(self._h, _ptr(out)))
+        return out
+
+    def search(self, queries, count_to_check=0):
+        q, space = _prep(queries, np.float32, "float32")
+        nq = int(q.shape[0])
+        dev = getattr(q, "device", None)
+        idx = _out((nq,), np.int32, "int32", space == DEVICE, dev)
+        dist = _out((nq,), np.float32, "float32", space == DEVICE, dev)
+        below = _out((nq,), np.uint8, "uint8", space == DEVICE, dev)
+        evals = _out((nq,), np.int32, "int32", space == DEVICE, dev)
+        _check(lib().fir_dem_search(self._h, _ptr(q), nq, int(count_to_check), space, _ptr(idx), _ptr(dist), _ptr(below), _ptr(evals)))
+        return idx, dist, below, evals

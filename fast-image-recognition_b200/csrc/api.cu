@@ -1,0 +1,342 @@
+// api.cu — the C-ABI of libfir_b200.so (include/fir_b200.h): handles, staging, kernel orchestration.
+// There is no CPU fallback in this file or anywhere below it: every compute entry point needs a CUDA
+// device and fails with FIR_ERR_CUDA otherwise.
+#include "fir_common.cuh"
+#include "handles.hpp"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <mutex>
+
+namespace fir {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+int Workspace::reserve(size_t bytes) {
+    off = 0;
+    if (bytes <= cap) return FIR_OK;
+    if (base) {
+        FIR_CUDA_TRY(cudaStreamSynchronize(stream));
+        FIR_CUDA_TRY(cudaFree(base));
+        base = nullptr; cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + (1 << 20);
+    FIR_CUDA_TRY(cudaMalloc(&base, want));
+    cap = want;
+    return FIR_OK;
+}
+void* Workspace::take(size_t bytes) {
+    size_t a = (off + 255) & ~(size_t)255;
+    if (a + bytes > cap) return nullptr;
+    off = a + bytes;
+    return base + a;
+}
+void Workspace::release() {
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0; off = 0;
+}
+
+static size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// Make `queries` (nq x d, host or device) available as zero-padded device rows [nq][dp].
+static int stage_queries(fir_gallery* g, const float* queries, int64_t nq, int memspace, const float** dq) {
+    const int d = g->d, dp = g->dp;
+    if (memspace == FIR_DEVICE && d == dp) { *dq = queries; return FIR_OK; }
+    float* buf = (float*)g->ws.take(sizeof(float) * (size_t)nq * dp);
+    if (!buf) return fail(FIR_ERR_INTERNAL, "workspace underestimated (queries)");
+    if (memspace == FIR_HOST) {
+        if (d != dp) FIR_CUDA_TRY(cudaMemsetAsync(buf, 0, sizeof(float) * (size_t)nq * dp, g->stream));
+        FIR_CUDA_TRY(cudaMemcpy2DAsync(buf, sizeof(float) * dp, queries, sizeof(float) * d, sizeof(float) * d, (size_t)nq,
+                                       cudaMemcpyHostToDevice, g->stream));
+    } else {
+        FIR_TRY(launch_pad_rows(queries, nq, d, buf, dp, g->stream));
+        g->stats.gpu_launches++;
+    }
+    *dq = buf;
+    return FIR_OK;
+}
+
+static int pick_nsplit(int64_t nq, int64_t n, int n_sm) {
+    int64_t qblocks = ceil_div(nq, kExactTile);
+    int64_t ntiles = ceil_div(n, kExactTile);
+    int64_t want = ceil_div((int64_t)n_sm * 4, qblocks);
+    want = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, ntiles), 64));
+    return (int)want;
+}
+
+// exact CUDA-core top-k over (optionally) a subset of queries; results to device out_* [nq][k]
+int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_end, const int32_t* qmap,
+                      const int32_t* n_active, float* part_d, int32_t* part_i, int nsplit, float* od, int32_t* oi) {
+    ExactParams p{};
+    p.q = dq; p.nq = nq; p.ldq = g->dp;
+    p.x = g->rows; p.n = g->n; p.ldx = g->dp;
+    p.labels = g->labels;
+    p.d_end = d_end; p.k = k; p.mode = MODE_TOPK;
+    p.nsplit = nsplit;
+    p.tiles_per_split = ceil_div(ceil_div(g->n, kExactTile), nsplit);
+    p.part_dist = part_d; p.part_idx = part_i;
+    p.qmap = qmap; p.n_active = n_active;
+    FIR_TRY(launch_exact_tiles(g->metric, p, g->stream));
+    FIR_TRY(launch_merge_parts(part_d, part_i, nsplit, k, (int64_t)nsplit * k, nq, k, g->index_offset, qmap, n_active, od, oi, g->stream));
+    g->stats.gpu_launches += 2;
+    return FIR_OK;
+}
+
+}  // namespace fir
+
+using namespace fir;
+
+extern "C" {
+
+const char* fir_last_error_string(void) { return g_last_error.c_str(); }
+int fir_version(void) { return FIR_B200_VERSION; }
+
+int fir_device_count(int* count) {
+    if (!count) return fail(FIR_ERR_BAD_ARG, "count is null");
+    *count = 0;
+    FIR_CUDA_TRY(cudaGetDeviceCount(count));
+    return FIR_OK;
+}
+int fir_set_device(int device) {
+    FIR_CUDA_TRY(cudaSetDevice(device));
+    return FIR_OK;
+}
+
+int fir_gallery_create(const float* rows, const int32_t* labels, int64_t n, int32_t d, int32_t metric, int32_t memspace,
+                       int64_t index_offset, fir_gallery** out) {
+    if (!out) return fail(FIR_ERR_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (!rows || n <= 0 || d <= 0) return fail(FIR_ERR_BAD_ARG, "empty gallery (the reference returns -1 for every query; create no handle)");
+    if (metric < FIR_L2 || metric > FIR_KL) return fail(FIR_ERR_BAD_ARG, "unknown metric");
+    if (n + index_offset > (int64_t)std::numeric_limits<int32_t>::max()) return fail(FIR_ERR_UNSUPPORTED, "global gallery index exceeds int32");
+    fir_gallery* g = new fir_gallery();
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { delete g; return fail(FIR_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e)); }
+    g->device = dev;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) { delete g; return fail(FIR_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e)); }
+    g->n_sm = prop.multiProcessorCount;
+    g->cc_major = prop.major;
+    g->n = n; g->d = d; g->dp = round_up(d, kRowPad); g->metric = metric; g->index_offset = index_offset;
+    auto cleanup = [&](int code) { fir_gallery_destroy(g); return code; };
+    e = cudaMalloc(&g->rows, sizeof(float) * (size_t)n * g->dp);
+    if (e != cudaSuccess) return cleanup(fail(FIR_ERR_OOM, std::string("gallery rows: ") + cudaGetErrorString(e)));
+    e = cudaMalloc(&g->labels, sizeof(int32_t) * (size_t)n);
+    if (e != cudaSuccess) return cleanup(fail(FIR_ERR_OOM, std::string("gallery labels: ") + cudaGetErrorString(e)));
+    cudaMemcpyKind kind = memspace == FIR_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (g->dp != d) {
+        e = cudaMemset(g->rows, 0, sizeof(float) * (size_t)n * g->dp);
+        if (e != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, cudaGetErrorString(e)));
+    }
+    e = cudaMemcpy2D(g->rows, sizeof(float) * g->dp, rows, sizeof(float) * d, sizeof(float) * d, (size_t)n, kind);
+    if (e != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, std::string("gallery upload: ") + cudaGetErrorString(e)));
+    // labels: class ids; n_classes = max+1 (host copy kept for DEM build / classmin sizing)
+    g->h_labels.assign((size_t)n, 0);
+    if (labels) {
+        if (memspace == FIR_HOST) std::memcpy(g->h_labels.data(), labels, sizeof(int32_t) * (size_t)n);
+        else {
+            e = cudaMemcpy(g->h_labels.data(), labels, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, cudaGetErrorString(e)));
+        }
+    }
+    int32_t mx = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (g->h_labels[i] < 0) return cleanup(fail(FIR_ERR_BAD_ARG, "negative class label"));
+        mx = std::max(mx, g->h_labels[i]);
+    }
+    g->n_classes = mx + 1;
+    e = cudaMemcpy(g->labels, g->h_labels.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, cudaGetErrorString(e)));
+    *out = g;
+    return FIR_OK;
+}
+
+int fir_gallery_destroy(fir_gallery* g) {
+    if (!g) return FIR_OK;
+    cudaStreamSynchronize(g->stream);
+    if (g->rows) cudaFree(g->rows);
+    if (g->labels) cudaFree(g->labels);
+    if (g->tensor_buf) cudaFree(g->tensor_buf);
+    if (g->d_stats) cudaFree(g->d_stats);
+    g->ws.release();
+    delete g;
+    return FIR_OK;
+}
+
+int fir_gallery_set_stream(fir_gallery* g, void* cuda_stream) {
+    if (!g) return fail(FIR_ERR_BAD_ARG, "gallery is null");
+    g->stream = (cudaStream_t)cuda_stream;
+    g->ws.stream = g->stream;
+    return FIR_OK;
+}
+
+int fir_gallery_info(const fir_gallery* g, int64_t* n, int32_t* d, int32_t* metric, int32_t* n_classes) {
+    if (!g) return fail(FIR_ERR_BAD_ARG, "gallery is null");
+    if (n) *n = g->n;
+    if (d) *d = g->d;
+    if (metric) *metric = g->metric;
+    if (n_classes) *n_classes = g->n_classes;
+    return FIR_OK;
+}
+
+int fir_normalize_rows(float* rows, int64_t n, int32_t d, int32_t metric, int32_t memspace, void* cuda_stream) {
+    if (!rows || n < 0 || d <= 0) return fail(FIR_ERR_BAD_ARG, "bad rows");
+    if (n == 0) return FIR_OK;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    if (memspace == FIR_DEVICE) return launch_normalize_rows(rows, n, d, d, metric, s);
+    float* buf = nullptr;
+    FIR_CUDA_TRY(cudaMalloc(&buf, sizeof(float) * (size_t)n * d));
+    int st = FIR_OK;
+    cudaError_t e = cudaMemcpyAsync(buf, rows, sizeof(float) * (size_t)n * d, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) st = launch_normalize_rows(buf, n, d, d, metric, s);
+    if (e == cudaSuccess && st == FIR_OK) e = cudaMemcpyAsync(rows, buf, sizeof(float) * (size_t)n * d, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(buf);
+    if (st != FIR_OK) return st;
+    if (e != cudaSuccess) return fail(FIR_ERR_CUDA, cudaGetErrorString(e));
+    return FIR_OK;
+}
+
+int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k, int32_t max_features, int32_t path,
+                    int32_t memspace, int32_t* out_idx, float* out_dist) {
+    if (!g) return fail(FIR_ERR_BAD_ARG, "gallery is null");
+    if (nq < 0 || (nq > 0 && (!queries || !out_idx))) return fail(FIR_ERR_BAD_ARG, "bad query/output pointers");
+    if (k < 1 || k > 1024) return fail(FIR_ERR_BAD_ARG, "k must be in [1,1024]");
+    if (max_features < 0 || max_features > g->d) return fail(FIR_ERR_BAD_ARG, "max_features out of range");
+    g->stats = fir_search_stats{};
+    if (nq == 0) return FIR_OK;
+    FIR_CUDA_TRY(cudaSetDevice(g->device));
+    const int d_end = max_features > 0 ? max_features : g->d;
+    bool tensor_ok = g->metric == FIR_L2 && max_features == 0 && tensor_path_supported(g->d) && g->cc_major >= 10 && k <= 28;
+    if (path == FIR_PATH_TENSOR && !tensor_ok)
+        return fail(FIR_ERR_UNSUPPORTED, "tensor path needs L2, all dimensions, k<=28 and an sm_100 device");
+    bool use_tensor = (path == FIR_PATH_TENSOR) || (path == FIR_PATH_AUTO && tensor_ok && nq * g->n >= (int64_t)1 << 22);
+    if (use_tensor) return tensor_search_topk(g, queries, nq, k, memspace, out_idx, out_dist);
+
+    const int nsplit = pick_nsplit(nq, g->n, g->n_sm);
+    size_t need = al(sizeof(float) * (size_t)nq * g->dp) + 2 * al((size_t)nq * nsplit * k * 4) + 2 * al((size_t)nq * k * 4) + 4096;
+    FIR_TRY(g->ws.reserve(need));
+    const float* dq = nullptr;
+    FIR_TRY(stage_queries(g, queries, nq, memspace, &dq));
+    float* part_d = (float*)g->ws.take((size_t)nq * nsplit * k * 4);
+    int32_t* part_i = (int32_t*)g->ws.take((size_t)nq * nsplit * k * 4);
+    float* od = out_dist; int32_t* oi = out_idx;
+    if (memspace == FIR_HOST || !out_dist) od = (float*)g->ws.take((size_t)nq * k * 4);
+    if (memspace == FIR_HOST) oi = (int32_t*)g->ws.take((size_t)nq * k * 4);
+    if (!part_d || !part_i || !od || !oi) return fail(FIR_ERR_INTERNAL, "workspace underestimated (topk)");
+    FIR_TRY(exact_topk_device(g, dq, nq, k, d_end, nullptr, nullptr, part_d, part_i, nsplit, od, oi));
+    g->stats.path_used = FIR_PATH_EXACT;
+    if (memspace == FIR_HOST) {
+        FIR_CUDA_TRY(cudaMemcpyAsync(out_idx, oi, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
+        if (out_dist) FIR_CUDA_TRY(cudaMemcpyAsync(out_dist, od, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
+        FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    }
+    return FIR_OK;
+}
+
+int fir_search_last_stats(const fir_gallery* g, fir_search_stats* stats) {
+    if (!g || !stats) return fail(FIR_ERR_BAD_ARG, "null argument");
+    *stats = g->stats;
+    return FIR_OK;
+}
+
+int fir_pair_distances(fir_gallery* g, const float* queries, int64_t nq, const int32_t* cand_idx, int32_t r, int32_t gallery_is_lhs,
+                       int32_t memspace, float* out_dist) {
+    if (!g) return fail(FIR_ERR_BAD_ARG, "gallery is null");
+    if (nq < 0 || r < 1 || (nq > 0 && (!queries || !cand_idx || !out_dist))) return fail(FIR_ERR_BAD_ARG, "bad arguments");
+    if (nq == 0) return FIR_OK;
+    FIR_CUDA_TRY(cudaSetDevice(g->device));
+    size_t need = al(sizeof(float) * (size_t)nq * g->dp) + 2 * al((size_t)nq * r * 4) + 4096;
+    FIR_TRY(g->ws.reserve(need));
+    const float* dq = nullptr;
+    FIR_TRY(stage_queries(g, queries, nq, memspace, &dq));
+    const int32_t* dc = cand_idx; float* od = out_dist;
+    if (memspace == FIR_HOST) {
+        int32_t* c = (int32_t*)g->ws.take((size_t)nq * r * 4);
+        od = (float*)g->ws.take((size_t)nq * r * 4);
+        if (!c || !od) return fail(FIR_ERR_INTERNAL, "workspace underestimated (pairs)");
+        FIR_CUDA_TRY(cudaMemcpyAsync(c, cand_idx, (size_t)nq * r * 4, cudaMemcpyHostToDevice, g->stream));
+        dc = c;
+    }
+    FIR_TRY(launch_pair_distances(g->metric, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, dc, r, gallery_is_lhs, od, g->stream));
+    if (memspace == FIR_HOST) {
+        FIR_CUDA_TRY(cudaMemcpyAsync(out_dist, od, (size_t)nq * r * 4, cudaMemcpyDeviceToHost, g->stream));
+        FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    }
+    return FIR_OK;
+}
+
+static int class_reduce(fir_gallery* g, const float* queries, int64_t nq, int memspace, int mode, double var, int64_t n_total,
+                        float* out_min, int32_t* out_arg, double* out_scores, int32_t* out_label) {
+    if (!g) return fail(FIR_ERR_BAD_ARG, "gallery is null");
+    if (nq < 0 || (nq > 0 && !queries)) return fail(FIR_ERR_BAD_ARG, "bad query pointer");
+    if (nq == 0) return FIR_OK;
+    FIR_CUDA_TRY(cudaSetDevice(g->device));
+    const int C = g->n_classes;
+    const size_t cells = (size_t)nq * C;
+    size_t need = al(sizeof(float) * (size_t)nq * g->dp) + al(cells * 8) + al(cells * 4) * 2 + al((size_t)nq * 4) + 4096;
+    FIR_TRY(g->ws.reserve(need));
+    const float* dq = nullptr;
+    FIR_TRY(stage_queries(g, queries, nq, memspace, &dq));
+    ExactParams p{};
+    p.q = dq; p.nq = nq; p.ldq = g->dp;
+    p.x = g->rows; p.n = g->n; p.ldx = g->dp;
+    p.labels = g->labels; p.d_end = g->d; p.k = 0; p.mode = mode;
+    p.nsplit = pick_nsplit(nq, g->n, g->n_sm);
+    p.tiles_per_split = ceil_div(ceil_div(g->n, kExactTile), p.nsplit);
+    p.n_classes = C;
+    if (mode == MODE_CLASSMIN) {
+        if (!out_min || !out_arg) return fail(FIR_ERR_BAD_ARG, "null outputs");
+        unsigned long long* keys = (unsigned long long*)g->ws.take(cells * 8);
+        float* dmin = out_min; int32_t* darg = out_arg;
+        if (memspace == FIR_HOST) { dmin = (float*)g->ws.take(cells * 4); darg = (int32_t*)g->ws.take(cells * 4); }
+        if (!keys || !dmin || !darg) return fail(FIR_ERR_INTERNAL, "workspace underestimated (classmin)");
+        FIR_TRY(launch_fill_u64(keys, (int64_t)cells, ~0ull, g->stream));
+        p.cls_key = keys;
+        FIR_TRY(launch_exact_tiles(g->metric, p, g->stream));
+        FIR_TRY(launch_classmin_finalize(keys, (int64_t)cells, g->index_offset, dmin, darg, g->stream));
+        if (memspace == FIR_HOST) {
+            FIR_CUDA_TRY(cudaMemcpyAsync(out_min, dmin, cells * 4, cudaMemcpyDeviceToHost, g->stream));
+            FIR_CUDA_TRY(cudaMemcpyAsync(out_arg, darg, cells * 4, cudaMemcpyDeviceToHost, g->stream));
+            FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
+        }
+    } else {
+        if (!(var > 0)) return fail(FIR_ERR_BAD_ARG, "var must be > 0");
+        double* sc = out_scores; int32_t* lab = out_label;
+        if (memspace == FIR_HOST || !out_scores) sc = (double*)g->ws.take(cells * 8);
+        if (memspace == FIR_HOST && out_label) lab = (int32_t*)g->ws.take((size_t)nq * 4);
+        if (!sc) return fail(FIR_ERR_INTERNAL, "workspace underestimated (pnn)");
+        FIR_CUDA_TRY(cudaMemsetAsync(sc, 0, cells * 8, g->stream));
+        p.cls_score = sc; p.two_var = 2 * var;
+        FIR_TRY(launch_exact_tiles(g->metric, p, g->stream));
+        FIR_TRY(launch_pnn_finalize(sc, nq, C, (double)(n_total > 0 ? n_total : g->n), lab, g->stream));
+        if (memspace == FIR_HOST) {
+            if (out_scores) FIR_CUDA_TRY(cudaMemcpyAsync(out_scores, sc, cells * 8, cudaMemcpyDeviceToHost, g->stream));
+            if (out_label) FIR_CUDA_TRY(cudaMemcpyAsync(out_label, lab, (size_t)nq * 4, cudaMemcpyDeviceToHost, g->stream));
+            FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
+        }
+    }
+    return FIR_OK;
+}
+
+int fir_class_min(fir_gallery* g, const float* queries, int64_t nq, int32_t memspace, float* out_min, int32_t* out_arg) {
+    return class_reduce(g, queries, nq, memspace, MODE_CLASSMIN, 0, 0, out_min, out_arg, nullptr, nullptr);
+}
+
+int fir_pnn_scores(fir_gallery* g, const float* queries, int64_t nq, double var, int64_t n_total, int32_t memspace,
+                   double* out_scores, int32_t* out_label) {
+    return class_reduce(g, queries, nq, memspace, MODE_PNN, var, n_total, nullptr, nullptr, out_scores, out_label);
+}
+
+int fir_merge_topk(const float* parts_dist, const int32_t* parts_idx, int32_t n_parts, int64_t nq, int32_t k, float* out_dist,
+                   int32_t* out_idx, void* cuda_stream) {
+    if (!parts_dist || !parts_idx || !out_dist || !out_idx || n_parts < 1 || k < 1 || nq < 0) return fail(FIR_ERR_BAD_ARG, "bad arguments");
+    return launch_merge_parts(parts_dist, parts_idx, n_parts, nq * k, k, nq, k, 0, nullptr, nullptr, out_dist, out_idx, (cudaStream_t)cuda_stream);
+}
+
+}  // extern "C"

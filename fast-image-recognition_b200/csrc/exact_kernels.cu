@@ -1,0 +1,444 @@
+// exact_kernels.cu — bit-faithful CUDA-core kernels for the matching path.
+//
+// Every distance here reproduces feature_distance (qt_cpp/db_features.cpp:22-42) bit for bit: one
+// thread owns a (query, gallery row) pair and accumulates over the dimensions in index order with
+// separately rounded fp32 sub/mul/add(/div/logf) — parallelism comes from the Q x N pairs, never from
+// splitting a sum.  The tile kernel fuses the reductions the reference performs right after the
+// distance loop: argmin / top-k (ann.cpp:117-123, db_features.cpp:325-333), per-class minimum, and the
+// Parzen sum of PNNClassifier::predict_bf (classification.cpp:213).
+#include "fir_common.cuh"
+
+namespace fir {
+
+// ---------------------------------------------------------------------------------------------------
+// cp.async helpers (LDGSTS): 16-byte global->shared copies, zero-filled when src_bytes == 0
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+constexpr int TS = kExactTile;        // 64
+constexpr int CH = kExactChunk;       // 32
+constexpr int LDT = CH + 4;           // smem row stride in floats: 36 ⇒ LDS.128 conflict-free for 8 consecutive rows
+constexpr int LDD = TS + 1;
+
+static size_t exact_smem_bytes(int k, int mode) {
+    size_t b = sizeof(float) * (size_t)(4 * TS * LDT + TS * LDD) + sizeof(int) * TS;
+    if (mode == MODE_TOPK) b += (size_t)TS * k * 8;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Tile kernel: block = 64 queries x (a split of the gallery, walked in 64-row tiles); 256 threads,
+// thread (ty,tx) owns the 4x4 pairs {ty+16a} x {tx+16b}.  Dimensions are staged 32 at a time through a
+// 2-stage cp.async ring; after the last chunk the 64x64 distances go to shared memory and one thread
+// per query folds them, in gallery order, into its running reduction.
+// ---------------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* qs = reinterpret_cast<float*>(smem_raw);   // [2][TS][LDT]
+    float* xs = qs + 2 * TS * LDT;                    // [2][TS][LDT]
+    float* ds = xs + 2 * TS * LDT;                    // [TS][LDD]
+    int* ls = reinterpret_cast<int*>(ds + TS * LDD);  // [TS]
+    float* tkd = reinterpret_cast<float*>(ls + TS);   // [TS][k]
+    int* tki = reinterpret_cast<int*>(tkd + TS * p.k);
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t n_active = p.n_active ? (int64_t)*p.n_active : p.nq;
+    const int64_t q0 = (int64_t)blockIdx.x * TS;
+    if (q0 >= n_active) return;
+    const int64_t ntiles = (p.n + TS - 1) / TS;
+    const int64_t t_lo = (int64_t)blockIdx.y * p.tiles_per_split;
+    const int64_t t_hi = min(ntiles, t_lo + p.tiles_per_split);
+    const int nchunks = (p.d_end + CH - 1) / CH;
+    const float inv_den = (float)p.d_end;
+
+    // this thread's two (row, 16B column) slots of each 64x32 stage tile
+    const int lr0 = tid >> 3, lc = (tid & 7) * 4;     // rows lr0 and lr0+32
+    int64_t qrow[2];
+    bool qok[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int64_t qi = q0 + lr0 + 32 * h;
+        qok[h] = qi < n_active;
+        int64_t src = qok[h] ? (p.qmap ? (int64_t)p.qmap[qi] : qi) : 0;
+        qrow[h] = src * p.ldq;
+    }
+
+    if (p.mode == MODE_TOPK) {
+        for (int i = tid; i < TS * p.k; i += 256) { tkd[i] = 100000.0f; tki[i] = -1; }
+    }
+    // per-query running state for the class reductions (only threads < TS use it)
+    int cur_c = -1;
+    unsigned long long cur_key = ~0ull;
+    double cur_sum = 0.0;
+    const int64_t my_q = q0 + tid;
+    const int64_t my_q_out = (tid < TS && my_q < n_active) ? (p.qmap ? (int64_t)p.qmap[my_q] : my_q) : -1;
+
+    for (int64_t t = t_lo; t < t_hi; ++t) {
+        const int64_t x0 = t * TS;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+        auto load_chunk = [&](int c, int st) {
+            const int kk = c * CH + lc;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int r = lr0 + 32 * h;
+                cp_async16(&qs[(st * TS + r) * LDT + lc], p.q + qrow[h] + kk, qok[h] ? 16 : 0);
+                int64_t xr = x0 + r;
+                bool ok = xr < p.n;
+                cp_async16(&xs[(st * TS + r) * LDT + lc], p.x + (ok ? xr : 0) * p.ldx + kk, ok ? 16 : 0);
+            }
+        };
+
+        load_chunk(0, 0);
+        cp_async_commit();
+        if (tid < TS && p.mode != MODE_TOPK) ls[tid] = (x0 + tid < p.n) ? p.labels[x0 + tid] : -1;
+
+        for (int c = 0; c < nchunks; ++c) {
+            const int st = c & 1;
+            if (c + 1 < nchunks) load_chunk(c + 1, st ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncthreads();
+            const float* qb = qs + st * TS * LDT;
+            const float* xb = xs + st * TS * LDT;
+            const int kmax = min(CH, p.d_end - c * CH);
+            if (kmax == CH) {
+#pragma unroll
+                for (int k4 = 0; k4 < CH / 4; ++k4) {
+                    float4 qa[4], xa[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) qa[a] = *reinterpret_cast<const float4*>(&qb[(ty + 16 * a) * LDT + k4 * 4]);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) xa[b] = *reinterpret_cast<const float4*>(&xb[(tx + 16 * b) * LDT + k4 * 4]);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            dist_step<METRIC>(acc[a][b], qa[a].x, xa[b].x);
+                            dist_step<METRIC>(acc[a][b], qa[a].y, xa[b].y);
+                            dist_step<METRIC>(acc[a][b], qa[a].z, xa[b].z);
+                            dist_step<METRIC>(acc[a][b], qa[a].w, xa[b].w);
+                        }
+                }
+            } else {
+                for (int kk = 0; kk < kmax; ++kk) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            dist_step<METRIC>(acc[a][b], qb[(ty + 16 * a) * LDT + kk], xb[(tx + 16 * b) * LDT + kk]);
+                }
+            }
+            __syncthreads();
+        }
+
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) ds[(ty + 16 * a) * LDD + tx + 16 * b] = __fdiv_rn(acc[a][b], inv_den);   // db_features.cpp:40
+        __syncthreads();
+
+        if (my_q_out >= 0) {
+            const int jmax = (int)min((int64_t)TS, p.n - x0);
+            const float* drow = ds + tid * LDD;
+            if (p.mode == MODE_TOPK) {
+                const int k = p.k;
+                float* ld = tkd + tid * k;
+                int* li = tki + tid * k;
+                float worst = ld[k - 1];
+                for (int j = 0; j < jmax; ++j) {
+                    float d = drow[j];
+                    if (d < worst) {          // strict '<': an equal distance never displaces an earlier index
+                        int pos = k - 1;
+                        while (pos > 0 && d < ld[pos - 1]) { ld[pos] = ld[pos - 1]; li[pos] = li[pos - 1]; --pos; }
+                        ld[pos] = d;
+                        li[pos] = (int)(x0 + j);
+                        worst = ld[k - 1];
+                    }
+                }
+            } else if (p.mode == MODE_CLASSMIN) {
+                for (int j = 0; j < jmax; ++j) {
+                    float d = drow[j];
+                    if (!(d < 100000.0f)) continue;
+                    int c = ls[j];
+                    unsigned long long key = ((unsigned long long)ordered_bits(d) << 32) | (uint32_t)(x0 + j);
+                    if (c != cur_c) {
+                        if (cur_c >= 0) atomicMin(&p.cls_key[my_q_out * p.n_classes + cur_c], cur_key);
+                        cur_c = c; cur_key = key;
+                    } else if (key < cur_key) cur_key = key;
+                }
+            } else {
+                for (int j = 0; j < jmax; ++j) {
+                    int c = ls[j];
+                    double e = exp(-(double)drow[j] / p.two_var);
+                    if (c != cur_c) {
+                        if (cur_c >= 0) atomicAdd(&p.cls_score[my_q_out * p.n_classes + cur_c], cur_sum);
+                        cur_c = c; cur_sum = e;
+                    } else cur_sum += e;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (p.mode == MODE_TOPK) {
+        for (int i = tid; i < TS * p.k; i += 256) {
+            int r = i / p.k, s = i - r * p.k;
+            int64_t qi = q0 + r;
+            if (qi < n_active) {
+                int64_t qo = p.qmap ? (int64_t)p.qmap[qi] : qi;
+                int64_t o = (qo * p.nsplit + blockIdx.y) * p.k + s;
+                p.part_dist[o] = tkd[i];
+                p.part_idx[o] = tki[i];
+            }
+        }
+    } else if (my_q_out >= 0 && cur_c >= 0) {
+        if (p.mode == MODE_CLASSMIN) atomicMin(&p.cls_key[my_q_out * p.n_classes + cur_c], cur_key);
+        else atomicAdd(&p.cls_score[my_q_out * p.n_classes + cur_c], cur_sum);
+    }
+}
+
+int launch_exact_tiles(int metric, const ExactParams& p, cudaStream_t s) {
+    if (p.nq <= 0 || p.n <= 0) return FIR_OK;
+    size_t smem = exact_smem_bytes(p.k, p.mode);
+    if (smem > 200 * 1024) return fail(FIR_ERR_UNSUPPORTED, "k too large for the exact tile kernel");
+    dim3 grid((unsigned)ceil_div(p.nq, TS), (unsigned)p.nsplit);
+    auto go = [&](auto kern) -> int {
+        FIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 256, smem, s>>>(p);
+        FIR_CUDA_TRY(cudaGetLastError());
+        return FIR_OK;
+    };
+    switch (metric) {
+        case FIR_L2: return go(exact_tile_kernel<FIR_L2>);
+        case FIR_CHI2: return go(exact_tile_kernel<FIR_CHI2>);
+        case FIR_KL: return go(exact_tile_kernel<FIR_KL>);
+    }
+    return fail(FIR_ERR_BAD_ARG, "unknown metric");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lexicographic (dist, idx) merge of n_parts sorted lists per query.  idx < 0 marks an empty slot.
+// Used for the gallery splits of one GPU and for the all-gathered per-GPU lists (fir_merge_topk).
+// ---------------------------------------------------------------------------------------------------
+__global__ void merge_parts_kernel(const float* __restrict__ pd, const int32_t* __restrict__ pi, int n_parts,
+                                   int64_t part_stride, int64_t q_stride, int64_t nq, int k, int64_t index_offset,
+                                   const int32_t* qmap, const int32_t* n_active, float* od, int32_t* oi) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t na = n_active ? (int64_t)*n_active : nq;
+    if (i >= na) return;
+    int64_t q = qmap ? (int64_t)qmap[i] : i;
+    constexpr int MAXP = 64;
+    unsigned char head[MAXP];
+    for (int s = 0; s < n_parts; ++s) head[s] = 0;
+    for (int r = 0; r < k; ++r) {
+        float bd = 0.f; int32_t bi = -1; int bs = -1;
+        for (int s = 0; s < n_parts; ++s) {
+            int h = head[s];
+            if (h >= k) continue;
+            int64_t o = (int64_t)s * part_stride + q * q_stride + h;
+            int32_t ci = pi[o];
+            if (ci < 0) continue;
+            float cd = pd[o];
+            if (bs < 0 || cd < bd || (cd == bd && ci < bi)) { bd = cd; bi = ci; bs = s; }
+        }
+        if (bs >= 0) { head[bs]++; od[q * k + r] = bd; oi[q * k + r] = (int32_t)(bi + index_offset); }
+        else { od[q * k + r] = 0.f; oi[q * k + r] = -1; }
+    }
+}
+
+int launch_merge_parts(const float* pd, const int32_t* pi, int n_parts, int64_t part_stride, int64_t q_stride,
+                       int64_t nq, int k, int64_t index_offset, const int32_t* qmap, const int32_t* n_active,
+                       float* od, int32_t* oi, cudaStream_t s) {
+    if (nq <= 0) return FIR_OK;
+    if (n_parts > 64) return fail(FIR_ERR_UNSUPPORTED, "more than 64 parts to merge");
+    merge_parts_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(pd, pi, n_parts, part_stride, q_stride, nq, k, index_offset,
+                                                                   qmap, n_active, od, oi);
+    FIR_CUDA_TRY(cudaGetLastError());
+    return FIR_OK;
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, int64_t n, unsigned long long v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+int launch_fill_u64(unsigned long long* p, int64_t n, unsigned long long v, cudaStream_t s) {
+    if (n <= 0) return FIR_OK;
+    fill_u64_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(p, n, v);
+    FIR_CUDA_TRY(cudaGetLastError());
+    return FIR_OK;
+}
+
+__global__ void classmin_finalize_kernel(const unsigned long long* keys, int64_t n, int64_t index_offset, float* omin, int32_t* oarg) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long key = keys[i];
+    if (key == ~0ull) { omin[i] = 100000.0f; oarg[i] = -1; }
+    else { omin[i] = from_ordered_bits((uint32_t)(key >> 32)); oarg[i] = (int32_t)((uint32_t)key + index_offset); }
+}
+int launch_classmin_finalize(const unsigned long long* keys, int64_t n, int64_t index_offset, float* omin, int32_t* oarg, cudaStream_t s) {
+    if (n <= 0) return FIR_OK;
+    classmin_finalize_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(keys, n, index_offset, omin, oarg);
+    FIR_CUDA_TRY(cudaGetLastError());
+    return FIR_OK;
+}
+
+// scores /= n_total (classification.cpp:215), argmax with strict '<' from -DBL_MAX (:217-225)
+__global__ void pnn_finalize_kernel(double* scores, int64_t nq, int n_classes, double n_total, int32_t* olabel) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    double mx = -1.7976931348623157e308; int best = -1;
+    double* s = scores + q * n_classes;
+    for (int c = 0; c < n_classes; ++c) {
+        double v = s[c] / n_total;
+        s[c] = v;
+        if (mx < v) { mx = v; best = c; }
+    }
+    if (olabel) olabel[q] = best;
+}
+int launch_pnn_finalize(double* scores, int64_t nq, int n_classes, double n_total, int32_t* olabel, cudaStream_t s) {
+    if (nq <= 0) return FIR_OK;
+    pnn_finalize_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(scores, nq, n_classes, n_total, olabel);
+    FIR_CUDA_TRY(cudaGetLastError());
+    return FIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Exact distances for explicit (query, gallery row) pairs — the fp32 rerank of the tensor path and the
+// candidate evaluation of directed enumeration.  One warp = one query x 32 candidates: the 32 candidate
+// rows are staged 128 dims at a time into shared memory with coalesced 512-byte loads, then lane c
+// walks row c sequentially.
+// ---------------------------------------------------------------------------------------------------
+constexpr int PW = 4;            // warps per block
+constexpr int PCH = 128;         // dims per stage
+constexpr int PLD = PCH + 4;     // 132 ⇒ LDS.128 conflict-free across 8 consecutive rows
+
+template <int METRIC>
+__global__ void __launch_bounds__(PW * 32) pair_distance_kernel(const float* __restrict__ q, int64_t nq, int ldq,
+                                                                const float* __restrict__ x, int ldx, int64_t n, int d_end,
+                                                                const int32_t* __restrict__ cand, int r, int gallery_is_lhs,
+                                                                float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (32 * PLD + PCH);
+    float* qv = tile + 32 * PLD;
+    const int groups = (r + 31) / 32;
+    const int64_t item = (int64_t)blockIdx.x * PW + warp;
+    if (item >= nq * groups) return;
+    const int64_t qi = item / groups;
+    const int g = (int)(item - qi * groups);
+    const int slot = g * 32 + lane;
+    int32_t my = (slot < r) ? cand[qi * r + slot] : -1;
+    if (my >= n) my = -1;
+    float acc = 0.f;
+    const int ld_lim = ldx;   // rows are zero padded up to ldx
+    for (int c0 = 0; c0 < d_end; c0 += PCH) {
+        const int col = c0 + lane * 4;
+        for (int c = 0; c < 32; ++c) {
+            int32_t ci = __shfl_sync(0xffffffffu, my, c);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ci >= 0 && col < ld_lim) v = *reinterpret_cast<const float4*>(x + (int64_t)ci * ldx + col);
+            *reinterpret_cast<float4*>(&tile[c * PLD + lane * 4]) = v;
+        }
+        {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col < ldq) v = *reinterpret_cast<const float4*>(q + qi * ldq + col);
+            *reinterpret_cast<float4*>(&qv[lane * 4]) = v;
+        }
+        __syncwarp();
+        const int kmax = min(PCH, d_end - c0);
+        const float* row = tile + lane * PLD;
+        int kk = 0;
+        if (gallery_is_lhs) {
+            for (; kk + 4 <= kmax; kk += 4) {
+                float4 a = *reinterpret_cast<const float4*>(&row[kk]);
+                float4 b = *reinterpret_cast<const float4*>(&qv[kk]);
+                dist_step<METRIC>(acc, a.x, b.x); dist_step<METRIC>(acc, a.y, b.y);
+                dist_step<METRIC>(acc, a.z, b.z); dist_step<METRIC>(acc, a.w, b.w);
+            }
+            for (; kk < kmax; ++kk) dist_step<METRIC>(acc, row[kk], qv[kk]);
+        } else {
+            for (; kk + 4 <= kmax; kk += 4) {
+                float4 a = *reinterpret_cast<const float4*>(&row[kk]);
+                float4 b = *reinterpret_cast<const float4*>(&qv[kk]);
+                dist_step<METRIC>(acc, b.x, a.x); dist_step<METRIC>(acc, b.y, a.y);
+                dist_step<METRIC>(acc, b.z, a.z); dist_step<METRIC>(acc, b.w, a.w);
+            }
+            for (; kk < kmax; ++kk) dist_step<METRIC>(acc, qv[kk], row[kk]);
+        }
+        __syncwarp();
+    }
+    if (slot < r) out[qi * r + slot] = (my >= 0) ? __fdiv_rn(acc, (float)d_end) : __int_as_float(0x7f800000);
+}
+
+int launch_pair_distances(int metric, const float* q, int64_t nq, int ldq, const float* x, int ldx, int64_t n, int d_end,
+                          const int32_t* cand, int r, int gallery_is_lhs, float* out, cudaStream_t s) {
+    if (nq <= 0 || r <= 0) return FIR_OK;
+    const int groups = (r + 31) / 32;
+    size_t smem = sizeof(float) * (size_t)PW * (32 * PLD + PCH);
+    unsigned grid = (unsigned)ceil_div(nq * groups, PW);
+    auto go = [&](auto kern) -> int {
+        FIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, PW * 32, smem, s>>>(q, nq, ldq, x, ldx, n, d_end, cand, r, gallery_is_lhs, out);
+        FIR_CUDA_TRY(cudaGetLastError());
+        return FIR_OK;
+    };
+    switch (metric) {
+        case FIR_L2: return go(pair_distance_kernel<FIR_L2>);
+        case FIR_CHI2: return go(pair_distance_kernel<FIR_CHI2>);
+        case FIR_KL: return go(pair_distance_kernel<FIR_KL>);
+    }
+    return fail(FIR_ERR_BAD_ARG, "unknown metric");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Loader normalisation (qt_cpp/db_features.cpp:79-101), one thread per row, sequential fp32 sums.
+// ---------------------------------------------------------------------------------------------------
+__global__ void normalize_rows_kernel(float* rows, int64_t n, int d, int ld, int metric) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float* f = rows + r * ld;
+    float sum = 0.f;
+    for (int i = 0; i < d; ++i) {
+        float v = f[i];
+        if ((double)fabsf(v) < 0.0001) v = 0.f;                               // :85-86 (float |x| against a double literal)
+        f[i] = v;
+        sum = (metric == FIR_L2) ? __fadd_rn(sum, __fmul_rn(v, v)) : __fadd_rn(sum, v);   // :91 / :93
+    }
+    if (metric == FIR_L2) sum = __fsqrt_rn(sum);                              // :98
+    for (int i = 0; i < d; ++i) f[i] = __fdiv_rn(f[i], sum);                  // :100-101
+}
+int launch_normalize_rows(float* rows, int64_t n, int d, int ld, int metric, cudaStream_t s) {
+    if (n <= 0) return FIR_OK;
+    normalize_rows_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(rows, n, d, ld, metric);
+    FIR_CUDA_TRY(cudaGetLastError());
+    return FIR_OK;
+}
+
+// rows [n][d] → zero-padded [n][ld]
+__global__ void pad_rows_kernel(const float* __restrict__ src, int64_t n, int d, float* __restrict__ dst, int ld) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = n * ld;
+    if (i >= total) return;
+    int64_t r = i / ld;
+    int c = (int)(i - r * ld);
+    dst[i] = (c < d) ? src[r * d + c] : 0.f;
+}
+int launch_pad_rows(const float* src, int64_t n, int d, float* dst, int ld, cudaStream_t s) {
+    if (n <= 0) return FIR_OK;
+    pad_rows_kernel<<<(unsigned)ceil_div(n * ld, 256), 256, 0, s>>>(src, n, d, dst, ld);
+    FIR_CUDA_TRY(cudaGetLastError());
+    return FIR_OK;
+}
+
+}  // namespace fir

@@ -1,0 +1,185 @@
+// fir_common.cuh — shared declarations for libfir_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/fir_b200.h"
+
+namespace fir {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define FIR_CUDA_TRY(expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            return ::fir::fail(_e == cudaErrorMemoryAllocation ? FIR_ERR_OOM : FIR_ERR_CUDA,       \
+                               std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+        }                                                                                           \
+    } while (0)
+
+#define FIR_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != FIR_OK) return _s;  \
+    } while (0)
+
+// Growable device scratch, bump-allocated per call (256-byte aligned).
+struct Workspace {
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    cudaStream_t stream = 0;
+    int reserve(size_t bytes);   // make sure cap >= bytes (may sync + realloc); resets off
+    void* take(size_t bytes);    // nullptr if it does not fit
+    void release();
+};
+
+constexpr int kExactTile = 64;   // queries x gallery rows per block tile of the exact kernel
+constexpr int kExactChunk = 32;  // dims staged per cp.async stage
+constexpr int kRowPad = 32;      // fp32 rows are stored zero-padded to a multiple of this
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// exact tile kernel modes
+enum { MODE_TOPK = 0, MODE_CLASSMIN = 1, MODE_PNN = 2 };
+
+struct ExactParams {
+    const float* q;   int64_t nq;  int ldq;
+    const float* x;   int64_t n;   int ldx;
+    const int32_t* labels;
+    int d_end;                       // dims used (max_features or D); the mean divides by this
+    int k;                           // MODE_TOPK list length
+    int mode;
+    int nsplit; int64_t tiles_per_split;
+    float* part_dist; int32_t* part_idx;       // [nq][nsplit][k], local row indices
+    unsigned long long* cls_key;               // [nq][C] packed (ordered dist bits, local idx)
+    double* cls_score;                         // [nq][C]
+    int n_classes; double two_var;
+    const int32_t* qmap; const int32_t* n_active;   // optional query indirection (tensor-path fallback)
+};
+
+int launch_exact_tiles(int metric, const ExactParams& p, cudaStream_t s);
+int launch_merge_parts(const float* pd, const int32_t* pi, int n_parts, int64_t part_stride, int64_t q_stride,
+                       int64_t nq, int k, int64_t index_offset, const int32_t* qmap, const int32_t* n_active,
+                       float* od, int32_t* oi, cudaStream_t s);
+int launch_fill_u64(unsigned long long* p, int64_t n, unsigned long long v, cudaStream_t s);
+int launch_classmin_finalize(const unsigned long long* keys, int64_t n, int64_t index_offset, float* omin, int32_t* oarg, cudaStream_t s);
+int launch_pnn_finalize(double* scores, int64_t nq, int n_classes, double n_total, int32_t* olabel, cudaStream_t s);
+int launch_pair_distances(int metric, const float* q, int64_t nq, int ldq, const float* x, int ldx, int64_t n, int d_end,
+                          const int32_t* cand, int r, int gallery_is_lhs, float* out, cudaStream_t s);
+int launch_normalize_rows(float* rows, int64_t n, int d, int ld, int metric, cudaStream_t s);
+int launch_pad_rows(const float* src, int64_t n, int d, float* dst, int ld, cudaStream_t s);
+
+// ---- tensor-core (tcgen05) L2 candidate path: l2_tensor.cu -------------------------------------
+struct TensorSide {              // fp16 shadow of a set of fp32 rows
+    __half* h = nullptr;         // [rows_padded][dph], scaled by `scale`
+    float* norm2 = nullptr;      // ||x||^2 (fp32 of the fp64 sum), +inf for padding rows
+    float* resid = nullptr;      // ||x - h/scale|| rounded up
+    int64_t rows = 0, rows_padded = 0;
+    int dph = 0;
+    float scale = 1.f;
+};
+struct TensorGalleryStats { float max_norm, max_resid; };
+
+size_t tensor_side_bytes(int64_t rows, int d, int row_tile);
+int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out,
+                     float* d_stats /*[2]: max ||x||, max resid (device)*/, cudaStream_t s);
+struct TensorSearchArgs {
+    const TensorSide* gal; const TensorSide* qry;
+    const CUtensorMap* tmap_a; const CUtensorMap* tmap_b;
+    int d; int R;                 // candidates kept per (query, slot)
+    int n_slots;
+    float* cand_val; int32_t* cand_idx;   // [nq][n_slots][R]
+    float* slot_bound;                    // [nq][n_slots]
+    int grid;
+};
+int tensor_plan(int64_t nq, int64_t n, int n_sm, int* grid, int* n_slots);
+int tensor_encode_map(CUtensorMap* map, const __half* base, int64_t rows_padded, int dph, int box_rows);
+int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s);
+int launch_tensor_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots,
+                         int R, int k, int d, const float* q_norm2, const float* q_resid, const float* gal_stats,
+                         int64_t index_offset, float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged,
+                         float* max_bound, cudaStream_t s);
+bool tensor_path_supported(int d);
+
+}  // namespace fir
+
+// device-side helpers ------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace fir {
+
+__device__ __forceinline__ uint32_t ordered_bits(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(b);
+}
+
+// glibc 2.39 logf, __logf_fma build (see oracle/fir_oracle.c for provenance of the constants).
+__device__ const double kLogfTab[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2},
+};
+
+__device__ __forceinline__ float glibc_logf(float x) {
+    uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix * 2 == 0) return -__int_as_float(0x7f800000);
+        if (ix == 0x7f800000u) return x;
+        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return __int_as_float(0x7fc00000);
+        ix = __float_as_uint(__fmul_rn(x, 8388608.0f));
+        ix -= 23u << 23;
+    }
+    uint32_t tmp = ix - 0x3f330000u;
+    int i = (int)((tmp >> 19) & 15u);
+    int k = (int)tmp >> 23;
+    uint32_t iz = ix - (tmp & 0xff800000u);
+    double invc = kLogfTab[i][0], logc = kLogfTab[i][1];
+    double z = (double)__uint_as_float(iz);
+    double r = __fma_rn(z, invc, -1.0);
+    double y0 = __fma_rn((double)k, 0x1.62e42fefa39efp-1, logc);
+    double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
+    y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
+    y = __fma_rn(y, r2, __dadd_rn(y0, r));
+    return __double2float_rn(y);
+}
+
+// One step of feature_distance (qt_cpp/db_features.cpp:26,29-36): fp32, no FMA contraction,
+// IEEE round-to-nearest for every operation, in the reference's operation order.
+template <int METRIC>
+__device__ __forceinline__ void dist_step(float& acc, float l, float r) {
+    if (METRIC == FIR_L2) {
+        float d = __fsub_rn(l, r);
+        acc = __fadd_rn(acc, __fmul_rn(d, d));
+    } else if (METRIC == FIR_CHI2) {
+        float s = __fadd_rn(l, r);
+        if (s > 0.f) {
+            float d = __fsub_rn(l, r);
+            acc = __fadd_rn(acc, __fdiv_rn(__fmul_rn(d, d), s));
+        }
+    } else {
+        float s = __fadd_rn(l, r);
+        if (s > 0.f) {
+            if (l > 0.f) acc = __fadd_rn(acc, __fmul_rn(l, glibc_logf(__fdiv_rn(__fmul_rn(2.f, l), s))));
+            if (r > 0.f) acc = __fadd_rn(acc, __fmul_rn(r, glibc_logf(__fdiv_rn(__fmul_rn(2.f, r), s))));
+        }
+    }
+}
+
+}  // namespace fir
+#endif

@@ -1,0 +1,29 @@
+// handles.hpp — the opaque handle types behind include/fir_b200.h.
+#pragma once
+#include "fir_common.cuh"
+
+// replaces std::vector<ImageInfo> dbImages + the ImagesDatabase it borrows (qt_cpp/db_features.h:14-29):
+// packed, zero-padded, device-resident, owned by the handle.
+struct fir_gallery {
+    int device = 0, n_sm = 148, cc_major = 0;
+    cudaStream_t stream = 0;
+    int64_t n = 0, index_offset = 0;
+    int d = 0, dp = 0, metric = 0, n_classes = 1;
+    float* rows = nullptr;        // [n][dp] fp32, zero padded
+    int32_t* labels = nullptr;    // [n]
+    std::vector<int32_t> h_labels;
+    // tensor-core L2 path (built lazily on first use)
+    bool tensor_ready = false;
+    void* tensor_buf = nullptr;
+    fir::TensorSide tside;
+    CUtensorMap tmap_b;
+    float* d_stats = nullptr;     // [2] max ||x||, max ||x - fp16(x)||
+    fir::Workspace ws;
+    fir_search_stats stats{};
+};
+
+namespace fir {
+int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_end, const int32_t* qmap,
+                      const int32_t* n_active, float* part_d, int32_t* part_i, int nsplit, float* od, int32_t* oi);
+int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
+}

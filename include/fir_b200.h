@@ -1,0 +1,168 @@
+/* fir_b200.h — C-ABI of the B200-native matching engine (libfir_b200.so).
+ *
+ * This is the drop-in boundary for the matching hot path of av-savchenko/fast-image-recognition's
+ * qt_cpp recognizer.  The reference has no FFI layer; its path sits behind ordinary C++ declarations
+ * (qt_cpp/db_features.h, qt_cpp/ann.h, and the Classifier shape inside qt_cpp/classification.cpp).
+ * Each entry point below names the reference interface it replaces (paths relative to
+ * /root/reference/).  Same-named C++ adapters over this C-ABI live in include/fir_b200_compat.hpp;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns a fir_status (0 = ok) and records a
+ *     message retrievable with fir_last_error_string() (thread-local).
+ *   - `memspace` says whether the data pointers of THAT call are host (FIR_HOST: the call copies
+ *     host<->device on the handle's stream and synchronises before returning) or device
+ *     (FIR_DEVICE: fully asynchronous on the handle's stream, no synchronisation).
+ *   - gallery/query rows are row-major fp32, D contiguous floats per row, "as loaded by
+ *     db_features" (qt_cpp/db_features.cpp:79-101), i.e. already normalised by the caller or by
+ *     fir_normalize_rows().
+ *   - indices written to the caller are GLOBAL gallery indices (local row + index_offset) as int32;
+ *     -1 means "no match" exactly as in the reference (qt_cpp/ann.cpp:100, db_features.cpp:322).
+ *   - there is NO CPU fallback anywhere behind this interface: without a CUDA device every compute
+ *     entry point fails with FIR_ERR_CUDA.
+ */
+#ifndef FIR_B200_H
+#define FIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIR_B200_VERSION 100
+
+typedef enum fir_status {
+    FIR_OK = 0,
+    FIR_ERR_BAD_ARG = 1,
+    FIR_ERR_CUDA = 2,
+    FIR_ERR_OOM = 3,
+    FIR_ERR_UNSUPPORTED = 4,
+    FIR_ERR_INTERNAL = 5
+} fir_status;
+
+/* compile-time switch of the reference: USE_L2_DISTANCE (qt_cpp/db_features.h:12) and the
+ * chi-square / KL `#if` (qt_cpp/db_features.cpp:30) become a run-time metric. */
+typedef enum fir_metric { FIR_L2 = 0, FIR_CHI2 = 1, FIR_KL = 2 } fir_metric;
+typedef enum fir_memspace { FIR_HOST = 0, FIR_DEVICE = 1 } fir_memspace;
+/* which kernels serve fir_search_topk */
+typedef enum fir_path {
+    FIR_PATH_AUTO = 0,   /* L2: tensor-core candidates + exact rerank; chi2/KL: exact CUDA-core tiles */
+    FIR_PATH_EXACT = 1,  /* exact CUDA-core tile kernel for every metric                              */
+    FIR_PATH_TENSOR = 2  /* force the tcgen05 path (L2 only)                                          */
+} fir_path;
+
+typedef struct fir_gallery fir_gallery;       /* vector<ImageInfo> dbImages + its ImagesDatabase      */
+typedef struct fir_dem fir_dem;               /* DirectedEnumeration                                  */
+typedef struct fir_classifier fir_classifier; /* the fp64 training-set state of classification.cpp    */
+
+/* per-call counters of the last fir_search_topk on a gallery */
+typedef struct fir_search_stats {
+    int32_t path_used;        /* fir_path actually taken                                              */
+    int32_t n_fallback;       /* queries the tensor path could not certify and re-ran exactly        */
+    int32_t n_candidates;     /* exact reranked candidates per query (tensor path)                    */
+    int32_t gpu_launches;     /* kernels launched by the call                                         */
+    float approx_err_bound;   /* max certified |approx - true| squared-distance bound over queries    */
+    float reserved;
+} fir_search_stats;
+
+const char* fir_last_error_string(void);
+int fir_version(void);
+int fir_device_count(int* count);
+int fir_set_device(int device);
+
+/* ---- data model -------------------------------------------------------------------------------
+ * replaces: ImagesDatabase / ImageInfo (qt_cpp/db_features.h:14-29) as consumed through
+ * `std::vector<ImageInfo>& dbImages` by ClassificationMethod (qt_cpp/ann.h:11,28).
+ * The handle COPIES rows/labels to the device (the reference borrows them); the caller may free its
+ * buffers afterwards.  index_offset is the global index of local row 0 (gallery row-sharding across
+ * GPUs: one handle per process/GPU). */
+int fir_gallery_create(const float* rows, const int32_t* labels, int64_t n, int32_t d, int32_t metric,
+                       int32_t memspace, int64_t index_offset, fir_gallery** out);
+int fir_gallery_destroy(fir_gallery* g);
+int fir_gallery_set_stream(fir_gallery* g, void* cuda_stream);
+int fir_gallery_info(const fir_gallery* g, int64_t* n, int32_t* d, int32_t* metric, int32_t* n_classes);
+
+/* replaces: the normalisation loop of loadImages (qt_cpp/db_features.cpp:79-101): zero |x|<1e-4,
+ * then x /= sqrtf(sum x*x) (L2) or x /= sum x (chi2/KL), fp32, sequential.  In place. */
+int fir_normalize_rows(float* rows, int64_t n, int32_t d, int32_t metric, int32_t memspace, void* cuda_stream);
+
+/* ---- brute force ------------------------------------------------------------------------------
+ * replaces: BruteForce::recognize (qt_cpp/ann.cpp:113-126) and recognize_image_bf
+ * (qt_cpp/db_features.cpp:319-335) looped over the query set by
+ * ClassificationMethod::testSetRecognition (qt_cpp/ann.cpp:94-109).
+ * Writes, per query, the k lexicographically smallest (feature_distance, gallery index) pairs —
+ * k = 1 is the reference argmin (strict '<' ⇒ lowest index on ties, -1 if nothing is < 100000).
+ * max_features > 0 restricts the distance to the first max_features dimensions and divides by it
+ * (recognize_image_bf's prefix mode); 0 = all D.  out_idx/out_dist: nq x k. */
+int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k, int32_t max_features,
+                    int32_t path, int32_t memspace, int32_t* out_idx, float* out_dist);
+int fir_search_last_stats(const fir_gallery* g, fir_search_stats* stats);
+
+/* replaces: ImageInfo::distance / feature_distance (qt_cpp/db_features.h:24-26, db_features.cpp:22-42)
+ * for explicit (query, gallery index) pairs: cand_idx is nq x r LOCAL row indices (-1 = skip),
+ * out_dist nq x r.  gallery_is_lhs != 0 evaluates feature_distance(gallery, query) — the operand
+ * order of the DEM build (qt_cpp/ann.cpp:309); it only matters for KL. */
+int fir_pair_distances(fir_gallery* g, const float* queries, int64_t nq, const int32_t* cand_idx, int32_t r,
+                       int32_t gallery_is_lhs, int32_t memspace, float* out_dist);
+
+/* per-class nearest neighbour: out_min/out_arg are nq x n_classes; classes without a match get
+ * (100000, -1).  (Fused class reduction of the same distance tiles; no reference counterpart beyond
+ * the argmin above.) */
+int fir_class_min(fir_gallery* g, const float* queries, int64_t nq, int32_t memspace, float* out_min,
+                  int32_t* out_arg);
+
+/* PNN-style class scores over the gallery's fp32 divergence (the Parzen reducer of
+ * PNNClassifier::predict_bf, qt_cpp/classification.cpp:213-225, with the divergence swapped in):
+ * score[c] = (1/n_total) * sum_{j in class c} exp(-dist(q, x_j) / (2 * var)), fp64; label = argmax with
+ * strict '<' (lowest class on ties).  n_total <= 0 means the handle's own row count (use the global
+ * count when the gallery is sharded; the caller then sums scores across shards). */
+int fir_pnn_scores(fir_gallery* g, const float* queries, int64_t nq, double var, int64_t n_total,
+                   int32_t memspace, double* out_scores, int32_t* out_label);
+
+/* k-way merge of per-shard top-k lists (multi-GPU candidate merge after an all-gather):
+ * parts_* are n_parts x nq x k, each list sorted by (dist, idx), idx = -1 marks an empty slot;
+ * out_* are nq x k.  Device pointers only. */
+int fir_merge_topk(const float* parts_dist, const int32_t* parts_idx, int32_t n_parts, int64_t nq, int32_t k,
+                   float* out_dist, int32_t* out_idx, void* cuda_stream);
+
+/* ---- fp64 kNN / PNN ---------------------------------------------------------------------------
+ * replaces: the file-scope training state of qt_cpp/classification.cpp:53-62 as left by
+ * split_train_test (:942-990) — training rows in class-major order (the order predict() walks
+ * training_set), their class labels, and avgValues — plus KNNClassifier::predict (:116-170) and
+ * PNNClassifier::predict_bf (:188-226). */
+int fir_classifier_create(const double* train_rows, const int32_t* train_labels, int64_t n, int32_t d,
+                          int32_t n_classes, const double* avg, fir_classifier** out);
+int fir_classifier_destroy(fir_classifier* c);
+int fir_classifier_knn(fir_classifier* c, const double* queries, int64_t nq, int32_t K, int32_t* out_label);
+int fir_classifier_pnn(fir_classifier* c, const double* queries, int64_t nq, double* out_scores /* nq x C or NULL */,
+                       int32_t* out_label);
+
+/* ---- directed enumeration ---------------------------------------------------------------------
+ * replaces: DirectedEnumeration (qt_cpp/ann.h:61-100): ctor + init (qt_cpp/ann.cpp:270-348,357-386),
+ * getThreshold (:84-93), recognize (:416-507), setImageCountToCheck (qt_cpp/ann.h:20-22). */
+typedef struct fir_dem_params {
+    int32_t pivot0;          /* first pivot (the reference takes the head of an unseeded random_shuffle,
+                                ann.cpp:366-369); < 0 ⇒ derived from `seed`                              */
+    uint32_t seed;
+    float false_accept_rate; /* 0.01f, ann.h:64                                                          */
+    float threshold;         /* > 0 overrides the FAR quantile, ann.cpp:277-279,340                      */
+    int32_t max_chain;       /* pivot-chain rows to walk; <= 0 ⇒ the reference's max(5,(int)(n*0.015))  */
+    int32_t max_pivots;      /* pivots kept for search; <= 0 ⇒ 32, ann.cpp:332-333                       */
+} fir_dem_params;
+
+int fir_dem_build(fir_gallery* g, const fir_dem_params* params, fir_dem** out);
+int fir_dem_destroy(fir_dem* dem);
+int fir_dem_info(const fir_dem* dem, int32_t* n_pivots, int32_t* chain_rows, float* threshold);
+int fir_dem_get_pivots(const fir_dem* dem, int32_t* out_pivots /* n_pivots */);
+int fir_dem_get_pivot_matrix(const fir_dem* dem, float* out_P /* n_pivots x n, host */);
+int fir_dem_get_min_other(const fir_dem* dem, float* out /* chain_rows, host */);
+/* out_idx: local row (+index_offset) or -1; out_dist = bestDistance; out_below = isFoundLessThreshold;
+ * out_evals = distanceCalcCount.  count_to_check follows setImageCountToCheck. */
+int fir_dem_search(fir_dem* dem, const float* queries, int64_t nq, int32_t count_to_check, int32_t memspace,
+                   int32_t* out_idx, float* out_dist, uint8_t* out_below, int32_t* out_evals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIR_B200_H */

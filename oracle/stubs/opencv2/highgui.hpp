@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY — see core.hpp in this directory.
+#include "core.hpp"

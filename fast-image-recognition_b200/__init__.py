@@ -31,7 +31,7 @@ EXPORTS = [
     "fir_last_error_string", "fir_version", "fir_device_count", "fir_set_device",
     "fir_gallery_create", "fir_gallery_destroy", "fir_gallery_set_stream", "fir_gallery_info",
     "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
-    "fir_class_min", "fir_pnn_scores", "fir_merge_topk",
+    "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates",
     "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn",
     "fir_dem_build", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
     "fir_dem_get_min_other", "fir_dem_search",
@@ -75,6 +75,7 @@ def lib():
     L.fir_normalize_rows.argtypes = [vp, i64, i32, i32, i32, vp]
     L.fir_search_topk.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, vp]
     L.fir_search_last_stats.argtypes = [vp, C.POINTER(SearchStats)]
+    L.fir_debug_tensor_candidates.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp]
     L.fir_pair_distances.argtypes = [vp, vp, i64, vp, i32, i32, i32, vp]
     L.fir_class_min.argtypes = [vp, vp, i64, i32, vp, vp]
     L.fir_pnn_scores.argtypes = [vp, vp, i64, f64, i64, i32, vp, vp]
@@ -198,6 +199,17 @@ class Gallery:
         s = SearchStats()
         _check(lib().fir_search_last_stats(self._h, C.byref(s)))
         return {f[0]: getattr(s, f[0]) for f in SearchStats._fields_}
+
+    def debug_candidates(self, nq):
+        """(idx, approx d^2, exact feature_distance) of the last tensor-path search: arrays [nq, n_slots*R]."""
+        ns, r = C.c_int32(0), C.c_int32(0)
+        _check(lib().fir_debug_tensor_candidates(self._h, C.byref(ns), C.byref(r), None, None, None))
+        shape = (nq, ns.value * r.value)
+        idx = np.empty(shape, np.int32)
+        approx = np.empty(shape, np.float32)
+        exact = np.empty(shape, np.float32)
+        _check(lib().fir_debug_tensor_candidates(self._h, None, None, _ptr(idx), _ptr(approx), _ptr(exact)))
+        return idx, approx, exact
 
     def distances(self, queries, cand_idx, gallery_is_lhs=False):
         q, space = _prep(queries, np.float32, "float32")

@@ -241,6 +241,15 @@ int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k,
 
 int fir_search_last_stats(const fir_gallery* g, fir_search_stats* stats) {
     if (!g || !stats) return fail(FIR_ERR_BAD_ARG, "null argument");
+    if (g->stats.path_used == FIR_PATH_TENSOR && g->stats.n_fallback < 0 && g->d_stats) {
+        fir_gallery* m = const_cast<fir_gallery*>(g);      // device-side counters are fetched on demand
+        int32_t nf = 0; float mb = 0.f;
+        FIR_CUDA_TRY(cudaStreamSynchronize(m->stream));
+        FIR_CUDA_TRY(cudaMemcpy(&nf, m->d_stats + 4, 4, cudaMemcpyDeviceToHost));
+        FIR_CUDA_TRY(cudaMemcpy(&mb, m->d_stats + 5, 4, cudaMemcpyDeviceToHost));
+        m->stats.n_fallback = nf;
+        m->stats.approx_err_bound = mb;
+    }
     *stats = g->stats;
     return FIR_OK;
 }

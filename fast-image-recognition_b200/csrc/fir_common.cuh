@@ -80,11 +80,10 @@ struct TensorSide {              // fp16 shadow of a set of fp32 rows
     __half* h = nullptr;         // [rows_padded][dph], scaled by `scale`
     float* norm2 = nullptr;      // ||x||^2 (fp32 of the fp64 sum), +inf for padding rows
     float* resid = nullptr;      // ||x - h/scale|| rounded up
+    unsigned int* meta = nullptr; // [0] = bits of max|x|, [1] = bits of the power-of-two scale (device)
     int64_t rows = 0, rows_padded = 0;
     int dph = 0;
-    float scale = 1.f;
 };
-struct TensorGalleryStats { float max_norm, max_resid; };
 
 size_t tensor_side_bytes(int64_t rows, int d, int row_tile);
 int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out,

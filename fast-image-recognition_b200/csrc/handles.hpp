@@ -19,6 +19,9 @@ struct fir_gallery {
     CUtensorMap tmap_b;
     float* d_stats = nullptr;     // [2] max ||x||, max ||x - fp16(x)||
     fir::Workspace ws;
+    // diagnostics: where the last tensor-path call left its candidate lists (valid until the next call)
+    const float* dbg_cand_val = nullptr; const float* dbg_cand_exact = nullptr; const int32_t* dbg_cand_idx = nullptr;
+    int64_t dbg_nq = 0; int dbg_slots = 0, dbg_R = 0;
     fir_search_stats stats{};
 };
 

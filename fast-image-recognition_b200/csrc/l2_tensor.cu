@@ -1,7 +1,683 @@
-// placeholder until the tcgen05 path lands (replaced in the next milestone)
+// l2_tensor.cu — Euclidean brute force as a tensor-core contraction with a certified exact rerank.
+//
+//   d²(q,x) = ‖q‖² + ‖x‖² − 2·q·xᵀ
+//
+// Stage 1 (this file, `l2_candidates_kernel`): q·xᵀ on tcgen05 tensor cores — fp16 operands staged by
+// TMA into 128B-swizzled shared memory, fp32 accumulators in TMEM (two 128x256 buffers), one elected
+// thread issuing `tcgen05.mma`.  The epilogue never materialises the Q x N matrix: each of the 128
+// epilogue threads owns one query row of the accumulator (TMEM lane = row), reads it with `tcgen05.ld`
+// and keeps that query's R best approximate distances in registers.
+// Stage 2 (exact_kernels.cu: pair_distance_kernel): the reference's own fp32 arithmetic
+// (feature_distance, qt_cpp/db_features.cpp:22-42) on the R·slots survivors.
+// Stage 3 (`tensor_select_kernel`): top-k by (exact distance, index) and a CERTIFICATE that no
+// non-candidate can beat the k-th exact distance, from a rigorous bound on |approx − true|
+// (Cauchy–Schwarz on the fp16 rounding residuals, which are measured per vector at pack time).
+// Queries whose certificate fails are re-run through the exact CUDA-core kernel on the GPU, so the
+// returned indices/distances are always bit-identical to BruteForce::recognize (qt_cpp/ann.cpp:113-126).
 #include "fir_common.cuh"
 #include "handles.hpp"
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
 namespace fir {
-bool tensor_path_supported(int) { return false; }
-int tensor_search_topk(fir_gallery*, const float*, int64_t, int, int, int32_t*, float*) { return fail(FIR_ERR_UNSUPPORTED, "tensor path not built"); }
+
+constexpr int BM = 128;          // queries per CTA tile  (UMMA M)
+constexpr int BN = 256;          // gallery rows per tile (UMMA N)
+constexpr int BK = 64;           // fp16 elements per 128-byte swizzle row
+constexpr int UK = 16;           // UMMA K for 16-bit inputs
+constexpr int A_KB_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int B_KB_BYTES = BN * BK * 2;   // 32 KiB
+constexpr int MAX_RES_KB = 8;    // A stays resident in shared memory when D <= 512
+constexpr int TMEM_COLS = 512;   // two 256-column accumulators
+
+bool tensor_path_supported(int d) { return d >= 16; }
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if ((++spins & 0xfff) == 0) {          // watchdog: a protocol bug must fault, never hang the GPU
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000LL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in [0,14),
+// leading byte offset (unused for swizzled K-major, = 1) in [16,30), stride byte offset = 8 rows x 128 B
+// = 1024 B (>> 4 = 64) in [32,46), descriptor version 1 in [46,48), layout type 2 (SWIZZLE_128B) in [61,64).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------------
+// fp16 shadow copies: h = fp16(x * scale) with |h| < 2^-14 flushed to zero (no reliance on fp16
+// subnormal handling), ‖x‖² in fp64 → fp32, and the residual norm ‖x − h/scale‖ that feeds the certificate.
+// ---------------------------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ rows, int64_t n, int ld, int d, unsigned int* out_bits) {
+    int64_t total = n * d;
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / d;
+        int c = (int)(i - r * d);
+        m = fmaxf(m, fabsf(rows[r * ld + c]));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// meta[0] = absmax bits (in), meta[1] = scale (out, float bits)
+__global__ void pack_rows_kernel(const float* __restrict__ rows, int64_t n, int64_t rows_padded, int ld, int d, int dph,
+                                 __half* __restrict__ h, float* __restrict__ norm2, float* __restrict__ resid,
+                                 unsigned int* meta, unsigned int* stats_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows_padded) return;
+    float amax = __uint_as_float(meta[0]);
+    float scale = 1.f;
+    if (amax > 0.f && isfinite(amax)) {
+        int e;
+        frexpf(amax, &e);                 // amax = m * 2^e, m in [0.5,1)  ⇒  amax * 2^-e in [0.5,1)
+        scale = ldexpf(1.f, -e);
+    }
+    if (row == 0 && lane == 0) meta[1] = __float_as_uint(scale);
+    __half* hr = h + row * dph;
+    if (row >= n) {
+        for (int c = lane; c < dph; c += 32) hr[c] = __float2half_rn(0.f);
+        if (lane == 0) { norm2[row] = __int_as_float(0x7f800000); resid[row] = 0.f; }
+        return;
+    }
+    const float inv = 1.f / scale;        // exact: power of two
+    double n2 = 0.0, r2 = 0.0;
+    for (int c = lane; c < dph; c += 32) {
+        float x = c < d ? rows[row * ld + c] : 0.f;
+        float xs = x * scale;
+        __half hv = __float2half_rn(xs);
+        if (fabsf(__half2float(hv)) < 6.103515625e-05f) hv = __float2half_rn(0.f);
+        hr[c] = hv;
+        float back = __half2float(hv) * inv;
+        double df = (double)x - (double)back;
+        n2 += (double)x * (double)x;
+        r2 += df * df;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
+    if (lane == 0) {
+        float nf = __double2float_ru(n2);
+        float rf = __double2float_ru(sqrt(r2) * (1.0 + 1e-9));
+        norm2[row] = (float)n2;
+        resid[row] = rf;
+        if (stats_bits) {
+            atomicMax(&stats_bits[0], __float_as_uint(__double2float_ru(sqrt((double)nf))));
+            atomicMax(&stats_bits[1], __float_as_uint(rf));
+        }
+    }
+}
+
+static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+size_t tensor_side_bytes(int64_t rows, int d, int row_tile) {
+    int64_t rp = ceil_div(rows, row_tile) * row_tile;
+    int dph = round_up(d, BK);
+    return al256((size_t)rp * dph * 2) + 2 * al256((size_t)rp * 4) + 256 + 1024;
+}
+
+int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out, float* d_stats,
+                     cudaStream_t s) {
+    int64_t rp = ceil_div(n, row_tile) * row_tile;
+    int dph = round_up(d, BK);
+    char* p = (char*)(((uintptr_t)buf + 1023) & ~(uintptr_t)1023);     // TMA global address alignment (>=16B); keep 1 KiB
+    out->h = (__half*)p; p += al256((size_t)rp * dph * 2);
+    out->norm2 = (float*)p; p += al256((size_t)rp * 4);
+    out->resid = (float*)p; p += al256((size_t)rp * 4);
+    out->meta = (unsigned int*)p;
+    out->rows = n; out->rows_padded = rp; out->dph = dph;
+    FIR_CUDA_TRY(cudaMemsetAsync(out->meta, 0, 16, s));
+    int blocks = (int)std::min<int64_t>(1184, ceil_div(n * d, 256 * 8));
+    absmax_kernel<<<std::max(blocks, 1), 256, 0, s>>>(rows, n, ld, d, out->meta);
+    FIR_CUDA_TRY(cudaGetLastError());
+    pack_rows_kernel<<<(unsigned)ceil_div(rp, 8), 256, 0, s>>>(rows, n, rp, ld, d, dph, out->h, out->norm2, out->resid, out->meta,
+                                                              (unsigned int*)d_stats);
+    FIR_CUDA_TRY(cudaGetLastError());
+    return FIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point fetched through the runtime: no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+int tensor_encode_map(CUtensorMap* map, const __half* base, int64_t rows_padded, int dph, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(FIR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)dph, (cuuint64_t)rows_padded};
+    cuuint64_t strides[1] = {(cuuint64_t)dph * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FIR_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return FIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Work partition: items are (query block, gallery tile) pairs in query-block-major order, cut into
+// `grid` contiguous, equally sized ranges — one per CTA.  A query block is therefore covered by at
+// most n_slots consecutive CTAs, each of which writes its own candidate slot.
+// ---------------------------------------------------------------------------------------------------
+struct Partition { int64_t ntiles, nqb, total; int grid; };
+__host__ __device__ inline int64_t part_lo(const Partition& P, int64_t c) { return c * P.total / P.grid; }
+__host__ __device__ inline int64_t part_first_cta(const Partition& P, int64_t item) { return ((item + 1) * P.grid - 1) / P.total; }
+
+int tensor_plan(int64_t nq, int64_t n, int n_sm, int* grid, int* n_slots) {
+    Partition P;
+    P.ntiles = ceil_div(n, BN);
+    P.nqb = ceil_div(nq, BM);
+    P.total = P.ntiles * P.nqb;
+    P.grid = (int)std::min<int64_t>(P.total, n_sm);
+    int slots = 1;
+    for (int64_t qb = 0; qb < P.nqb; ++qb) {
+        int64_t c0 = part_first_cta(P, qb * P.ntiles), c1 = part_first_cta(P, (qb + 1) * P.ntiles - 1);
+        slots = std::max<int>(slots, (int)(c1 - c0 + 1));
+    }
+    *grid = P.grid;
+    *n_slots = slots;
+    return FIR_OK;
+}
+
+struct CandParams {
+    Partition part;
+    int64_t nq, n;
+    int nkb;
+    int n_slots;
+    const float* gal_norm2;
+    const float* qry_norm2;
+    const unsigned int* gal_meta;
+    const unsigned int* qry_meta;
+    float* cand_val;
+    int32_t* cand_idx;
+    float* slot_bound;
+};
+
+template <int R>
+__device__ __forceinline__ void topr_insert(float (&lv)[R], int (&li)[R], float v, int j) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (v < lv[r]) {
+            float tv = lv[r]; lv[r] = v; v = tv;
+            int tj = li[r]; li[r] = j; j = tj;
+        }
+    }
+}
+
+template <int R, bool A_RES>
+__global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                               const __grid_constant__ CUtensorMap tmap_b, const CandParams p) {
+    constexpr int STAGES = A_RES ? 3 : 4;
+    constexpr int STAGE_BYTES = A_RES ? B_KB_BYTES : (A_KB_BYTES + B_KB_BYTES);
+    constexpr int A_RES_BYTES = A_RES ? MAX_RES_KB * A_KB_BYTES : 0;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* a_res = smem;
+    unsigned char* stage0 = smem + A_RES_BYTES;
+    float* nx_s = reinterpret_cast<float*>(stage0 + STAGES * STAGE_BYTES);          // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(nx_s + 2 * BN);
+    uint64_t* full_bar = bars;                    // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* a_full = bars + 2 * STAGES;
+    uint64_t* a_empty = a_full + 1;
+    uint64_t* tmem_full = a_empty + 1;            // [2]
+    uint64_t* tmem_empty = tmem_full + 2;         // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Partition P = p.part;
+    const int64_t item_lo = part_lo(P, blockIdx.x), item_hi = part_lo(P, (int64_t)blockIdx.x + 1);
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) __trap();     // SWIZZLE_128B tiles need 1 KiB alignment
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        mbar_init(smem_u32(a_full), 1);
+        mbar_init(smem_u32(a_empty), 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        int stage = 0; uint32_t phase = 0; uint32_t a_loads = 0;
+        int64_t cur_qb = -1;
+        for (int64_t it = item_lo; it < item_hi; ++it) {
+            const int64_t qb = it / P.ntiles, tile = it - qb * P.ntiles;
+            if (A_RES && qb != cur_qb) {
+                mbar_wait(smem_u32(a_empty), (a_loads & 1) ^ 1);      // every MMA that read the old A has retired
+                mbar_expect_tx(smem_u32(a_full), (uint32_t)p.nkb * A_KB_BYTES);
+                for (int kb = 0; kb < p.nkb; ++kb)
+                    tma_load_2d(smem_u32(a_res + kb * A_KB_BYTES), &tmap_a, smem_u32(a_full), kb * BK, (int)(qb * BM));
+                ++a_loads;
+            }
+            cur_qb = qb;
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                unsigned char* st = stage0 + stage * STAGE_BYTES;
+                mbar_expect_tx(smem_u32(&full_bar[stage]), STAGE_BYTES);
+                if (!A_RES) tma_load_2d(smem_u32(st + B_KB_BYTES), &tmap_a, smem_u32(&full_bar[stage]), kb * BK, (int)(qb * BM));
+                tma_load_2d(smem_u32(st), &tmap_b, smem_u32(&full_bar[stage]), kb * BK, (int)(tile * BN));
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer (single thread) =====
+        int stage = 0; uint32_t phase = 0; uint32_t a_uses = 0;
+        int as = 0; uint32_t aphase = 0;
+        int64_t cur_qb = -1;
+        for (int64_t it = item_lo; it < item_hi; ++it) {
+            const int64_t qb = it / P.ntiles;
+            if (A_RES && qb != cur_qb) { mbar_wait(smem_u32(a_full), a_uses & 1); ++a_uses; }
+            cur_qb = qb;
+            mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);         // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)as * BN;
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                tc_fence_after();
+                unsigned char* st = stage0 + stage * STAGE_BYTES;
+                const uint64_t bdesc = make_sw128_desc(smem_u32(st));
+                const uint64_t adesc = make_sw128_desc(A_RES ? smem_u32(a_res + kb * A_KB_BYTES) : smem_u32(st + B_KB_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k)      // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle atom
+                    tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc, (kb | k) ? 1u : 0u);
+                tc_commit(smem_u32(&empty_bar[stage]));               // frees the smem slot when these MMAs retire
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(smem_u32(&tmem_full[as]));                      // accumulator ready for the epilogue
+            if (A_RES) {
+                const bool last_of_qb = (it + 1 == item_hi) || ((it + 1) / P.ntiles != qb);
+                if (last_of_qb) tc_commit(smem_u32(a_empty));
+            }
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread = one query row; running top-R in registers =====
+        const int ew = warp - 4;                       // TMEM lane group of this warp = warp % 4
+        const int row = ew * 32 + lane;
+        const int et = threadIdx.x - 128;              // 0..127
+        const float sg = __uint_as_float(p.gal_meta[1]), sq = __uint_as_float(p.qry_meta[1]);
+        const float negc = -2.0f / (sg * sq);
+        float lv[R]; int li[R];
+        int64_t cur_qb = -1;
+        int as = 0; uint32_t aphase = 0;
+        auto flush = [&](int64_t qb) {
+            const int64_t qrow = qb * BM + row;
+            if (qrow < p.nq) {
+                const int slot = (int)(blockIdx.x - part_first_cta(P, qb * P.ntiles));
+                const float nqv = p.qry_norm2[qrow];
+                const int64_t o = (qrow * p.n_slots + slot) * R;
+#pragma unroll
+                for (int r = 0; r < R; ++r) { p.cand_val[o + r] = lv[r] + nqv; p.cand_idx[o + r] = li[r]; }
+                p.slot_bound[qrow * p.n_slots + slot] = (li[R - 1] >= 0) ? lv[R - 1] + nqv : __int_as_float(0x7f800000);
+            }
+        };
+        float2 nx_next = make_float2(0.f, 0.f);
+        if (item_lo < item_hi) {
+            const int64_t tile0 = item_lo % P.ntiles;
+            nx_next = *reinterpret_cast<const float2*>(p.gal_norm2 + tile0 * BN + et * 2);
+        }
+        for (int64_t it = item_lo; it < item_hi; ++it) {
+            const int64_t qb = it / P.ntiles, tile = it - qb * P.ntiles;
+            if (qb != cur_qb) {
+                if (cur_qb >= 0) flush(cur_qb);
+#pragma unroll
+                for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = -1; }
+                cur_qb = qb;
+            }
+            // stage this tile's ‖x‖² (prefetched one tile ahead), then prefetch the next tile's
+            *reinterpret_cast<float2*>(&nx_s[as * BN + et * 2]) = nx_next;
+            if (it + 1 < item_hi) {
+                const int64_t nt = (it + 1) % P.ntiles;
+                nx_next = *reinterpret_cast<const float2*>(p.gal_norm2 + nt * BN + et * 2);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(smem_u32(&tmem_full[as]), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * BN;
+            const float* nxs = nx_s + as * BN;
+            const int jbase = (int)(tile * BN);
+            float thr = lv[R - 1];
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t rr[32];
+                tc_ld32(taddr + c0, rr);
+                tc_wait_ld();
+                float vmin = __int_as_float(0x7f800000);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
+                    float v0 = fmaf(negc, __uint_as_float(rr[i + 0]), nx4.x);
+                    float v1 = fmaf(negc, __uint_as_float(rr[i + 1]), nx4.y);
+                    float v2 = fmaf(negc, __uint_as_float(rr[i + 2]), nx4.z);
+                    float v3 = fmaf(negc, __uint_as_float(rr[i + 3]), nx4.w);
+                    rr[i + 0] = __float_as_uint(v0); rr[i + 1] = __float_as_uint(v1);
+                    rr[i + 2] = __float_as_uint(v2); rr[i + 3] = __float_as_uint(v3);
+                    vmin = fminf(vmin, fminf(fminf(v0, v1), fminf(v2, v3)));
+                }
+                if (vmin < thr) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = __uint_as_float(rr[i]);
+                        if (v < thr) { topr_insert<R>(lv, li, v, jbase + c0 + i); thr = lv[R - 1]; }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[as]));
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
+        if (cur_qb >= 0) flush(cur_qb);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+static size_t cand_smem_bytes(bool a_res) {
+    size_t stages = a_res ? 3 * (size_t)B_KB_BYTES : 4 * (size_t)(A_KB_BYTES + B_KB_BYTES);
+    return (a_res ? (size_t)MAX_RES_KB * A_KB_BYTES : 0) + stages + 2 * BN * 4 + 16 * 8 + 16;
+}
+
+int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
+    CandParams p{};
+    p.part.ntiles = ceil_div(a.gal->rows, BN);
+    p.part.nqb = ceil_div(a.qry->rows, BM);
+    p.part.total = p.part.ntiles * p.part.nqb;
+    p.part.grid = a.grid;
+    p.nq = a.qry->rows; p.n = a.gal->rows;
+    p.nkb = a.gal->dph / BK;
+    p.n_slots = a.n_slots;
+    p.gal_norm2 = a.gal->norm2; p.qry_norm2 = a.qry->norm2;
+    p.gal_meta = a.gal->meta; p.qry_meta = a.qry->meta;
+    p.cand_val = a.cand_val; p.cand_idx = a.cand_idx; p.slot_bound = a.slot_bound;
+    const bool a_res = p.nkb <= MAX_RES_KB;
+    const size_t smem = cand_smem_bytes(a_res);
+    auto go = [&](auto kern) -> int {
+        FIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<a.grid, 256, smem, s>>>(*a.tmap_a, *a.tmap_b, p);
+        FIR_CUDA_TRY(cudaGetLastError());
+        return FIR_OK;
+    };
+#define FIR_GO(RR) (a_res ? go(l2_candidates_kernel<RR, true>) : go(l2_candidates_kernel<RR, false>))
+    switch (a.R) {
+        case 8: return FIR_GO(8);
+        case 16: return FIR_GO(16);
+        case 32: return FIR_GO(32);
+    }
+#undef FIR_GO
+    return fail(FIR_ERR_INTERNAL, "unsupported candidate list length");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Selection + certificate.  One thread per query.
+//   approx(q,x) = ‖q‖² + ‖x‖² − 2·(q̂·x̂);   true(q,x) = ‖q − x‖²
+//   |approx − true| ≤ E = 2(‖δq‖(‖x‖+‖δx‖) + ‖q‖‖δx‖) + 2γ‖q‖‖x‖ + η,   δ = fp16 rounding residual (measured),
+//   γ bounds the tensor core's fp32 accumulation error, η the fp32 roundings of the norms and of the fma.
+//   The reference distance is fl-sum/D with relative error ≤ ρ = (D+4)·2⁻²⁴ around true/D.
+// Every non-candidate row has approx ≥ B = min over slots of the slot's R-th approx, hence
+// reference·D ≥ (B − E)(1 − ρ).  The result is certified when that exceeds the k-th exact distance.
+// ---------------------------------------------------------------------------------------------------
+__global__ void tensor_select_kernel(const float* __restrict__ cand_exact, const int32_t* __restrict__ cand_idx,
+                                     const float* __restrict__ slot_bound, int64_t nq, int n_slots, int R, int k, int d, int nkb,
+                                     const float* __restrict__ q_norm2, const float* __restrict__ q_resid,
+                                     const float* __restrict__ gal_stats, int64_t index_offset, float* __restrict__ out_dist,
+                                     int32_t* __restrict__ out_idx, int32_t* flagged, int32_t* n_flagged, float* max_bound) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int rt = n_slots * R;
+    const float* ce = cand_exact + q * rt;
+    const int32_t* ci = cand_idx + q * rt;
+    float last_d = -1.f; int last_i = -1;
+    int found = 0;
+    float kth = 0.f;
+    for (int r = 0; r < k; ++r) {
+        float bd = 0.f; int bi = -1;
+        for (int c = 0; c < rt; ++c) {
+            const int i = ci[c];
+            if (i < 0) continue;
+            const float dd = ce[c];
+            if (!(dd < 100000.0f)) continue;                                   // ann.cpp:116: nothing ≥ 100000 is ever accepted
+            if (r > 0 && !(dd > last_d || (dd == last_d && i > last_i))) continue;
+            if (bi < 0 || dd < bd || (dd == bd && i < bi)) { bd = dd; bi = i; }
+        }
+        if (bi >= 0) { out_dist[q * k + r] = bd; out_idx[q * k + r] = (int32_t)(bi + index_offset); last_d = bd; last_i = bi; ++found; kth = bd; }
+        else { out_dist[q * k + r] = 0.f; out_idx[q * k + r] = -1; last_d = __int_as_float(0x7f800000); }
+    }
+    double B = __longlong_as_double(0x7ff0000000000000LL);
+    for (int s = 0; s < n_slots; ++s) {
+        const float b = slot_bound[q * n_slots + s];
+        if (b == b && (double)b < B) B = (double)b;                            // NaN = slot never written = nothing excluded there
+    }
+    const double nq2 = (double)q_norm2[q], nqn = sqrt(nq2), rq = (double)q_resid[q];
+    const double NX = (double)gal_stats[0], RX = (double)gal_stats[1];
+    const double gamma = (double)(4 * nkb + 8) * 2.384185791015625e-07;        // (#UMMA K-steps + 8) · 2⁻²²
+    const double E = 2.0 * (rq * (NX + RX) + nqn * RX) + 2.0 * gamma * nqn * NX + 1e-6 * (nq2 + NX * NX + 2.0 * nqn * NX);
+    const double rho = (double)(d + 4) * 5.9604644775390625e-08;
+    bool ok;
+    if (isinf(B)) ok = true;                                                   // every row of the gallery was a candidate
+    else if (found < k) ok = false;
+    else ok = (B - E) * (1.0 - rho) > (double)kth * (double)d * (1.0 + rho);
+    if (!ok) { int pos = atomicAdd(n_flagged, 1); flagged[pos] = (int32_t)q; }
+    atomicMax(reinterpret_cast<unsigned int*>(max_bound), __float_as_uint((float)E));
+}
+
+int launch_tensor_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots, int R,
+                         int k, int d, const float* q_norm2, const float* q_resid, const float* gal_stats, int64_t index_offset,
+                         float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged, float* max_bound, cudaStream_t s) {
+    const int nkb = round_up(d, BK) / BK;
+    tensor_select_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, d, nkb, q_norm2,
+                                                                     q_resid, gal_stats, index_offset, out_dist, out_idx, flagged,
+                                                                     n_flagged, max_bound);
+    FIR_CUDA_TRY(cudaGetLastError());
+    return FIR_OK;
+}
+
+// flagged-query lists must come out in a deterministic order for the exact re-run's partial buffers: they
+// do not need to (each flagged query owns its output rows), so no sort is required.
+
+// ---------------------------------------------------------------------------------------------------
+// Orchestration of one fir_search_topk call on the tensor path
+// ---------------------------------------------------------------------------------------------------
+static int ensure_gallery_side(fir_gallery* g) {
+    if (g->tensor_ready) return FIR_OK;
+    size_t bytes = tensor_side_bytes(g->n, g->d, BN);
+    FIR_CUDA_TRY(cudaMalloc(&g->tensor_buf, bytes));
+    FIR_CUDA_TRY(cudaMalloc(&g->d_stats, 64));
+    FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, 64, g->stream));
+    FIR_TRY(tensor_pack_side(g->rows, g->n, g->dp, g->d, BN, g->tensor_buf, &g->tside, g->d_stats, g->stream));
+    FIR_TRY(tensor_encode_map(&g->tmap_b, g->tside.h, g->tside.rows_padded, g->tside.dph, BN));
+    g->tensor_ready = true;
+    return FIR_OK;
+}
+
+int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist) {
+    FIR_TRY(ensure_gallery_side(g));
+    const int R = k <= 4 ? 8 : (k <= 12 ? 16 : 32);
+    int grid = 0, n_slots = 1;
+    FIR_TRY(tensor_plan(nq, g->n, g->n_sm, &grid, &n_slots));
+    const int rt = n_slots * R;
+    const int nsplit_fb = 8;
+    const size_t qside = tensor_side_bytes(nq, g->d, BM);
+    size_t need = al256(sizeof(float) * (size_t)nq * g->dp) + qside + 3 * al256((size_t)nq * rt * 4) + al256((size_t)nq * n_slots * 4) +
+                  al256((size_t)nq * 4) + 2 * al256((size_t)nq * k * 4) + 2 * al256((size_t)nq * nsplit_fb * k * 4) + 8192;
+    FIR_TRY(g->ws.reserve(need));
+    // fp32 queries, zero padded (for the exact rerank and the certificate fallback)
+    const float* dq = nullptr;
+    {
+        const int d = g->d, dp = g->dp;
+        if (memspace == FIR_DEVICE && d == dp) dq = queries;
+        else {
+            float* buf = (float*)g->ws.take(sizeof(float) * (size_t)nq * dp);
+            if (!buf) return fail(FIR_ERR_INTERNAL, "workspace underestimated (tensor queries)");
+            if (memspace == FIR_HOST) {
+                if (d != dp) FIR_CUDA_TRY(cudaMemsetAsync(buf, 0, sizeof(float) * (size_t)nq * dp, g->stream));
+                FIR_CUDA_TRY(cudaMemcpy2DAsync(buf, sizeof(float) * dp, queries, sizeof(float) * d, sizeof(float) * d, (size_t)nq,
+                                               cudaMemcpyHostToDevice, g->stream));
+            } else {
+                FIR_TRY(launch_pad_rows(queries, nq, d, buf, dp, g->stream));
+                g->stats.gpu_launches++;
+            }
+            dq = buf;
+        }
+    }
+    void* qbuf = g->ws.take(qside);
+    float* cand_val = (float*)g->ws.take((size_t)nq * rt * 4);
+    int32_t* cand_idx = (int32_t*)g->ws.take((size_t)nq * rt * 4);
+    float* cand_exact = (float*)g->ws.take((size_t)nq * rt * 4);
+    float* slot_bound = (float*)g->ws.take((size_t)nq * n_slots * 4);
+    int32_t* flagged = (int32_t*)g->ws.take((size_t)nq * 4);
+    float* od = out_dist; int32_t* oi = out_idx;
+    if (memspace == FIR_HOST || !out_dist) od = (float*)g->ws.take((size_t)nq * k * 4);
+    if (memspace == FIR_HOST) oi = (int32_t*)g->ws.take((size_t)nq * k * 4);
+    float* part_d = (float*)g->ws.take((size_t)nq * nsplit_fb * k * 4);
+    int32_t* part_i = (int32_t*)g->ws.take((size_t)nq * nsplit_fb * k * 4);
+    if (!qbuf || !cand_val || !cand_idx || !cand_exact || !slot_bound || !flagged || !od || !oi || !part_d || !part_i)
+        return fail(FIR_ERR_INTERNAL, "workspace underestimated (tensor path)");
+    int32_t* n_flagged = reinterpret_cast<int32_t*>(g->d_stats + 4);
+    float* max_bound = g->d_stats + 5;
+    FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats + 4, 0, 8, g->stream));
+
+    TensorSide qs;
+    FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, qbuf, &qs, nullptr, g->stream));
+    CUtensorMap tmap_a;
+    FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
+    FIR_CUDA_TRY(cudaMemsetAsync(cand_idx, 0xFF, (size_t)nq * rt * 4, g->stream));
+    FIR_CUDA_TRY(cudaMemsetAsync(slot_bound, 0xFF, (size_t)nq * n_slots * 4, g->stream));
+    TensorSearchArgs a{};
+    a.gal = &g->tside; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = &g->tmap_b;
+    a.d = g->d; a.R = R; a.n_slots = n_slots; a.cand_val = cand_val; a.cand_idx = cand_idx; a.slot_bound = slot_bound; a.grid = grid;
+    FIR_TRY(launch_tensor_candidates(a, g->stream));
+    FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, cand_idx, rt, 0, cand_exact, g->stream));
+    FIR_TRY(launch_tensor_select(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, g->d, qs.norm2, qs.resid, g->d_stats, g->index_offset, od,
+                                 oi, flagged, n_flagged, max_bound, g->stream));
+    // certificate failures: exact CUDA-core re-run of just those queries (device-side count, no host sync)
+    FIR_TRY(exact_topk_device(g, dq, nq, k, g->d, flagged, n_flagged, part_d, part_i, nsplit_fb, od, oi));
+    g->stats.gpu_launches += 5;   // absmax, pack, candidates, rerank, select (+2 counted by exact_topk_device)
+    g->stats.path_used = FIR_PATH_TENSOR;
+    g->stats.n_candidates = rt;
+    g->stats.n_fallback = -1;     // resolved lazily by fir_search_last_stats
+    g->dbg_cand_val = cand_val; g->dbg_cand_exact = cand_exact; g->dbg_cand_idx = cand_idx;
+    g->dbg_nq = nq; g->dbg_slots = n_slots; g->dbg_R = R;
+    if (memspace == FIR_HOST) {
+        FIR_CUDA_TRY(cudaMemcpyAsync(out_idx, oi, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
+        if (out_dist) FIR_CUDA_TRY(cudaMemcpyAsync(out_dist, od, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
+        FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    }
+    return FIR_OK;
+}
+
+}  // namespace fir
+
+extern "C" int fir_debug_tensor_candidates(fir_gallery* g, int32_t* n_slots, int32_t* R, int32_t* idx, float* approx, float* exact) {
+    using namespace fir;
+    if (!g || !g->dbg_cand_idx) return fail(FIR_ERR_BAD_ARG, "no tensor-path call recorded on this gallery");
+    if (n_slots) *n_slots = g->dbg_slots;
+    if (R) *R = g->dbg_R;
+    const size_t cells = (size_t)g->dbg_nq * g->dbg_slots * g->dbg_R;
+    FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    if (idx) FIR_CUDA_TRY(cudaMemcpy(idx, g->dbg_cand_idx, cells * 4, cudaMemcpyDeviceToHost));
+    if (approx) FIR_CUDA_TRY(cudaMemcpy(approx, g->dbg_cand_val, cells * 4, cudaMemcpyDeviceToHost));
+    if (exact) FIR_CUDA_TRY(cudaMemcpy(exact, g->dbg_cand_exact, cells * 4, cudaMemcpyDeviceToHost));
+    return FIR_OK;
 }

@@ -99,6 +99,11 @@ int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k,
                     int32_t path, int32_t memspace, int32_t* out_idx, float* out_dist);
 int fir_search_last_stats(const fir_gallery* g, fir_search_stats* stats);
 
+/* diagnostic: the candidate lists of the last tensor-path fir_search_topk on this gallery (valid until the
+ * next call): nq x n_slots x R local indices (-1 = empty), their tensor-core approximate squared distances
+ * and their exact fp32 feature_distance values.  Pass NULL arrays to query n_slots/R first. */
+int fir_debug_tensor_candidates(fir_gallery* g, int32_t* n_slots, int32_t* R, int32_t* idx, float* approx, float* exact);
+
 /* replaces: ImageInfo::distance / feature_distance (qt_cpp/db_features.h:24-26, db_features.cpp:22-42)
  * for explicit (query, gallery index) pairs: cand_idx is nq x r LOCAL row indices (-1 = skip),
  * out_dist nq x r.  gallery_is_lhs != 0 evaluates feature_distance(gallery, query) — the operand

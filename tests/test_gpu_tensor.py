@@ -1,0 +1,91 @@
+"""GPU parity: the tcgen05/TMA tensor-core L2 path (candidates + exact rerank + certificate) against the
+oracle, through the C-ABI.  Indices and distances must be bit-identical to the reference argmin / top-k."""
+import numpy as np
+import pytest
+
+from util import bits, make_data
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # n, nq, d, classes
+    (3000, 300, 512, 30),     # A resident in shared memory (D <= 512)
+    (1000, 130, 128, 10),
+    (777, 45, 100, 7),        # ragged everything: D % 64 != 0, N % 256 != 0, Q % 128 != 0
+    (200, 5, 64, 4),          # gallery smaller than one tile
+    (2500, 140, 1536, 25),    # reference default D (db.h:86): A streamed per k-block
+]
+
+
+@pytest.mark.parametrize("n,nq,d,c", SHAPES)
+def test_tensor_topk_matches_oracle(fir, port, n, nq, d, c):
+    g, gl, q, ql = make_data(port, "l2", n, nq, d, c, seed=n % 7)
+    gal = fir.Gallery(g, gl, "l2")
+    for k in (1, 10, 20):
+        idx, dist = gal.search(q, k=k, path=fir.PATH_TENSOR)
+        st = gal.stats()
+        assert st["path_used"] == fir.PATH_TENSOR
+        oi, od = port.topk("l2", g, q, k, nthreads=8)
+        assert np.array_equal(idx, oi), "k=%d fallback=%d" % (k, st["n_fallback"])
+        assert np.array_equal(bits(dist), bits(od))
+    gal.close()
+
+
+def test_tensor_matches_reference_build(fir, port, ref_l2):
+    g, gl, q, ql = make_data(port, "l2", 4000, 256, 512, 40, seed=5)
+    gal = fir.Gallery(g, gl, "l2")
+    idx, dist = gal.search(q, k=1, path=fir.PATH_TENSOR)
+    ri, rd = ref_l2.bf(g, q, gl, nthreads=8)
+    assert np.array_equal(idx[:, 0], ri) and np.array_equal(bits(dist[:, 0]), bits(rd))
+    assert gal.stats()["n_fallback"] == 0          # clustered data: every query certified by the bound
+    gal.close()
+
+
+def test_tensor_duplicates_fall_back_exactly(fir, port):
+    """Mass exact ties defeat any finite candidate list: the certificate must fail and the exact re-run must
+    still return the reference answer (lowest index first)."""
+    g, gl, q, ql = make_data(port, "l2", 600, 64, 128, 3, seed=9)
+    g[:] = g[:40].repeat(15, axis=0)               # 15 copies of each of 40 rows
+    gal = fir.Gallery(g, None, "l2")
+    idx, dist = gal.search(q, k=10, path=fir.PATH_TENSOR)
+    oi, od = port.topk("l2", g, q, 10)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+    gal.close()
+
+
+def test_tensor_iid_noise_and_unnormalised(fir, port):
+    rng = np.random.default_rng(3)
+    g = rng.standard_normal((5000, 256)).astype(np.float32)          # i.i.d., NOT normalised, |x| up to ~5
+    q = rng.standard_normal((200, 256)).astype(np.float32)
+    gal = fir.Gallery(g, None, "l2")
+    idx, dist = gal.search(q, k=5, path=fir.PATH_TENSOR)
+    oi, od = port.topk("l2", g, q, 5, nthreads=8)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+    gal.close()
+
+
+def test_tensor_error_bound_is_respected(fir, port):
+    """Evidence for the certificate: the measured |approx - exact| of every candidate stays below the bound E."""
+    g, gl, q, ql = make_data(port, "l2", 8192, 256, 512, 64, seed=2)
+    gal = fir.Gallery(g, gl, "l2")
+    gal.search(q, k=10, path=fir.PATH_TENSOR)
+    st = gal.stats()
+    ci, ca, ce = gal.debug_candidates(q.shape[0])
+    ok = ci >= 0
+    err = np.abs(ca[ok].astype(np.float64) - ce[ok].astype(np.float64) * 512)
+    assert ok.sum() > 1000
+    assert err.max() < st["approx_err_bound"], (err.max(), st["approx_err_bound"])
+    assert err.max() < 0.25 * st["approx_err_bound"]     # the Cauchy-Schwarz bound is loose by a wide margin
+    print("max |approx-exact| = %.3g, certified bound E = %.3g, fallback = %d" % (err.max(), st["approx_err_bound"], st["n_fallback"]))
+    gal.close()
+
+
+def test_tensor_device_pointers(fir, port):
+    import torch
+    g, gl, q, ql = make_data(port, "l2", 2048, 128, 512, 16, seed=4)
+    gal = fir.Gallery(torch.from_numpy(g).cuda(), torch.from_numpy(gl).cuda(), "l2")
+    gal.set_stream(torch.cuda.current_stream().cuda_stream)
+    idx, dist = gal.search(torch.from_numpy(q).cuda(), k=10, path=fir.PATH_TENSOR)
+    torch.cuda.synchronize()
+    oi, od = port.topk("l2", g, q, 10, nthreads=8)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(bits(dist.cpu().numpy()), bits(od))
+    gal.close()

@@ -31,7 +31,7 @@ EXPORTS = [
     "fir_last_error_string", "fir_version", "fir_device_count", "fir_set_device",
     "fir_gallery_create", "fir_gallery_destroy", "fir_gallery_set_stream", "fir_gallery_info",
     "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
-    "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates",
+    "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates", "fir_profile_enable", "fir_profile_read",
     "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn",
     "fir_dem_build", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
     "fir_dem_get_min_other", "fir_dem_search",
@@ -76,6 +76,8 @@ def lib():
     L.fir_search_topk.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, vp]
     L.fir_search_last_stats.argtypes = [vp, C.POINTER(SearchStats)]
     L.fir_debug_tensor_candidates.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp]
+    L.fir_profile_enable.argtypes = [vp, i32]
+    L.fir_profile_read.argtypes = [vp, i32, C.POINTER(f64), C.POINTER(i32)]
     L.fir_pair_distances.argtypes = [vp, vp, i64, vp, i32, i32, i32, vp]
     L.fir_class_min.argtypes = [vp, vp, i64, i32, vp, vp]
     L.fir_pnn_scores.argtypes = [vp, vp, i64, f64, i64, i32, vp, vp]
@@ -199,6 +201,15 @@ class Gallery:
         s = SearchStats()
         _check(lib().fir_search_last_stats(self._h, C.byref(s)))
         return {f[0]: getattr(s, f[0]) for f in SearchStats._fields_}
+
+    def profile(self, on=True):
+        _check(lib().fir_profile_enable(self._h, int(on)))
+
+    def profile_read(self, kernel=0):
+        """(total ms, launches) of the given kernel class since profile(True)."""
+        ms, n = C.c_double(0), C.c_int32(0)
+        _check(lib().fir_profile_read(self._h, kernel, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def debug_candidates(self, nq):
         """(idx, approx d^2, exact feature_distance) of the last tensor-path search: arrays [nq, n_slots*R]."""

@@ -79,7 +79,7 @@ int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_
     p.tiles_per_split = ceil_div(ceil_div(g->n, kExactTile), nsplit);
     p.part_dist = part_d; p.part_idx = part_i;
     p.qmap = qmap; p.n_active = n_active;
-    FIR_TRY(launch_exact_tiles(g->metric, p, g->stream));
+    { auto* ev = g->prof_begin(FIR_KERNEL_EXACT_TILES); int st_ = launch_exact_tiles(g->metric, p, g->stream); g->prof_end(ev); FIR_TRY(st_); }
     FIR_TRY(launch_merge_parts(part_d, part_i, nsplit, k, (int64_t)nsplit * k, nq, k, g->index_offset, qmap, n_active, od, oi, g->stream));
     g->stats.gpu_launches += 2;
     return FIR_OK;
@@ -163,6 +163,7 @@ int fir_gallery_destroy(fir_gallery* g) {
     if (g->labels) cudaFree(g->labels);
     if (g->tensor_buf) cudaFree(g->tensor_buf);
     if (g->d_stats) cudaFree(g->d_stats);
+    for (auto& e : g->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     g->ws.release();
     delete g;
     return FIR_OK;
@@ -236,6 +237,28 @@ int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k,
         if (out_dist) FIR_CUDA_TRY(cudaMemcpyAsync(out_dist, od, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
         FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
     }
+    return FIR_OK;
+}
+
+int fir_profile_enable(fir_gallery* g, int32_t on) {
+    if (!g) return fail(FIR_ERR_BAD_ARG, "gallery is null");
+    g->profiling = on != 0;
+    g->ev_used = 0;
+    return FIR_OK;
+}
+
+int fir_profile_read(fir_gallery* g, int32_t kernel, double* total_ms, int32_t* launches) {
+    if (!g) return fail(FIR_ERR_BAD_ARG, "gallery is null");
+    FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    double tot = 0; int cnt = 0;
+    for (size_t i = 0; i < g->ev_used; ++i) {
+        if (g->ev_pool[i].kind != kernel) continue;
+        float ms = 0.f;
+        FIR_CUDA_TRY(cudaEventElapsedTime(&ms, g->ev_pool[i].a, g->ev_pool[i].b));
+        tot += ms; ++cnt;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = cnt;
     return FIR_OK;
 }
 

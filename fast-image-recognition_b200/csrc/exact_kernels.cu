@@ -196,8 +196,7 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
             int r = i / p.k, s = i - r * p.k;
             int64_t qi = q0 + r;
             if (qi < n_active) {
-                int64_t qo = p.qmap ? (int64_t)p.qmap[qi] : qi;
-                int64_t o = (qo * p.nsplit + blockIdx.y) * p.k + s;
+                int64_t o = (qi * p.nsplit + blockIdx.y) * p.k + s;     // partial lists are indexed by ACTIVE position
                 p.part_dist[o] = tkd[i];
                 p.part_idx[o] = tki[i];
             }
@@ -238,15 +237,15 @@ __global__ void merge_parts_kernel(const float* __restrict__ pd, const int32_t* 
     int64_t na = n_active ? (int64_t)*n_active : nq;
     if (i >= na) return;
     int64_t q = qmap ? (int64_t)qmap[i] : i;
-    constexpr int MAXP = 64;
-    unsigned char head[MAXP];
+    constexpr int MAXP = 256;
+    unsigned short head[MAXP];
     for (int s = 0; s < n_parts; ++s) head[s] = 0;
     for (int r = 0; r < k; ++r) {
         float bd = 0.f; int32_t bi = -1; int bs = -1;
         for (int s = 0; s < n_parts; ++s) {
             int h = head[s];
             if (h >= k) continue;
-            int64_t o = (int64_t)s * part_stride + q * q_stride + h;
+            int64_t o = (int64_t)s * part_stride + i * q_stride + h;   // parts are indexed by active position, outputs by query
             int32_t ci = pi[o];
             if (ci < 0) continue;
             float cd = pd[o];
@@ -261,7 +260,7 @@ int launch_merge_parts(const float* pd, const int32_t* pi, int n_parts, int64_t 
                        int64_t nq, int k, int64_t index_offset, const int32_t* qmap, const int32_t* n_active,
                        float* od, int32_t* oi, cudaStream_t s) {
     if (nq <= 0) return FIR_OK;
-    if (n_parts > 64) return fail(FIR_ERR_UNSUPPORTED, "more than 64 parts to merge");
+    if (n_parts > 256) return fail(FIR_ERR_UNSUPPORTED, "more than 256 parts to merge");
     merge_parts_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(pd, pi, n_parts, part_stride, q_stride, nq, k, index_offset,
                                                                    qmap, n_active, od, oi);
     FIR_CUDA_TRY(cudaGetLastError());

@@ -22,6 +22,16 @@ struct fir_gallery {
     // diagnostics: where the last tensor-path call left its candidate lists (valid until the next call)
     const float* dbg_cand_val = nullptr; const float* dbg_cand_exact = nullptr; const int32_t* dbg_cand_idx = nullptr;
     int64_t dbg_nq = 0; int dbg_slots = 0, dbg_R = 0;
+    // optional per-kernel timing: CUDA event pairs recorded on the launching stream around the dominant kernel
+    bool profiling = false;
+    struct EvPair { cudaEvent_t a, b; int kind; };
+    std::vector<EvPair> ev_pool; size_t ev_used = 0;
+    EvPair* prof_begin(int kind) {
+        if (!profiling) return nullptr;
+        if (ev_used == ev_pool.size()) { EvPair e{}; cudaEventCreate(&e.a); cudaEventCreate(&e.b); ev_pool.push_back(e); }
+        EvPair* e = &ev_pool[ev_used++]; e->kind = kind; cudaEventRecord(e->a, stream); return e;
+    }
+    void prof_end(EvPair* e) { if (e) cudaEventRecord(e->b, stream); }
     fir_search_stats stats{};
 };
 

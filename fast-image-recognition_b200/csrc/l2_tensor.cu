@@ -133,7 +133,7 @@ __global__ void absmax_kernel(const float* __restrict__ rows, int64_t n, int ld,
 // meta[0] = absmax bits (in), meta[1] = scale (out, float bits)
 __global__ void pack_rows_kernel(const float* __restrict__ rows, int64_t n, int64_t rows_padded, int ld, int d, int dph,
                                  __half* __restrict__ h, float* __restrict__ norm2, float* __restrict__ resid,
-                                 unsigned int* meta, unsigned int* stats_bits) {
+                                 unsigned int* meta, unsigned int* stats_bits, int64_t perm_a, int64_t perm_b) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows_padded) return;
@@ -152,9 +152,10 @@ __global__ void pack_rows_kernel(const float* __restrict__ rows, int64_t n, int6
         return;
     }
     const float inv = 1.f / scale;        // exact: power of two
+    const int64_t src_row = (row * perm_a + perm_b) % n;
     double n2 = 0.0, r2 = 0.0;
     for (int c = lane; c < dph; c += 32) {
-        float x = c < d ? rows[row * ld + c] : 0.f;
+        float x = c < d ? rows[src_row * ld + c] : 0.f;
         float xs = x * scale;
         __half hv = __float2half_rn(xs);
         if (fabsf(__half2float(hv)) < 6.103515625e-05f) hv = __float2half_rn(0.f);
@@ -188,8 +189,10 @@ size_t tensor_side_bytes(int64_t rows, int d, int row_tile) {
     return al256((size_t)rp * dph * 2) + 2 * al256((size_t)rp * 4) + 256 + 1024;
 }
 
+static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
+
 int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out, float* d_stats,
-                     cudaStream_t s) {
+                     bool permute, cudaStream_t s) {
     int64_t rp = ceil_div(n, row_tile) * row_tile;
     int dph = round_up(d, BK);
     char* p = (char*)(((uintptr_t)buf + 1023) & ~(uintptr_t)1023);     // TMA global address alignment (>=16B); keep 1 KiB
@@ -198,12 +201,21 @@ int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, 
     out->resid = (float*)p; p += al256((size_t)rp * 4);
     out->meta = (unsigned int*)p;
     out->rows = n; out->rows_padded = rp; out->dph = dph;
+    // Gallery shadow rows are stored in a strided permutation so that rows which are neighbours in the caller's
+    // (class-major) order are far apart in scan order: the running top-R threshold then tightens like on i.i.d. data.
+    out->perm_a = 1; out->perm_b = 0;
+    if (permute && n > 2) {
+        int64_t a = (int64_t)((double)n * 0.6180339887498949);
+        if (a < 1) a = 1;
+        while (gcd64(a, n) != 1) ++a;
+        out->perm_a = a % n; out->perm_b = n / 3;
+    }
     FIR_CUDA_TRY(cudaMemsetAsync(out->meta, 0, 16, s));
     int blocks = (int)std::min<int64_t>(1184, ceil_div(n * d, 256 * 8));
     absmax_kernel<<<std::max(blocks, 1), 256, 0, s>>>(rows, n, ld, d, out->meta);
     FIR_CUDA_TRY(cudaGetLastError());
     pack_rows_kernel<<<(unsigned)ceil_div(rp, 8), 256, 0, s>>>(rows, n, rp, ld, d, dph, out->h, out->norm2, out->resid, out->meta,
-                                                              (unsigned int*)d_stats);
+                                                              (unsigned int*)d_stats, out->perm_a, out->perm_b);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
@@ -268,6 +280,7 @@ int tensor_plan(int64_t nq, int64_t n, int n_sm, int* grid, int* n_slots) {
 struct CandParams {
     Partition part;
     int64_t nq, n;
+    int64_t perm_a, perm_b;     // shadow row p holds original row (p * perm_a + perm_b) mod n
     int nkb;
     int n_slots;
     const float* gal_norm2;
@@ -307,7 +320,8 @@ __global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_cons
     uint64_t* a_empty = a_full + 1;
     uint64_t* tmem_full = a_empty + 1;            // [2]
     uint64_t* tmem_empty = tmem_full + 2;         // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* nx_full = tmem_empty + 2;           // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(nx_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Partition P = p.part;
@@ -318,7 +332,7 @@ __global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_cons
         for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
         mbar_init(smem_u32(a_full), 1);
         mbar_init(smem_u32(a_empty), 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), 4); mbar_init(smem_u32(&nx_full[s]), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -386,11 +400,24 @@ __global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_cons
             }
             as ^= 1; if (as == 0) aphase ^= 1;
         }
+    } else if (warp == 3) {
+        // ===== norm loader: stages each tile's 256 gallery norms into nx_s[as] for the epilogue warps =====
+        int as = 0; uint32_t aphase = 0;
+        for (int64_t it = item_lo; it < item_hi; ++it) {
+            const int64_t tile = it % P.ntiles;
+            mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);         // epilogue finished with this buffer pair
+            const float4* src = reinterpret_cast<const float4*>(p.gal_norm2 + tile * BN + lane * 8);
+            const float4 v0 = src[0], v1 = src[1];
+            float4* dst = reinterpret_cast<float4*>(&nx_s[as * BN + lane * 8]);
+            dst[0] = v0; dst[1] = v1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&nx_full[as]));
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
     } else if (warp >= 4) {
         // ===== epilogue: thread = one query row; running top-R in registers =====
         const int ew = warp - 4;                       // TMEM lane group of this warp = warp % 4
         const int row = ew * 32 + lane;
-        const int et = threadIdx.x - 128;              // 0..127
         const float sg = __uint_as_float(p.gal_meta[1]), sq = __uint_as_float(p.qry_meta[1]);
         const float negc = -2.0f / (sg * sq);
         float lv[R]; int li[R];
@@ -403,15 +430,14 @@ __global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_cons
                 const float nqv = p.qry_norm2[qrow];
                 const int64_t o = (qrow * p.n_slots + slot) * R;
 #pragma unroll
-                for (int r = 0; r < R; ++r) { p.cand_val[o + r] = lv[r] + nqv; p.cand_idx[o + r] = li[r]; }
+                for (int r = 0; r < R; ++r) {
+                    p.cand_val[o + r] = lv[r] + nqv;
+                    // shadow position -> original gallery row (the fp16 copy is stored in a strided permutation)
+                    p.cand_idx[o + r] = li[r] < 0 ? -1 : (int32_t)(((int64_t)li[r] * p.perm_a + p.perm_b) % p.n);
+                }
                 p.slot_bound[qrow * p.n_slots + slot] = (li[R - 1] >= 0) ? lv[R - 1] + nqv : __int_as_float(0x7f800000);
             }
         };
-        float2 nx_next = make_float2(0.f, 0.f);
-        if (item_lo < item_hi) {
-            const int64_t tile0 = item_lo % P.ntiles;
-            nx_next = *reinterpret_cast<const float2*>(p.gal_norm2 + tile0 * BN + et * 2);
-        }
         for (int64_t it = item_lo; it < item_hi; ++it) {
             const int64_t qb = it / P.ntiles, tile = it - qb * P.ntiles;
             if (qb != cur_qb) {
@@ -420,13 +446,7 @@ __global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_cons
                 for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = -1; }
                 cur_qb = qb;
             }
-            // stage this tile's ‖x‖² (prefetched one tile ahead), then prefetch the next tile's
-            *reinterpret_cast<float2*>(&nx_s[as * BN + et * 2]) = nx_next;
-            if (it + 1 < item_hi) {
-                const int64_t nt = (it + 1) % P.ntiles;
-                nx_next = *reinterpret_cast<const float2*>(p.gal_norm2 + nt * BN + et * 2);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(smem_u32(&nx_full[as]), aphase);
             mbar_wait(smem_u32(&tmem_full[as]), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * BN;
@@ -450,10 +470,28 @@ __global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_cons
                     rr[i + 2] = __float_as_uint(v2); rr[i + 3] = __float_as_uint(v3);
                     vmin = fminf(vmin, fminf(fminf(v0, v1), fminf(v2, v3)));
                 }
-                if (vmin < thr) {
+                if (__any_sync(0xffffffffu, vmin < thr)) {
+                    // Rare path.  Per-lane hit mask, then ONE insertion body shared by every column: the column
+                    // index is made warp-uniform (OR-reduction of the masks) so selecting rr[i] is a uniform switch.
+                    uint32_t m = 0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float v = __uint_as_float(rr[i]);
+                    for (int i = 0; i < 32; ++i) m |= (__uint_as_float(rr[i]) < thr) ? (1u << i) : 0u;
+                    uint32_t many = __reduce_or_sync(0xffffffffu, m);
+#pragma unroll 1
+                    while (many) {
+                        const int i = __ffs(many) - 1;
+                        many &= many - 1;
+                        uint32_t bits;
+                        switch (i) {
+#define FIR_CASE(I) case I: bits = rr[I]; break;
+                            FIR_CASE(0) FIR_CASE(1) FIR_CASE(2) FIR_CASE(3) FIR_CASE(4) FIR_CASE(5) FIR_CASE(6) FIR_CASE(7)
+                            FIR_CASE(8) FIR_CASE(9) FIR_CASE(10) FIR_CASE(11) FIR_CASE(12) FIR_CASE(13) FIR_CASE(14) FIR_CASE(15)
+                            FIR_CASE(16) FIR_CASE(17) FIR_CASE(18) FIR_CASE(19) FIR_CASE(20) FIR_CASE(21) FIR_CASE(22) FIR_CASE(23)
+                            FIR_CASE(24) FIR_CASE(25) FIR_CASE(26) FIR_CASE(27) FIR_CASE(28) FIR_CASE(29) FIR_CASE(30)
+                            default: bits = rr[31]; break;
+#undef FIR_CASE
+                        }
+                        const float v = __uint_as_float(bits);
                         if (v < thr) { topr_insert<R>(lv, li, v, jbase + c0 + i); thr = lv[R - 1]; }
                     }
                 }
@@ -476,7 +514,7 @@ __global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_cons
 
 static size_t cand_smem_bytes(bool a_res) {
     size_t stages = a_res ? 3 * (size_t)B_KB_BYTES : 4 * (size_t)(A_KB_BYTES + B_KB_BYTES);
-    return (a_res ? (size_t)MAX_RES_KB * A_KB_BYTES : 0) + stages + 2 * BN * 4 + 16 * 8 + 16;
+    return (a_res ? (size_t)MAX_RES_KB * A_KB_BYTES : 0) + stages + 2 * BN * 4 + 18 * 8 + 16;
 }
 
 int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
@@ -486,6 +524,7 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     p.part.total = p.part.ntiles * p.part.nqb;
     p.part.grid = a.grid;
     p.nq = a.qry->rows; p.n = a.gal->rows;
+    p.perm_a = a.gal->perm_a; p.perm_b = a.gal->perm_b;
     p.nkb = a.gal->dph / BK;
     p.n_slots = a.n_slots;
     p.gal_norm2 = a.gal->norm2; p.qry_norm2 = a.qry->norm2;
@@ -585,7 +624,7 @@ static int ensure_gallery_side(fir_gallery* g) {
     FIR_CUDA_TRY(cudaMalloc(&g->tensor_buf, bytes));
     FIR_CUDA_TRY(cudaMalloc(&g->d_stats, 64));
     FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, 64, g->stream));
-    FIR_TRY(tensor_pack_side(g->rows, g->n, g->dp, g->d, BN, g->tensor_buf, &g->tside, g->d_stats, g->stream));
+    FIR_TRY(tensor_pack_side(g->rows, g->n, g->dp, g->d, BN, g->tensor_buf, &g->tside, g->d_stats, true, g->stream));
     FIR_TRY(tensor_encode_map(&g->tmap_b, g->tside.h, g->tside.rows_padded, g->tside.dph, BN));
     g->tensor_ready = true;
     return FIR_OK;
@@ -597,7 +636,9 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     int grid = 0, n_slots = 1;
     FIR_TRY(tensor_plan(nq, g->n, g->n_sm, &grid, &n_slots));
     const int rt = n_slots * R;
-    const int nsplit_fb = 8;
+    // certificate failures are rare: spread each flagged query block over many gallery splits (bounded scratch)
+    const int nsplit_fb = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(256, ceil_div(g->n, 64 * 4)),
+                                                                     ((int64_t)64 << 20) / std::max<int64_t>(1, nq * k * 8)));
     const size_t qside = tensor_side_bytes(nq, g->d, BM);
     size_t need = al256(sizeof(float) * (size_t)nq * g->dp) + qside + 3 * al256((size_t)nq * rt * 4) + al256((size_t)nq * n_slots * 4) +
                   al256((size_t)nq * 4) + 2 * al256((size_t)nq * k * 4) + 2 * al256((size_t)nq * nsplit_fb * k * 4) + 8192;
@@ -639,7 +680,7 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats + 4, 0, 8, g->stream));
 
     TensorSide qs;
-    FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, qbuf, &qs, nullptr, g->stream));
+    FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, qbuf, &qs, nullptr, false, g->stream));
     CUtensorMap tmap_a;
     FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
     FIR_CUDA_TRY(cudaMemsetAsync(cand_idx, 0xFF, (size_t)nq * rt * 4, g->stream));
@@ -647,7 +688,7 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     TensorSearchArgs a{};
     a.gal = &g->tside; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = &g->tmap_b;
     a.d = g->d; a.R = R; a.n_slots = n_slots; a.cand_val = cand_val; a.cand_idx = cand_idx; a.slot_bound = slot_bound; a.grid = grid;
-    FIR_TRY(launch_tensor_candidates(a, g->stream));
+    { auto* ev = g->prof_begin(FIR_KERNEL_L2_CANDIDATES); int st_ = launch_tensor_candidates(a, g->stream); g->prof_end(ev); FIR_TRY(st_); }
     FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, cand_idx, rt, 0, cand_exact, g->stream));
     FIR_TRY(launch_tensor_select(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, g->d, qs.norm2, qs.resid, g->d_stats, g->index_offset, od,
                                  oi, flagged, n_flagged, max_bound, g->stream));

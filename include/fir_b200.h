@@ -99,6 +99,13 @@ int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k,
                     int32_t path, int32_t memspace, int32_t* out_idx, float* out_dist);
 int fir_search_last_stats(const fir_gallery* g, fir_search_stats* stats);
 
+/* measurement aid: when enabled, CUDA event pairs are recorded on the handle's stream around every launch
+ * of the dominant kernels; fir_profile_read synchronises and returns their summed duration and count since
+ * fir_profile_enable(g, 1) was last called. */
+typedef enum fir_kernel { FIR_KERNEL_L2_CANDIDATES = 0, FIR_KERNEL_EXACT_TILES = 1, FIR_KERNEL_DEM_LIKELIHOOD = 2 } fir_kernel;
+int fir_profile_enable(fir_gallery* g, int32_t on);
+int fir_profile_read(fir_gallery* g, int32_t kernel, double* total_ms, int32_t* launches);
+
 /* diagnostic: the candidate lists of the last tensor-path fir_search_topk on this gallery (valid until the
  * next call): nq x n_slots x R local indices (-1 = empty), their tensor-core approximate squared distances
  * and their exact fp32 feature_distance values.  Pass NULL arrays to query n_slots/R first. */

@@ -33,7 +33,7 @@ EXPORTS = [
     "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
     "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates", "fir_profile_enable", "fir_profile_read",
     "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn",
-    "fir_dem_build", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
+    "fir_dem_build", "fir_dem_from_state", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
     "fir_dem_get_min_other", "fir_dem_search",
 ]
 
@@ -87,6 +87,7 @@ def lib():
     L.fir_classifier_knn.argtypes = [vp, vp, i64, i32, vp]
     L.fir_classifier_pnn.argtypes = [vp, vp, i64, vp, vp]
     L.fir_dem_build.argtypes = [vp, C.POINTER(DemParams), C.POINTER(vp)]
+    L.fir_dem_from_state.argtypes = [vp, vp, i32, vp, C.c_float, C.POINTER(vp)]
     L.fir_dem_destroy.argtypes = [vp]
     L.fir_dem_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float)]
     L.fir_dem_get_pivots.argtypes = [vp, vp]
@@ -302,11 +303,16 @@ class Classifier:
 class Dem:
     """DirectedEnumeration over a Gallery (kept alive by this object)."""
 
-    def __init__(self, gallery, pivot0=-1, seed=0, false_accept_rate=0.01, threshold=0.0, max_chain=0, max_pivots=0):
+    def __init__(self, gallery, pivot0=-1, seed=0, false_accept_rate=0.01, threshold=0.0, max_chain=0, max_pivots=0, state=None):
         self.gallery = gallery
-        p = DemParams(int(pivot0), int(seed), float(false_accept_rate), float(threshold), int(max_chain), int(max_pivots))
         h = C.c_void_p(None)
-        _check(lib().fir_dem_build(gallery._h, C.byref(p), C.byref(h)))
+        if state is not None:      # (pivots, P, threshold): adopt an existing build
+            piv = np.ascontiguousarray(state[0], dtype=np.int32)
+            P = np.ascontiguousarray(state[1], dtype=np.float32)
+            _check(lib().fir_dem_from_state(gallery._h, _ptr(piv), len(piv), _ptr(P), float(state[2]), C.byref(h)))
+        else:
+            p = DemParams(int(pivot0), int(seed), float(false_accept_rate), float(threshold), int(max_chain), int(max_pivots))
+            _check(lib().fir_dem_build(gallery._h, C.byref(p), C.byref(h)))
         self._h = h
         a, b, t = C.c_int32(0), C.c_int32(0), C.c_float(0)
         _check(lib().fir_dem_info(self._h, C.byref(a), C.byref(b), C.byref(t)))

@@ -1,0 +1,268 @@
+// cls_kernels.cu — the fp64 kNN / PNN classifiers of qt_cpp/classification.cpp on the GPU.
+//
+// Reference semantics (classification.cpp:116-170, 188-226): features are double, both operands are
+// mean-centred first (normalize(), :103-105: x - avg, q - avg — two separate roundings), the squared
+// distance is accumulated sequentially over the dimensions in fp64, kNN divides by D and walks the
+// neighbours in ascending distance until a class owns K votes, PNN sums exp(-dist / (2*D*var)) per class
+// in training-set order.  One thread owns one (query, training row) pair and uses separately rounded
+// __dsub_rn/__dmul_rn/__dadd_rn, so the distances are bit-identical to the reference's.
+#include "fir_common.cuh"
+#include <algorithm>
+#include <cstring>
+
+struct fir_classifier {
+    int device = 0;
+    cudaStream_t stream = 0;
+    int64_t n = 0;
+    int d = 0, n_classes = 0;
+    double* xc = nullptr;        // [n][d] training rows, already centred: fl(x - avg)
+    double* avg = nullptr;       // [d]
+    int32_t* labels = nullptr;   // [n] class of each training row (class-major order)
+    int32_t* cls_begin = nullptr; // [C+1] row range of every class (rows are class-major)
+    bool class_major = true;
+    fir::Workspace ws;
+};
+
+namespace fir {
+
+__global__ void centre_rows_kernel(const double* __restrict__ src, const double* __restrict__ avg, int64_t n, int d, double* __restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * d) return;
+    dst[i] = __dsub_rn(src[i], avg[i % d]);                                     // classification.cpp:104
+}
+
+constexpr int CT = 64;     // tile: 64 queries x 64 training rows
+constexpr int CK = 16;     // dims per stage
+constexpr int CLD = CK + 1;
+
+// dist[q][t] = sum_fi fl(fl(xc[t][fi] - qc[q][fi])^2), sequential in fi   (classification.cpp:127-142, 201-212)
+__global__ void __launch_bounds__(256) cls_dist_kernel(const double* __restrict__ qc, int64_t nq, const double* __restrict__ xc, int64_t n,
+                                                       int d, double* __restrict__ out) {
+    __shared__ double qs[CT * CLD];
+    __shared__ double xs[CT * CLD];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t q0 = (int64_t)blockIdx.y * CT, x0 = (int64_t)blockIdx.x * CT;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int k0 = 0; k0 < d; k0 += CK) {
+        for (int i = tid; i < CT * CK; i += 256) {
+            int r = i / CK, c = i - r * CK;
+            int64_t qi = q0 + r, xi = x0 + r;
+            qs[r * CLD + c] = (qi < nq && k0 + c < d) ? qc[qi * d + k0 + c] : 0.0;
+            xs[r * CLD + c] = (xi < n && k0 + c < d) ? xc[xi * d + k0 + c] : 0.0;
+        }
+        __syncthreads();
+        const int kmax = min(CK, d - k0);
+        for (int kk = 0; kk < kmax; ++kk) {
+            double qa[4], xa[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) qa[a] = qs[(ty + 16 * a) * CLD + kk];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) xa[b] = xs[(tx + 16 * b) * CLD + kk];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    double diff = __dsub_rn(xa[b], qa[a]);                      // :137 / :209  diff = x' - q'
+                    acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(diff, diff));    // :141 / :211
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int64_t qi = q0 + ty + 16 * a, xi = x0 + tx + 16 * b;
+            if (qi < nq && xi < n) out[qi * n + xi] = acc[a][b];
+        }
+}
+
+// PNN: one thread per (query, class); sums in training-set order (classification.cpp:195-216)
+__global__ void pnn_class_sum_kernel(const double* __restrict__ dist, int64_t nq, int64_t n, int n_classes, const int32_t* __restrict__ cls_begin,
+                                     const int32_t* __restrict__ labels, int class_major, double den, double n_total, double* __restrict__ scores) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * n_classes) return;
+    const int64_t q = i / n_classes;
+    const int c = (int)(i - q * n_classes);
+    const double* dr = dist + q * n;
+    double s = 0.0;
+    if (class_major) {
+        for (int t = cls_begin[c]; t < cls_begin[c + 1]; ++t) s += exp(-dr[t] / den);      // :213
+    } else {
+        for (int64_t t = 0; t < n; ++t)
+            if (labels[t] == c) s += exp(-dr[t] / den);
+    }
+    scores[i] = s / n_total;                                                               // :215
+}
+
+__global__ void argmax_double_kernel(const double* __restrict__ scores, int64_t nq, int n_classes, int32_t* __restrict__ label) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    double mx = -1.7976931348623157e308; int best = -1;                                    // :217-225
+    for (int c = 0; c < n_classes; ++c) {
+        double v = scores[q * n_classes + c];
+        if (mx < v) { mx = v; best = c; }
+    }
+    label[q] = best;
+}
+
+// kNN vote: one warp per query.  Neighbours are produced in ascending (dist/D, index) order by repeated
+// warp-wide "smallest pair greater than the last one" scans; lane 0 counts votes until a class reaches K
+// (classification.cpp:143, 151-160), then takes the arg-max over classes with strict '<' (:161-169).
+__global__ void __launch_bounds__(128) knn_vote_kernel(const double* __restrict__ dist, int64_t nq, int64_t n, int d, int n_classes,
+                                                       const int32_t* __restrict__ labels, int K, float* __restrict__ votes_scratch,
+                                                       int32_t* __restrict__ out_label) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const double* dr = dist + q * n;
+    float* votes = votes_scratch + q * n_classes;
+    for (int c = lane; c < n_classes; c += 32) votes[c] = 0.f;
+    __syncwarp();
+    const double dd = (double)(size_t)d;
+    double last_d = -1.0; int64_t last_i = -1;
+    bool done = false;
+    for (int64_t step = 0; step < n && !done; ++step) {
+        double bd = 0.0; int64_t bi = -1;
+        for (int64_t t = lane; t < n; t += 32) {
+            double v = dr[t] / dd;                                                         // :143
+            if (step > 0 && !(v > last_d || (v == last_d && t > last_i))) continue;
+            if (bi < 0 || v < bd || (v == bd && t < bi)) { bd = v; bi = t; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            long long oi = __shfl_xor_sync(0xffffffffu, (long long)bi, o);
+            if (oi >= 0 && (bi < 0 || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; }
+        }
+        if (bi < 0) break;
+        last_d = bd; last_i = bi;
+        if (lane == 0) {
+            int c = labels[bi];
+            float v = votes[c] + 1.f;                                                      // :156
+            votes[c] = v;
+            done = v >= (float)K;                                                          // :157
+        }
+        done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float mx = -__int_as_float(0x7f800000); int best = -1;                             // (float)-DBL_MAX == -inf
+        for (int c = 0; c < n_classes; ++c)
+            if (mx < votes[c]) { mx = votes[c]; best = c; }
+        out_label[q] = best;
+    }
+}
+
+}  // namespace fir
+
+using namespace fir;
+
+extern "C" {
+
+int fir_classifier_create(const double* train_rows, const int32_t* train_labels, int64_t n, int32_t d, int32_t n_classes,
+                          const double* avg, fir_classifier** out) {
+    if (!out) return fail(FIR_ERR_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (!train_rows || !train_labels || !avg || n <= 0 || d <= 0 || n_classes <= 0) return fail(FIR_ERR_BAD_ARG, "bad training set");
+    fir_classifier* c = new fir_classifier();
+    cudaError_t e = cudaGetDevice(&c->device);
+    if (e != cudaSuccess) { delete c; return fail(FIR_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e)); }
+    c->n = n; c->d = d; c->n_classes = n_classes;
+    std::vector<int32_t> begin((size_t)n_classes + 1, 0);
+    bool major = true;
+    for (int64_t t = 0; t < n; ++t) {
+        int32_t l = train_labels[t];
+        if (l < 0 || l >= n_classes) { delete c; return fail(FIR_ERR_BAD_ARG, "training label out of range"); }
+        if (t > 0 && l < train_labels[t - 1]) major = false;
+        begin[(size_t)l + 1]++;
+    }
+    for (int k = 0; k < n_classes; ++k) begin[(size_t)k + 1] += begin[(size_t)k];
+    c->class_major = major;
+    double* raw = nullptr;
+    auto cleanup = [&](int code) { if (raw) cudaFree(raw); fir_classifier_destroy(c); return code; };
+    if (cudaMalloc(&c->xc, sizeof(double) * (size_t)n * d) != cudaSuccess || cudaMalloc(&raw, sizeof(double) * (size_t)n * d) != cudaSuccess ||
+        cudaMalloc(&c->avg, sizeof(double) * d) != cudaSuccess || cudaMalloc(&c->labels, sizeof(int32_t) * (size_t)n) != cudaSuccess ||
+        cudaMalloc(&c->cls_begin, sizeof(int32_t) * ((size_t)n_classes + 1)) != cudaSuccess)
+        return cleanup(fail(FIR_ERR_OOM, "classifier allocation failed"));
+    if (cudaMemcpy(raw, train_rows, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->avg, avg, sizeof(double) * d, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->labels, train_labels, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->cls_begin, begin.data(), sizeof(int32_t) * ((size_t)n_classes + 1), cudaMemcpyHostToDevice) != cudaSuccess)
+        return cleanup(fail(FIR_ERR_CUDA, "classifier upload failed"));
+    centre_rows_kernel<<<(unsigned)ceil_div(n * d, 256), 256>>>(raw, c->avg, n, d, c->xc);
+    e = cudaDeviceSynchronize();
+    cudaFree(raw); raw = nullptr;
+    if (e != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, std::string("centre_rows_kernel: ") + cudaGetErrorString(e)));
+    *out = c;
+    return FIR_OK;
+}
+
+int fir_classifier_destroy(fir_classifier* c) {
+    if (!c) return FIR_OK;
+    if (c->xc) cudaFree(c->xc);
+    if (c->avg) cudaFree(c->avg);
+    if (c->labels) cudaFree(c->labels);
+    if (c->cls_begin) cudaFree(c->cls_begin);
+    c->ws.release();
+    delete c;
+    return FIR_OK;
+}
+
+// shared driver: distances for a chunk of queries, then the requested reducer
+static int classify(fir_classifier* c, const double* queries, int64_t nq, int K, bool pnn, double* out_scores, int32_t* out_label) {
+    if (!c) return fail(FIR_ERR_BAD_ARG, "classifier is null");
+    if (nq < 0 || (nq > 0 && (!queries || !out_label))) return fail(FIR_ERR_BAD_ARG, "bad arguments");
+    if (!pnn && K < 1) return fail(FIR_ERR_BAD_ARG, "K must be >= 1");
+    if (nq == 0) return FIR_OK;
+    FIR_CUDA_TRY(cudaSetDevice(c->device));
+    const int64_t n = c->n; const int d = c->d, C = c->n_classes;
+    const int64_t chunk = std::max<int64_t>(64, std::min<int64_t>(nq, ((int64_t)512 << 20) / (8 * n)));   // <= 512 MiB of distances
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t need = 2 * al(sizeof(double) * (size_t)chunk * d) + al(sizeof(double) * (size_t)chunk * n) + al(sizeof(double) * (size_t)chunk * C) +
+                  al(sizeof(float) * (size_t)chunk * C) + al(sizeof(int32_t) * (size_t)chunk) + 4096;
+    FIR_TRY(c->ws.reserve(need));
+    double* qraw = (double*)c->ws.take(sizeof(double) * (size_t)chunk * d);
+    double* qc = (double*)c->ws.take(sizeof(double) * (size_t)chunk * d);
+    double* dist = (double*)c->ws.take(sizeof(double) * (size_t)chunk * n);
+    double* sc = (double*)c->ws.take(sizeof(double) * (size_t)chunk * C);
+    float* votes = (float*)c->ws.take(sizeof(float) * (size_t)chunk * C);
+    int32_t* lab = (int32_t*)c->ws.take(sizeof(int32_t) * (size_t)chunk);
+    if (!qraw || !qc || !dist || !sc || !votes || !lab) return fail(FIR_ERR_INTERNAL, "workspace underestimated (classifier)");
+    double var = 0.00002;                                       // classification.cpp:190
+    if (d > 2000) var /= 10;                                    // :192-193
+    const double den = (double)(size_t)(2 * (size_t)d) * var;   // :213  2*num_of_cont_features*var
+    cudaStream_t s = c->stream;
+    for (int64_t lo = 0; lo < nq; lo += chunk) {
+        const int64_t m = std::min(chunk, nq - lo);
+        FIR_CUDA_TRY(cudaMemcpyAsync(qraw, queries + lo * d, sizeof(double) * (size_t)m * d, cudaMemcpyHostToDevice, s));
+        centre_rows_kernel<<<(unsigned)ceil_div(m * d, 256), 256, 0, s>>>(qraw, c->avg, m, d, qc);
+        dim3 grid((unsigned)ceil_div(n, CT), (unsigned)ceil_div(m, CT));
+        cls_dist_kernel<<<grid, 256, 0, s>>>(qc, m, c->xc, n, d, dist);
+        if (pnn) {
+            pnn_class_sum_kernel<<<(unsigned)ceil_div(m * C, 128), 128, 0, s>>>(dist, m, n, C, c->cls_begin, c->labels, c->class_major ? 1 : 0, den,
+                                                                               (double)n, sc);
+            argmax_double_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, s>>>(sc, m, C, lab);
+            if (out_scores) FIR_CUDA_TRY(cudaMemcpyAsync(out_scores + lo * C, sc, sizeof(double) * (size_t)m * C, cudaMemcpyDeviceToHost, s));
+        } else {
+            knn_vote_kernel<<<(unsigned)ceil_div(m, 4), 128, 0, s>>>(dist, m, n, d, C, c->labels, K, votes, lab);
+        }
+        FIR_CUDA_TRY(cudaGetLastError());
+        FIR_CUDA_TRY(cudaMemcpyAsync(out_label + lo, lab, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, s));
+        FIR_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return FIR_OK;
+}
+
+int fir_classifier_knn(fir_classifier* c, const double* queries, int64_t nq, int32_t K, int32_t* out_label) {
+    return classify(c, queries, nq, K, false, nullptr, out_label);
+}
+
+int fir_classifier_pnn(fir_classifier* c, const double* queries, int64_t nq, double* out_scores, int32_t* out_label) {
+    return classify(c, queries, nq, 0, true, out_scores, out_label);
+}
+
+}  // extern "C"

@@ -1,0 +1,663 @@
+// dem_kernels.cu — directed-enumeration ANN (qt_cpp/ann.cpp:270-507, the PIVOT build) on the GPU.
+//
+// Build  (ctor, ann.cpp:302-342): a sequential farthest-point pivot chain.  Step ii computes the exact distance
+//         row P[ii][j] = feature_distance(db[j], db[pivot_ii]) for every gallery row (HBM-bound stream of the
+//         gallery), adds it to fp64 running far-sums (the reference recomputes the same sums from scratch in the
+//         same order, :315-321 — identical bits), takes the arg-max as the next pivot and the minimum other-class
+//         distance for the false-accept threshold.  The chain lives entirely on the device: the next pivot index is
+//         read by the next step's kernels from device memory, so there is no host round trip per step.
+// Search (recognize, :416-507), batched over queries:
+//         pivot distances → early exit → likelihood[ν] = Σ_i (d_i − P[i][ν])² (fp32, sequential in i) → candidates
+//         in ascending (likelihood, index) order until one is under the threshold or the budget is spent.
+//         The ordered walk is evaluated in rounds of geometrically growing size: a two-pass 16+16-bit radix select
+//         finds the likelihood key that closes the round, the round's candidates are collected in index order,
+//         their exact distances are evaluated in parallel, and a per-query reduction reproduces what the
+//         sequential walk would have returned (first hit in order, else first minimum in order) plus its
+//         distanceCalcCount.
+#include "fir_common.cuh"
+#include "handles.hpp"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <set>
+
+struct fir_dem {
+    fir_gallery* g = nullptr;
+    int n_pivots = 0, chain_rows = 0;
+    float threshold = 0.f;
+    std::vector<int32_t> pivots;       // chain_rows entries; the first n_pivots are used by search
+    std::vector<float> min_other;      // chain_rows entries
+    float* P_raw = nullptr;            // [n_pivots][n] true pivot distances (device)
+    float* P_search = nullptr;         // [n_pivots][n] with -1 where the reference's index walk skips (ν, step)
+    unsigned char* in_tail = nullptr;  // [n] 1 = ν is a candidate after the pivot phase
+    int32_t* d_pivots = nullptr;       // [n_pivots]
+    int64_t tail_size = 0;
+};
+
+namespace fir {
+
+// ---------------------------------------------------------------------------------------------------
+// build
+// ---------------------------------------------------------------------------------------------------
+constexpr int RB = 256;   // threads per block of the reduction kernels
+
+// far-sum update + block-level arg-max / min-other for one chain step
+__global__ void __launch_bounds__(RB) dem_step_kernel(const float* __restrict__ row, int64_t n, const int32_t* __restrict__ labels,
+                                                      const int32_t* __restrict__ cur_pivot, double* __restrict__ far_sum,
+                                                      float* __restrict__ keep_row, double* __restrict__ blk_max, int32_t* __restrict__ blk_arg,
+                                                      float* __restrict__ blk_min) {
+    __shared__ double s_max[RB];
+    __shared__ int32_t s_arg[RB];
+    __shared__ float s_min[RB];
+    const int pivot = *cur_pivot;
+    const int pl = labels[pivot];
+    double best = 0.0; int32_t arg = -1;                     // maxFarDist = 0, mostFarModel = -1  (ann.cpp:305-306)
+    float mn = 3.402823466e+38f;                             // numeric_limits<float>::max()      (:307)
+    for (int64_t j = (int64_t)blockIdx.x * RB + threadIdx.x; j < n; j += (int64_t)gridDim.x * RB) {
+        const float d = row[j];
+        if (keep_row) keep_row[j] = d;                       // :311
+        if (labels[j] != pl && d < mn) mn = d;               // :312-314
+        double s = (j == pivot) ? -1000000.0 : far_sum[j] + (double)d;   // :317-320
+        far_sum[j] = s;
+        if (s > best) { best = s; arg = (int32_t)j; }        // :322-325 (strict '>' ⇒ lowest j; j ascends within a thread)
+    }
+    s_max[threadIdx.x] = best; s_arg[threadIdx.x] = arg; s_min[threadIdx.x] = mn;
+    __syncthreads();
+    for (int o = RB / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            double ob = s_max[threadIdx.x + o]; int32_t oa = s_arg[threadIdx.x + o];
+            double mb = s_max[threadIdx.x]; int32_t ma = s_arg[threadIdx.x];
+            if (oa >= 0 && (ma < 0 || ob > mb || (ob == mb && oa < ma))) { s_max[threadIdx.x] = ob; s_arg[threadIdx.x] = oa; }
+            s_min[threadIdx.x] = fminf(s_min[threadIdx.x], s_min[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { blk_max[blockIdx.x] = s_max[0]; blk_arg[blockIdx.x] = s_arg[0]; blk_min[blockIdx.x] = s_min[0]; }
+}
+
+__global__ void __launch_bounds__(RB) dem_step_final_kernel(const double* __restrict__ blk_max, const int32_t* __restrict__ blk_arg,
+                                                            const float* __restrict__ blk_min, int nblk, int step, int chain_rows,
+                                                            int32_t* __restrict__ pivots, float* __restrict__ min_other,
+                                                            int32_t* __restrict__ cur_pivot) {
+    __shared__ double s_max[RB];
+    __shared__ int32_t s_arg[RB];
+    __shared__ float s_min[RB];
+    double best = 0.0; int32_t arg = -1; float mn = 3.402823466e+38f;
+    for (int b = threadIdx.x; b < nblk; b += RB) {
+        double ob = blk_max[b]; int32_t oa = blk_arg[b];
+        if (oa >= 0 && (arg < 0 || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+        mn = fminf(mn, blk_min[b]);
+    }
+    s_max[threadIdx.x] = best; s_arg[threadIdx.x] = arg; s_min[threadIdx.x] = mn;
+    __syncthreads();
+    for (int o = RB / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            double ob = s_max[threadIdx.x + o]; int32_t oa = s_arg[threadIdx.x + o];
+            double mb = s_max[threadIdx.x]; int32_t ma = s_arg[threadIdx.x];
+            if (oa >= 0 && (ma < 0 || ob > mb || (ob == mb && oa < ma))) { s_max[threadIdx.x] = ob; s_arg[threadIdx.x] = oa; }
+            s_min[threadIdx.x] = fminf(s_min[threadIdx.x], s_min[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        min_other[step] = s_min[0];                                             // ann.cpp:327
+        if (step + 1 < chain_rows) { pivots[step + 1] = s_arg[0]; *cur_pivot = s_arg[0] < 0 ? 0 : s_arg[0]; }   // :328-330
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------------
+struct QState {          // per query, device
+    float best_dist;     // bestDistance
+    int32_t best_idx;    // bestIndex (local row)
+    int32_t count;       // distanceCalcCount
+    int32_t done;        // 1 = result final (hit under threshold, or budget spent)
+    int32_t below;       // isFoundLessThreshold
+    uint32_t last_key;   // (key, idx) of the last candidate position consumed so far
+    int32_t last_idx;
+    int32_t started;     // 0 until the first round consumed something
+};
+
+// pivot phase (ann.cpp:441-446 + CHECK_FOR_BEST_DIST :390-400)
+__global__ void dem_pivot_phase_kernel(const float* __restrict__ pd, int64_t nq, int S, const int32_t* __restrict__ pivots, float threshold,
+                                       int M, QState* __restrict__ st) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    QState s;
+    s.best_dist = 3.402823466e+38f; s.best_idx = -1; s.count = 0; s.done = 0; s.below = 0; s.last_key = 0; s.last_idx = -1; s.started = 0;
+    for (int i = 0; i < S; ++i) {
+        const float d = pd[q * S + i];
+        ++s.count;
+        if (d < s.best_dist) {
+            s.best_dist = d; s.best_idx = pivots[i];
+            if (d < threshold) { s.below = 1; s.done = 1; break; }
+        }
+    }
+    if (!s.done && s.count >= M) s.done = 1;                  // while (distanceCalcCount < imageCountToCheck) never runs (:472)
+    st[q] = s;
+}
+
+// likelihood[q][ν] = Σ_i fl((d_i − P[i][ν])²) over the steps whose P entry is ≥ 0 (ann.cpp:453-461); +inf outside the tail
+__global__ void __launch_bounds__(256) dem_likelihood_kernel(const float* __restrict__ pd, const int32_t* __restrict__ qlist, int nqc, int S,
+                                                             const float* __restrict__ P, int64_t n, const unsigned char* __restrict__ in_tail,
+                                                             float* __restrict__ lik) {
+    __shared__ float dq[8][32];
+    const int q0 = blockIdx.y * 8;
+    if (threadIdx.x < 8 * 32) {
+        int qq = threadIdx.x >> 5, i = threadIdx.x & 31;
+        dq[qq][i] = (q0 + qq < nqc && i < S) ? pd[(int64_t)qlist[q0 + qq] * S + i] : 0.f;
+    }
+    __syncthreads();
+    const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (v >= n) return;
+    float acc[8];
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) acc[qq] = 0.f;
+    for (int i = 0; i < S; ++i) {
+        const float m = P[(int64_t)i * n + v];
+        if (m >= 0.f) {                                                         // :456
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+                const float t = __fsub_rn(dq[qq][i], m);                        // :457
+                acc[qq] = __fadd_rn(acc[qq], __fmul_rn(t, t));                  // :458
+            }
+        }
+    }
+    const bool tail = in_tail[v] != 0;
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq)
+        if (q0 + qq < nqc) lik[(int64_t)(q0 + qq) * n + v] = tail ? acc[qq] : __int_as_float(0x7f800000);
+}
+
+__device__ __forceinline__ bool after_last(uint32_t key, int32_t idx, const QState& s) {
+    return !s.started || key > s.last_key || (key == s.last_key && idx > s.last_idx);
+}
+
+// radix select, pass 1 / pass 2: histogram of the high / low 16 bits of the likelihood key over the not-yet-consumed tail
+__global__ void __launch_bounds__(256) dem_hist_kernel(const float* __restrict__ lik, const int32_t* __restrict__ qlist, int nqc, int64_t n,
+                                                       const QState* __restrict__ st, int pass, const uint32_t* __restrict__ hi_sel,
+                                                       uint32_t* __restrict__ hist) {
+    const int qc = blockIdx.y;
+    const QState s = st[qlist[qc]];
+    if (s.done) return;
+    const float* lr = lik + (int64_t)qc * n;
+    uint32_t* h = hist + (size_t)qc * 65536;
+    const uint32_t sel = pass ? hi_sel[qc] : 0;
+    for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < n; v += (int64_t)gridDim.x * 256) {
+        const uint32_t key = __float_as_uint(lr[v]);
+        if (key >= 0x7f800000u) continue;                    // +inf: not in the tail
+        if (!after_last(key, (int32_t)v, s)) continue;
+        if (!pass) atomicAdd(&h[key >> 16], 1u);
+        else if ((key >> 16) == sel) atomicAdd(&h[key & 0xffffu], 1u);
+    }
+}
+
+// one block per query: prefix-scan the 65536 bins to find where the cumulative count reaches `want`
+__global__ void __launch_bounds__(256) dem_pick_kernel(const uint32_t* __restrict__ hist, const int32_t* __restrict__ qlist, int nqc,
+                                                       const QState* __restrict__ st, int pass, const int32_t* __restrict__ want_in,
+                                                       uint32_t* __restrict__ hi_sel, int32_t* __restrict__ below_cnt,
+                                                       uint32_t* __restrict__ key_sel, int32_t* __restrict__ tie_take, int32_t* __restrict__ round_n) {
+    __shared__ uint32_t part[256];
+    const int qc = blockIdx.x;
+    const QState s = st[qlist[qc]];
+    if (s.done) { if (threadIdx.x == 0 && pass) round_n[qc] = 0; return; }
+    const uint32_t* h = hist + (size_t)qc * 65536;
+    const int want = pass ? (want_in[qc] - below_cnt[qc]) : want_in[qc];
+    uint32_t sum = 0;
+    for (int b = 0; b < 256; ++b) sum += h[threadIdx.x * 256 + b];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t cum = 0; int seg = -1;
+        for (int t = 0; t < 256; ++t) { if (cum + part[t] >= (uint32_t)want) { seg = t; break; } cum += part[t]; }
+        if (seg < 0) {                       // fewer than `want` keys remain: take everything that is left
+            if (!pass) { hi_sel[qc] = 0xffffffffu; below_cnt[qc] = (int32_t)cum; }
+            else { key_sel[qc] = 0xffffffffu; tie_take[qc] = 0; round_n[qc] = below_cnt[qc] + (int32_t)cum; }
+            return;
+        }
+        int bin = seg * 256;
+        for (;; ++bin) { if (cum + h[bin] >= (uint32_t)want) break; cum += h[bin]; }
+        if (!pass) { hi_sel[qc] = (uint32_t)bin; below_cnt[qc] = (int32_t)cum; }
+        else {
+            key_sel[qc] = (hi_sel[qc] << 16) | (uint32_t)bin;
+            tie_take[qc] = want - (int32_t)cum;                   // how many keys equal to key_sel close the round, lowest index first
+            round_n[qc] = below_cnt[qc] + want;
+        }
+    }
+}
+
+// one warp per query: collect the round's candidates in INDEX order (ballot compaction keeps the order)
+__global__ void __launch_bounds__(128) dem_collect_kernel(const float* __restrict__ lik, const int32_t* __restrict__ qlist, int nqc, int64_t n,
+                                                          const QState* __restrict__ st, const uint32_t* __restrict__ hi_sel,
+                                                          const uint32_t* __restrict__ key_sel, const int32_t* __restrict__ tie_take,
+                                                          int cap, int32_t* __restrict__ cand, uint32_t* __restrict__ cand_key,
+                                                          int32_t* __restrict__ last_tie_idx) {
+    const int lane = threadIdx.x & 31;
+    const int qc = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (qc >= nqc) return;
+    const QState s = st[qlist[qc]];
+    int32_t* out = cand + (int64_t)qc * cap;
+    uint32_t* outk = cand_key + (int64_t)qc * cap;
+    if (s.done) return;
+    const float* lr = lik + (int64_t)qc * n;
+    const bool take_all = hi_sel[qc] == 0xffffffffu || key_sel[qc] == 0xffffffffu;
+    const uint32_t ksel = key_sel[qc];
+    int ties_left = tie_take[qc];
+    int cnt = 0, ltie = -1;
+    for (int64_t base = 0; base < n; base += 32) {
+        const int64_t v = base + lane;
+        bool ok = false, tie = false;
+        uint32_t key = 0;
+        if (v < n) {
+            key = __float_as_uint(lr[v]);
+            if (key < 0x7f800000u && after_last(key, (int32_t)v, s)) {
+                if (take_all || key < ksel) ok = true;
+                else if (key == ksel) tie = true;
+            }
+        }
+        const uint32_t tmask = __ballot_sync(0xffffffffu, tie);
+        if (tie) {                                                              // the first `ties_left` ties in index order are in the round
+            const int rank = __popc(tmask & ((1u << lane) - 1));
+            if (rank < ties_left) ok = true;
+        }
+        const int taken_ties = min(__popc(tmask), ties_left);
+        if (taken_ties > 0) {
+            // index of the last tie taken in this group
+            uint32_t mm = tmask; int seen = 0, li = -1;
+            while (mm && seen < taken_ties) { li = __ffs(mm) - 1; mm &= mm - 1; ++seen; }
+            ltie = (int)(base + li);
+        }
+        ties_left -= taken_ties;
+        const uint32_t omask = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const int pos = cnt + __popc(omask & ((1u << lane) - 1));
+            if (pos < cap) { out[pos] = (int32_t)v; outk[pos] = key; }
+        }
+        cnt += __popc(omask);
+    }
+    for (int i = cnt + lane; i < cap; i += 32) out[i] = -1;
+    if (lane == 0) last_tie_idx[qc] = ltie;
+}
+
+// one warp per query: fold the round's exact distances into the query state exactly as the sequential walk would
+__global__ void __launch_bounds__(128) dem_reduce_kernel(const float* __restrict__ cdist, const int32_t* __restrict__ cand,
+                                                         const uint32_t* __restrict__ cand_key, const int32_t* __restrict__ qlist, int nqc,
+                                                         int cap, const int32_t* __restrict__ round_n, const uint32_t* __restrict__ key_sel,
+                                                         const int32_t* __restrict__ last_tie_idx, float threshold, int M, int64_t tail_size, int S,
+                                                         QState* __restrict__ st, int32_t* __restrict__ n_active) {
+    const int lane = threadIdx.x & 31;
+    const int qc = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (qc >= nqc) return;
+    QState s = st[qlist[qc]];
+    if (s.done) return;
+    const int m = min(round_n[qc], cap);
+    const int32_t* ci = cand + (int64_t)qc * cap;
+    const uint32_t* ck = cand_key + (int64_t)qc * cap;
+    const float* cd = cdist + (int64_t)qc * cap;
+    // first hit in (key, idx) order; otherwise the first minimum in (dist, key, idx) order
+    uint32_t hk = 0xffffffffu; int32_t hi = 0x7fffffff; float hd = 0.f; bool hit = false;
+    float bd = 3.402823466e+38f; uint32_t bk = 0xffffffffu; int32_t bi = 0x7fffffff; bool any = false;
+    for (int i = lane; i < m; i += 32) {
+        const float d = cd[i]; const uint32_t k = ck[i]; const int32_t v = ci[i];
+        if (d < threshold && (!hit || k < hk || (k == hk && v < hi))) { hit = true; hk = k; hi = v; hd = d; }
+        if (!any || d < bd || (d == bd && (k < bk || (k == bk && v < bi)))) { any = true; bd = d; bk = k; bi = v; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const int oh = __shfl_xor_sync(0xffffffffu, (int)hit, o);
+        const uint32_t ohk = __shfl_xor_sync(0xffffffffu, hk, o); const int32_t ohi = __shfl_xor_sync(0xffffffffu, hi, o);
+        const float ohd = __shfl_xor_sync(0xffffffffu, hd, o);
+        if (oh && (!hit || ohk < hk || (ohk == hk && ohi < hi))) { hit = true; hk = ohk; hi = ohi; hd = ohd; }
+        const int oa = __shfl_xor_sync(0xffffffffu, (int)any, o);
+        const float obd = __shfl_xor_sync(0xffffffffu, bd, o); const uint32_t obk = __shfl_xor_sync(0xffffffffu, bk, o);
+        const int32_t obi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oa && (!any || obd < bd || (obd == bd && (obk < bk || (obk == bk && obi < bi))))) { any = true; bd = obd; bk = obk; bi = obi; }
+    }
+    if (hit) {
+        // While walking, bestDistance ≥ threshold (else the walk would already have stopped), so the first candidate in
+        // order that is under the threshold also beats bestDistance: it is the answer (CHECK_FOR_BEST_DIST, ann.cpp:390-400).
+        int rank = 0;
+        for (int i = lane; i < m; i += 32) {
+            const uint32_t k = ck[i]; const int32_t v = ci[i];
+            if (k < hk || (k == hk && v < hi)) ++rank;
+        }
+        for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        if (lane == 0) {
+            s.best_dist = hd; s.best_idx = hi; s.below = 1; s.done = 1;
+            s.count += rank + 1;
+            st[qlist[qc]] = s;
+        }
+        return;
+    }
+    if (lane == 0) {
+        if (any && bd < s.best_dist) { s.best_dist = bd; s.best_idx = bi; }
+        s.count += m;
+        s.started = 1;
+        // position of the end of this round in (key, idx) order
+        if (key_sel[qc] == 0xffffffffu) { s.done = 1; }                          // tail exhausted
+        else {
+            s.last_key = key_sel[qc];
+            s.last_idx = last_tie_idx[qc];
+        }
+        if (s.count >= M || (int64_t)(s.count - S) >= tail_size) s.done = 1;
+        if (!s.done) atomicAdd(n_active, 1);
+        st[qlist[qc]] = s;
+    }
+}
+
+__global__ void dem_fill_pivot_cand_kernel(const int32_t* __restrict__ pivots, int S, int64_t nq, int32_t* __restrict__ cand) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq * S) cand[i] = pivots[i % S];
+}
+__global__ void dem_want_kernel(const QState* __restrict__ st, const int32_t* __restrict__ qlist, int nqc, int round_size, int M, int32_t* want) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nqc) return;
+    const QState s = st[qlist[i]];
+    int w = s.done ? 0 : min(round_size, M - s.count);
+    want[i] = max(w, 0);
+}
+__global__ void dem_output_kernel(const QState* __restrict__ st, int64_t nq, int64_t index_offset, int32_t* idx, float* dist, uint8_t* below, int32_t* evals) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const QState s = st[q];
+    idx[q] = s.best_idx < 0 ? -1 : (int32_t)(s.best_idx + index_offset);
+    if (dist) dist[q] = s.best_dist;
+    if (below) below[q] = (uint8_t)s.below;
+    if (evals) evals[q] = s.count;
+}
+__global__ void dem_active_list_kernel(const QState* __restrict__ st, int64_t nq, int32_t* list, int32_t* count) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    if (!st[q].done) { int p = atomicAdd(count, 1); list[p] = (int32_t)q; }
+}
+
+}  // namespace fir
+
+using namespace fir;
+
+// Replay the reference's likelihood_indices walk (ann.cpp:432-446) once on the host: it is query independent.
+// li starts as the identity; step i does li[p_i] = li[i]; li[i] = p_i.  ν receives the likelihood term of step i iff it
+// sits at a position > i afterwards; it is a candidate iff it sits at a position ≥ S at the end.
+static int finalize_search_state(fir_dem* dm) {
+    fir_gallery* g = dm->g;
+    cudaStream_t s = g->stream;
+    const int64_t n = g->n;
+    const int S = dm->n_pivots;
+    std::map<int64_t, int64_t> li;                       // sparse overrides of the identity
+    auto get = [&](int64_t pos) { auto it = li.find(pos); return it == li.end() ? pos : it->second; };
+    std::set<int64_t> special;
+    for (int i = 0; i < S; ++i) { special.insert(i); special.insert(dm->pivots[i]); }
+    std::vector<int64_t> sp(special.begin(), special.end());
+    std::vector<std::vector<unsigned char> > member(S, std::vector<unsigned char>(sp.size(), 0));
+    for (int i = 0; i < S; ++i) {
+        const int64_t p = dm->pivots[i];
+        li[p] = get(i);
+        li[i] = p;
+        for (size_t k = 0; k < sp.size(); ++k) {
+            const int64_t v = sp[k];
+            int mult = 0;
+            for (auto& kv : li) if (kv.first > i && kv.second == v) ++mult;
+            if (li.find(v) == li.end() && v > i) ++mult;                    // still at its identity position
+            if (mult > 1) return fail(FIR_ERR_UNSUPPORTED, "pivot list repeats a pivot: the reference's index walk duplicates a candidate");
+            member[i][k] = (unsigned char)mult;
+        }
+    }
+    FIR_CUDA_TRY(cudaMemcpyAsync(dm->P_search, dm->P_raw, 4 * (size_t)S * n, cudaMemcpyDeviceToDevice, s));
+    FIR_CUDA_TRY(cudaMemsetAsync(dm->in_tail, 1, (size_t)n, s));
+    const float neg = -1.f; const unsigned char zero = 0;
+    for (size_t k = 0; k < sp.size(); ++k) {
+        for (int i = 0; i < S; ++i)
+            if (!member[i][k]) FIR_CUDA_TRY(cudaMemcpyAsync(dm->P_search + (size_t)i * n + sp[k], &neg, 4, cudaMemcpyHostToDevice, s));
+        if (!member[S - 1][k]) FIR_CUDA_TRY(cudaMemcpyAsync(dm->in_tail + sp[k], &zero, 1, cudaMemcpyHostToDevice, s));
+    }
+    dm->tail_size = n - S;                               // each step moves exactly one position into the prefix
+    FIR_CUDA_TRY(cudaMemcpyAsync(dm->d_pivots, dm->pivots.data(), 4 * (size_t)S, cudaMemcpyHostToDevice, s));
+    FIR_CUDA_TRY(cudaStreamSynchronize(s));
+    return FIR_OK;
+}
+
+extern "C" {
+
+int fir_dem_build(fir_gallery* g, const fir_dem_params* params, fir_dem** out) {
+    if (!out) return fail(FIR_ERR_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (!g || !params) return fail(FIR_ERR_BAD_ARG, "null argument");
+    FIR_CUDA_TRY(cudaSetDevice(g->device));
+    const int64_t n = g->n;
+    if (n < 2) return fail(FIR_ERR_BAD_ARG, "directed enumeration needs at least 2 gallery rows");
+    int np = (int)((double)n * 0.015);                              // ann.cpp:373  (int)(dbSize*0.015)
+    if (np < 5) np = 5;                                             // :374-375
+    if (params->max_chain > 0 && params->max_chain < np) np = params->max_chain;
+    if (np > n) np = (int)n;
+    int keep = params->max_pivots > 0 ? std::min(params->max_pivots, 32) : 32;   // :332-333 (search mask is 32 bits wide)
+    keep = std::min(keep, np);
+    int pivot0 = params->pivot0;
+    if (pivot0 < 0) {                                               // stand-in for random_shuffle's head (:366-369)
+        uint64_t z = (uint64_t)params->seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+        z ^= z >> 31; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 29;
+        pivot0 = (int)(z % (uint64_t)n);
+    }
+    if (pivot0 >= n) return fail(FIR_ERR_BAD_ARG, "pivot0 out of range");
+
+    fir_dem* dm = new fir_dem();
+    dm->g = g;
+    dm->chain_rows = np;
+    dm->n_pivots = keep;
+    cudaStream_t s = g->stream;
+    const int nblk = (int)std::min<int64_t>(ceil_div(n, RB), 1184);
+    float* row = nullptr; double* far_sum = nullptr; double* blk_max = nullptr; int32_t* blk_arg = nullptr; float* blk_min = nullptr;
+    int32_t* d_chain = nullptr; float* d_min_other = nullptr; int32_t* cur = nullptr;
+    auto cleanup = [&](int code) {
+        cudaFree(row); cudaFree(far_sum); cudaFree(blk_max); cudaFree(blk_arg); cudaFree(blk_min); cudaFree(d_chain); cudaFree(d_min_other); cudaFree(cur);
+        if (code != FIR_OK) fir_dem_destroy(dm);
+        return code;
+    };
+    if (cudaMalloc(&row, 4 * (size_t)n) != cudaSuccess || cudaMalloc(&far_sum, 8 * (size_t)n) != cudaSuccess ||
+        cudaMalloc(&blk_max, 8 * (size_t)nblk) != cudaSuccess || cudaMalloc(&blk_arg, 4 * (size_t)nblk) != cudaSuccess ||
+        cudaMalloc(&blk_min, 4 * (size_t)nblk) != cudaSuccess || cudaMalloc(&d_chain, 4 * (size_t)np) != cudaSuccess ||
+        cudaMalloc(&d_min_other, 4 * (size_t)np) != cudaSuccess || cudaMalloc(&cur, 4) != cudaSuccess ||
+        cudaMalloc(&dm->P_raw, 4 * (size_t)keep * n) != cudaSuccess || cudaMalloc(&dm->P_search, 4 * (size_t)keep * n) != cudaSuccess ||
+        cudaMalloc(&dm->in_tail, (size_t)n) != cudaSuccess || cudaMalloc(&dm->d_pivots, 4 * (size_t)keep) != cudaSuccess)
+        return cleanup(fail(FIR_ERR_OOM, "DEM build allocation failed"));
+    cudaMemsetAsync(far_sum, 0, 8 * (size_t)n, s);
+    cudaMemsetAsync(d_chain, 0xFF, 4 * (size_t)np, s);
+    cudaMemcpyAsync(d_chain, &pivot0, 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(cur, &pivot0, 4, cudaMemcpyHostToDevice, s);
+    for (int ii = 0; ii < np; ++ii) {
+        // P[ii][j] = feature_distance(db[j], db[pivot])  (lhs = gallery row j, rhs = pivot, ann.cpp:309)
+        int st_ = launch_pair_distances(g->metric, nullptr, 1, g->dp, g->rows, g->dp, n, g->d, nullptr, (int)n, 1, row, s, cur);
+        if (st_ != FIR_OK) return cleanup(st_);
+        dem_step_kernel<<<nblk, RB, 0, s>>>(row, n, g->labels, cur, far_sum, ii < keep ? dm->P_raw + (size_t)ii * n : nullptr, blk_max, blk_arg, blk_min);
+        dem_step_final_kernel<<<1, RB, 0, s>>>(blk_max, blk_arg, blk_min, nblk, ii, np, d_chain, d_min_other, cur);
+    }
+    if (cudaGetLastError() != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, "DEM build kernel launch failed"));
+    dm->pivots.resize(np);
+    dm->min_other.resize(np);
+    cudaError_t e = cudaMemcpyAsync(dm->pivots.data(), d_chain, 4 * (size_t)np, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dm->min_other.data(), d_min_other, 4 * (size_t)np, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, std::string("DEM build: ") + cudaGetErrorString(e)));
+    for (int i = 0; i < np; ++i)
+        if (dm->pivots[i] < 0) return cleanup(fail(FIR_ERR_UNSUPPORTED, "degenerate gallery: the farthest-point chain found no next pivot (the reference indexes dbImages[-1] here)"));
+    // threshold: getThreshold(otherClassesDists, FAR) = element (int)(size*FAR) of the sorted list (ann.cpp:84-93), unless overridden (:277-279,340)
+    if (params->threshold > 0) dm->threshold = params->threshold;
+    else {
+        std::vector<float> o(dm->min_other);
+        int ind = (int)((float)o.size() * params->false_accept_rate);
+        ind = std::max(0, std::min(ind, (int)o.size() - 1));
+        std::nth_element(o.begin(), o.begin() + ind, o.end());
+        dm->threshold = o[ind];
+    }
+    { int st2 = finalize_search_state(dm); if (st2 != FIR_OK) return cleanup(st2); }
+    *out = dm;
+    return cleanup(FIR_OK);
+}
+
+int fir_dem_from_state(fir_gallery* g, const int32_t* pivots, int32_t n_pivots, const float* P, float threshold, fir_dem** out) {
+    if (!out) return fail(FIR_ERR_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (!g || !pivots || !P || n_pivots < 1 || n_pivots > 32 || n_pivots > g->n) return fail(FIR_ERR_BAD_ARG, "bad DEM state");
+    for (int i = 0; i < n_pivots; ++i)
+        if (pivots[i] < 0 || pivots[i] >= g->n) return fail(FIR_ERR_BAD_ARG, "pivot out of range");
+    FIR_CUDA_TRY(cudaSetDevice(g->device));
+    fir_dem* dm = new fir_dem();
+    dm->g = g; dm->n_pivots = n_pivots; dm->chain_rows = n_pivots; dm->threshold = threshold;
+    dm->pivots.assign(pivots, pivots + n_pivots);
+    dm->min_other.assign((size_t)n_pivots, 0.f);
+    const int64_t n = g->n;
+    if (cudaMalloc(&dm->P_raw, 4 * (size_t)n_pivots * n) != cudaSuccess || cudaMalloc(&dm->P_search, 4 * (size_t)n_pivots * n) != cudaSuccess ||
+        cudaMalloc(&dm->in_tail, (size_t)n) != cudaSuccess || cudaMalloc(&dm->d_pivots, 4 * (size_t)n_pivots) != cudaSuccess) {
+        fir_dem_destroy(dm);
+        return fail(FIR_ERR_OOM, "DEM state allocation failed");
+    }
+    cudaError_t e = cudaMemcpy(dm->P_raw, P, 4 * (size_t)n_pivots * n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { fir_dem_destroy(dm); return fail(FIR_ERR_CUDA, cudaGetErrorString(e)); }
+    int st = finalize_search_state(dm);
+    if (st != FIR_OK) { fir_dem_destroy(dm); return st; }
+    *out = dm;
+    return FIR_OK;
+}
+
+int fir_dem_destroy(fir_dem* dm) {
+    if (!dm) return FIR_OK;
+    cudaFree(dm->P_raw); cudaFree(dm->P_search); cudaFree(dm->in_tail); cudaFree(dm->d_pivots);
+    delete dm;
+    return FIR_OK;
+}
+
+int fir_dem_info(const fir_dem* dm, int32_t* n_pivots, int32_t* chain_rows, float* threshold) {
+    if (!dm) return fail(FIR_ERR_BAD_ARG, "dem is null");
+    if (n_pivots) *n_pivots = dm->n_pivots;
+    if (chain_rows) *chain_rows = dm->chain_rows;
+    if (threshold) *threshold = dm->threshold;
+    return FIR_OK;
+}
+int fir_dem_get_pivots(const fir_dem* dm, int32_t* out_pivots) {
+    if (!dm || !out_pivots) return fail(FIR_ERR_BAD_ARG, "null argument");
+    std::memcpy(out_pivots, dm->pivots.data(), 4 * (size_t)dm->n_pivots);
+    return FIR_OK;
+}
+int fir_dem_get_pivot_matrix(const fir_dem* dm, float* out_P) {
+    if (!dm || !out_P) return fail(FIR_ERR_BAD_ARG, "null argument");
+    FIR_CUDA_TRY(cudaMemcpy(out_P, dm->P_raw, 4 * (size_t)dm->n_pivots * dm->g->n, cudaMemcpyDeviceToHost));
+    return FIR_OK;
+}
+int fir_dem_get_min_other(const fir_dem* dm, float* out) {
+    if (!dm || !out) return fail(FIR_ERR_BAD_ARG, "null argument");
+    std::memcpy(out, dm->min_other.data(), 4 * (size_t)dm->chain_rows);
+    return FIR_OK;
+}
+
+int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_to_check, int32_t memspace, int32_t* out_idx,
+                   float* out_dist, uint8_t* out_below, int32_t* out_evals) {
+    if (!dm) return fail(FIR_ERR_BAD_ARG, "dem is null");
+    if (nq < 0 || (nq > 0 && (!queries || !out_idx))) return fail(FIR_ERR_BAD_ARG, "bad arguments");
+    if (nq == 0) return FIR_OK;
+    fir_gallery* g = dm->g;
+    FIR_CUDA_TRY(cudaSetDevice(g->device));
+    cudaStream_t s = g->stream;
+    const int64_t n = g->n;
+    const int S = dm->n_pivots;
+    const int M = (count_to_check > 0 && count_to_check < n) ? count_to_check : (int)n;     // ann.h:20-22
+    // (the reference has undefined behaviour for M < S — partial_sort with middle < first, ann.cpp:469; here the
+    //  candidate phase simply does not run, which is also what its while-loop at :472 does.)
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const int QC = (int)std::max<int64_t>(8, std::min<int64_t>(std::min<int64_t>(nq, 1024), ((int64_t)1 << 30) / (4 * n)));   // lik chunk ≤ 1 GiB
+    const int cap_max = (int)std::min<int64_t>(n, std::max<int64_t>(256, ((int64_t)256 << 20) / ((int64_t)QC * 12)));
+    size_t need = al(4 * (size_t)nq * g->dp) + 2 * al(4 * (size_t)nq * S) + al(sizeof(QState) * (size_t)nq) + al(4 * (size_t)nq) +
+                  al(4 * (size_t)QC * n) + al(4 * (size_t)QC * 65536) + 3 * al(4 * (size_t)QC * cap_max) + 8 * al(4 * (size_t)QC) +
+                  al((size_t)nq * 9) + al(4 * (size_t)nq) * 2 + 65536;
+    FIR_TRY(g->ws.reserve(need));
+    // queries → zero-padded device rows
+    const float* dq = nullptr;
+    if (memspace == FIR_DEVICE && g->d == g->dp) dq = queries;
+    else {
+        float* buf = (float*)g->ws.take(4 * (size_t)nq * g->dp);
+        if (!buf) return fail(FIR_ERR_INTERNAL, "workspace underestimated (dem queries)");
+        if (memspace == FIR_HOST) {
+            if (g->d != g->dp) FIR_CUDA_TRY(cudaMemsetAsync(buf, 0, 4 * (size_t)nq * g->dp, s));
+            FIR_CUDA_TRY(cudaMemcpy2DAsync(buf, 4 * (size_t)g->dp, queries, 4 * (size_t)g->d, 4 * (size_t)g->d, (size_t)nq, cudaMemcpyHostToDevice, s));
+        } else FIR_TRY(launch_pad_rows(queries, nq, g->d, buf, g->dp, s));
+        dq = buf;
+    }
+    int32_t* pcand = (int32_t*)g->ws.take(4 * (size_t)nq * S);
+    float* pd = (float*)g->ws.take(4 * (size_t)nq * S);
+    QState* st = (QState*)g->ws.take(sizeof(QState) * (size_t)nq);
+    int32_t* active = (int32_t*)g->ws.take(4 * (size_t)nq);
+    float* lik = (float*)g->ws.take(4 * (size_t)QC * n);
+    uint32_t* hist = (uint32_t*)g->ws.take(4 * (size_t)QC * 65536);
+    int32_t* cand = (int32_t*)g->ws.take(4 * (size_t)QC * cap_max);
+    uint32_t* cand_key = (uint32_t*)g->ws.take(4 * (size_t)QC * cap_max);
+    float* cdist = (float*)g->ws.take(4 * (size_t)QC * cap_max);
+    int32_t* want = (int32_t*)g->ws.take(4 * (size_t)QC);
+    uint32_t* hi_sel = (uint32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* below_cnt = (int32_t*)g->ws.take(4 * (size_t)QC);
+    uint32_t* key_sel = (uint32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* tie_take = (int32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* round_n = (int32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* last_tie = (int32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* counters = (int32_t*)g->ws.take(64);
+    int32_t* o_idx = out_idx; float* o_dist = out_dist; uint8_t* o_below = out_below; int32_t* o_evals = out_evals;
+    if (memspace == FIR_HOST) {
+        o_idx = (int32_t*)g->ws.take(4 * (size_t)nq);
+        o_dist = (float*)g->ws.take(4 * (size_t)nq);
+        o_evals = (int32_t*)g->ws.take(4 * (size_t)nq);
+        o_below = (uint8_t*)g->ws.take((size_t)nq);
+    }
+    if (!pcand || !pd || !st || !active || !lik || !hist || !cand || !cand_key || !cdist || !want || !hi_sel || !below_cnt || !key_sel ||
+        !tie_take || !round_n || !last_tie || !counters || !o_idx || (memspace == FIR_HOST && (!o_dist || !o_evals || !o_below)))
+        return fail(FIR_ERR_INTERNAL, "workspace underestimated (dem search)");
+
+    // 1. pivot distances + pivot phase
+    dem_fill_pivot_cand_kernel<<<(unsigned)ceil_div(nq * S, 256), 256, 0, s>>>(dm->d_pivots, S, nq, pcand);
+    FIR_TRY(launch_pair_distances(g->metric, dq, nq, g->dp, g->rows, g->dp, n, g->d, pcand, S, 0, pd, s));
+    dem_pivot_phase_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(pd, nq, S, dm->d_pivots, dm->threshold, M, st);
+    // 2. queries that go on to the candidate walk
+    FIR_CUDA_TRY(cudaMemsetAsync(counters, 0, 64, s));
+    dem_active_list_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(st, nq, active, counters);
+    int32_t n_act = 0;
+    FIR_CUDA_TRY(cudaMemcpyAsync(&n_act, counters, 4, cudaMemcpyDeviceToHost, s));
+    FIR_CUDA_TRY(cudaStreamSynchronize(s));
+    for (int lo = 0; lo < n_act; lo += QC) {
+        const int nqc = std::min(QC, n_act - lo);
+        const int32_t* ql = active + lo;
+        dim3 lg((unsigned)ceil_div(n, 256), (unsigned)ceil_div(nqc, 8));
+        { auto* ev = g->prof_begin(FIR_KERNEL_DEM_LIKELIHOOD);
+          dem_likelihood_kernel<<<lg, 256, 0, s>>>(pd, ql, nqc, S, dm->P_search, n, dm->in_tail, lik);
+          g->prof_end(ev); }
+        int round_size = 256;
+        int remaining = nqc;
+        while (remaining > 0) {
+            const int cap = (int)std::min<int64_t>(round_size, cap_max);
+            dem_want_kernel<<<(unsigned)ceil_div(nqc, 128), 128, 0, s>>>(st, ql, nqc, cap, M, want);
+            const unsigned hb = (unsigned)std::min<int64_t>(ceil_div(n, 256 * 8), 512);
+            for (int pass = 0; pass < 2; ++pass) {
+                FIR_CUDA_TRY(cudaMemsetAsync(hist, 0, 4 * (size_t)nqc * 65536, s));
+                dem_hist_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, pass, hi_sel, hist);
+                dem_pick_kernel<<<(unsigned)nqc, 256, 0, s>>>(hist, ql, nqc, st, pass, want, hi_sel, below_cnt, key_sel, tie_take, round_n);
+            }
+            dem_collect_kernel<<<(unsigned)ceil_div(nqc, 4), 128, 0, s>>>(lik, ql, nqc, n, st, hi_sel, key_sel, tie_take, cap, cand, cand_key, last_tie);
+            // exact distances of the round's candidates: queries are addressed through the active list
+            FIR_TRY(launch_pair_distances(g->metric, dq, nqc, g->dp, g->rows, g->dp, n, g->d, cand, cap, 0, cdist, s, nullptr, ql));
+            FIR_CUDA_TRY(cudaMemsetAsync(counters + 1, 0, 4, s));
+            dem_reduce_kernel<<<(unsigned)ceil_div(nqc, 4), 128, 0, s>>>(cdist, cand, cand_key, ql, nqc, cap, round_n, key_sel, last_tie, dm->threshold, M,
+                                                                       dm->tail_size, S, st, counters + 1);
+            FIR_CUDA_TRY(cudaMemcpyAsync(&remaining, counters + 1, 4, cudaMemcpyDeviceToHost, s));
+            FIR_CUDA_TRY(cudaStreamSynchronize(s));
+            if (round_size < cap_max) round_size = (int)std::min<int64_t>((int64_t)round_size * 8, cap_max);
+        }
+    }
+    dem_output_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(st, nq, g->index_offset, o_idx, o_dist, o_below, o_evals);
+    FIR_CUDA_TRY(cudaGetLastError());
+    if (memspace == FIR_HOST) {
+        FIR_CUDA_TRY(cudaMemcpyAsync(out_idx, o_idx, 4 * (size_t)nq, cudaMemcpyDeviceToHost, s));
+        if (out_dist) FIR_CUDA_TRY(cudaMemcpyAsync(out_dist, o_dist, 4 * (size_t)nq, cudaMemcpyDeviceToHost, s));
+        if (out_below) FIR_CUDA_TRY(cudaMemcpyAsync(out_below, o_below, (size_t)nq, cudaMemcpyDeviceToHost, s));
+        if (out_evals) FIR_CUDA_TRY(cudaMemcpyAsync(out_evals, o_evals, 4 * (size_t)nq, cudaMemcpyDeviceToHost, s));
+        FIR_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return FIR_OK;
+}
+
+}  // extern "C"

@@ -326,7 +326,8 @@ template <int METRIC>
 __global__ void __launch_bounds__(PW * 32) pair_distance_kernel(const float* __restrict__ q, int64_t nq, int ldq,
                                                                 const float* __restrict__ x, int ldx, int64_t n, int d_end,
                                                                 const int32_t* __restrict__ cand, int r, int gallery_is_lhs,
-                                                                float* __restrict__ out) {
+                                                                float* __restrict__ out, const int32_t* __restrict__ qsel,
+                                                                const int32_t* __restrict__ qmap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (32 * PLD + PCH);
@@ -337,8 +338,16 @@ __global__ void __launch_bounds__(PW * 32) pair_distance_kernel(const float* __r
     const int64_t qi = item / groups;
     const int g = (int)(item - qi * groups);
     const int slot = g * 32 + lane;
-    int32_t my = (slot < r) ? cand[qi * r + slot] : -1;
+    // cand == nullptr: candidate list is the identity (every gallery row); qsel: the query IS gallery row qsel[qi]
+    int32_t my = (slot < r) ? (cand ? cand[qi * (int64_t)r + slot] : slot) : -1;
     if (my >= n) my = -1;
+    if (__all_sync(0xffffffffu, my < 0)) {
+        if (slot < r) out[qi * (int64_t)r + slot] = __int_as_float(0x7f800000);
+        return;
+    }
+    // qmap: query qi of this launch is row qmap[qi] of the query matrix (active-list addressing)
+    const float* qrow = qsel ? (x + (int64_t)qsel[qi] * ldx) : (q + (qmap ? (int64_t)qmap[qi] : qi) * ldq);
+    const int ldq_eff = qsel ? ldx : ldq;
     float acc = 0.f;
     const int ld_lim = ldx;   // rows are zero padded up to ldx
     for (int c0 = 0; c0 < d_end; c0 += PCH) {
@@ -351,7 +360,7 @@ __global__ void __launch_bounds__(PW * 32) pair_distance_kernel(const float* __r
         }
         {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col < ldq) v = *reinterpret_cast<const float4*>(q + qi * ldq + col);
+            if (col < ldq_eff) v = *reinterpret_cast<const float4*>(qrow + col);
             *reinterpret_cast<float4*>(&qv[lane * 4]) = v;
         }
         __syncwarp();
@@ -377,18 +386,19 @@ __global__ void __launch_bounds__(PW * 32) pair_distance_kernel(const float* __r
         }
         __syncwarp();
     }
-    if (slot < r) out[qi * r + slot] = (my >= 0) ? __fdiv_rn(acc, (float)d_end) : __int_as_float(0x7f800000);
+    if (slot < r) out[qi * (int64_t)r + slot] = (my >= 0) ? __fdiv_rn(acc, (float)d_end) : __int_as_float(0x7f800000);
 }
 
 int launch_pair_distances(int metric, const float* q, int64_t nq, int ldq, const float* x, int ldx, int64_t n, int d_end,
-                          const int32_t* cand, int r, int gallery_is_lhs, float* out, cudaStream_t s) {
+                          const int32_t* cand, int r, int gallery_is_lhs, float* out, cudaStream_t s, const int32_t* qsel,
+                          const int32_t* qmap) {
     if (nq <= 0 || r <= 0) return FIR_OK;
     const int groups = (r + 31) / 32;
     size_t smem = sizeof(float) * (size_t)PW * (32 * PLD + PCH);
     unsigned grid = (unsigned)ceil_div(nq * groups, PW);
     auto go = [&](auto kern) -> int {
         FIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, PW * 32, smem, s>>>(q, nq, ldq, x, ldx, n, d_end, cand, r, gallery_is_lhs, out);
+        kern<<<grid, PW * 32, smem, s>>>(q, nq, ldq, x, ldx, n, d_end, cand, r, gallery_is_lhs, out, qsel, qmap);
         FIR_CUDA_TRY(cudaGetLastError());
         return FIR_OK;
     };

@@ -71,7 +71,8 @@ int launch_fill_u64(unsigned long long* p, int64_t n, unsigned long long v, cuda
 int launch_classmin_finalize(const unsigned long long* keys, int64_t n, int64_t index_offset, float* omin, int32_t* oarg, cudaStream_t s);
 int launch_pnn_finalize(double* scores, int64_t nq, int n_classes, double n_total, int32_t* olabel, cudaStream_t s);
 int launch_pair_distances(int metric, const float* q, int64_t nq, int ldq, const float* x, int ldx, int64_t n, int d_end,
-                          const int32_t* cand, int r, int gallery_is_lhs, float* out, cudaStream_t s);
+                          const int32_t* cand, int r, int gallery_is_lhs, float* out, cudaStream_t s, const int32_t* qsel = nullptr,
+                          const int32_t* qmap = nullptr);
 int launch_normalize_rows(float* rows, int64_t n, int d, int ld, int metric, cudaStream_t s);
 int launch_pad_rows(const float* src, int64_t n, int d, float* dst, int ld, cudaStream_t s);
 

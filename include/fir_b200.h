@@ -164,6 +164,9 @@ typedef struct fir_dem_params {
 } fir_dem_params;
 
 int fir_dem_build(fir_gallery* g, const fir_dem_params* params, fir_dem** out);
+/* adopt an existing build (pivot list, n_pivots x n pivot-distance rows on the host, threshold) instead of running the
+ * chain: the at-scale recipe of SURVEY.md §8(c), persisted indices, and parity tests of the search alone. */
+int fir_dem_from_state(fir_gallery* g, const int32_t* pivots, int32_t n_pivots, const float* P, float threshold, fir_dem** out);
 int fir_dem_destroy(fir_dem* dem);
 int fir_dem_info(const fir_dem* dem, int32_t* n_pivots, int32_t* chain_rows, float* threshold);
 int fir_dem_get_pivots(const fir_dem* dem, int32_t* out_pivots /* n_pivots */);

@@ -1,0 +1,108 @@
+"""GPU parity: fp64 kNN / PNN (classification.cpp) and directed enumeration (ann.cpp) against the oracle."""
+import numpy as np
+import pytest
+
+from util import bits, make_data
+
+pytestmark = pytest.mark.gpu
+
+
+def _cls_problem(port, n, d, c, seed):
+    g, gl, q, ql = make_data(port, "l2", n, n // 3, d, c, seed=seed)
+    rows = np.concatenate([g, q]).astype(np.float64)
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)           # load_image_dataset normalises in double (:829-847)
+    return rows, np.concatenate([gl, ql]).astype(np.int32)
+
+
+def test_knn_pnn_match_reference_build(fir, port, ref_l2):
+    rows, labels = _cls_problem(port, 900, 96, 12, seed=1)
+    tr, trl, te, avg = ref_l2.cls_setup(rows, labels, 12, 20, seed=5)      # verbatim split_train_test
+    clf = fir.Classifier(rows[tr], trl, 12, avg)
+    for K in (1, 3, 7):
+        assert np.array_equal(clf.knn(rows[te], K), ref_l2.cls_knn(K, 0, len(te)))
+    lab, sc = clf.pnn(rows[te])
+    rlab, rsc = ref_l2.cls_pnn(0, len(te))
+    assert np.array_equal(lab, rlab)
+    np.testing.assert_allclose(sc, rsc, rtol=1e-5, atol=0)        # north_star: PNN scores within 1e-5 relative
+    clf.close()
+
+
+def test_knn_pnn_match_port_ragged(fir, port):
+    rows, labels = _cls_problem(port, 333, 50, 5, seed=2)
+    order = np.argsort(labels[:250], kind="stable")
+    tr, te = order, np.arange(250, len(rows))
+    avg = rows[tr].mean(axis=0)
+    clf = fir.Classifier(rows[tr], labels[tr], 5, avg)
+    for K in (1, 5):
+        assert np.array_equal(clf.knn(rows[te], K), port.knn(rows[tr], labels[tr], 5, avg, rows[te], K))
+    lab, sc = clf.pnn(rows[te])
+    psc, plab = port.pnn(rows[tr], labels[tr], 5, avg, rows[te])
+    assert np.array_equal(lab, plab)
+    np.testing.assert_allclose(sc, psc, rtol=1e-5, atol=0)
+    clf.close()
+
+
+@pytest.mark.parametrize("metric", ["l2", "chi2"])
+def test_dem_build_matches_reference(fir, port, metric, request):
+    ref = request.getfixturevalue("ref_" + metric)
+    g, gl, q, ql = make_data(port, metric, 3000, 100, 64, 25, seed=3)
+    rd = ref.dem_create(g, gl, seed=11)                           # verbatim ctor (random_shuffle seeded through srand)
+    gal = fir.Gallery(g, gl, metric)
+    dem = fir.Dem(gal, pivot0=int(rd.pivots[0]))
+    assert dem.n_pivots == rd.n_pivots and dem.chain_rows == 45
+    assert np.array_equal(dem.pivots, rd.pivots)
+    assert np.array_equal(bits(dem.P), bits(rd.P()))
+    assert bits(np.float32(dem.threshold)) == bits(np.float32(rd.threshold))
+    pb = port.dem_build(metric, g, gl, int(rd.pivots[0]))
+    assert np.array_equal(bits(dem.min_other), bits(pb["min_other"]))
+    for M in (0, 50, 300):
+        out = dem.search(q, M)
+        want = rd.search(q, M)
+        for a, b in zip(out, want):
+            assert np.array_equal(a, b)
+    rd.close()
+    dem.close()
+    gal.close()
+
+
+def test_dem_search_candidate_walk(fir, port, ref_l2):
+    """Thresholds far below the data's distances force the ordered candidate walk (ann.cpp:469-477)."""
+    g, gl, q, ql = make_data(port, "l2", 4000, 120, 64, 30, seed=4)
+    gal = fir.Gallery(g, gl, "l2")
+    dem0 = fir.Dem(gal, pivot0=17)
+    piv, P = dem0.pivots, dem0.P
+    d1, _ = port.bf("l2", g, q)
+    nn = port.distance  # noqa
+    bf_i, bf_d = port.bf("l2", g, q)
+    for thr in (float(np.median(bf_d)), float(bf_d.min()) * 0.5):          # ~half the queries can hit / nobody can
+        dem = fir.Dem(gal, state=(piv, P, thr))
+        rdem = ref_l2.dem_create_injected(g, gl, piv, P, thr)
+        for M in (20, 33, 100, 700, 2500, 0):
+            out = dem.search(q, M)
+            want = rdem.search(q, M)
+            pw = port.dem_search("l2", g, piv, P, thr, M, q)
+            for a, b, c in zip(out, want, pw):
+                assert np.array_equal(a, c), (thr, M)                      # defined (likelihood, index) order
+                assert np.array_equal(a, b), (thr, M)                      # and the verbatim reference
+        rdem.close()
+        dem.close()
+    dem0.close()
+    gal.close()
+
+
+def test_dem_index_walk_quirk(fir, port, ref_l2):
+    """A pivot whose gallery index is smaller than its ordinal makes the reference's index 'swap' drop one
+    candidate and keep a pivot in the tail; the GPU replay must agree."""
+    g, gl, q, ql = make_data(port, "l2", 1500, 80, 48, 10, seed=6)
+    gal = fir.Gallery(g, gl, "l2")
+    piv = np.array([900, 5, 1, 700, 2, 40, 3, 1200], np.int32)             # p_2 = 1 < 2, p_4 = 2 < 4, p_6 = 3 < 6
+    P = ref_l2.all_distances(g, g[piv], gallery_is_lhs=True)
+    thr = 1e-9
+    dem = fir.Dem(gal, state=(piv, P, thr))
+    rdem = ref_l2.dem_create_injected(g, gl, piv, P, thr)
+    for M in (9, 30, 400, 0):
+        for a, b in zip(dem.search(q, M), rdem.search(q, M)):
+            assert np.array_equal(a, b), M
+    rdem.close()
+    dem.close()
+    gal.close()

@@ -182,15 +182,15 @@ def run_gpu(args):
 
     gathered_d = gathered_i = None
     if world > 1:
-        gathered_d = torch.empty((world, N_QUERY, k), dtype=torch.float32, device=dev)
-        gathered_i = torch.empty((world, N_QUERY, k), dtype=torch.int32, device=dev)
+        gathered_d = torch.empty((world * N_QUERY, k), dtype=torch.float32, device=dev)
+        gathered_i = torch.empty((world * N_QUERY, k), dtype=torch.int32, device=dev)
 
     def step_device():
         idx, dd = gal.search(q_dev, k=k, path=fir_b200.PATH_AUTO)
         if world > 1:
             dist.all_gather_into_tensor(gathered_d, dd)
             dist.all_gather_into_tensor(gathered_i, idx)
-            idx, dd = fir_b200.merge_topk(gathered_d, gathered_i, stream=stream)
+            idx, dd = fir_b200.merge_topk(gathered_d.view(world, N_QUERY, k), gathered_i.view(world, N_QUERY, k), stream=stream)
         return idx, dd
 
     def step_host():
@@ -201,7 +201,7 @@ def run_gpu(args):
             di, ddv = torch.from_numpy(idx).to(dev, non_blocking=True), torch.from_numpy(dd).to(dev, non_blocking=True)
             dist.all_gather_into_tensor(gathered_d, ddv)
             dist.all_gather_into_tensor(gathered_i, di)
-            mi, md = fir_b200.merge_topk(gathered_d, gathered_i, stream=stream)
+            mi, md = fir_b200.merge_topk(gathered_d.view(world, N_QUERY, k), gathered_i.view(world, N_QUERY, k), stream=stream)
             idx_host.copy_(mi, non_blocking=True)
             dist_host.copy_(md, non_blocking=True)
             torch.cuda.synchronize()

@@ -1,0 +1,98 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference code (oracle/_ref, built from /root/reference by
+oracle/Makefile).  Run in the build container only:  python tests/golden/make_golden.py
+The reference ships no golden vectors of its own; these frozen known-answer files are outputs of
+the reference's own translation units on inputs fixed here, and pin both the C restatement (CPU tests) and the
+CUDA path (GPU tests) on machines where /root/reference does not exist."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import oracle_py  # noqa: E402
+import importlib  # noqa: E402
+
+synth = importlib.import_module("fast-image-recognition_b200.synth")
+
+
+def raw(metric, n, nq, d, c, seed):
+    return synth.make_split(n, nq, d, c, metric, seed=seed)
+
+
+def main():
+    oracle_py.build()
+    for metric in ("l2", "chi2", "kl"):
+        ref = oracle_py.Ref(metric)
+        out = {}
+        for d in (8, 32, 100):
+            g, gl, q, ql = raw(metric, 96, 12, d, 6, seed=d)
+            # normalise through the reference's own loader: write its text format, loadImages, no split randomisation
+            path = os.path.join(HERE, "_tmp_%s_%d.txt" % (metric, d))
+            synth.write_features_file(path, np.concatenate([g, q]), ["c%02d" % l for l in np.concatenate([gl, ql])])
+            # loader parses '{:f}' text, so feed the parsed values to everything downstream
+            gr, grl, gri, tr, trl, tri = ref.load_split(path, d, seed=13, randomize=False)
+            os.remove(path)
+            rows = np.concatenate([gr, tr])      # under USE_CALTECH the first 30 per class go to the gallery (db_features.cpp:133)
+            out["d%d_gallery" % d], out["d%d_gallery_labels" % d] = gr, grl
+            out["d%d_test" % d], out["d%d_test_labels" % d] = tr, trl
+            out["d%d_raw" % d] = np.concatenate([g, q])
+            out["d%d_raw_labels" % d] = np.concatenate([gl, ql])
+            if len(tr) == 0:      # every class has <= 30 images here: use the tail of the gallery as queries instead
+                tr = gr[-12:]
+            out["d%d_all_dist" % d] = ref.all_distances(gr, tr)
+            out["d%d_all_dist_gallery_lhs" % d] = ref.all_distances(gr, tr, gallery_is_lhs=True)
+            bi, bd = ref.bf(gr, tr, grl)
+            out["d%d_bf_idx" % d], out["d%d_bf_dist" % d] = bi, bd
+            bi, bd = ref.bf(gr, tr, grl, max_features=d // 2)
+            out["d%d_bf_half_idx" % d], out["d%d_bf_half_dist" % d] = bi, bd
+            out["d%d_queries" % d] = tr
+        # ties: duplicated gallery rows
+        g = out["d32_gallery"].copy()
+        h = len(g) // 2
+        g[h:2 * h] = g[:h]
+        out["ties_gallery"] = g
+        bi, bd = ref.bf(g, out["d32_queries"], None)
+        out["ties_bf_idx"], out["ties_bf_dist"] = bi, bd
+        # directed enumeration: verbatim ctor (srand(7)) + recognize at several budgets / an injected low threshold
+        g, gl, q, ql = raw(metric, 400, 40, 24, 8, seed=77)
+        port = oracle_py.Port()
+        g, q = port.normalize_rows(metric, g), port.normalize_rows(metric, q)
+        assert np.array_equal(ref.all_distances(g, q), np.array([[port.distance(metric, a, b) for b in g] for a in q], np.float32))
+        dem = ref.dem_create(g, gl, seed=7)
+        out["dem_gallery"], out["dem_labels"], out["dem_queries"] = g, gl, q
+        out["dem_pivots"], out["dem_threshold"], out["dem_P"] = dem.pivots, np.float32(dem.threshold), dem.P()
+        for M in (0, 10, 60):
+            r = dem.search(q, M)
+            for name, a in zip(("idx", "dist", "below", "evals"), r):
+                out["dem_M%d_%s" % (M, name)] = a
+        low = np.float32(dem.threshold * 0.05)
+        dinj = ref.dem_create_injected(g, gl, dem.pivots, dem.P(), low)
+        out["dem_low_threshold"] = low
+        for M in (8, 40, 150, 0):
+            r = dinj.search(q, M)
+            for name, a in zip(("idx", "dist", "below", "evals"), r):
+                out["demlow_M%d_%s" % (M, name)] = a
+        dem.close()
+        dinj.close()
+        np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % metric), **out)
+        print(metric, "->", len(out), "arrays")
+    # fp64 kNN / PNN (classification.cpp), verbatim split_train_test with srand(5)
+    ref = oracle_py.Ref("l2")
+    g, gl, q, ql = raw("l2", 300, 100, 40, 7, seed=5)
+    rows = np.concatenate([g, q]).astype(np.float64)
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    labels = np.concatenate([gl, ql]).astype(np.int32)
+    tr, trl, te, avg = ref.cls_setup(rows, labels, 7, 12, seed=5)
+    out = dict(rows=rows, labels=labels, train_idx=tr, train_labels=trl, test_idx=te, avg=avg)
+    for K in (1, 3):
+        out["knn%d" % K] = ref.cls_knn(K, 0, len(te))
+    out["pnn_label"], out["pnn_scores"] = ref.cls_pnn(0, len(te))
+    np.savez_compressed(os.path.join(HERE, "ref_classification.npz"), **out)
+    print("classification ->", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

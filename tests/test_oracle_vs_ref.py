@@ -1,0 +1,45 @@
+"""CPU: the C restatement against the live reference build (oracle/_ref) on fresh random inputs — wider
+coverage than the frozen vectors.  Skipped where oracle/_ref was not built (no /root/reference and no prebuilt .so)."""
+import numpy as np
+import pytest
+
+from util import bits, make_data
+
+
+@pytest.mark.parametrize("metric", ["l2", "chi2", "kl"])
+def test_distances_and_bf(port, metric, request):
+    ref = request.getfixturevalue("ref_" + metric)
+    for (n, nq, d, c, seed) in ((257, 19, 96, 7, 1), (64, 5, 1536, 4, 2), (500, 9, 33, 11, 3)):
+        g, gl, q, ql = make_data(port, metric, n, nq, d, c, seed=seed)
+        D = ref.all_distances(g, q)
+        Dp = np.array([[port.distance(metric, a, b) for b in g] for a in q], np.float32)
+        assert np.array_equal(bits(D), bits(Dp))
+        ri, rd = ref.bf(g, q, gl)
+        pi, pd = port.bf(metric, g, q)
+        assert np.array_equal(ri, pi) and np.array_equal(bits(rd), bits(pd))
+        ri, rd = ref.bf(g, q, gl, nthreads=4)
+        assert np.array_equal(ri, pi)
+
+
+def test_dem_and_classifiers(port, ref_l2):
+    g, gl, q, ql = make_data(port, "l2", 1200, 60, 48, 12, seed=9)
+    dem = ref_l2.dem_create(g, gl, seed=3)
+    b = port.dem_build("l2", g, gl, int(dem.pivots[0]))
+    assert np.array_equal(dem.pivots, b["pivots"][: b["n_pivots"]]) and np.array_equal(bits(dem.P()), bits(b["P"]))
+    assert bits(np.float32(dem.threshold)) == bits(np.float32(b["threshold"]))
+    low = float(dem.threshold) * 0.02
+    dinj = ref_l2.dem_create_injected(g, gl, dem.pivots, dem.P(), low)
+    for M in (0, 33, 200):
+        for a, c in zip(dinj.search(q, M), port.dem_search("l2", g, dem.pivots, dem.P(), low, M, q)):
+            assert np.array_equal(a, c)
+    dem.close()
+    dinj.close()
+    rows = np.concatenate([g, q]).astype(np.float64)
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    labels = np.concatenate([gl, ql]).astype(np.int32)
+    tr, trl, te, avg = ref_l2.cls_setup(rows, labels, 12, 15, seed=2)
+    for K in (1, 3):
+        assert np.array_equal(ref_l2.cls_knn(K, 0, len(te)), port.knn(rows[tr], trl, 12, avg, rows[te], K))
+    rl, rs = ref_l2.cls_pnn(0, len(te))
+    ps, pl = port.pnn(rows[tr], trl, 12, avg, rows[te])
+    assert np.array_equal(rl, pl) and np.array_equal(bits(rs), bits(ps))

@@ -1,0 +1,392 @@
+// fir_b200_compat.hpp — header-only C++ adapters that keep the reference's entry points for the matching
+// path and forward them to the C-ABI in fir_b200.h (libfir_b200.so).  A caller of
+//   qt_cpp/db_features.h  (FeaturesVector, ImagesDatabase, ImageInfo, feature_distance, loadImages,
+//                          getTrainingAndTestImages, recognize_image_bf)
+//   qt_cpp/ann.h          (ClassificationMethod, BruteForce, DirectedEnumeration)
+//   qt_cpp/classification.cpp's Classifier shape (Feature_vector, Classifier, KNNClassifier, PNNClassifier)
+// includes this header instead and links -lfir_b200; names, argument meaning and return conventions are the
+// reference's (index -1 = no match, matcher objects borrow `std::vector<ImageInfo>&`).  Differences, all additive:
+//   * FEATURES_COUNT is a run-time value (fir::features_count()) instead of the macro in qt_cpp/db.h:86,
+//     the metric is run time too (fir::metric()) instead of USE_L2_DISTANCE / the `#if` in db_features.cpp:30;
+//   * constructors pack the gallery and upload it once; recognize()/predict() are batch-of-1 calls, and
+//     testSetRecognition() / recognize_batch() / predict_batch() hand the whole query set to the GPU at once;
+//   * the file-scope training state of classification.cpp:53-62 becomes an explicit fir::TrainingSet.
+// Everything lives in namespace fir_compat; `using namespace fir_compat;` gives the reference's spelling.
+#ifndef FIR_B200_COMPAT_HPP
+#define FIR_B200_COMPAT_HPP
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "fir_b200.h"
+
+namespace fir {
+inline int& features_count() { static int d = 1536; return d; }          // qt_cpp/db.h:86 default
+inline int& metric() { static int m = FIR_L2; return m; }                // qt_cpp/db_features.h:12 default
+inline double& fraction() { static double f = 0.03; return f; }          // qt_cpp/db.h:72 (USE_CALTECH)
+inline bool& caltech_mode() { static bool c = true; return c; }          // qt_cpp/db.h:11
+inline void check(int status, const char* what) {
+    if (status != FIR_OK) throw std::runtime_error(std::string(what) + ": " + fir_last_error_string());
+}
+}  // namespace fir
+
+namespace fir_compat {
+
+typedef std::vector<float> FeaturesVector;                               // db_features.h:14
+typedef std::vector<std::vector<FeaturesVector> > ImagesDatabase;        // db_features.h:15
+
+class ImageInfo;
+float feature_distance(const FeaturesVector& lhs, const FeaturesVector& rhs, int start_pos = 0, int end_pos = -1);
+
+class ImageInfo {                                                        // db_features.h:19-29
+public:
+    ImageInfo(int no, int ind, const FeaturesVector& feat) : classNo(no), indexInDatabase(ind), features(feat) {}
+    float distance(const ImageInfo& rhs, int start_pos = 0, int end_pos = -1) const {
+        return feature_distance(features, rhs.features, start_pos, end_pos);
+    }
+    const int classNo, indexInDatabase;
+    const FeaturesVector& features;
+};
+
+namespace detail {
+// a device gallery built from a vector<ImageInfo>; rows are packed in dbImages order (= the tie-break order)
+struct PackedGallery {
+    fir_gallery* g;
+    int d;
+    PackedGallery(const std::vector<ImageInfo>& db, int metric) : g(0), d(db.empty() ? 0 : (int)db[0].features.size()) {
+        if (db.empty()) return;                                          // the reference answers -1 for every query
+        std::vector<float> rows((size_t)db.size() * d);
+        std::vector<int32_t> labels(db.size());
+        for (size_t j = 0; j < db.size(); ++j) {
+            std::copy(db[j].features.begin(), db[j].features.begin() + d, rows.begin() + j * (size_t)d);
+            labels[j] = db[j].classNo;
+        }
+        fir::check(fir_gallery_create(rows.data(), labels.data(), (int64_t)db.size(), d, metric, FIR_HOST, 0, &g), "fir_gallery_create");
+    }
+    ~PackedGallery() { fir_gallery_destroy(g); }
+private:
+    PackedGallery(const PackedGallery&);
+    PackedGallery& operator=(const PackedGallery&);
+};
+inline std::vector<float> pack_queries(const std::vector<ImageInfo>& q, int d) {
+    std::vector<float> rows((size_t)q.size() * d);
+    for (size_t i = 0; i < q.size(); ++i) std::copy(q[i].features.begin(), q[i].features.begin() + d, rows.begin() + i * (size_t)d);
+    return rows;
+}
+}  // namespace detail
+
+// feature_distance (db_features.cpp:22-42): a one-row gallery and a one-row query through fir_pair_distances.
+// start_pos must be 0 (every caller on the path passes 0); end_pos < 0 means all dimensions.
+inline float feature_distance(const FeaturesVector& lhs, const FeaturesVector& rhs, int start_pos, int end_pos) {
+    const int d = (int)std::min(lhs.size(), rhs.size());
+    if (end_pos < 0 || end_pos > d) end_pos = d;
+    if (start_pos != 0) throw std::invalid_argument("feature_distance: start_pos != 0 is not on the accelerated path");
+    fir_gallery* g = 0;
+    fir::check(fir_gallery_create(rhs.data(), 0, 1, end_pos, fir::metric(), FIR_HOST, 0, &g), "fir_gallery_create");
+    int32_t idx = 0; float out = 0.f;
+    int st = fir_pair_distances(g, lhs.data(), 1, &idx, 1, 0, FIR_HOST, &out);
+    fir_gallery_destroy(g);
+    fir::check(st, "fir_pair_distances");
+    return out;
+}
+
+// loadImages (db_features.cpp:44-116): same text format (3 lines per image: file, class, D floats), same class
+// numbering (first seen), same Caltech background filter; the zeroing + normalisation loop runs on the GPU.
+inline int loadImages(ImagesDatabase& imagesDb, std::string features_file, std::unordered_map<std::string, int>& person2indexMap,
+                      bool /*early_stop*/ = false) {
+    person2indexMap.clear();
+    std::ifstream in(features_file.c_str());
+    if (!in) return 0;                                                   // missing file ⇒ empty DB, 0 images (db_features.cpp:49,115)
+    const int d = fir::features_count();
+    std::vector<float> packed;
+    std::vector<int> cls;
+    std::string file_name, class_name, values;
+    while (std::getline(in, file_name) && std::getline(in, class_name) && std::getline(in, values)) {
+        size_t first = class_name.find_first_not_of(" \t\n\r\f\v");
+        class_name = first == std::string::npos ? std::string() : class_name.substr(first);
+        if (fir::caltech_mode() && (class_name.find("BACKGROUND_Google") != std::string::npos || class_name.find("257.clutter") != std::string::npos))
+            continue;
+        std::unordered_map<std::string, int>::iterator it = person2indexMap.find(class_name);
+        if (it == person2indexMap.end()) it = person2indexMap.insert(std::make_pair(class_name, (int)person2indexMap.size())).first;
+        std::istringstream ss(values);
+        float v = 0.f;
+        for (int i = 0; i < d; ++i) { ss >> v; packed.push_back(v); }   // a short line repeats the last parsed value, like the reference's loop
+        cls.push_back(it->second);
+    }
+    const int total = (int)cls.size();
+    if (total == 0) return 0;
+    fir::check(fir_normalize_rows(packed.data(), total, d, fir::metric(), FIR_HOST, 0), "fir_normalize_rows");
+    imagesDb.resize(person2indexMap.size());
+    for (int i = 0; i < total; ++i)
+        imagesDb[cls[i]].push_back(FeaturesVector(packed.begin() + (size_t)i * d, packed.begin() + (size_t)(i + 1) * d));
+    return total;
+}
+
+// getTrainingAndTestImages (db_features.cpp:117-162): one shuffled index table of 400 shared by every class; the
+// first db_size shuffled images of a class go to the gallery, the rest (below 400) to the test set.
+inline void getTrainingAndTestImages(const ImagesDatabase& totalImages, std::vector<ImageInfo>& dbImages, std::vector<ImageInfo>& testImages,
+                                     bool randomize = true) {
+    const int kTable = 400;
+    std::vector<int> order(kTable);
+    for (int i = 0; i < kTable; ++i) order[i] = i;
+    if (randomize) {
+#if __cplusplus < 201703L
+        std::random_shuffle(order.begin(), order.end());                 // rand()-driven in libstdc++, like the reference
+#else
+        for (int i = kTable - 1; i > 0; --i) std::swap(order[i], order[std::rand() % (i + 1)]);
+#endif
+    }
+    dbImages.clear();
+    testImages.clear();
+    int base = 0;
+    for (size_t c = 0; c < totalImages.size(); ++c) {
+        const int count = (int)totalImages[c].size();
+        int db_size = 30;
+        if (!fir::caltech_mode()) {
+            db_size = (int)std::ceil((float)(count * fir::fraction()));
+            if (db_size == count) db_size = count - 1;
+            if (db_size == 0) db_size = 1;
+        }
+        int taken = 0;
+        for (int i = 0; i < kTable; ++i) {
+            const int j = order[i];
+            if (j >= count) continue;
+            ImageInfo info((int)c, base + j, totalImages[c][j]);
+            if (taken < db_size) dbImages.push_back(info); else testImages.push_back(info);
+            ++taken;
+        }
+        base += count;
+    }
+}
+
+// recognize_image_bf (db_features.cpp:319-335): 1-NN over the first max_features dimensions (0 = all)
+inline int recognize_image_bf(const std::vector<ImageInfo>& dbImages, const ImageInfo& testImageInfo, int max_features = 0) {
+    if (dbImages.empty()) return -1;
+    detail::PackedGallery pg(dbImages, fir::metric());
+    int32_t idx = -1;
+    fir::check(fir_search_topk(pg.g, testImageInfo.features.data(), 1, 1, max_features >= pg.d ? 0 : max_features, FIR_PATH_EXACT, FIR_HOST, &idx, 0),
+               "fir_search_topk");
+    return idx;
+}
+
+class ClassificationMethod {                                             // ann.h:9-39
+public:
+    ClassificationMethod(std::string name, std::vector<ImageInfo>& db) : method_name(name), dbImages(db), avgCheckedPercent(0) {
+        imageCountToCheck = (int)dbImages.size();
+    }
+    virtual ~ClassificationMethod() {}
+    virtual int recognize(ImageInfo& testImageInfo) = 0;
+    // one GPU call for the whole query set; the default loops recognize()
+    virtual std::vector<int> recognize_batch(std::vector<ImageInfo>& testImages) {
+        std::vector<int> out(testImages.size());
+        for (size_t i = 0; i < testImages.size(); ++i) out[i] = recognize(testImages[i]);
+        return out;
+    }
+    // ann.cpp:94-109: error %, ms per query, checked %
+    void testSetRecognition(std::vector<ImageInfo>& testImages) {
+        avgCheckedPercent = 0;
+        std::chrono::high_resolution_clock::time_point t1 = std::chrono::high_resolution_clock::now();
+        std::vector<int> best = recognize_batch(testImages);
+        std::chrono::high_resolution_clock::time_point t2 = std::chrono::high_resolution_clock::now();
+        int errors = 0;
+        for (size_t i = 0; i < testImages.size(); ++i)
+            if (best[i] == -1 || testImages[i].classNo != dbImages[best[i]].classNo) ++errors;
+        lastErrorRate = testImages.empty() ? 0.0 : 100.0 * errors / testImages.size();
+        const double ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+        std::cout << method_name << " error=" << lastErrorRate << "% total_time (ms)" << (testImages.empty() ? 0.0 : ms / testImages.size())
+                  << " checkedPercent=" << (avgCheckedPercent > 0 ? avgCheckedPercent / testImages.size() : -1) << std::endl;
+    }
+    virtual void setImageCountToCheck(int count) {                       // ann.h:20-22
+        imageCountToCheck = (count > 0 && count < (int)dbImages.size()) ? count : (int)dbImages.size();
+    }
+    static float getThreshold(std::vector<float>& otherClassesDists, float falseAcceptRate) {   // ann.cpp:84-93
+        int ind = (int)(otherClassesDists.size() * falseAcceptRate);
+        std::nth_element(otherClassesDists.begin(), otherClassesDists.begin() + ind, otherClassesDists.end());
+        return otherClassesDists[ind];
+    }
+    double lastErrorRate = 0;
+protected:
+    std::string method_name;
+    std::vector<ImageInfo>& dbImages;
+    int distanceCalcCount = 0;
+    float avgCheckedPercent;
+    int imageCountToCheck;
+};
+
+class BruteForce : public ClassificationMethod {                         // ann.h:42-47, ann.cpp:113-126
+public:
+    BruteForce(std::vector<ImageInfo>& db) : ClassificationMethod("BF", db), pg(db, fir::metric()) {}
+    int recognize(ImageInfo& testImage) {
+        std::vector<ImageInfo> one(1, testImage);
+        return recognize_batch(one)[0];
+    }
+    std::vector<int> recognize_batch(std::vector<ImageInfo>& testImages) {
+        std::vector<int> out(testImages.size(), -1);
+        if (!pg.g || testImages.empty()) return out;
+        std::vector<float> q = detail::pack_queries(testImages, pg.d);
+        std::vector<int32_t> idx(testImages.size());
+        fir::check(fir_search_topk(pg.g, q.data(), (int64_t)testImages.size(), 1, 0, FIR_PATH_AUTO, FIR_HOST, idx.data(), 0), "fir_search_topk");
+        distanceCalcCount = (int)dbImages.size();
+        for (size_t i = 0; i < out.size(); ++i) out[i] = idx[i];
+        return out;
+    }
+private:
+    detail::PackedGallery pg;
+};
+
+class DirectedEnumeration : public ClassificationMethod {                // ann.h:61-100, ann.cpp:270-507
+public:
+    // pivot0 < 0: the first pivot comes from `seed` (the reference takes the head of an unseeded random_shuffle)
+    DirectedEnumeration(std::vector<ImageInfo>& faceImages, float falseAcceptRate = 0.01f, float threshold = 0, int imageCountToCheck = 0,
+                        int pivot0 = -1, unsigned seed = 0)
+        : ClassificationMethod("dem", faceImages), isFoundLessThreshold(false), bestDistance(0), pg(faceImages, fir::metric()), dem(0) {
+        setImageCountToCheck(imageCountToCheck);
+        fir_dem_params p;
+        p.pivot0 = pivot0; p.seed = seed; p.false_accept_rate = falseAcceptRate; p.threshold = threshold; p.max_chain = 0; p.max_pivots = 0;
+        std::chrono::high_resolution_clock::time_point t1 = std::chrono::high_resolution_clock::now();
+        fir::check(fir_dem_build(pg.g, &p, &dem), "fir_dem_build");
+        std::cout << "init took " << std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - t1).count()
+                  << " milliseconds" << std::endl;
+    }
+    ~DirectedEnumeration() { fir_dem_destroy(dem); }
+    int recognize(ImageInfo& testImage) {
+        std::vector<ImageInfo> one(1, testImage);
+        return recognize_batch(one)[0];
+    }
+    std::vector<int> recognize_batch(std::vector<ImageInfo>& testImages) {
+        const size_t nq = testImages.size();
+        std::vector<int> out(nq, -1);
+        if (nq == 0) return out;
+        std::vector<float> q = detail::pack_queries(testImages, pg.d);
+        std::vector<int32_t> idx(nq), evals(nq);
+        std::vector<float> dist(nq);
+        std::vector<uint8_t> below(nq);
+        fir::check(fir_dem_search(dem, q.data(), (int64_t)nq, imageCountToCheck, FIR_HOST, idx.data(), dist.data(), below.data(), evals.data()), "fir_dem_search");
+        for (size_t i = 0; i < nq; ++i) {
+            out[i] = idx[i];
+            avgCheckedPercent += (float)(100. * evals[i] / dbImages.size());        // ann.cpp:505
+        }
+        isFoundLessThreshold = below[nq - 1] != 0; bestDistance = dist[nq - 1]; distanceCalcCount = evals[nq - 1];
+        return out;
+    }
+    float threshold() const { float t = 0; fir_dem_info(dem, 0, 0, &t); return t; }
+    bool isFoundLessThreshold;
+    float bestDistance;
+private:
+    detail::PackedGallery pg;
+    fir_dem* dem;
+};
+
+// ---- classification.cpp ------------------------------------------------------------------------------
+class Feature_vector {                                                   // classification.cpp:35-43
+public:
+    Feature_vector(const std::vector<double>& fv, double out) : features(fv), output(out) {}
+    std::vector<double> features;
+    double output;
+};
+}  // namespace fir_compat
+
+namespace fir {
+// the state classification.cpp keeps in file-scope globals (:53-62) after split_train_test (:942-990):
+// training rows in class-major order, their labels, the per-feature mean of the training rows
+struct TrainingSet {
+    fir_classifier* c;
+    int n_classes, d;
+    TrainingSet(const std::vector<fir_compat::Feature_vector>& rows, const std::vector<std::vector<size_t> >& training_set) : c(0) {
+        n_classes = (int)training_set.size();
+        d = rows.empty() ? 0 : (int)rows[0].features.size();
+        std::vector<double> packed, avg((size_t)d, 0.0);
+        std::vector<int32_t> labels;
+        size_t count = 0;
+        for (size_t k = 0; k < training_set.size(); ++k)
+            for (size_t t = 0; t < training_set[k].size(); ++t) {
+                const std::vector<double>& f = rows[training_set[k][t]].features;
+                packed.insert(packed.end(), f.begin(), f.begin() + d);
+                labels.push_back((int32_t)k);
+                ++count;
+            }
+        for (int fi = 0; fi < d; ++fi) {                                 // avgValues, classification.cpp:969-987 (same summation order)
+            double s = 0;
+            for (size_t r = 0; r < count; ++r) s += packed[r * (size_t)d + fi];
+            avg[fi] = s / (int)count;
+        }
+        check(fir_classifier_create(packed.data(), labels.data(), (int64_t)count, d, n_classes, avg.data(), &c), "fir_classifier_create");
+    }
+    ~TrainingSet() { fir_classifier_destroy(c); }
+private:
+    TrainingSet(const TrainingSet&);
+    TrainingSet& operator=(const TrainingSet&);
+};
+}  // namespace fir
+
+namespace fir_compat {
+class Classifier {                                                       // classification.cpp:82-95
+public:
+    Classifier(std::string name, fir::TrainingSet& ts) : method_name(name), train_set(ts) {}
+    virtual ~Classifier() {}
+    virtual void train() {}
+    virtual int predict(const Feature_vector& inputFeatures) {
+        std::vector<Feature_vector> one(1, inputFeatures);
+        return predict_batch(one)[0];
+    }
+    virtual std::vector<int> predict_batch(const std::vector<Feature_vector>& inputs) = 0;
+    std::string get_name() { return method_name; }
+protected:
+    std::string method_name;
+    fir::TrainingSet& train_set;
+    std::vector<double> pack(const std::vector<Feature_vector>& in) const {
+        std::vector<double> q;
+        for (size_t i = 0; i < in.size(); ++i) q.insert(q.end(), in[i].features.begin(), in[i].features.begin() + train_set.d);
+        return q;
+    }
+};
+
+class KNNClassifier : public Classifier {                                // classification.cpp:108-170
+public:
+    KNNClassifier(int k, fir::TrainingSet& ts) : Classifier("k-NN, " + std::to_string(k), ts), K(k) {}
+    std::vector<int> predict_batch(const std::vector<Feature_vector>& inputs) {
+        std::vector<double> q = pack(inputs);
+        std::vector<int32_t> lab(inputs.size());
+        fir::check(fir_classifier_knn(train_set.c, q.data(), (int64_t)inputs.size(), K, lab.data()), "fir_classifier_knn");
+        return std::vector<int>(lab.begin(), lab.end());
+    }
+private:
+    int K;
+};
+
+class PNNClassifier : public Classifier {                                // classification.cpp:173-226 (predict_bf)
+public:
+    PNNClassifier(fir::TrainingSet& ts, bool bf = true, std::string name = "PNN") : Classifier(name, ts) {
+        if (!bf) throw std::invalid_argument("PNNClassifier(bf=false): predict_sequentional is outside the accelerated path");
+    }
+    std::vector<int> predict_batch(const std::vector<Feature_vector>& inputs) {
+        std::vector<double> q = pack(inputs);
+        std::vector<int32_t> lab(inputs.size());
+        scores.assign(inputs.size() * (size_t)train_set.n_classes, 0.0);
+        fir::check(fir_classifier_pnn(train_set.c, q.data(), (int64_t)inputs.size(), scores.data(), lab.data()), "fir_classifier_pnn");
+        return std::vector<int>(lab.begin(), lab.end());
+    }
+    std::vector<double> scores;                                          // per-class outputs of the last call (locals in the reference, :194)
+};
+
+// BruteForceClassifier (ImageTesting.cpp:58-71): recognize_image_bf over a dimension prefix
+class BruteForceClassifier {
+public:
+    explicit BruteForceClassifier(int max_feats = 0) : max_features(max_feats) {}
+    int recognize(std::vector<ImageInfo>& db, ImageInfo& testImageInfo) { return recognize_image_bf(db, testImageInfo, max_features); }
+private:
+    int max_features;
+};
+
+}  // namespace fir_compat
+
+#endif  // FIR_B200_COMPAT_HPP

@@ -1,0 +1,54 @@
+"""GPU: the C++ drop-in adapters (include/fir_b200_compat.hpp) compiled with the reference's own language level
+(-std=c++11, recognition_testing.pro:38) against libfir_b200.so, driven like testANN, checked against the oracle."""
+import importlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import bits
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+synth = importlib.import_module("fast-image-recognition_b200.synth")
+
+
+def test_cpp_adapters_match_oracle(port, tmp_path):
+    d, n_classes = 48, 9
+    g, gl, q, ql = synth.make_split(9 * 45, 1, d, n_classes, "l2", seed=21)    # USE_CALTECH split: 30 per class to the gallery, rest to test
+    txt = str(tmp_path / "features.txt")
+    synth.write_features_file(txt, g, ["class_%02d" % c for c in gl])
+    exe = str(tmp_path / "compat_test")
+    pkg = os.path.join(ROOT, "fast-image-recognition_b200")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "compat_test.cpp"),
+                    "-o", exe, "-L", pkg, "-lfir_b200", "-Wl,-rpath," + pkg], check=True)
+    # expected: parse the same text, loader normalisation, class-major split without shuffling
+    parsed = np.array([[np.float32(float("{:f}".format(float(v)))) for v in row] for row in g], np.float32)
+    rows = port.normalize_rows("l2", parsed)
+    db_i, te_i = [], []
+    for c in range(n_classes):
+        idx = np.flatnonzero(gl == c)
+        db_i += list(idx[:30])
+        te_i += list(idx[30:400])
+    db, test = rows[db_i], rows[te_i]
+    dbl, tel = gl[db_i], gl[te_i]
+    pivot0 = 7
+    out = subprocess.run([exe, txt, str(d), str(pivot0)], check=True, capture_output=True, text=True).stdout
+    lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l.split()[0].isupper()}
+    assert lines["LOADED"][0] == str(len(g)) and int(lines["LOADED"][4]) == len(db) and int(lines["LOADED"][6]) == len(test)
+    bi, bd = port.bf("l2", db, test)
+    assert [int(x) for x in lines["BF"]] == bi.tolist()
+    assert int(lines["BF1"][0]) == bi[0] and int(lines["BF1"][2]) == bi[0]
+    assert int(lines["BF1"][4]) == port.bf("l2", db, test[:1], max_features=d // 2)[0][0]
+    assert bits(np.float32(float(lines["DIST"][0]))) == bits(port.distance("l2", test[0], db[3]))
+    b = port.dem_build("l2", db, dbl, pivot0)
+    assert bits(np.float32(float(lines["THRESHOLD"][0]))) == bits(np.float32(b["threshold"]))
+    di = port.dem_search("l2", db, b["pivots"][: b["n_pivots"]], b["P"], b["threshold"], int(0.2 * len(db)), test)[0]
+    assert [int(x) for x in lines["DEM"]] == di.tolist()
+    tr64, te64 = db.astype(np.float64), test.astype(np.float64)
+    avg = np.array([np.add.reduce(tr64[:, f]) for f in range(d)])          # sequential left-to-right like the adapter
+    avg = np.array([sum(tr64[:, f].tolist()) for f in range(d)]) / len(tr64)
+    assert [int(x) for x in lines["KNN3"]] == port.knn(tr64, dbl, n_classes, avg, te64, 3).tolist()
+    sc, pl = port.pnn(tr64, dbl, n_classes, avg, te64)
+    assert [int(x) for x in lines["PNN"]] == pl.tolist() and int(lines["PNN1"][0]) == pl[0]

@@ -69,7 +69,8 @@ static int pick_nsplit(int64_t nq, int64_t n, int n_sm) {
 
 // exact CUDA-core top-k over (optionally) a subset of queries; results to device out_* [nq][k]
 int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_end, const int32_t* qmap,
-                      const int32_t* n_active, float* part_d, int32_t* part_i, int nsplit, float* od, int32_t* oi) {
+                      const int32_t* n_active, float* part_d, int32_t* part_i, int nsplit, float* od, int32_t* oi,
+                      int64_t active_offset, int64_t active_cap) {
     ExactParams p{};
     p.q = dq; p.nq = nq; p.ldq = g->dp;
     p.x = g->rows; p.n = g->n; p.ldx = g->dp;
@@ -78,9 +79,11 @@ int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_
     p.nsplit = nsplit;
     p.tiles_per_split = ceil_div(ceil_div(g->n, kExactTile), nsplit);
     p.part_dist = part_d; p.part_idx = part_i;
-    p.qmap = qmap; p.n_active = n_active;
+    p.qmap = qmap; p.n_active = n_active; p.active_offset = active_offset; p.active_cap = active_cap;
+    if (active_cap > 0) p.nq = std::min<int64_t>(nq, active_cap);       // grid covers one window of the active list
     { auto* ev = g->prof_begin(FIR_KERNEL_EXACT_TILES); int st_ = launch_exact_tiles(g->metric, p, g->stream); g->prof_end(ev); FIR_TRY(st_); }
-    FIR_TRY(launch_merge_parts(part_d, part_i, nsplit, k, (int64_t)nsplit * k, nq, k, g->index_offset, qmap, n_active, od, oi, g->stream));
+    FIR_TRY(launch_merge_parts(part_d, part_i, nsplit, k, (int64_t)nsplit * k, active_cap > 0 ? std::min<int64_t>(nq, active_cap) : nq, k, g->index_offset, qmap, n_active, od, oi, g->stream,
+                               active_offset, active_cap));
     g->stats.gpu_launches += 2;
     return FIR_OK;
 }
@@ -268,7 +271,10 @@ int fir_search_last_stats(const fir_gallery* g, fir_search_stats* stats) {
         fir_gallery* m = const_cast<fir_gallery*>(g);      // device-side counters are fetched on demand
         int32_t nf = 0; float mb = 0.f;
         FIR_CUDA_TRY(cudaStreamSynchronize(m->stream));
-        FIR_CUDA_TRY(cudaMemcpy(&nf, m->d_stats + 4, 4, cudaMemcpyDeviceToHost));
+        FIR_CUDA_TRY(cudaMemcpy(&nf, m->d_stats + 4, 4, cudaMemcpyDeviceToHost));     // queries that needed more than pass 1
+        int32_t nfinal = 0;
+        FIR_CUDA_TRY(cudaMemcpy(&nfinal, m->d_stats + 7, 4, cudaMemcpyDeviceToHost)); // of those, re-run exactly on CUDA cores
+        m->stats.reserved = (float)nfinal;
         FIR_CUDA_TRY(cudaMemcpy(&mb, m->d_stats + 5, 4, cudaMemcpyDeviceToHost));
         m->stats.n_fallback = nf;
         m->stats.approx_err_bound = mb;

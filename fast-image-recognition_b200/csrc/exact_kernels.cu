@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
     int* tki = reinterpret_cast<int*>(tkd + TS * p.k);
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int64_t n_active = p.n_active ? (int64_t)*p.n_active : p.nq;
+    int64_t n_active = p.n_active ? (int64_t)*p.n_active : p.nq;
+    const int32_t* qmap_ = p.qmap ? p.qmap + p.active_offset : nullptr;          // chunked fallback: window of the active list
+    if (p.n_active) { n_active = max((int64_t)0, n_active - p.active_offset); if (p.active_cap > 0) n_active = min(n_active, p.active_cap); }
     const int64_t q0 = (int64_t)blockIdx.x * TS;
     if (q0 >= n_active) return;
     const int64_t ntiles = (p.n + TS - 1) / TS;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
     for (int h = 0; h < 2; ++h) {
         int64_t qi = q0 + lr0 + 32 * h;
         qok[h] = qi < n_active;
-        int64_t src = qok[h] ? (p.qmap ? (int64_t)p.qmap[qi] : qi) : 0;
+        int64_t src = qok[h] ? (qmap_ ? (int64_t)qmap_[qi] : qi) : 0;
         qrow[h] = src * p.ldq;
     }
 
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
     unsigned long long cur_key = ~0ull;
     double cur_sum = 0.0;
     const int64_t my_q = q0 + tid;
-    const int64_t my_q_out = (tid < TS && my_q < n_active) ? (p.qmap ? (int64_t)p.qmap[my_q] : my_q) : -1;
+    const int64_t my_q_out = (tid < TS && my_q < n_active) ? (qmap_ ? (int64_t)qmap_[my_q] : my_q) : -1;
 
     for (int64_t t = t_lo; t < t_hi; ++t) {
         const int64_t x0 = t * TS;
@@ -232,11 +234,13 @@ int launch_exact_tiles(int metric, const ExactParams& p, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void merge_parts_kernel(const float* __restrict__ pd, const int32_t* __restrict__ pi, int n_parts,
                                    int64_t part_stride, int64_t q_stride, int64_t nq, int k, int64_t index_offset,
-                                   const int32_t* qmap, const int32_t* n_active, float* od, int32_t* oi) {
+                                   const int32_t* qmap, const int32_t* n_active, float* od, int32_t* oi, int64_t active_offset,
+                                   int64_t active_cap) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t na = n_active ? (int64_t)*n_active : nq;
+    if (n_active) { na = max((int64_t)0, na - active_offset); if (active_cap > 0) na = min(na, active_cap); }
     if (i >= na) return;
-    int64_t q = qmap ? (int64_t)qmap[i] : i;
+    int64_t q = qmap ? (int64_t)qmap[active_offset + i] : i;
     constexpr int MAXP = 256;
     unsigned short head[MAXP];
     for (int s = 0; s < n_parts; ++s) head[s] = 0;
@@ -258,11 +262,11 @@ __global__ void merge_parts_kernel(const float* __restrict__ pd, const int32_t* 
 
 int launch_merge_parts(const float* pd, const int32_t* pi, int n_parts, int64_t part_stride, int64_t q_stride,
                        int64_t nq, int k, int64_t index_offset, const int32_t* qmap, const int32_t* n_active,
-                       float* od, int32_t* oi, cudaStream_t s) {
+                       float* od, int32_t* oi, cudaStream_t s, int64_t active_offset, int64_t active_cap) {
     if (nq <= 0) return FIR_OK;
     if (n_parts > 256) return fail(FIR_ERR_UNSUPPORTED, "more than 256 parts to merge");
     merge_parts_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(pd, pi, n_parts, part_stride, q_stride, nq, k, index_offset,
-                                                                   qmap, n_active, od, oi);
+                                                                   qmap, n_active, od, oi, active_offset, active_cap);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
@@ -352,11 +356,17 @@ __global__ void __launch_bounds__(PW * 32) pair_distance_kernel(const float* __r
     const int ld_lim = ldx;   // rows are zero padded up to ldx
     for (int c0 = 0; c0 < d_end; c0 += PCH) {
         const int col = c0 + lane * 4;
-        for (int c = 0; c < 32; ++c) {
-            int32_t ci = __shfl_sync(0xffffffffu, my, c);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ci >= 0 && col < ld_lim) v = *reinterpret_cast<const float4*>(x + (int64_t)ci * ldx + col);
-            *reinterpret_cast<float4*>(&tile[c * PLD + lane * 4]) = v;
+#pragma unroll 2
+        for (int c = 0; c < 32; c += 4) {                    // 4 independent row loads in flight per lane
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int32_t ci = __shfl_sync(0xffffffffu, my, c + u);
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ci >= 0 && col < ld_lim) v[u] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)ci * ldx + col));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(&tile[(c + u) * PLD + lane * 4]) = v[u];
         }
         {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);

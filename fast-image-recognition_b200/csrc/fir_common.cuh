@@ -61,12 +61,13 @@ struct ExactParams {
     double* cls_score;                         // [nq][C]
     int n_classes; double two_var;
     const int32_t* qmap; const int32_t* n_active;   // optional query indirection (tensor-path fallback)
+    int64_t active_offset; int64_t active_cap;      // this launch serves active positions [offset, offset+cap) (cap 0 = all)
 };
 
 int launch_exact_tiles(int metric, const ExactParams& p, cudaStream_t s);
 int launch_merge_parts(const float* pd, const int32_t* pi, int n_parts, int64_t part_stride, int64_t q_stride,
                        int64_t nq, int k, int64_t index_offset, const int32_t* qmap, const int32_t* n_active,
-                       float* od, int32_t* oi, cudaStream_t s);
+                       float* od, int32_t* oi, cudaStream_t s, int64_t active_offset = 0, int64_t active_cap = 0);
 int launch_fill_u64(unsigned long long* p, int64_t n, unsigned long long v, cudaStream_t s);
 int launch_classmin_finalize(const unsigned long long* keys, int64_t n, int64_t index_offset, float* omin, int32_t* oarg, cudaStream_t s);
 int launch_pnn_finalize(double* scores, int64_t nq, int n_classes, double n_total, int32_t* olabel, cudaStream_t s);
@@ -98,14 +99,16 @@ struct TensorSearchArgs {
     float* cand_val; int32_t* cand_idx;   // [nq][n_slots][R]
     float* slot_bound;                    // [nq][n_slots]
     int grid;
+    int ctas;                     // 1: cta_group::1 kernel, 2: CTA-pair kernel (grid counts pairs)
 };
-int tensor_plan(int64_t nq, int64_t n, int n_sm, int* grid, int* n_slots);
+int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots);
+int tensor_cta_mode();
 int tensor_encode_map(CUtensorMap* map, const __half* base, int64_t rows_padded, int dph, int box_rows);
 int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s);
 int launch_tensor_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots,
                          int R, int k, int d, const float* q_norm2, const float* q_resid, const float* gal_stats,
                          int64_t index_offset, float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged,
-                         float* max_bound, cudaStream_t s);
+                         unsigned char* fail_flags, float* max_bound, cudaStream_t s);
 bool tensor_path_supported(int d);
 
 }  // namespace fir

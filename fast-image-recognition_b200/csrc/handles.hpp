@@ -16,7 +16,8 @@ struct fir_gallery {
     bool tensor_ready = false;
     void* tensor_buf = nullptr;
     fir::TensorSide tside;
-    CUtensorMap tmap_b;
+    CUtensorMap tmap_b;           // box 64 x 256 rows (single-CTA kernel)
+    CUtensorMap tmap_b_half;      // box 64 x 128 rows (each CTA of a pair loads half a tile)
     float* d_stats = nullptr;     // [2] max ||x||, max ||x - fp16(x)||
     fir::Workspace ws;
     // diagnostics: where the last tensor-path call left its candidate lists (valid until the next call)
@@ -37,6 +38,7 @@ struct fir_gallery {
 
 namespace fir {
 int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_end, const int32_t* qmap,
-                      const int32_t* n_active, float* part_d, int32_t* part_i, int nsplit, float* od, int32_t* oi);
+                      const int32_t* n_active, float* part_d, int32_t* part_i, int nsplit, float* od, int32_t* oi,
+                      int64_t active_offset = 0, int64_t active_cap = 0);
 int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
 }

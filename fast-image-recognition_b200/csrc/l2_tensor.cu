@@ -18,6 +18,7 @@
 #include "handles.hpp"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 
 namespace fir {
@@ -32,6 +33,12 @@ constexpr int MAX_RES_KB = 8;    // A stays resident in shared memory when D <= 
 constexpr int TMEM_COLS = 512;   // two 256-column accumulators
 
 bool tensor_path_supported(int d) { return d >= 16; }
+
+// 1 = one CTA per tile (cta_group::1); 2 = CTA pairs (cta_group::2).  FIR_TENSOR_CTAS overrides for A/B measurements.
+int tensor_cta_mode() {
+    static int mode = [] { const char* e = getenv("FIR_TENSOR_CTAS"); int m = e ? atoi(e) : 2; return (m == 1 || m == 2) ? m : 2; }();
+    return mode;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -261,12 +268,12 @@ struct Partition { int64_t ntiles, nqb, total; int grid; };
 __host__ __device__ inline int64_t part_lo(const Partition& P, int64_t c) { return c * P.total / P.grid; }
 __host__ __device__ inline int64_t part_first_cta(const Partition& P, int64_t item) { return ((item + 1) * P.grid - 1) / P.total; }
 
-int tensor_plan(int64_t nq, int64_t n, int n_sm, int* grid, int* n_slots) {
+int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots) {
     Partition P;
     P.ntiles = ceil_div(n, BN);
-    P.nqb = ceil_div(nq, BM);
+    P.nqb = ceil_div(nq, BM * ctas);
     P.total = P.ntiles * P.nqb;
-    P.grid = (int)std::min<int64_t>(P.total, n_sm);
+    P.grid = (int)std::min<int64_t>(P.total, n_sm / ctas);     // work units: CTAs, or CTA pairs
     int slots = 1;
     for (int64_t qb = 0; qb < P.nqb; ++qb) {
         int64_t c0 = part_first_cta(P, qb * P.ntiles), c1 = part_first_cta(P, (qb + 1) * P.ntiles - 1);
@@ -292,19 +299,97 @@ struct CandParams {
     float* slot_bound;
 };
 
+// Running top-R of one query row, UNSORTED, in registers: thr is the current maximum (+inf until the list is full).
+// A better value replaces one slot holding the maximum, then the maximum is recomputed — 5R mostly independent
+// instructions (a sorted insert is a 5R-deep dependent chain, and this code runs with a single warp per scheduler).
 template <int R>
-__device__ __forceinline__ void topr_insert(float (&lv)[R], int (&li)[R], float v, int j) {
+__device__ __forceinline__ void topr_replace(float (&lv)[R], int (&li)[R], float& thr, float v, int j) {
+    bool placed = false;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        if (v < lv[r]) {
-            float tv = lv[r]; lv[r] = v; v = tv;
-            int tj = li[r]; li[r] = j; j = tj;
+        const bool hit = !placed && (lv[r] == thr);
+        lv[r] = hit ? v : lv[r];
+        li[r] = hit ? j : li[r];
+        placed = placed || hit;
+    }
+    float m = lv[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) m = fmaxf(m, lv[r]);
+    thr = m;
+}
+
+constexpr int EPI_WARPS = 8;                 // 2 per scheduler: warp e owns TMEM lanes 32*(e%4).. and columns 128*(e/4)..
+constexpr int EPI_COLS = BN / (EPI_WARPS / 4);   // 128 columns per epilogue warp
+constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
+
+// One accumulator tile (this warp's 32 rows x EPI_COLS columns): v = ‖x‖² − 2·s·acc, keep each row's R smallest.
+template <int R>
+__device__ __forceinline__ void epilogue_scan_tile(uint32_t taddr, const float* __restrict__ nxs, int jbase, float negc,
+                                                   float (&lv)[R], int (&li)[R], float& thr) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
+        uint32_t rr[32];
+        tc_ld32(taddr + c0, rr);
+        tc_wait_ld();
+        float vmin = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
+            float v0 = fmaf(negc, __uint_as_float(rr[i + 0]), nx4.x);
+            float v1 = fmaf(negc, __uint_as_float(rr[i + 1]), nx4.y);
+            float v2 = fmaf(negc, __uint_as_float(rr[i + 2]), nx4.z);
+            float v3 = fmaf(negc, __uint_as_float(rr[i + 3]), nx4.w);
+            rr[i + 0] = __float_as_uint(v0); rr[i + 1] = __float_as_uint(v1);
+            rr[i + 2] = __float_as_uint(v2); rr[i + 3] = __float_as_uint(v3);
+            vmin = fminf(vmin, fminf(fminf(v0, v1), fminf(v2, v3)));
+        }
+        if (__any_sync(0xffffffffu, vmin < thr)) {
+            // Rare path.  Per-lane hit mask, then ONE replacement body shared by every column: the column index is made
+            // warp-uniform (OR-reduction of the masks) so selecting rr[i] is a uniform switch, not 32 inlined bodies.
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m |= (__uint_as_float(rr[i]) < thr) ? (1u << i) : 0u;
+            uint32_t many = __reduce_or_sync(0xffffffffu, m);
+#pragma unroll 1
+            while (many) {
+                const int i = __ffs(many) - 1;
+                many &= many - 1;
+                uint32_t bits;
+                switch (i) {
+#define FIR_CASE(I) case I: bits = rr[I]; break;
+                    FIR_CASE(0) FIR_CASE(1) FIR_CASE(2) FIR_CASE(3) FIR_CASE(4) FIR_CASE(5) FIR_CASE(6) FIR_CASE(7)
+                    FIR_CASE(8) FIR_CASE(9) FIR_CASE(10) FIR_CASE(11) FIR_CASE(12) FIR_CASE(13) FIR_CASE(14) FIR_CASE(15)
+                    FIR_CASE(16) FIR_CASE(17) FIR_CASE(18) FIR_CASE(19) FIR_CASE(20) FIR_CASE(21) FIR_CASE(22) FIR_CASE(23)
+                    FIR_CASE(24) FIR_CASE(25) FIR_CASE(26) FIR_CASE(27) FIR_CASE(28) FIR_CASE(29) FIR_CASE(30)
+                    default: bits = rr[31]; break;
+#undef FIR_CASE
+                }
+                const float v = __uint_as_float(bits);
+                if (v < thr) topr_replace<R>(lv, li, thr, v, jbase + c0 + i);
+            }
         }
     }
 }
 
+// write one row's list: cand_val/cand_idx [(qrow * n_slots + slot) * R ..], slot_bound = the list's maximum if it is full
+template <int R>
+__device__ __forceinline__ void epilogue_flush(const CandParams& p, int64_t qrow, int slot, const float (&lv)[R], const int (&li)[R], float thr) {
+    if (qrow >= p.nq) return;
+    const float nqv = p.qry_norm2[qrow];
+    const int64_t o = (qrow * p.n_slots + slot) * R;
+    bool full = true;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        p.cand_val[o + r] = lv[r] + nqv;
+        // shadow position -> original gallery row (the fp16 copy is stored in a strided permutation)
+        p.cand_idx[o + r] = li[r] < 0 ? -1 : (int32_t)(((int64_t)li[r] * p.perm_a + p.perm_b) % p.n);
+        full = full && (li[r] >= 0);
+    }
+    p.slot_bound[qrow * p.n_slots + slot] = full ? thr + nqv : __int_as_float(0x7f800000);
+}
+
 template <int R, bool A_RES>
-__global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_constant__ CUtensorMap tmap_a,
+__global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                const __grid_constant__ CUtensorMap tmap_b, const CandParams p) {
     constexpr int STAGES = A_RES ? 3 : 4;
     constexpr int STAGE_BYTES = A_RES ? B_KB_BYTES : (A_KB_BYTES + B_KB_BYTES);
@@ -332,7 +417,7 @@ __global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_cons
         for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
         mbar_init(smem_u32(a_full), 1);
         mbar_init(smem_u32(a_empty), 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), 4); mbar_init(smem_u32(&nx_full[s]), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), EPI_WARPS); mbar_init(smem_u32(&nx_full[s]), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -415,93 +500,35 @@ __global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_cons
             as ^= 1; if (as == 0) aphase ^= 1;
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread = one query row; running top-R in registers =====
-        const int ew = warp - 4;                       // TMEM lane group of this warp = warp % 4
-        const int row = ew * 32 + lane;
+        // ===== epilogue: 8 warps; warp e = (TMEM lane group e%4, column half e/4); thread = one query row =====
+        const int e = warp - 4;
+        const int lg = e & 3, half = e >> 2;
+        const int row = lg * 32 + lane;
         const float sg = __uint_as_float(p.gal_meta[1]), sq = __uint_as_float(p.qry_meta[1]);
         const float negc = -2.0f / (sg * sq);
-        float lv[R]; int li[R];
+        float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000);
         int64_t cur_qb = -1;
         int as = 0; uint32_t aphase = 0;
-        auto flush = [&](int64_t qb) {
-            const int64_t qrow = qb * BM + row;
-            if (qrow < p.nq) {
-                const int slot = (int)(blockIdx.x - part_first_cta(P, qb * P.ntiles));
-                const float nqv = p.qry_norm2[qrow];
-                const int64_t o = (qrow * p.n_slots + slot) * R;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    p.cand_val[o + r] = lv[r] + nqv;
-                    // shadow position -> original gallery row (the fp16 copy is stored in a strided permutation)
-                    p.cand_idx[o + r] = li[r] < 0 ? -1 : (int32_t)(((int64_t)li[r] * p.perm_a + p.perm_b) % p.n);
-                }
-                p.slot_bound[qrow * p.n_slots + slot] = (li[R - 1] >= 0) ? lv[R - 1] + nqv : __int_as_float(0x7f800000);
-            }
-        };
         for (int64_t it = item_lo; it < item_hi; ++it) {
             const int64_t qb = it / P.ntiles, tile = it - qb * P.ntiles;
             if (qb != cur_qb) {
-                if (cur_qb >= 0) flush(cur_qb);
+                if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * BM + row), (int)(blockIdx.x - part_first_cta(P, cur_qb * P.ntiles)) * 2 + half, lv, li, thr);
 #pragma unroll
                 for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = -1; }
+                thr = __int_as_float(0x7f800000);
                 cur_qb = qb;
             }
             mbar_wait(smem_u32(&nx_full[as]), aphase);
             mbar_wait(smem_u32(&tmem_full[as]), aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * BN;
-            const float* nxs = nx_s + as * BN;
-            const int jbase = (int)(tile * BN);
-            float thr = lv[R - 1];
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t rr[32];
-                tc_ld32(taddr + c0, rr);
-                tc_wait_ld();
-                float vmin = __int_as_float(0x7f800000);
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
-                    float v0 = fmaf(negc, __uint_as_float(rr[i + 0]), nx4.x);
-                    float v1 = fmaf(negc, __uint_as_float(rr[i + 1]), nx4.y);
-                    float v2 = fmaf(negc, __uint_as_float(rr[i + 2]), nx4.z);
-                    float v3 = fmaf(negc, __uint_as_float(rr[i + 3]), nx4.w);
-                    rr[i + 0] = __float_as_uint(v0); rr[i + 1] = __float_as_uint(v1);
-                    rr[i + 2] = __float_as_uint(v2); rr[i + 3] = __float_as_uint(v3);
-                    vmin = fminf(vmin, fminf(fminf(v0, v1), fminf(v2, v3)));
-                }
-                if (__any_sync(0xffffffffu, vmin < thr)) {
-                    // Rare path.  Per-lane hit mask, then ONE insertion body shared by every column: the column
-                    // index is made warp-uniform (OR-reduction of the masks) so selecting rr[i] is a uniform switch.
-                    uint32_t m = 0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) m |= (__uint_as_float(rr[i]) < thr) ? (1u << i) : 0u;
-                    uint32_t many = __reduce_or_sync(0xffffffffu, m);
-#pragma unroll 1
-                    while (many) {
-                        const int i = __ffs(many) - 1;
-                        many &= many - 1;
-                        uint32_t bits;
-                        switch (i) {
-#define FIR_CASE(I) case I: bits = rr[I]; break;
-                            FIR_CASE(0) FIR_CASE(1) FIR_CASE(2) FIR_CASE(3) FIR_CASE(4) FIR_CASE(5) FIR_CASE(6) FIR_CASE(7)
-                            FIR_CASE(8) FIR_CASE(9) FIR_CASE(10) FIR_CASE(11) FIR_CASE(12) FIR_CASE(13) FIR_CASE(14) FIR_CASE(15)
-                            FIR_CASE(16) FIR_CASE(17) FIR_CASE(18) FIR_CASE(19) FIR_CASE(20) FIR_CASE(21) FIR_CASE(22) FIR_CASE(23)
-                            FIR_CASE(24) FIR_CASE(25) FIR_CASE(26) FIR_CASE(27) FIR_CASE(28) FIR_CASE(29) FIR_CASE(30)
-                            default: bits = rr[31]; break;
-#undef FIR_CASE
-                        }
-                        const float v = __uint_as_float(bits);
-                        if (v < thr) { topr_insert<R>(lv, li, v, jbase + c0 + i); thr = lv[R - 1]; }
-                    }
-                }
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + half * EPI_COLS);
+            epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, thr);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[as]));
+            if (lane == 0) { mbar_arrive(smem_u32(&tmem_empty[as])); }
             as ^= 1; if (as == 0) aphase ^= 1;
         }
-        if (cur_qb >= 0) flush(cur_qb);
+        if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * BM + row), (int)(blockIdx.x - part_first_cta(P, cur_qb * P.ntiles)) * 2 + half, lv, li, thr);
     }
 
     tc_fence_before();
@@ -512,6 +539,218 @@ __global__ void __launch_bounds__(256, 1) l2_candidates_kernel(const __grid_cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2).  Two CTAs of a cluster (the two SMs of a TPC) share every gallery tile:
+// each loads HALF of the 256-row B tile (128 rows x 64 k, 16 KiB per k-block) and keeps its own 128 query rows
+// of a 256-query block resident; one `tcgen05.mma.cta_group::2` (M = 256) issued by the leader CTA consumes both
+// halves and writes each CTA's 128 x 256 accumulator into that CTA's TMEM.  Per SM this halves the L2→SMEM bytes
+// per flop and doubles the number of k-blocks the same shared memory keeps in flight, which is what the single-CTA
+// kernel is bound by (ncu: tensor pipe 24 % active, TMA-wait dominated).
+//   barriers in the LEADER only : full[stage] (TMA bytes of both CTAs), a_full, tmem_empty[2] (8 epilogue warps)
+//   barriers in BOTH CTAs       : empty[stage], a_empty, tmem_full[2] (multicast tcgen05.commit), nx_full/nx_empty (local)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    // executed by both CTAs; clearing the peer bit of the barrier address makes the bytes count on CTA 0's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {     // arrive on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {   // arrive on CTA 0's copy of this barrier
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(0));
+    // relaxed: the arriving thread publishes no memory; its TMEM reads are already complete (tcgen05.wait::ld)
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// NOTE: waits stay at CTA scope.  A cluster-scope acquire in the try_wait loop makes ptxas emit CCTL.IVALL (an L1
+// invalidate) on every spin (ncu: 12 % of all stall samples); nothing waited for here is ordinary memory written by the
+// peer CTA — TMA bytes are published by complete_tx, accumulators by tcgen05.commit + tcgen05.fence::after_thread_sync.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256
+constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;   // 16 KiB
+
+template <int R, bool A_RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const CandParams p) {
+    constexpr int STAGES = 6;
+    constexpr int STAGE_BYTES = A_RES ? B_HALF_BYTES : (A_KB_BYTES + B_HALF_BYTES);
+    constexpr int A_RES_BYTES = A_RES ? MAX_RES_KB * A_KB_BYTES : 0;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* a_res = smem;
+    unsigned char* stage0 = smem + A_RES_BYTES;
+    float* nx_s = reinterpret_cast<float*>(stage0 + STAGES * STAGE_BYTES);          // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(nx_s + 2 * BN);
+    uint64_t* full_bar = bars;                    // [STAGES]  (leader's copy is the live one)
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* a_full = bars + 2 * STAGES;
+    uint64_t* a_empty = a_full + 1;
+    uint64_t* tmem_full = a_empty + 1;            // [2]
+    uint64_t* tmem_empty = tmem_full + 2;         // [2]  (leader's copy is the live one)
+    uint64_t* nx_full = tmem_empty + 2;           // [2]
+    uint64_t* nx_empty = nx_full + 2;             // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(nx_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1;
+    const Partition P = p.part;
+    const int64_t item_lo = part_lo(P, pair), item_hi = part_lo(P, (int64_t)pair + 1);
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        mbar_init(smem_u32(a_full), 1);
+        mbar_init(smem_u32(a_empty), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), 2 * EPI_WARPS);
+            mbar_init(smem_u32(&nx_full[s]), 1); mbar_init(smem_u32(&nx_empty[s]), EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer (both CTAs; every load reports to the leader's barriers) =====
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        int stage = 0; uint32_t phase = 0; uint32_t a_loads = 0;
+        int64_t cur_qb = -1;
+        for (int64_t it = item_lo; it < item_hi; ++it) {
+            const int64_t qb = it / P.ntiles, tile = it - qb * P.ntiles;
+            const int arow = (int)(qb * (2 * BM) + rank * BM);
+            if (A_RES && qb != cur_qb) {
+                mbar_wait(smem_u32(a_empty), (a_loads & 1) ^ 1);
+                if (leader) mbar_expect_tx(smem_u32(a_full), 2u * (uint32_t)p.nkb * A_KB_BYTES);
+                for (int kb = 0; kb < p.nkb; ++kb)
+                    tma_load_2d_2sm(smem_u32(a_res + kb * A_KB_BYTES), &tmap_a, smem_u32(a_full), kb * BK, arow);
+                ++a_loads;
+            }
+            cur_qb = qb;
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                unsigned char* st = stage0 + stage * STAGE_BYTES;
+                if (leader) mbar_expect_tx(smem_u32(&full_bar[stage]), 2u * STAGE_BYTES);
+                if (!A_RES) tma_load_2d_2sm(smem_u32(st + B_HALF_BYTES), &tmap_a, smem_u32(&full_bar[stage]), kb * BK, arow);
+                tma_load_2d_2sm(smem_u32(st), &tmap_b, smem_u32(&full_bar[stage]), kb * BK, (int)(tile * BN + rank * (BN / 2)));
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+        int stage = 0; uint32_t phase = 0; uint32_t a_uses = 0;
+        int as = 0; uint32_t aphase = 0;
+        int64_t cur_qb = -1;
+        for (int64_t it = item_lo; it < item_hi; ++it) {
+            const int64_t qb = it / P.ntiles;
+            if (A_RES && qb != cur_qb) { mbar_wait_cluster(smem_u32(a_full), a_uses & 1); ++a_uses; }
+            cur_qb = qb;
+            mbar_wait_cluster(smem_u32(&tmem_empty[as]), aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)as * BN;
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                mbar_wait_cluster(smem_u32(&full_bar[stage]), phase);
+                tc_fence_after();
+                unsigned char* st = stage0 + stage * STAGE_BYTES;
+                const uint64_t bdesc = make_sw128_desc(smem_u32(st));
+                const uint64_t adesc = make_sw128_desc(A_RES ? smem_u32(a_res + kb * A_KB_BYTES) : smem_u32(st + B_HALF_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k)
+                    tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc2, (kb | k) ? 1u : 0u);
+                tc_commit_2sm(smem_u32(&empty_bar[stage]));
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit_2sm(smem_u32(&tmem_full[as]));
+            if (A_RES) {
+                const bool last_of_qb = (it + 1 == item_hi) || ((it + 1) / P.ntiles != qb);
+                if (last_of_qb) tc_commit_2sm(smem_u32(a_empty));
+            }
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
+    } else if (warp == 3) {
+        // ===== norm loader (per CTA) =====
+        int as = 0; uint32_t aphase = 0;
+        for (int64_t it = item_lo; it < item_hi; ++it) {
+            const int64_t tile = it % P.ntiles;
+            mbar_wait(smem_u32(&nx_empty[as]), aphase ^ 1);
+            const float4* src = reinterpret_cast<const float4*>(p.gal_norm2 + tile * BN + lane * 8);
+            const float4 v0 = src[0], v1 = src[1];
+            float4* dst = reinterpret_cast<float4*>(&nx_s[as * BN + lane * 8]);
+            dst[0] = v0; dst[1] = v1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&nx_full[as]));
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: 8 warps; warp e = (TMEM lane group e%4, column half e/4); thread = one query row =====
+        const int e = warp - 4;
+        const int lg = e & 3, half = e >> 2;
+        const int row = lg * 32 + lane;
+        const float sg = __uint_as_float(p.gal_meta[1]), sq = __uint_as_float(p.qry_meta[1]);
+        const float negc = -2.0f / (sg * sq);
+        float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000);
+        int64_t cur_qb = -1;
+        int as = 0; uint32_t aphase = 0;
+        for (int64_t it = item_lo; it < item_hi; ++it) {
+            const int64_t qb = it / P.ntiles, tile = it - qb * P.ntiles;
+            if (qb != cur_qb) {
+                if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), (int)(pair - part_first_cta(P, cur_qb * P.ntiles)) * 2 + half, lv, li, thr);
+#pragma unroll
+                for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = -1; }
+                thr = __int_as_float(0x7f800000);
+                cur_qb = qb;
+            }
+            mbar_wait(smem_u32(&nx_full[as]), aphase);
+            mbar_wait_cluster(smem_u32(&tmem_full[as]), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + half * EPI_COLS);
+            epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, thr);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(smem_u32(&nx_empty[as])); if (leader) mbar_arrive(smem_u32(&tmem_empty[as])); else mbar_arrive_leader(smem_u32(&tmem_empty[as])); }
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
+        if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), (int)(pair - part_first_cta(P, cur_qb * P.ntiles)) * 2 + half, lv, li, thr);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();          // neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+static size_t cand_smem_bytes_2cta(bool a_res) {
+    size_t stages = 6 * (size_t)(a_res ? B_HALF_BYTES : (A_KB_BYTES + B_HALF_BYTES));
+    return (a_res ? (size_t)MAX_RES_KB * A_KB_BYTES : 0) + stages + 2 * BN * 4 + (2 * 6 + 10) * 8 + 16;
+}
+
 static size_t cand_smem_bytes(bool a_res) {
     size_t stages = a_res ? 3 * (size_t)B_KB_BYTES : 4 * (size_t)(A_KB_BYTES + B_KB_BYTES);
     return (a_res ? (size_t)MAX_RES_KB * A_KB_BYTES : 0) + stages + 2 * BN * 4 + 18 * 8 + 16;
@@ -520,7 +759,7 @@ static size_t cand_smem_bytes(bool a_res) {
 int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     CandParams p{};
     p.part.ntiles = ceil_div(a.gal->rows, BN);
-    p.part.nqb = ceil_div(a.qry->rows, BM);
+    p.part.nqb = ceil_div(a.qry->rows, BM * a.ctas);
     p.part.total = p.part.ntiles * p.part.nqb;
     p.part.grid = a.grid;
     p.nq = a.qry->rows; p.n = a.gal->rows;
@@ -531,38 +770,95 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     p.gal_meta = a.gal->meta; p.qry_meta = a.qry->meta;
     p.cand_val = a.cand_val; p.cand_idx = a.cand_idx; p.slot_bound = a.slot_bound;
     const bool a_res = p.nkb <= MAX_RES_KB;
-    const size_t smem = cand_smem_bytes(a_res);
+    const size_t smem = a.ctas == 2 ? cand_smem_bytes_2cta(a_res) : cand_smem_bytes(a_res);
     auto go = [&](auto kern) -> int {
         FIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<a.grid, 256, smem, s>>>(*a.tmap_a, *a.tmap_b, p);
+        kern<<<a.grid * a.ctas, NUM_THREADS, smem, s>>>(*a.tmap_a, *a.tmap_b, p);      // a.grid counts work units (CTAs or CTA pairs)
         FIR_CUDA_TRY(cudaGetLastError());
         return FIR_OK;
     };
-#define FIR_GO(RR) (a_res ? go(l2_candidates_kernel<RR, true>) : go(l2_candidates_kernel<RR, false>))
+#define FIR_GO(RR) (a.ctas == 2 ? (a_res ? go(l2_candidates_kernel_2cta<RR, true>) : go(l2_candidates_kernel_2cta<RR, false>)) \
+                                : (a_res ? go(l2_candidates_kernel<RR, true>) : go(l2_candidates_kernel<RR, false>)))
     switch (a.R) {
+        case 4: return FIR_GO(4);
         case 8: return FIR_GO(8);
         case 16: return FIR_GO(16);
-        case 32: return FIR_GO(32);
     }
 #undef FIR_GO
     return fail(FIR_ERR_INTERNAL, "unsupported candidate list length");
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Selection + certificate.  One thread per query.
+// Pruning, selection and certificate.  One warp per query.
 //   approx(q,x) = ‖q‖² + ‖x‖² − 2·(q̂·x̂);   true(q,x) = ‖q − x‖²
-//   |approx − true| ≤ E = 2(‖δq‖(‖x‖+‖δx‖) + ‖q‖‖δx‖) + 2γ‖q‖‖x‖ + η,   δ = fp16 rounding residual (measured),
+//   |approx − true| ≤ E = 2(‖δq‖(‖x‖+‖δx‖) + ‖q‖‖δx‖) + 2γ‖q‖‖x‖ + η,   δ = fp16 rounding residual (measured per vector),
 //   γ bounds the tensor core's fp32 accumulation error, η the fp32 roundings of the norms and of the fma.
 //   The reference distance is fl-sum/D with relative error ≤ ρ = (D+4)·2⁻²⁴ around true/D.
-// Every non-candidate row has approx ≥ B = min over slots of the slot's R-th approx, hence
-// reference·D ≥ (B − E)(1 − ρ).  The result is certified when that exceeds the k-th exact distance.
+// prune : a candidate whose approx exceeds the k-th smallest approx by more than 2E(1+ρ)-ish is strictly worse than k
+//         other candidates in the reference's own arithmetic — it cannot be in the answer, so it is not reranked.
+// select: top-k by (exact distance, index) over the reranked survivors.
+// certify: every non-candidate row has approx ≥ B = min over lists of the list's maximum, hence
+//         reference·D ≥ (B − E)(1 − ρ); certified when that exceeds the k-th exact distance (strictly).
 // ---------------------------------------------------------------------------------------------------
-__global__ void tensor_select_kernel(const float* __restrict__ cand_exact, const int32_t* __restrict__ cand_idx,
-                                     const float* __restrict__ slot_bound, int64_t nq, int n_slots, int R, int k, int d, int nkb,
-                                     const float* __restrict__ q_norm2, const float* __restrict__ q_resid,
-                                     const float* __restrict__ gal_stats, int64_t index_offset, float* __restrict__ out_dist,
-                                     int32_t* __restrict__ out_idx, int32_t* flagged, int32_t* n_flagged, float* max_bound) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ double approx_error_bound(double nq2, double rq, double NX, double RX, int nkb) {
+    const double nqn = sqrt(nq2);
+    const double gamma = (double)(4 * nkb + 8) * 2.384185791015625e-07;        // (#UMMA K-steps + 8) · 2⁻²²
+    return 2.0 * (rq * (NX + RX) + nqn * RX) + 2.0 * gamma * nqn * NX + 1e-6 * (nq2 + NX * NX + 2.0 * nqn * NX);
+}
+
+__global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ cand_val, int32_t* __restrict__ cand_idx, int64_t nq, int rt, int k,
+                                                           int d, int nkb, const float* __restrict__ q_norm2, const float* __restrict__ q_resid,
+                                                           const float* __restrict__ gal_stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    float* cv = cand_val + q * rt;
+    int32_t* ci = cand_idx + q * rt;
+    // k-th smallest approx among valid candidates: k rounds of "smallest value greater than the previous" (duplicates counted)
+    float kth = -__int_as_float(0x7f800000);
+    int taken = 0;
+    while (taken < k) {
+        float best = __int_as_float(0x7f800000); int cnt = 0;
+        for (int c = lane; c < rt; c += 32) {
+            if (ci[c] < 0) continue;
+            const float v = cv[c];
+            if (v > kth && v < best) best = v;
+        }
+        for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (!(best < __int_as_float(0x7f800000))) break;                       // fewer than k valid candidates
+        for (int c = lane; c < rt; c += 32) cnt += (ci[c] >= 0 && cv[c] == best) ? 1 : 0;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        kth = best; taken += cnt;
+    }
+    if (taken < k) return;                                                     // keep everything
+    const double E = approx_error_bound((double)q_norm2[q], (double)q_resid[q], (double)gal_stats[0], (double)gal_stats[1], nkb);
+    const double rho = (double)(d + 4) * 5.9604644775390625e-08;
+    // c is dominated when (approx_c − E)(1−ρ) > (kth + E)(1+ρ): then reference(c) > reference(each of the k best-by-approx)
+    const double cut = ((double)kth + E) * (1.0 + rho) / (1.0 - rho) + E;
+    // compact the survivors to the front (order is irrelevant downstream)
+    int base = 0;
+    for (int c0 = 0; c0 < rt; c0 += 32) {
+        const int c = c0 + lane;
+        int32_t idx = -1; float v = 0.f;
+        if (c < rt) { idx = ci[c]; v = cv[c]; }
+        const bool keep = idx >= 0 && !((double)v > cut);
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) { const int o = base + __popc(m & ((1u << lane) - 1)); ci[o] = idx; cv[o] = v; }   // o ≤ c: never overwrites an unread slot of a later group
+        base += __popc(m);
+    }
+    __syncwarp();
+    for (int c = base + lane; c < rt; c += 32) ci[c] = -1;
+}
+
+__global__ void __launch_bounds__(128) tensor_select_kernel(const float* __restrict__ cand_exact, const int32_t* __restrict__ cand_idx,
+                                                            const float* __restrict__ slot_bound, int64_t nq, int n_slots, int R, int k, int d, int nkb,
+                                                            const float* __restrict__ q_norm2, const float* __restrict__ q_resid,
+                                                            const float* __restrict__ gal_stats, int64_t index_offset, float* __restrict__ out_dist,
+                                                            int32_t* __restrict__ out_idx, int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags,
+                                                            float* max_bound) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (q >= nq) return;
     const int rt = n_slots * R;
     const float* ce = cand_exact + q * rt;
@@ -571,49 +867,61 @@ __global__ void tensor_select_kernel(const float* __restrict__ cand_exact, const
     int found = 0;
     float kth = 0.f;
     for (int r = 0; r < k; ++r) {
-        float bd = 0.f; int bi = -1;
-        for (int c = 0; c < rt; ++c) {
+        float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff;
+        for (int c = lane; c < rt; c += 32) {
             const int i = ci[c];
             if (i < 0) continue;
             const float dd = ce[c];
             if (!(dd < 100000.0f)) continue;                                   // ann.cpp:116: nothing ≥ 100000 is ever accepted
             if (r > 0 && !(dd > last_d || (dd == last_d && i > last_i))) continue;
-            if (bi < 0 || dd < bd || (dd == bd && i < bi)) { bd = dd; bi = i; }
+            if (dd < bd || (dd == bd && i < bi)) { bd = dd; bi = i; }
         }
-        if (bi >= 0) { out_dist[q * k + r] = bd; out_idx[q * k + r] = (int32_t)(bi + index_offset); last_d = bd; last_i = bi; ++found; kth = bd; }
-        else { out_dist[q * k + r] = 0.f; out_idx[q * k + r] = -1; last_d = __int_as_float(0x7f800000); }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (bi != 0x7fffffff) {
+            if (lane == 0) { out_dist[q * k + r] = bd; out_idx[q * k + r] = (int32_t)(bi + index_offset); }
+            last_d = bd; last_i = bi; ++found; kth = bd;
+        } else {
+            if (lane == 0) { out_dist[q * k + r] = 0.f; out_idx[q * k + r] = -1; }
+            last_d = __int_as_float(0x7f800000);
+        }
     }
+    if (lane != 0) return;
     double B = __longlong_as_double(0x7ff0000000000000LL);
     for (int s = 0; s < n_slots; ++s) {
         const float b = slot_bound[q * n_slots + s];
-        if (b == b && (double)b < B) B = (double)b;                            // NaN = slot never written = nothing excluded there
+        if (b == b && (double)b < B) B = (double)b;                            // NaN = list never written = nothing excluded there
     }
-    const double nq2 = (double)q_norm2[q], nqn = sqrt(nq2), rq = (double)q_resid[q];
-    const double NX = (double)gal_stats[0], RX = (double)gal_stats[1];
-    const double gamma = (double)(4 * nkb + 8) * 2.384185791015625e-07;        // (#UMMA K-steps + 8) · 2⁻²²
-    const double E = 2.0 * (rq * (NX + RX) + nqn * RX) + 2.0 * gamma * nqn * NX + 1e-6 * (nq2 + NX * NX + 2.0 * nqn * NX);
+    const double E = approx_error_bound((double)q_norm2[q], (double)q_resid[q], (double)gal_stats[0], (double)gal_stats[1], nkb);
     const double rho = (double)(d + 4) * 5.9604644775390625e-08;
     bool ok;
     if (isinf(B)) ok = true;                                                   // every row of the gallery was a candidate
     else if (found < k) ok = false;
     else ok = (B - E) * (1.0 - rho) > (double)kth * (double)d * (1.0 + rho);
-    if (!ok) { int pos = atomicAdd(n_flagged, 1); flagged[pos] = (int32_t)q; }
+    if (!ok) { int pos = atomicAdd(n_flagged, 1); flagged[pos] = (int32_t)q; if (fail_flags) fail_flags[q] = 1; }
     atomicMax(reinterpret_cast<unsigned int*>(max_bound), __float_as_uint((float)E));
 }
 
-int launch_tensor_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots, int R,
-                         int k, int d, const float* q_norm2, const float* q_resid, const float* gal_stats, int64_t index_offset,
-                         float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged, float* max_bound, cudaStream_t s) {
+int launch_tensor_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, int d, const float* q_norm2, const float* q_resid,
+                        const float* gal_stats, cudaStream_t s) {
     const int nkb = round_up(d, BK) / BK;
-    tensor_select_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, d, nkb, q_norm2,
-                                                                     q_resid, gal_stats, index_offset, out_dist, out_idx, flagged,
-                                                                     n_flagged, max_bound);
+    tensor_prune_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cand_val, cand_idx, nq, rt, k, d, nkb, q_norm2, q_resid, gal_stats);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
 
-// flagged-query lists must come out in a deterministic order for the exact re-run's partial buffers: they
-// do not need to (each flagged query owns its output rows), so no sort is required.
+int launch_tensor_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots, int R,
+                         int k, int d, const float* q_norm2, const float* q_resid, const float* gal_stats, int64_t index_offset,
+                         float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags, float* max_bound, cudaStream_t s) {
+    const int nkb = round_up(d, BK) / BK;
+    tensor_select_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, d, nkb, q_norm2,
+                                                                   q_resid, gal_stats, index_offset, out_dist, out_idx, flagged,
+                                                                   n_flagged, fail_flags, max_bound);
+    FIR_CUDA_TRY(cudaGetLastError());
+    return FIR_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Orchestration of one fir_search_topk call on the tensor path
@@ -626,22 +934,101 @@ static int ensure_gallery_side(fir_gallery* g) {
     FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, 64, g->stream));
     FIR_TRY(tensor_pack_side(g->rows, g->n, g->dp, g->d, BN, g->tensor_buf, &g->tside, g->d_stats, true, g->stream));
     FIR_TRY(tensor_encode_map(&g->tmap_b, g->tside.h, g->tside.rows_padded, g->tside.dph, BN));
+    FIR_TRY(tensor_encode_map(&g->tmap_b_half, g->tside.h, g->tside.rows_padded, g->tside.dph, BN / 2));
     g->tensor_ready = true;
     return FIR_OK;
 }
 
+// second-chance plumbing ---------------------------------------------------------------------------
+__global__ void gather_flagged_rows_kernel(const float* __restrict__ q, int ld, const int32_t* __restrict__ flagged,
+                                           const int32_t* __restrict__ n_flagged, int64_t cap, float* __restrict__ out) {
+    const int64_t i = blockIdx.x;                       // compact row
+    const int64_t nf = min((int64_t)*n_flagged, cap);
+    const float* src = i < nf ? q + (int64_t)flagged[i] * ld : nullptr;
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) out[i * ld + c] = src ? src[c] : 0.f;
+}
+// results of the second pass go back to their queries; what it could not certify either (or what did not fit in the
+// second pass) is queued for the exact re-run
+__global__ void escalation_scatter_kernel(const int32_t* __restrict__ flagged, const int32_t* __restrict__ n_flagged, int64_t cap,
+                                          const unsigned char* __restrict__ fail2, const float* __restrict__ d2, const int32_t* __restrict__ i2,
+                                          int k, float* __restrict__ od, int32_t* __restrict__ oi, int32_t* __restrict__ final_list,
+                                          int32_t* __restrict__ n_final) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nf = *n_flagged;
+    if (i >= nf) return;
+    const int32_t q = flagged[i];
+    if (i < cap && !fail2[i]) {
+        for (int r = 0; r < k; ++r) { od[(int64_t)q * k + r] = d2[i * k + r]; oi[(int64_t)q * k + r] = i2[i * k + r]; }
+    } else {
+        final_list[atomicAdd(n_final, 1)] = q;
+    }
+}
+
+namespace {
+struct PassBuffers { void* qbuf; float* cand_val; int32_t* cand_idx; float* cand_exact; float* slot_bound; int n_slots, grid, R; size_t qside; };
+
+size_t pass_bytes(fir_gallery* g, int64_t nq, int R, int ctas, PassBuffers* pb) {
+    int grid = 0, n_slots = 1;
+    tensor_plan(nq, g->n, g->n_sm, ctas, &grid, &n_slots);
+    n_slots *= EPI_WARPS / 4;                           // one list per (CTA slot, column half)
+    pb->n_slots = n_slots; pb->grid = grid; pb->R = R;
+    pb->qside = tensor_side_bytes(nq, g->d, BM);
+    return pb->qside + 3 * al256((size_t)nq * n_slots * R * 4) + al256((size_t)nq * n_slots * 4) + 2048;
+}
+bool pass_take(fir_gallery* g, int64_t nq, PassBuffers* pb) {
+    const size_t cells = (size_t)nq * pb->n_slots * pb->R;
+    pb->qbuf = g->ws.take(pb->qside);
+    pb->cand_val = (float*)g->ws.take(cells * 4);
+    pb->cand_idx = (int32_t*)g->ws.take(cells * 4);
+    pb->cand_exact = (float*)g->ws.take(cells * 4);
+    pb->slot_bound = (float*)g->ws.take((size_t)nq * pb->n_slots * 4);
+    return pb->qbuf && pb->cand_val && pb->cand_idx && pb->cand_exact && pb->slot_bound;
+}
+// pack → tcgen05 candidates → exact rerank → select + certificate, for nq device-resident fp32 queries
+int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const PassBuffers& pb, int64_t index_offset, float* od, int32_t* oi,
+             int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags, float* max_bound) {
+    TensorSide qs;
+    FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, pb.qbuf, &qs, nullptr, false, g->stream));
+    CUtensorMap tmap_a;
+    FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
+    const int rt = pb.n_slots * pb.R;
+    FIR_CUDA_TRY(cudaMemsetAsync(pb.cand_idx, 0xFF, (size_t)nq * rt * 4, g->stream));
+    FIR_CUDA_TRY(cudaMemsetAsync(pb.slot_bound, 0xFF, (size_t)nq * pb.n_slots * 4, g->stream));
+    TensorSearchArgs a{};
+    a.gal = &g->tside; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = ctas == 2 ? &g->tmap_b_half : &g->tmap_b; a.ctas = ctas;
+    a.d = g->d; a.R = pb.R; a.n_slots = pb.n_slots; a.cand_val = pb.cand_val; a.cand_idx = pb.cand_idx; a.slot_bound = pb.slot_bound; a.grid = pb.grid;
+    { auto* ev = g->prof_begin(FIR_KERNEL_L2_CANDIDATES); int st_ = launch_tensor_candidates(a, g->stream); g->prof_end(ev); FIR_TRY(st_); }
+    FIR_TRY(launch_tensor_prune(pb.cand_val, pb.cand_idx, nq, rt, k, g->d, qs.norm2, qs.resid, g->d_stats, g->stream));
+    FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, pb.cand_idx, rt, 0, pb.cand_exact, g->stream));
+    FIR_TRY(launch_tensor_select(pb.cand_exact, pb.cand_idx, pb.slot_bound, nq, pb.n_slots, pb.R, k, g->d, qs.norm2, qs.resid, g->d_stats, index_offset, od,
+                                 oi, flagged, n_flagged, fail_flags, max_bound, g->stream));
+    g->stats.gpu_launches += 6;   // absmax, pack, candidates, prune, rerank, select
+    return FIR_OK;
+}
+}  // namespace
+
 int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist) {
     FIR_TRY(ensure_gallery_side(g));
-    const int R = k <= 4 ? 8 : (k <= 12 ? 16 : 32);
-    int grid = 0, n_slots = 1;
-    FIR_TRY(tensor_plan(nq, g->n, g->n_sm, &grid, &n_slots));
-    const int rt = n_slots * R;
-    // certificate failures are rare: spread each flagged query block over many gallery splits (bounded scratch)
-    const int nsplit_fb = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(256, ceil_div(g->n, 64 * 4)),
-                                                                     ((int64_t)64 << 20) / std::max<int64_t>(1, nq * k * 8)));
-    const size_t qside = tensor_side_bytes(nq, g->d, BM);
-    size_t need = al256(sizeof(float) * (size_t)nq * g->dp) + qside + 3 * al256((size_t)nq * rt * 4) + al256((size_t)nq * n_slots * 4) +
-                  al256((size_t)nq * 4) + 2 * al256((size_t)nq * k * 4) + 2 * al256((size_t)nq * nsplit_fb * k * 4) + 8192;
+    const int ctas = tensor_cta_mode();
+    // Pass 1: each query gets (slots x 2 column halves) short lists over disjoint, pseudo-randomly interleaved parts of the
+    // gallery — cheap to maintain (cost ~ R² per list).  A list that would have needed more than R of the k best makes the
+    // certificate fail; those few queries get a second tensor pass with long lists, and only what even that cannot
+    // certify (mass exact ties) is re-run through the exact CUDA-core kernel.  All counts stay on the device.
+    const int64_t cap2 = std::min<int64_t>(nq, 1024);                      // queries served by the second pass
+    PassBuffers p1{}, p2{};
+    pass_bytes(g, nq, 4, ctas, &p1);
+    pass_bytes(g, cap2, 4, ctas, &p2);
+    // list length from the number of lists L a query is spread over: room for ~2.5 k / L of the k best, plus slack
+    auto pick_R = [&](int lists, int extra) { int want = (5 * k + 2 * lists - 1) / (2 * lists) + 2 + extra; return want <= 4 ? 4 : (want <= 8 ? 8 : 16); };
+    const int R1 = pick_R(p1.n_slots, 0);
+    const int R2 = pick_R(p2.n_slots, p2.n_slots > p1.n_slots ? 0 : 8);    // same list structure ⇒ longer lists, else a re-deal is enough
+    const bool second = true;
+    const int64_t kFbWindow = 4096;
+    const int nsplit_fb = (int)std::max<int64_t>(1, std::min<int64_t>(64, ceil_div(g->n, 64 * 4)));
+    const int64_t fb_rows = std::min<int64_t>(nq, kFbWindow);
+    size_t need = al256(sizeof(float) * (size_t)nq * g->dp) + pass_bytes(g, nq, R1, ctas, &p1) + 3 * al256((size_t)nq * 4) +
+                  2 * al256((size_t)nq * k * 4) + 2 * al256((size_t)fb_rows * nsplit_fb * k * 4) + 16384;
+    if (second) need += pass_bytes(g, cap2, R2, ctas, &p2) + al256(sizeof(float) * (size_t)cap2 * g->dp) + 2 * al256((size_t)cap2 * k * 4) + 2 * al256((size_t)cap2 * 4);
     FIR_TRY(g->ws.reserve(need));
     // fp32 queries, zero padded (for the exact rerank and the certificate fallback)
     const float* dq = nullptr;
@@ -662,44 +1049,47 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
             dq = buf;
         }
     }
-    void* qbuf = g->ws.take(qside);
-    float* cand_val = (float*)g->ws.take((size_t)nq * rt * 4);
-    int32_t* cand_idx = (int32_t*)g->ws.take((size_t)nq * rt * 4);
-    float* cand_exact = (float*)g->ws.take((size_t)nq * rt * 4);
-    float* slot_bound = (float*)g->ws.take((size_t)nq * n_slots * 4);
     int32_t* flagged = (int32_t*)g->ws.take((size_t)nq * 4);
+    int32_t* final_list = (int32_t*)g->ws.take((size_t)nq * 4);
     float* od = out_dist; int32_t* oi = out_idx;
     if (memspace == FIR_HOST || !out_dist) od = (float*)g->ws.take((size_t)nq * k * 4);
     if (memspace == FIR_HOST) oi = (int32_t*)g->ws.take((size_t)nq * k * 4);
-    float* part_d = (float*)g->ws.take((size_t)nq * nsplit_fb * k * 4);
-    int32_t* part_i = (int32_t*)g->ws.take((size_t)nq * nsplit_fb * k * 4);
-    if (!qbuf || !cand_val || !cand_idx || !cand_exact || !slot_bound || !flagged || !od || !oi || !part_d || !part_i)
+    float* part_d = (float*)g->ws.take((size_t)fb_rows * nsplit_fb * k * 4);
+    int32_t* part_i = (int32_t*)g->ws.take((size_t)fb_rows * nsplit_fb * k * 4);
+    if (!pass_take(g, nq, &p1) || !flagged || !final_list || !od || !oi || !part_d || !part_i)
         return fail(FIR_ERR_INTERNAL, "workspace underestimated (tensor path)");
+    // device counters: [4] flagged after pass 1, [5] max bound, [6] flagged inside pass 2 (unused list), [7] final exact re-runs
     int32_t* n_flagged = reinterpret_cast<int32_t*>(g->d_stats + 4);
     float* max_bound = g->d_stats + 5;
-    FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats + 4, 0, 8, g->stream));
+    int32_t* n_flagged2 = reinterpret_cast<int32_t*>(g->d_stats + 6);
+    int32_t* n_final = reinterpret_cast<int32_t*>(g->d_stats + 7);
+    FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats + 4, 0, 16, g->stream));
 
-    TensorSide qs;
-    FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, qbuf, &qs, nullptr, false, g->stream));
-    CUtensorMap tmap_a;
-    FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
-    FIR_CUDA_TRY(cudaMemsetAsync(cand_idx, 0xFF, (size_t)nq * rt * 4, g->stream));
-    FIR_CUDA_TRY(cudaMemsetAsync(slot_bound, 0xFF, (size_t)nq * n_slots * 4, g->stream));
-    TensorSearchArgs a{};
-    a.gal = &g->tside; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = &g->tmap_b;
-    a.d = g->d; a.R = R; a.n_slots = n_slots; a.cand_val = cand_val; a.cand_idx = cand_idx; a.slot_bound = slot_bound; a.grid = grid;
-    { auto* ev = g->prof_begin(FIR_KERNEL_L2_CANDIDATES); int st_ = launch_tensor_candidates(a, g->stream); g->prof_end(ev); FIR_TRY(st_); }
-    FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, cand_idx, rt, 0, cand_exact, g->stream));
-    FIR_TRY(launch_tensor_select(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, g->d, qs.norm2, qs.resid, g->d_stats, g->index_offset, od,
-                                 oi, flagged, n_flagged, max_bound, g->stream));
-    // certificate failures: exact CUDA-core re-run of just those queries (device-side count, no host sync)
-    FIR_TRY(exact_topk_device(g, dq, nq, k, g->d, flagged, n_flagged, part_d, part_i, nsplit_fb, od, oi));
-    g->stats.gpu_launches += 5;   // absmax, pack, candidates, rerank, select (+2 counted by exact_topk_device)
+    FIR_TRY(run_pass(g, dq, nq, k, ctas, p1, g->index_offset, od, oi, flagged, n_flagged, nullptr, max_bound));
+    const int32_t* exact_list = flagged; const int32_t* exact_count = n_flagged;
+    if (second) {
+        float* dq2 = (float*)g->ws.take(sizeof(float) * (size_t)cap2 * g->dp);
+        float* od2 = (float*)g->ws.take((size_t)cap2 * k * 4);
+        int32_t* oi2 = (int32_t*)g->ws.take((size_t)cap2 * k * 4);
+        int32_t* flagged2 = (int32_t*)g->ws.take((size_t)cap2 * 4);
+        unsigned char* fail2 = (unsigned char*)g->ws.take((size_t)cap2);
+        if (!pass_take(g, cap2, &p2) || !dq2 || !od2 || !oi2 || !flagged2 || !fail2) return fail(FIR_ERR_INTERNAL, "workspace underestimated (second pass)");
+        gather_flagged_rows_kernel<<<(unsigned)cap2, 128, 0, g->stream>>>(dq, g->dp, flagged, n_flagged, cap2, dq2);
+        FIR_CUDA_TRY(cudaMemsetAsync(fail2, 0, (size_t)cap2, g->stream));
+        FIR_TRY(run_pass(g, dq2, cap2, k, ctas, p2, g->index_offset, od2, oi2, flagged2, n_flagged2, fail2, max_bound));
+        escalation_scatter_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, g->stream>>>(flagged, n_flagged, cap2, fail2, od2, oi2, k, od, oi, final_list, n_final);
+        FIR_CUDA_TRY(cudaGetLastError());
+        g->stats.gpu_launches += 2;
+        exact_list = final_list; exact_count = n_final;
+    }
+    // what is still uncertified: exact CUDA-core re-run (device-side count; windows past it exit immediately)
+    for (int64_t off = 0; off < nq; off += kFbWindow)
+        FIR_TRY(exact_topk_device(g, dq, nq, k, g->d, exact_list, exact_count, part_d, part_i, nsplit_fb, od, oi, off, kFbWindow));
     g->stats.path_used = FIR_PATH_TENSOR;
-    g->stats.n_candidates = rt;
+    g->stats.n_candidates = p1.n_slots * p1.R;
     g->stats.n_fallback = -1;     // resolved lazily by fir_search_last_stats
-    g->dbg_cand_val = cand_val; g->dbg_cand_exact = cand_exact; g->dbg_cand_idx = cand_idx;
-    g->dbg_nq = nq; g->dbg_slots = n_slots; g->dbg_R = R;
+    g->dbg_cand_val = p1.cand_val; g->dbg_cand_exact = p1.cand_exact; g->dbg_cand_idx = p1.cand_idx;
+    g->dbg_nq = nq; g->dbg_slots = p1.n_slots; g->dbg_R = p1.R;
     if (memspace == FIR_HOST) {
         FIR_CUDA_TRY(cudaMemcpyAsync(out_idx, oi, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
         if (out_dist) FIR_CUDA_TRY(cudaMemcpyAsync(out_dist, od, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));

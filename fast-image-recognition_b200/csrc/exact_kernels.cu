@@ -356,23 +356,20 @@ __global__ void __launch_bounds__(PW * 32) pair_distance_kernel(const float* __r
     const int ld_lim = ldx;   // rows are zero padded up to ldx
     for (int c0 = 0; c0 < d_end; c0 += PCH) {
         const int col = c0 + lane * 4;
-#pragma unroll 2
-        for (int c = 0; c < 32; c += 4) {                    // 4 independent row loads in flight per lane
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int32_t ci = __shfl_sync(0xffffffffu, my, c + u);
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ci >= 0 && col < ld_lim) v[u] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)ci * ldx + col));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(&tile[(c + u) * PLD + lane * 4]) = v[u];
+        // stage this 128-dim slab of every valid candidate row straight into shared memory with cp.async: all row
+        // fetches of the slab are in flight together (one DRAM round trip per slab instead of one per row)
+        for (int c = 0; c < 32; ++c) {
+            const int32_t ci = __shfl_sync(0xffffffffu, my, c);
+            if (ci < 0) { *reinterpret_cast<float4*>(&tile[c * PLD + lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f); continue; }   // warp-uniform
+            const bool ok = col < ld_lim;
+            cp_async16(&tile[c * PLD + lane * 4], x + (int64_t)ci * ldx + (ok ? col : 0), ok ? 16 : 0);
         }
         {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col < ldq_eff) v = *reinterpret_cast<const float4*>(qrow + col);
-            *reinterpret_cast<float4*>(&qv[lane * 4]) = v;
+            const bool ok = col < ldq_eff;
+            cp_async16(&qv[lane * 4], qrow + (ok ? col : 0), ok ? 16 : 0);
         }
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncwarp();
         const int kmax = min(PCH, d_end - c0);
         const float* row = tile + lane * PLD;

@@ -98,10 +98,10 @@ struct TensorSearchArgs {
     int n_slots;
     float* cand_val; int32_t* cand_idx;   // [nq][n_slots][R]
     float* slot_bound;                    // [nq][n_slots]
-    int grid;
+    int grid; int n_sm;
     int ctas;                     // 1: cta_group::1 kernel, 2: CTA-pair kernel (grid counts pairs)
 };
-int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots);
+int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots, int* min_slots = nullptr);
 int tensor_cta_mode();
 int tensor_encode_map(CUtensorMap* map, const __half* base, int64_t rows_padded, int dph, int box_rows);
 int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s);

@@ -264,23 +264,54 @@ int tensor_encode_map(CUtensorMap* map, const __half* base, int64_t rows_padded,
 // `grid` contiguous, equally sized ranges — one per CTA.  A query block is therefore covered by at
 // most n_slots consecutive CTAs, each of which writes its own candidate slot.
 // ---------------------------------------------------------------------------------------------------
-struct Partition { int64_t ntiles, nqb, total; int grid; };
-__host__ __device__ inline int64_t part_lo(const Partition& P, int64_t c) { return c * P.total / P.grid; }
-__host__ __device__ inline int64_t part_first_cta(const Partition& P, int64_t item) { return ((item + 1) * P.grid - 1) / P.total; }
-
-int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots) {
+// Work partition.  Units are CTAs (or CTA pairs); a query block is BM (or 2·BM) queries; an item is (query block, tile).
+//  * FULL ROUNDS: while at least `grid` query blocks remain, unit u takes query block r·grid + u and sweeps ALL gallery tiles
+//    from tile 0.  Every unit walks the gallery in the same order at the same pace, so a B tile is fetched from HBM once per
+//    round and served to the other units from L2 — this is what keeps a 10 GB gallery from being re-streamed per query block.
+//  * REMAINDER: the last nqb mod grid query blocks are cut, in query-block-major item order, into `grid` contiguous, equally
+//    sized ranges (perfect balance); a remainder query block is then covered by several consecutive units, one slot each.
+struct Partition { int64_t ntiles, nqb, full_rounds, rem_total; int grid; };
+__host__ __device__ inline int64_t part_rem_lo(const Partition& P, int64_t u) { return u * P.rem_total / P.grid; }
+__host__ __device__ inline int64_t part_count(const Partition& P, int64_t u) {
+    return P.full_rounds * P.ntiles + (part_rem_lo(P, u + 1) - part_rem_lo(P, u));
+}
+__host__ __device__ inline void part_locate(const Partition& P, int64_t u, int64_t li, int64_t& qb, int64_t& tile) {
+    const int64_t full_items = P.full_rounds * P.ntiles;
+    if (li < full_items) { const int64_t r = li / P.ntiles; qb = r * P.grid + u; tile = li - r * P.ntiles; }
+    else { const int64_t it = part_rem_lo(P, u) + (li - full_items); const int64_t q = it / P.ntiles; qb = P.full_rounds * P.grid + q; tile = it - q * P.ntiles; }
+}
+__host__ __device__ inline int part_slot(const Partition& P, int64_t u, int64_t qb) {
+    const int64_t rq = qb - P.full_rounds * P.grid;
+    if (rq < 0) return 0;
+    const int64_t first = ((rq * P.ntiles + 1) * P.grid - 1) / P.rem_total;     // first unit whose range reaches this query block
+    return (int)(u - first);
+}
+inline Partition make_partition(int64_t nq, int64_t n, int n_sm, int ctas) {
     Partition P;
     P.ntiles = ceil_div(n, BN);
     P.nqb = ceil_div(nq, BM * ctas);
-    P.total = P.ntiles * P.nqb;
-    P.grid = (int)std::min<int64_t>(P.total, n_sm / ctas);     // work units: CTAs, or CTA pairs
-    int slots = 1;
-    for (int64_t qb = 0; qb < P.nqb; ++qb) {
-        int64_t c0 = part_first_cta(P, qb * P.ntiles), c1 = part_first_cta(P, (qb + 1) * P.ntiles - 1);
-        slots = std::max<int>(slots, (int)(c1 - c0 + 1));
+    const int64_t units = std::max<int64_t>(1, n_sm / ctas);
+    P.full_rounds = P.nqb / units;
+    const int64_t rem_qb = P.nqb - P.full_rounds * units;
+    P.rem_total = rem_qb * P.ntiles;
+    P.grid = (int)(P.full_rounds > 0 ? units : std::min<int64_t>(units, std::max<int64_t>(1, P.rem_total)));
+    return P;
+}
+
+int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots, int* min_slots) {
+    const Partition P = make_partition(nq, n, n_sm, ctas);
+    int slots = 1, least = P.full_rounds > 0 ? 1 : (1 << 30);
+    const int64_t rem_qb = P.nqb - P.full_rounds * P.grid;
+    for (int64_t rq = 0; rq < rem_qb; ++rq) {
+        const int64_t qb = P.full_rounds * P.grid + rq;
+        const int64_t last_item = (rq + 1) * P.ntiles - 1;
+        const int64_t last_unit = ((last_item + 1) * P.grid - 1) / P.rem_total;
+        slots = std::max<int>(slots, part_slot(P, last_unit, qb) + 1);
+        least = std::min<int>(least, part_slot(P, last_unit, qb) + 1);
     }
     *grid = P.grid;
     *n_slots = slots;
+    if (min_slots) *min_slots = least == (1 << 30) ? 1 : least;
     return FIR_OK;
 }
 
@@ -410,7 +441,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Partition P = p.part;
-    const int64_t item_lo = part_lo(P, blockIdx.x), item_hi = part_lo(P, (int64_t)blockIdx.x + 1);
+    const int64_t unit = blockIdx.x;
+    const int64_t n_items = part_count(P, unit);
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();     // SWIZZLE_128B tiles need 1 KiB alignment
@@ -435,8 +467,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         int stage = 0; uint32_t phase = 0; uint32_t a_loads = 0;
         int64_t cur_qb = -1;
-        for (int64_t it = item_lo; it < item_hi; ++it) {
-            const int64_t qb = it / P.ntiles, tile = it - qb * P.ntiles;
+        for (int64_t it = 0; it < n_items; ++it) {
+            int64_t qb, tile;
+            part_locate(P, unit, it, qb, tile);
             if (A_RES && qb != cur_qb) {
                 mbar_wait(smem_u32(a_empty), (a_loads & 1) ^ 1);      // every MMA that read the old A has retired
                 mbar_expect_tx(smem_u32(a_full), (uint32_t)p.nkb * A_KB_BYTES);
@@ -459,8 +492,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
         int stage = 0; uint32_t phase = 0; uint32_t a_uses = 0;
         int as = 0; uint32_t aphase = 0;
         int64_t cur_qb = -1;
-        for (int64_t it = item_lo; it < item_hi; ++it) {
-            const int64_t qb = it / P.ntiles;
+        for (int64_t it = 0; it < n_items; ++it) {
+            int64_t qb, tile_unused;
+            part_locate(P, unit, it, qb, tile_unused);
             if (A_RES && qb != cur_qb) { mbar_wait(smem_u32(a_full), a_uses & 1); ++a_uses; }
             cur_qb = qb;
             mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);         // epilogue has drained this accumulator
@@ -480,7 +514,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
             }
             tc_commit(smem_u32(&tmem_full[as]));                      // accumulator ready for the epilogue
             if (A_RES) {
-                const bool last_of_qb = (it + 1 == item_hi) || ((it + 1) / P.ntiles != qb);
+                bool last_of_qb = it + 1 == n_items;
+                if (!last_of_qb) { int64_t nqb_, nt_; part_locate(P, unit, it + 1, nqb_, nt_); last_of_qb = nqb_ != qb; }
                 if (last_of_qb) tc_commit(smem_u32(a_empty));
             }
             as ^= 1; if (as == 0) aphase ^= 1;
@@ -488,8 +523,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
     } else if (warp == 3) {
         // ===== norm loader: stages each tile's 256 gallery norms into nx_s[as] for the epilogue warps =====
         int as = 0; uint32_t aphase = 0;
-        for (int64_t it = item_lo; it < item_hi; ++it) {
-            const int64_t tile = it % P.ntiles;
+        for (int64_t it = 0; it < n_items; ++it) {
+            int64_t qb_unused, tile;
+            part_locate(P, unit, it, qb_unused, tile);
             mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);         // epilogue finished with this buffer pair
             const float4* src = reinterpret_cast<const float4*>(p.gal_norm2 + tile * BN + lane * 8);
             const float4 v0 = src[0], v1 = src[1];
@@ -509,10 +545,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
         float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000);
         int64_t cur_qb = -1;
         int as = 0; uint32_t aphase = 0;
-        for (int64_t it = item_lo; it < item_hi; ++it) {
-            const int64_t qb = it / P.ntiles, tile = it - qb * P.ntiles;
+        for (int64_t it = 0; it < n_items; ++it) {
+            int64_t qb, tile;
+            part_locate(P, unit, it, qb, tile);
             if (qb != cur_qb) {
-                if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * BM + row), (int)(blockIdx.x - part_first_cta(P, cur_qb * P.ntiles)) * 2 + half, lv, li, thr);
+                if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
 #pragma unroll
                 for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = -1; }
                 thr = __int_as_float(0x7f800000);
@@ -528,7 +565,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
             if (lane == 0) { mbar_arrive(smem_u32(&tmem_empty[as])); }
             as ^= 1; if (as == 0) aphase ^= 1;
         }
-        if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * BM + row), (int)(blockIdx.x - part_first_cta(P, cur_qb * P.ntiles)) * 2 + half, lv, li, thr);
+        if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
     }
 
     tc_fence_before();
@@ -613,7 +650,8 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1;
     const Partition P = p.part;
-    const int64_t item_lo = part_lo(P, pair), item_hi = part_lo(P, (int64_t)pair + 1);
+    const int64_t unit = pair;
+    const int64_t n_items = part_count(P, unit);
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -641,8 +679,9 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         int stage = 0; uint32_t phase = 0; uint32_t a_loads = 0;
         int64_t cur_qb = -1;
-        for (int64_t it = item_lo; it < item_hi; ++it) {
-            const int64_t qb = it / P.ntiles, tile = it - qb * P.ntiles;
+        for (int64_t it = 0; it < n_items; ++it) {
+            int64_t qb, tile;
+            part_locate(P, unit, it, qb, tile);
             const int arow = (int)(qb * (2 * BM) + rank * BM);
             if (A_RES && qb != cur_qb) {
                 mbar_wait(smem_u32(a_empty), (a_loads & 1) ^ 1);
@@ -666,8 +705,9 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         int stage = 0; uint32_t phase = 0; uint32_t a_uses = 0;
         int as = 0; uint32_t aphase = 0;
         int64_t cur_qb = -1;
-        for (int64_t it = item_lo; it < item_hi; ++it) {
-            const int64_t qb = it / P.ntiles;
+        for (int64_t it = 0; it < n_items; ++it) {
+            int64_t qb, tile_unused;
+            part_locate(P, unit, it, qb, tile_unused);
             if (A_RES && qb != cur_qb) { mbar_wait_cluster(smem_u32(a_full), a_uses & 1); ++a_uses; }
             cur_qb = qb;
             mbar_wait_cluster(smem_u32(&tmem_empty[as]), aphase ^ 1);
@@ -687,7 +727,8 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
             }
             tc_commit_2sm(smem_u32(&tmem_full[as]));
             if (A_RES) {
-                const bool last_of_qb = (it + 1 == item_hi) || ((it + 1) / P.ntiles != qb);
+                bool last_of_qb = it + 1 == n_items;
+                if (!last_of_qb) { int64_t nqb_, nt_; part_locate(P, unit, it + 1, nqb_, nt_); last_of_qb = nqb_ != qb; }
                 if (last_of_qb) tc_commit_2sm(smem_u32(a_empty));
             }
             as ^= 1; if (as == 0) aphase ^= 1;
@@ -695,8 +736,9 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
     } else if (warp == 3) {
         // ===== norm loader (per CTA) =====
         int as = 0; uint32_t aphase = 0;
-        for (int64_t it = item_lo; it < item_hi; ++it) {
-            const int64_t tile = it % P.ntiles;
+        for (int64_t it = 0; it < n_items; ++it) {
+            int64_t qb_unused, tile;
+            part_locate(P, unit, it, qb_unused, tile);
             mbar_wait(smem_u32(&nx_empty[as]), aphase ^ 1);
             const float4* src = reinterpret_cast<const float4*>(p.gal_norm2 + tile * BN + lane * 8);
             const float4 v0 = src[0], v1 = src[1];
@@ -716,10 +758,11 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000);
         int64_t cur_qb = -1;
         int as = 0; uint32_t aphase = 0;
-        for (int64_t it = item_lo; it < item_hi; ++it) {
-            const int64_t qb = it / P.ntiles, tile = it - qb * P.ntiles;
+        for (int64_t it = 0; it < n_items; ++it) {
+            int64_t qb, tile;
+            part_locate(P, unit, it, qb, tile);
             if (qb != cur_qb) {
-                if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), (int)(pair - part_first_cta(P, cur_qb * P.ntiles)) * 2 + half, lv, li, thr);
+                if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
 #pragma unroll
                 for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = -1; }
                 thr = __int_as_float(0x7f800000);
@@ -735,7 +778,7 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
             if (lane == 0) { mbar_arrive(smem_u32(&nx_empty[as])); if (leader) mbar_arrive(smem_u32(&tmem_empty[as])); else mbar_arrive_leader(smem_u32(&tmem_empty[as])); }
             as ^= 1; if (as == 0) aphase ^= 1;
         }
-        if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), (int)(pair - part_first_cta(P, cur_qb * P.ntiles)) * 2 + half, lv, li, thr);
+        if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
     }
 
     tc_fence_before();
@@ -758,10 +801,7 @@ static size_t cand_smem_bytes(bool a_res) {
 
 int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     CandParams p{};
-    p.part.ntiles = ceil_div(a.gal->rows, BN);
-    p.part.nqb = ceil_div(a.qry->rows, BM * a.ctas);
-    p.part.total = p.part.ntiles * p.part.nqb;
-    p.part.grid = a.grid;
+    p.part = make_partition(a.qry->rows, a.gal->rows, a.n_sm, a.ctas);
     p.nq = a.qry->rows; p.n = a.gal->rows;
     p.perm_a = a.gal->perm_a; p.perm_b = a.gal->perm_b;
     p.nkb = a.gal->dph / BK;
@@ -783,6 +823,7 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
         case 4: return FIR_GO(4);
         case 8: return FIR_GO(8);
         case 16: return FIR_GO(16);
+        case 32: return FIR_GO(32);
     }
 #undef FIR_GO
     return fail(FIR_ERR_INTERNAL, "unsupported candidate list length");
@@ -965,13 +1006,13 @@ __global__ void escalation_scatter_kernel(const int32_t* __restrict__ flagged, c
 }
 
 namespace {
-struct PassBuffers { void* qbuf; float* cand_val; int32_t* cand_idx; float* cand_exact; float* slot_bound; int n_slots, grid, R; size_t qside; };
+struct PassBuffers { void* qbuf; float* cand_val; int32_t* cand_idx; float* cand_exact; float* slot_bound; int n_slots, min_lists, grid, R; size_t qside; };
 
 size_t pass_bytes(fir_gallery* g, int64_t nq, int R, int ctas, PassBuffers* pb) {
-    int grid = 0, n_slots = 1;
-    tensor_plan(nq, g->n, g->n_sm, ctas, &grid, &n_slots);
+    int grid = 0, n_slots = 1, least = 1;
+    tensor_plan(nq, g->n, g->n_sm, ctas, &grid, &n_slots, &least);
     n_slots *= EPI_WARPS / 4;                           // one list per (CTA slot, column half)
-    pb->n_slots = n_slots; pb->grid = grid; pb->R = R;
+    pb->n_slots = n_slots; pb->min_lists = least * (EPI_WARPS / 4); pb->grid = grid; pb->R = R;
     pb->qside = tensor_side_bytes(nq, g->d, BM);
     return pb->qside + 3 * al256((size_t)nq * n_slots * R * 4) + al256((size_t)nq * n_slots * 4) + 2048;
 }
@@ -996,7 +1037,7 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     FIR_CUDA_TRY(cudaMemsetAsync(pb.slot_bound, 0xFF, (size_t)nq * pb.n_slots * 4, g->stream));
     TensorSearchArgs a{};
     a.gal = &g->tside; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = ctas == 2 ? &g->tmap_b_half : &g->tmap_b; a.ctas = ctas;
-    a.d = g->d; a.R = pb.R; a.n_slots = pb.n_slots; a.cand_val = pb.cand_val; a.cand_idx = pb.cand_idx; a.slot_bound = pb.slot_bound; a.grid = pb.grid;
+    a.n_sm = g->n_sm; a.d = g->d; a.R = pb.R; a.n_slots = pb.n_slots; a.cand_val = pb.cand_val; a.cand_idx = pb.cand_idx; a.slot_bound = pb.slot_bound; a.grid = pb.grid;
     { auto* ev = g->prof_begin(FIR_KERNEL_L2_CANDIDATES); int st_ = launch_tensor_candidates(a, g->stream); g->prof_end(ev); FIR_TRY(st_); }
     FIR_TRY(launch_tensor_prune(pb.cand_val, pb.cand_idx, nq, rt, k, g->d, qs.norm2, qs.resid, g->d_stats, g->stream));
     FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, pb.cand_idx, rt, 0, pb.cand_exact, g->stream));
@@ -1018,10 +1059,11 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     PassBuffers p1{}, p2{};
     pass_bytes(g, nq, 4, ctas, &p1);
     pass_bytes(g, cap2, 4, ctas, &p2);
-    // list length from the number of lists L a query is spread over: room for ~2.5 k / L of the k best, plus slack
-    auto pick_R = [&](int lists, int extra) { int want = (5 * k + 2 * lists - 1) / (2 * lists) + 2 + extra; return want <= 4 ? 4 : (want <= 8 ? 8 : 16); };
-    const int R1 = pick_R(p1.n_slots, 0);
-    const int R2 = pick_R(p2.n_slots, p2.n_slots > p1.n_slots ? 0 : 8);    // same list structure ⇒ longer lists, else a re-deal is enough
+    // list length from the number of lists L a query is spread over: room for twice its fair share k / L of the k best, plus slack
+    auto pick_R = [&](int lists, int extra) { int want = (2 * k + lists - 1) / lists + 2 + extra; return want <= 4 ? 4 : (want <= 8 ? 8 : (want <= 16 ? 16 : 32)); };
+    // (sized for the queries spread over the FEWEST lists: a full-round query block has one slot, i.e. two lists)
+    const int R1 = pick_R(p1.min_lists, 0);
+    const int R2 = pick_R(p2.min_lists, p2.min_lists > p1.min_lists ? 0 : 8);    // same list structure ⇒ longer lists, else a re-deal is enough
     const bool second = true;
     const int64_t kFbWindow = 4096;
     const int nsplit_fb = (int)std::max<int64_t>(1, std::min<int64_t>(64, ceil_div(g->n, 64 * 4)));

@@ -13,6 +13,7 @@ SHAPES = [  # n, nq, d, classes
     (777, 45, 100, 7),        # ragged everything: D % 64 != 0, N % 256 != 0, Q % 128 != 0
     (200, 5, 64, 4),          # gallery smaller than one tile
     (2500, 140, 1536, 25),    # reference default D (db.h:86): A streamed per k-block
+    (700, 20100, 64, 8),      # more query blocks than SMs: full wave-synchronous rounds + a remainder round
 ]
 
 

@@ -45,6 +45,17 @@ def measured_peaks():
     return {"tensor_tflops": 1400.0, "tensor_tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def traffic_from_profiles():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu --set full
+    capture of this workload (profiles/r1_traffic.json); None when no capture is recorded."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return j.get("l2_candidates_kernel_2cta", {}).get("dram_bytes_per_launch")
+    return None
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -277,7 +288,7 @@ def run_gpu(args):
         e2e = evals_per_step * args.steps / t_e2e
         flops_per_launch = 2.0 * DIM * N_QUERY * N_GALLERY
         achieved = flops_per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e12 if k_n else None
-        cpu = cpu_reference_arm(g_np_norm(g_dev), q_host.numpy(), k) if world == 1 else None
+        cpu = cpu_reference_arm(g_np_norm(g_dev), q_host.numpy(), k) if (world == 1 and not args.skip_cpu) else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 tensor-core candidates + f32 exact rerank", "data": "synthetic",
@@ -292,12 +303,12 @@ def run_gpu(args):
                 "gpu_launches": launches_per_step * args.steps,
                 "k1": {"value": float(N_QUERY) * N_GALLERY / t_k1, "unit": UNIT, "ms": 1e3 * t_k1, "label_accuracy": acc},
                 "certificate_fallback_queries": st["n_fallback"], "reranked_candidates_per_query": st["n_candidates"],
-                "roofline": {"bound": "tensor", "kernel": "l2_candidates_kernel (tcgen05.mma kind::f16, TMA, TMEM)",
+                "roofline": {"bound": "tensor", "kernel": "l2_candidates_kernel_2cta, first pass (tcgen05.mma.cta_group::2 kind::f16, TMA, TMEM)",
                              "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
                              "frac": (achieved / peaks["tensor_tflops"]) if achieved else None,
                              "peak_source": "%s sustained fp16/bf16 dense (MEASURED_PEAKS.json)" % peaks["source"],
                              "kernel_ms": k_ms / max(k_n, 1), "kernel_share_of_step": (k_ms / 1e3) / t_dev if t_dev else None,
-                             "flops_per_launch": flops_per_launch, "traffic": None},
+                             "flops_per_launch": flops_per_launch, "traffic": traffic_from_profiles()},
                 "clocks": clocks}
         if cpu:
             line["cpu_baseline"] = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
@@ -319,6 +330,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1027,7 +1027,7 @@ bool pass_take(fir_gallery* g, int64_t nq, PassBuffers* pb) {
 }
 // pack → tcgen05 candidates → exact rerank → select + certificate, for nq device-resident fp32 queries
 int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const PassBuffers& pb, int64_t index_offset, float* od, int32_t* oi,
-             int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags, float* max_bound) {
+             int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags, float* max_bound, int prof_kind) {
     TensorSide qs;
     FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, pb.qbuf, &qs, nullptr, false, g->stream));
     CUtensorMap tmap_a;
@@ -1038,7 +1038,7 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     TensorSearchArgs a{};
     a.gal = &g->tside; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = ctas == 2 ? &g->tmap_b_half : &g->tmap_b; a.ctas = ctas;
     a.n_sm = g->n_sm; a.d = g->d; a.R = pb.R; a.n_slots = pb.n_slots; a.cand_val = pb.cand_val; a.cand_idx = pb.cand_idx; a.slot_bound = pb.slot_bound; a.grid = pb.grid;
-    { auto* ev = g->prof_begin(FIR_KERNEL_L2_CANDIDATES); int st_ = launch_tensor_candidates(a, g->stream); g->prof_end(ev); FIR_TRY(st_); }
+    { auto* ev = g->prof_begin(prof_kind); int st_ = launch_tensor_candidates(a, g->stream); g->prof_end(ev); FIR_TRY(st_); }
     FIR_TRY(launch_tensor_prune(pb.cand_val, pb.cand_idx, nq, rt, k, g->d, qs.norm2, qs.resid, g->d_stats, g->stream));
     FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, pb.cand_idx, rt, 0, pb.cand_exact, g->stream));
     FIR_TRY(launch_tensor_select(pb.cand_exact, pb.cand_idx, pb.slot_bound, nq, pb.n_slots, pb.R, k, g->d, qs.norm2, qs.resid, g->d_stats, index_offset, od,
@@ -1107,7 +1107,7 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     int32_t* n_final = reinterpret_cast<int32_t*>(g->d_stats + 7);
     FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats + 4, 0, 16, g->stream));
 
-    FIR_TRY(run_pass(g, dq, nq, k, ctas, p1, g->index_offset, od, oi, flagged, n_flagged, nullptr, max_bound));
+    FIR_TRY(run_pass(g, dq, nq, k, ctas, p1, g->index_offset, od, oi, flagged, n_flagged, nullptr, max_bound, FIR_KERNEL_L2_CANDIDATES));
     const int32_t* exact_list = flagged; const int32_t* exact_count = n_flagged;
     if (second) {
         float* dq2 = (float*)g->ws.take(sizeof(float) * (size_t)cap2 * g->dp);
@@ -1118,7 +1118,7 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
         if (!pass_take(g, cap2, &p2) || !dq2 || !od2 || !oi2 || !flagged2 || !fail2) return fail(FIR_ERR_INTERNAL, "workspace underestimated (second pass)");
         gather_flagged_rows_kernel<<<(unsigned)cap2, 128, 0, g->stream>>>(dq, g->dp, flagged, n_flagged, cap2, dq2);
         FIR_CUDA_TRY(cudaMemsetAsync(fail2, 0, (size_t)cap2, g->stream));
-        FIR_TRY(run_pass(g, dq2, cap2, k, ctas, p2, g->index_offset, od2, oi2, flagged2, n_flagged2, fail2, max_bound));
+        FIR_TRY(run_pass(g, dq2, cap2, k, ctas, p2, g->index_offset, od2, oi2, flagged2, n_flagged2, fail2, max_bound, FIR_KERNEL_L2_CANDIDATES_PASS2));
         escalation_scatter_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, g->stream>>>(flagged, n_flagged, cap2, fail2, od2, oi2, k, od, oi, final_list, n_final);
         FIR_CUDA_TRY(cudaGetLastError());
         g->stats.gpu_launches += 2;

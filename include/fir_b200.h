@@ -102,7 +102,12 @@ int fir_search_last_stats(const fir_gallery* g, fir_search_stats* stats);
 /* measurement aid: when enabled, CUDA event pairs are recorded on the handle's stream around every launch
  * of the dominant kernels; fir_profile_read synchronises and returns their summed duration and count since
  * fir_profile_enable(g, 1) was last called. */
-typedef enum fir_kernel { FIR_KERNEL_L2_CANDIDATES = 0, FIR_KERNEL_EXACT_TILES = 1, FIR_KERNEL_DEM_LIKELIHOOD = 2 } fir_kernel;
+typedef enum fir_kernel {
+    FIR_KERNEL_L2_CANDIDATES = 0,       /* tcgen05 candidate kernel, first pass (all queries)            */
+    FIR_KERNEL_EXACT_TILES = 1,
+    FIR_KERNEL_DEM_LIKELIHOOD = 2,
+    FIR_KERNEL_L2_CANDIDATES_PASS2 = 3  /* same kernel, second pass over the few uncertified queries      */
+} fir_kernel;
 int fir_profile_enable(fir_gallery* g, int32_t on);
 int fir_profile_read(fir_gallery* g, int32_t kernel, double* total_ms, int32_t* launches);
 

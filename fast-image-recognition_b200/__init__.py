@@ -29,7 +29,7 @@ PATH_AUTO, PATH_EXACT, PATH_TENSOR = 0, 1, 2
 
 EXPORTS = [
     "fir_last_error_string", "fir_version", "fir_device_count", "fir_set_device",
-    "fir_gallery_create", "fir_gallery_destroy", "fir_gallery_set_stream", "fir_gallery_info",
+    "fir_gallery_create", "fir_gallery_destroy", "fir_gallery_set_stream", "fir_gallery_info", "fir_gallery_set_num_classes",
     "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
     "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates", "fir_profile_enable", "fir_profile_read",
     "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn",
@@ -72,6 +72,7 @@ def lib():
     L.fir_gallery_destroy.argtypes = [vp]
     L.fir_gallery_set_stream.argtypes = [vp, vp]
     L.fir_gallery_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.fir_gallery_set_num_classes.argtypes = [vp, i32]
     L.fir_normalize_rows.argtypes = [vp, i64, i32, i32, i32, vp]
     L.fir_search_topk.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, vp]
     L.fir_search_last_stats.argtypes = [vp, C.POINTER(SearchStats)]
@@ -174,6 +175,10 @@ class Gallery:
         self.n_classes = nc.value
         if stream is not None:
             self.set_stream(stream)
+
+    def set_num_classes(self, n_classes):
+        _check(lib().fir_gallery_set_num_classes(self._h, int(n_classes)))
+        self.n_classes = int(n_classes)
 
     def set_stream(self, stream):
         _check(lib().fir_gallery_set_stream(self._h, C.c_void_p(int(stream))))

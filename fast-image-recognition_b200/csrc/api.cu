@@ -188,6 +188,15 @@ int fir_gallery_info(const fir_gallery* g, int64_t* n, int32_t* d, int32_t* metr
     return FIR_OK;
 }
 
+int fir_gallery_set_num_classes(fir_gallery* g, int32_t n_classes) {
+    if (!g) return fail(FIR_ERR_BAD_ARG, "gallery is null");
+    int32_t mx = 0;
+    for (int32_t l : g->h_labels) mx = std::max(mx, l);
+    if (n_classes <= mx) return fail(FIR_ERR_BAD_ARG, "n_classes must exceed the largest label of the handle");
+    g->n_classes = n_classes;
+    return FIR_OK;
+}
+
 int fir_normalize_rows(float* rows, int64_t n, int32_t d, int32_t metric, int32_t memspace, void* cuda_stream) {
     if (!rows || n < 0 || d <= 0) return fail(FIR_ERR_BAD_ARG, "bad rows");
     if (n == 0) return FIR_OK;

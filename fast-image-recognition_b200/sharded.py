@@ -36,6 +36,11 @@ class ShardedGallery:
         if local_factory is None:
             import fir_b200
             self.local = fir_b200.Gallery(rows, labels, metric, index_offset=lo)
+            if self.world > 1:      # per-class outputs must have the global width on every shard
+                import torch
+                nc = torch.tensor([self.local.n_classes], dtype=torch.int64, device=rows.device if hasattr(rows, 'device') else 'cpu')
+                dist.all_reduce(nc, op=dist.ReduceOp.MAX)
+                self.local.set_num_classes(int(nc.item()))
             self._merge = merge or (lambda pd, pi, k: fir_b200.merge_topk(pd, pi))
         else:
             self.local = local_factory(rows, labels, metric, lo)

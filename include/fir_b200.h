@@ -82,6 +82,9 @@ int fir_gallery_create(const float* rows, const int32_t* labels, int64_t n, int3
 int fir_gallery_destroy(fir_gallery* g);
 int fir_gallery_set_stream(fir_gallery* g, void* cuda_stream);
 int fir_gallery_info(const fir_gallery* g, int64_t* n, int32_t* d, int32_t* metric, int32_t* n_classes);
+/* the class count defaults to max(label)+1 of THIS handle's rows; a row shard sets the global count so that per-class
+ * outputs (fir_class_min, fir_pnn_scores) have the same width on every shard */
+int fir_gallery_set_num_classes(fir_gallery* g, int32_t n_classes);
 
 /* replaces: the normalisation loop of loadImages (qt_cpp/db_features.cpp:79-101): zero |x|<1e-4,
  * then x /= sqrtf(sum x*x) (L2) or x /= sum x (chi2/KL), fp32, sequential.  In place. */

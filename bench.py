@@ -175,9 +175,7 @@ def run_gpu(args):
     peaks = measured_peaks()
 
     # ---- synthetic workload: one 100k-row class-major shard per rank; queries replicated ------------------
-    g_np, gl_np, q_np, ql_np = synth.make_split(N_GALLERY, N_QUERY, DIM, N_CLASSES, "l2", seed=rank)
-    if world > 1:   # every rank must use the same queries
-        _, _, q_np, ql_np = synth.make_split(8, N_QUERY, DIM, N_CLASSES, "l2", seed=0)
+    g_np, gl_np, q_np, ql_np = synth.make_split(N_GALLERY, N_QUERY, DIM, N_CLASSES, "l2", seed=0, shard=rank)   # same classes + queries on every rank
     g_dev = torch.from_numpy(g_np).to(dev)
     q_dev = torch.from_numpy(q_np).to(dev)
     fir_b200.normalize_rows(g_dev, "l2")         # loader normalisation (db_features.cpp:79-101) on the GPU

@@ -241,7 +241,7 @@ __global__ void merge_parts_kernel(const float* __restrict__ pd, const int32_t* 
     if (n_active) { na = max((int64_t)0, na - active_offset); if (active_cap > 0) na = min(na, active_cap); }
     if (i >= na) return;
     int64_t q = qmap ? (int64_t)qmap[active_offset + i] : i;
-    constexpr int MAXP = 256;
+    constexpr int MAXP = 1024;
     unsigned short head[MAXP];
     for (int s = 0; s < n_parts; ++s) head[s] = 0;
     for (int r = 0; r < k; ++r) {
@@ -264,7 +264,7 @@ int launch_merge_parts(const float* pd, const int32_t* pi, int n_parts, int64_t 
                        int64_t nq, int k, int64_t index_offset, const int32_t* qmap, const int32_t* n_active,
                        float* od, int32_t* oi, cudaStream_t s, int64_t active_offset, int64_t active_cap) {
     if (nq <= 0) return FIR_OK;
-    if (n_parts > 256) return fail(FIR_ERR_UNSUPPORTED, "more than 256 parts to merge");
+    if (n_parts > 1024) return fail(FIR_ERR_UNSUPPORTED, "more than 1024 parts to merge");
     merge_parts_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(pd, pi, n_parts, part_stride, q_stride, nq, k, index_offset,
                                                                    qmap, n_active, od, oi, active_offset, active_cap);
     FIR_CUDA_TRY(cudaGetLastError());

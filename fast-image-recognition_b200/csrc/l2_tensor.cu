@@ -1065,11 +1065,16 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     const int R1 = pick_R(p1.min_lists, 0);
     const int R2 = pick_R(p2.min_lists, p2.min_lists > p1.min_lists ? 0 : 8);    // same list structure ⇒ longer lists, else a re-deal is enough
     const bool second = true;
-    const int64_t kFbWindow = 4096;
-    const int nsplit_fb = (int)std::max<int64_t>(1, std::min<int64_t>(64, ceil_div(g->n, 64 * 4)));
-    const int64_t fb_rows = std::min<int64_t>(nq, kFbWindow);
+    // Exact re-run of what two tensor passes could not certify (mass exact ties; normally nothing): the first kFbFast
+    // queries of the device-side list are spread over up to 1024 gallery splits each (one or two 64-row tiles per block, so
+    // even a single query is served by the whole machine); a second launch covers any overflow with coarse splits.  Both
+    // exit at once when their part of the list is empty.
+    const int64_t kFbFast = 64;
+    const int nsplit_fast = (int)std::max<int64_t>(1, std::min<int64_t>(1024, ceil_div(g->n, 64)));
+    const int nsplit_slow = (int)std::max<int64_t>(1, std::min<int64_t>(16, ceil_div(g->n, 64 * 8)));
+    const size_t fb_cells = std::max<size_t>((size_t)kFbFast * nsplit_fast, (size_t)nq * nsplit_slow) * k;
     size_t need = al256(sizeof(float) * (size_t)nq * g->dp) + pass_bytes(g, nq, R1, ctas, &p1) + 3 * al256((size_t)nq * 4) +
-                  2 * al256((size_t)nq * k * 4) + 2 * al256((size_t)fb_rows * nsplit_fb * k * 4) + 16384;
+                  2 * al256((size_t)nq * k * 4) + 2 * al256(fb_cells * 4) + 16384;
     if (second) need += pass_bytes(g, cap2, R2, ctas, &p2) + al256(sizeof(float) * (size_t)cap2 * g->dp) + 2 * al256((size_t)cap2 * k * 4) + 2 * al256((size_t)cap2 * 4);
     FIR_TRY(g->ws.reserve(need));
     // fp32 queries, zero padded (for the exact rerank and the certificate fallback)
@@ -1096,8 +1101,8 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     float* od = out_dist; int32_t* oi = out_idx;
     if (memspace == FIR_HOST || !out_dist) od = (float*)g->ws.take((size_t)nq * k * 4);
     if (memspace == FIR_HOST) oi = (int32_t*)g->ws.take((size_t)nq * k * 4);
-    float* part_d = (float*)g->ws.take((size_t)fb_rows * nsplit_fb * k * 4);
-    int32_t* part_i = (int32_t*)g->ws.take((size_t)fb_rows * nsplit_fb * k * 4);
+    float* part_d = (float*)g->ws.take(fb_cells * 4);
+    int32_t* part_i = (int32_t*)g->ws.take(fb_cells * 4);
     if (!pass_take(g, nq, &p1) || !flagged || !final_list || !od || !oi || !part_d || !part_i)
         return fail(FIR_ERR_INTERNAL, "workspace underestimated (tensor path)");
     // device counters: [4] flagged after pass 1, [5] max bound, [6] flagged inside pass 2 (unused list), [7] final exact re-runs
@@ -1124,9 +1129,10 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
         g->stats.gpu_launches += 2;
         exact_list = final_list; exact_count = n_final;
     }
-    // what is still uncertified: exact CUDA-core re-run (device-side count; windows past it exit immediately)
-    for (int64_t off = 0; off < nq; off += kFbWindow)
-        FIR_TRY(exact_topk_device(g, dq, nq, k, g->d, exact_list, exact_count, part_d, part_i, nsplit_fb, od, oi, off, kFbWindow));
+    // what is still uncertified: exact CUDA-core re-run (device-side count; see above)
+    FIR_TRY(exact_topk_device(g, dq, nq, k, g->d, exact_list, exact_count, part_d, part_i, nsplit_fast, od, oi, 0, kFbFast));
+    if (nq > kFbFast)
+        FIR_TRY(exact_topk_device(g, dq, nq, k, g->d, exact_list, exact_count, part_d, part_i, nsplit_slow, od, oi, kFbFast, nq - kFbFast));
     g->stats.path_used = FIR_PATH_TENSOR;
     g->stats.n_candidates = p1.n_slots * p1.R;
     g->stats.n_fallback = -1;     // resolved lazily by fir_search_last_stats

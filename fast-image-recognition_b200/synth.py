@@ -20,12 +20,13 @@ def centroids(n_classes, d, seed=SEED_CENTROID):
     return _rng(seed).standard_normal((n_classes, d), dtype=np.float32)
 
 
-def make_split(n_gallery, n_query, d, n_classes, metric="l2", sigma=0.5, seed=0):
-    """Raw (un-normalised) fp32 features: gallery rows class-major, labels int32."""
+def make_split(n_gallery, n_query, d, n_classes, metric="l2", sigma=0.5, seed=0, shard=0):
+    """Raw (un-normalised) fp32 features: gallery rows class-major, labels int32.  `shard` draws a different gallery
+    (labels + noise) around the SAME class centroids and with the SAME queries — one shard per GPU of a sharded run."""
     cen = centroids(n_classes, d, SEED_CENTROID + seed)
-    gl = np.sort(_rng(SEED_LABEL + seed, 0).integers(0, n_classes, n_gallery, dtype=np.int32), kind="stable")
+    gl = np.sort(_rng(SEED_LABEL + seed, 2 * shard).integers(0, n_classes, n_gallery, dtype=np.int32), kind="stable")
     ql = _rng(SEED_LABEL + seed, 1).integers(0, n_classes, n_query, dtype=np.int32)
-    g = cen[gl] + sigma * _rng(SEED_GALLERY + seed).standard_normal((n_gallery, d), dtype=np.float32)
+    g = cen[gl] + sigma * _rng(SEED_GALLERY + seed, shard).standard_normal((n_gallery, d), dtype=np.float32)
     q = cen[ql] + sigma * _rng(SEED_QUERY + seed).standard_normal((n_query, d), dtype=np.float32)
     if metric != "l2":
         np.maximum(g, 0, out=g)

@@ -175,62 +175,133 @@ __device__ __forceinline__ bool after_last(uint32_t key, int32_t idx, const QSta
     return !s.started || key > s.last_key || (key == s.last_key && idx > s.last_idx);
 }
 
-// radix select, pass 1 / pass 2: histogram of the high / low 16 bits of the likelihood key over the not-yet-consumed tail
+// Radix select of the round's closing likelihood key, 11 + 11 + 10 bits.  `prefix` holds the digits chosen so far.
+// Histograms are privatised in shared memory (the keys cluster in a few hundred bins — global atomics on 64 Ki bins spent
+// 3 ms per pass on contention) and only the non-empty bins are flushed.
+__device__ __forceinline__ bool radix_match(uint32_t key, int pass, uint32_t prefix) {
+    return pass == 0 || (pass == 1 ? (key >> 21) == prefix : (key >> 10) == prefix);
+}
+__device__ __forceinline__ uint32_t radix_digit(uint32_t key, int pass) {
+    return pass == 0 ? (key >> 21) : (pass == 1 ? ((key >> 10) & 0x7ffu) : (key & 0x3ffu));
+}
+
 __global__ void __launch_bounds__(256) dem_hist_kernel(const float* __restrict__ lik, const int32_t* __restrict__ qlist, int nqc, int64_t n,
-                                                       const QState* __restrict__ st, int pass, const uint32_t* __restrict__ hi_sel,
-                                                       uint32_t* __restrict__ hist) {
+                                                       const QState* __restrict__ st, int pass, const uint32_t* __restrict__ prefix,
+                                                       const int32_t* __restrict__ take_all, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[2048];
     const int qc = blockIdx.y;
     const QState s = st[qlist[qc]];
-    if (s.done) return;
+    if (s.done || (pass > 0 && take_all[qc])) return;
+    for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0;
+    __syncthreads();
     const float* lr = lik + (int64_t)qc * n;
-    uint32_t* h = hist + (size_t)qc * 65536;
-    const uint32_t sel = pass ? hi_sel[qc] : 0;
+    const uint32_t pre = pass ? prefix[qc] : 0;
     for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < n; v += (int64_t)gridDim.x * 256) {
         const uint32_t key = __float_as_uint(lr[v]);
         if (key >= 0x7f800000u) continue;                    // +inf: not in the tail
         if (!after_last(key, (int32_t)v, s)) continue;
-        if (!pass) atomicAdd(&h[key >> 16], 1u);
-        else if ((key >> 16) == sel) atomicAdd(&h[key & 0xffffu], 1u);
+        if (radix_match(key, pass, pre)) atomicAdd(&sh[radix_digit(key, pass)], 1u);
+    }
+    __syncthreads();
+    uint32_t* h = hist + (size_t)qc * 2048;
+    for (int i = threadIdx.x; i < 2048; i += 256)
+        if (sh[i]) atomicAdd(&h[i], sh[i]);
+}
+
+// one block per query: walk the bins until the cumulative count reaches what is still wanted
+__global__ void __launch_bounds__(32) dem_pick_kernel(const uint32_t* __restrict__ hist, const int32_t* __restrict__ qlist, int nqc,
+                                                      const QState* __restrict__ st, int pass, const int32_t* __restrict__ want_in,
+                                                      uint32_t* __restrict__ prefix, int32_t* __restrict__ want_rem, int32_t* __restrict__ take_all,
+                                                      uint32_t* __restrict__ key_sel, int32_t* __restrict__ tie_take, int32_t* __restrict__ round_n) {
+    const int qc = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const QState s = st[qlist[qc]];
+    if (s.done) { round_n[qc] = 0; take_all[qc] = 0; key_sel[qc] = 0; tie_take[qc] = 0; return; }
+    if (pass > 0 && take_all[qc]) return;
+    const uint32_t* h = hist + (size_t)qc * 2048;
+    const int want = pass == 0 ? want_in[qc] : want_rem[qc];
+    const int bins = pass == 2 ? 1024 : 2048;
+    uint32_t cum = 0; int bin = -1;
+    for (int b = 0; b < bins; ++b) { if (cum + h[b] >= (uint32_t)want) { bin = b; break; } cum += h[b]; }
+    if (pass == 0) {
+        if (bin < 0) {                                       // fewer than `want` keys remain: the round takes everything that is left
+            take_all[qc] = 1; key_sel[qc] = 0xffffffffu; tie_take[qc] = 0; round_n[qc] = (int32_t)cum;
+            return;
+        }
+        take_all[qc] = 0;
+        prefix[qc] = (uint32_t)bin; want_rem[qc] = want - (int32_t)cum;
+    } else if (pass == 1) {
+        prefix[qc] = (prefix[qc] << 11) | (uint32_t)bin; want_rem[qc] = want - (int32_t)cum;
+    } else {
+        key_sel[qc] = (prefix[qc] << 10) | (uint32_t)bin;
+        tie_take[qc] = want - (int32_t)cum;                  // how many keys equal to key_sel close the round, lowest index first
+        round_n[qc] = want_in[qc];
     }
 }
 
-// one block per query: prefix-scan the 65536 bins to find where the cumulative count reaches `want`
-__global__ void __launch_bounds__(256) dem_pick_kernel(const uint32_t* __restrict__ hist, const int32_t* __restrict__ qlist, int nqc,
-                                                       const QState* __restrict__ st, int pass, const int32_t* __restrict__ want_in,
-                                                       uint32_t* __restrict__ hi_sel, int32_t* __restrict__ below_cnt,
-                                                       uint32_t* __restrict__ key_sel, int32_t* __restrict__ tie_take, int32_t* __restrict__ round_n) {
-    __shared__ uint32_t part[256];
-    const int qc = blockIdx.x;
+// Parallel collection: everything below the closing key goes straight into the round's list (order is irrelevant, the
+// reduction compares (key, index) explicitly); rows AT the closing key go to a small side buffer so that exactly the
+// tie_take lowest indices can be taken afterwards.
+constexpr int TIE_CAP = 32;
+__global__ void __launch_bounds__(256) dem_collect_fast_kernel(const float* __restrict__ lik, const int32_t* __restrict__ qlist, int nqc, int64_t n,
+                                                               const QState* __restrict__ st, const int32_t* __restrict__ take_all,
+                                                               const uint32_t* __restrict__ key_sel, int cap, int32_t* __restrict__ cand,
+                                                               uint32_t* __restrict__ cand_key, int32_t* __restrict__ cnt,
+                                                               int32_t* __restrict__ tie_buf, int32_t* __restrict__ tie_cnt) {
+    const int qc = blockIdx.y;
     const QState s = st[qlist[qc]];
-    if (s.done) { if (threadIdx.x == 0 && pass) round_n[qc] = 0; return; }
-    const uint32_t* h = hist + (size_t)qc * 65536;
-    const int want = pass ? (want_in[qc] - below_cnt[qc]) : want_in[qc];
-    uint32_t sum = 0;
-    for (int b = 0; b < 256; ++b) sum += h[threadIdx.x * 256 + b];
-    part[threadIdx.x] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t cum = 0; int seg = -1;
-        for (int t = 0; t < 256; ++t) { if (cum + part[t] >= (uint32_t)want) { seg = t; break; } cum += part[t]; }
-        if (seg < 0) {                       // fewer than `want` keys remain: take everything that is left
-            if (!pass) { hi_sel[qc] = 0xffffffffu; below_cnt[qc] = (int32_t)cum; }
-            else { key_sel[qc] = 0xffffffffu; tie_take[qc] = 0; round_n[qc] = below_cnt[qc] + (int32_t)cum; }
-            return;
-        }
-        int bin = seg * 256;
-        for (;; ++bin) { if (cum + h[bin] >= (uint32_t)want) break; cum += h[bin]; }
-        if (!pass) { hi_sel[qc] = (uint32_t)bin; below_cnt[qc] = (int32_t)cum; }
-        else {
-            key_sel[qc] = (hi_sel[qc] << 16) | (uint32_t)bin;
-            tie_take[qc] = want - (int32_t)cum;                   // how many keys equal to key_sel close the round, lowest index first
-            round_n[qc] = below_cnt[qc] + want;
+    if (s.done) return;
+    const float* lr = lik + (int64_t)qc * n;
+    const bool all = take_all[qc] != 0;
+    const uint32_t ksel = key_sel[qc];
+    int32_t* out = cand + (int64_t)qc * cap;
+    uint32_t* outk = cand_key + (int64_t)qc * cap;
+    for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < n; v += (int64_t)gridDim.x * 256) {
+        const uint32_t key = __float_as_uint(lr[v]);
+        if (key >= 0x7f800000u || !after_last(key, (int32_t)v, s)) continue;
+        if (all || key < ksel) {
+            const int pos = atomicAdd(&cnt[qc], 1);
+            if (pos < cap) { out[pos] = (int32_t)v; outk[pos] = key; }
+        } else if (key == ksel) {
+            const int pos = atomicAdd(&tie_cnt[qc], 1);
+            if (pos < TIE_CAP) tie_buf[qc * TIE_CAP + pos] = (int32_t)v;
         }
     }
+}
+
+// one thread per query: append the tie_take lowest-index ties, pad the list; flags queries whose ties overflowed the buffer
+__global__ void dem_collect_fixup_kernel(const int32_t* __restrict__ qlist, int nqc, const QState* __restrict__ st, const int32_t* __restrict__ take_all,
+                                         const uint32_t* __restrict__ key_sel, const int32_t* __restrict__ tie_take, int cap,
+                                         int32_t* __restrict__ cand, uint32_t* __restrict__ cand_key, int32_t* __restrict__ cnt,
+                                         int32_t* __restrict__ tie_buf, const int32_t* __restrict__ tie_cnt, int32_t* __restrict__ last_tie_idx,
+                                         int32_t* __restrict__ overflow) {
+    const int qc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qc >= nqc) return;
+    overflow[qc] = 0;
+    if (st[qlist[qc]].done) return;
+    int32_t* out = cand + (int64_t)qc * cap;
+    uint32_t* outk = cand_key + (int64_t)qc * cap;
+    int c = min(cnt[qc], cap);
+    int ltie = -1;
+    if (!take_all[qc]) {
+        const int nt = tie_cnt[qc];
+        if (nt > TIE_CAP) { overflow[qc] = 1; return; }       // rare: mass ties at the closing key → ordered slow path
+        int32_t* tb = tie_buf + qc * TIE_CAP;
+        for (int i = 1; i < nt; ++i) {                        // insertion sort by index
+            const int32_t x = tb[i]; int j = i - 1;
+            while (j >= 0 && tb[j] > x) { tb[j + 1] = tb[j]; --j; }
+            tb[j + 1] = x;
+        }
+        const int take = min(tie_take[qc], nt);
+        for (int i = 0; i < take && c < cap; ++i) { out[c] = tb[i]; outk[c] = key_sel[qc]; ltie = tb[i]; ++c; }
+    }
+    for (int i = c; i < cap; ++i) out[i] = -1;
+    last_tie_idx[qc] = ltie;
 }
 
 // one warp per query: collect the round's candidates in INDEX order (ballot compaction keeps the order)
 __global__ void __launch_bounds__(128) dem_collect_kernel(const float* __restrict__ lik, const int32_t* __restrict__ qlist, int nqc, int64_t n,
-                                                          const QState* __restrict__ st, const uint32_t* __restrict__ hi_sel,
+                                                          const QState* __restrict__ st, const int32_t* __restrict__ overflow,
                                                           const uint32_t* __restrict__ key_sel, const int32_t* __restrict__ tie_take,
                                                           int cap, int32_t* __restrict__ cand, uint32_t* __restrict__ cand_key,
                                                           int32_t* __restrict__ last_tie_idx) {
@@ -240,9 +311,9 @@ __global__ void __launch_bounds__(128) dem_collect_kernel(const float* __restric
     const QState s = st[qlist[qc]];
     int32_t* out = cand + (int64_t)qc * cap;
     uint32_t* outk = cand_key + (int64_t)qc * cap;
-    if (s.done) return;
+    if (s.done || !overflow[qc]) return;                     // slow path: only queries whose closing-key ties overflowed the side buffer
     const float* lr = lik + (int64_t)qc * n;
-    const bool take_all = hi_sel[qc] == 0xffffffffu || key_sel[qc] == 0xffffffffu;
+    const bool take_all = key_sel[qc] == 0xffffffffu;
     const uint32_t ksel = key_sel[qc];
     int ties_left = tie_take[qc];
     int cnt = 0, ltie = -1;
@@ -566,7 +637,7 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
     const int QC = (int)std::max<int64_t>(8, std::min<int64_t>(std::min<int64_t>(nq, 1024), ((int64_t)1 << 30) / (4 * n)));   // lik chunk ≤ 1 GiB
     const int cap_max = (int)std::min<int64_t>(n, std::max<int64_t>(256, ((int64_t)256 << 20) / ((int64_t)QC * 12)));
     size_t need = al(4 * (size_t)nq * g->dp) + 2 * al(4 * (size_t)nq * S) + al(sizeof(QState) * (size_t)nq) + al(4 * (size_t)nq) +
-                  al(4 * (size_t)QC * n) + al(4 * (size_t)QC * 65536) + 3 * al(4 * (size_t)QC * cap_max) + 8 * al(4 * (size_t)QC) +
+                  al(4 * (size_t)QC * n) + al(4 * (size_t)QC * 2048) + 3 * al(4 * (size_t)QC * cap_max) + 14 * al(4 * (size_t)QC) + al(4 * (size_t)QC * TIE_CAP) +
                   al((size_t)nq * 9) + al(4 * (size_t)nq) * 2 + 65536;
     FIR_TRY(g->ws.reserve(need));
     // queries → zero-padded device rows
@@ -586,13 +657,18 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
     QState* st = (QState*)g->ws.take(sizeof(QState) * (size_t)nq);
     int32_t* active = (int32_t*)g->ws.take(4 * (size_t)nq);
     float* lik = (float*)g->ws.take(4 * (size_t)QC * n);
-    uint32_t* hist = (uint32_t*)g->ws.take(4 * (size_t)QC * 65536);
+    uint32_t* hist = (uint32_t*)g->ws.take(4 * (size_t)QC * 2048);
     int32_t* cand = (int32_t*)g->ws.take(4 * (size_t)QC * cap_max);
     uint32_t* cand_key = (uint32_t*)g->ws.take(4 * (size_t)QC * cap_max);
     float* cdist = (float*)g->ws.take(4 * (size_t)QC * cap_max);
     int32_t* want = (int32_t*)g->ws.take(4 * (size_t)QC);
-    uint32_t* hi_sel = (uint32_t*)g->ws.take(4 * (size_t)QC);
-    int32_t* below_cnt = (int32_t*)g->ws.take(4 * (size_t)QC);
+    uint32_t* prefix = (uint32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* want_rem = (int32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* take_all = (int32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* cnt = (int32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* tie_cnt = (int32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* overflow = (int32_t*)g->ws.take(4 * (size_t)QC);
+    int32_t* tie_buf = (int32_t*)g->ws.take(4 * (size_t)QC * TIE_CAP);
     uint32_t* key_sel = (uint32_t*)g->ws.take(4 * (size_t)QC);
     int32_t* tie_take = (int32_t*)g->ws.take(4 * (size_t)QC);
     int32_t* round_n = (int32_t*)g->ws.take(4 * (size_t)QC);
@@ -605,7 +681,7 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
         o_evals = (int32_t*)g->ws.take(4 * (size_t)nq);
         o_below = (uint8_t*)g->ws.take((size_t)nq);
     }
-    if (!pcand || !pd || !st || !active || !lik || !hist || !cand || !cand_key || !cdist || !want || !hi_sel || !below_cnt || !key_sel ||
+    if (!pcand || !pd || !st || !active || !lik || !hist || !cand || !cand_key || !cdist || !want || !prefix || !want_rem || !take_all || !cnt || !tie_cnt || !overflow || !tie_buf || !key_sel ||
         !tie_take || !round_n || !last_tie || !counters || !o_idx || (memspace == FIR_HOST && (!o_dist || !o_evals || !o_below)))
         return fail(FIR_ERR_INTERNAL, "workspace underestimated (dem search)");
 
@@ -631,13 +707,18 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
         while (remaining > 0) {
             const int cap = (int)std::min<int64_t>(round_size, cap_max);
             dem_want_kernel<<<(unsigned)ceil_div(nqc, 128), 128, 0, s>>>(st, ql, nqc, cap, M, want);
-            const unsigned hb = (unsigned)std::min<int64_t>(ceil_div(n, 256 * 8), 512);
-            for (int pass = 0; pass < 2; ++pass) {
-                FIR_CUDA_TRY(cudaMemsetAsync(hist, 0, 4 * (size_t)nqc * 65536, s));
-                dem_hist_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, pass, hi_sel, hist);
-                dem_pick_kernel<<<(unsigned)nqc, 256, 0, s>>>(hist, ql, nqc, st, pass, want, hi_sel, below_cnt, key_sel, tie_take, round_n);
+            const unsigned hb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 16), 64));
+            for (int pass = 0; pass < 3; ++pass) {
+                FIR_CUDA_TRY(cudaMemsetAsync(hist, 0, 4 * (size_t)nqc * 2048, s));
+                dem_hist_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, pass, prefix, take_all, hist);
+                dem_pick_kernel<<<(unsigned)nqc, 32, 0, s>>>(hist, ql, nqc, st, pass, want, prefix, want_rem, take_all, key_sel, tie_take, round_n);
             }
-            dem_collect_kernel<<<(unsigned)ceil_div(nqc, 4), 128, 0, s>>>(lik, ql, nqc, n, st, hi_sel, key_sel, tie_take, cap, cand, cand_key, last_tie);
+            FIR_CUDA_TRY(cudaMemsetAsync(cnt, 0, 4 * (size_t)nqc, s));
+            FIR_CUDA_TRY(cudaMemsetAsync(tie_cnt, 0, 4 * (size_t)nqc, s));
+            dem_collect_fast_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, take_all, key_sel, cap, cand, cand_key, cnt, tie_buf, tie_cnt);
+            dem_collect_fixup_kernel<<<(unsigned)ceil_div(nqc, 128), 128, 0, s>>>(ql, nqc, st, take_all, key_sel, tie_take, cap, cand, cand_key, cnt, tie_buf, tie_cnt,
+                                                                               last_tie, overflow);
+            dem_collect_kernel<<<(unsigned)ceil_div(nqc, 4), 128, 0, s>>>(lik, ql, nqc, n, st, overflow, key_sel, tie_take, cap, cand, cand_key, last_tie);
             // exact distances of the round's candidates: queries are addressed through the active list
             FIR_TRY(launch_pair_distances(g->metric, dq, nqc, g->dp, g->rows, g->dp, n, g->d, cand, cap, 0, cdist, s, nullptr, ql));
             FIR_CUDA_TRY(cudaMemsetAsync(counters + 1, 0, 4, s));

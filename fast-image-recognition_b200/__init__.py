@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfir_b200.so")
+LIB_PATH = os.environ.get("FIR_B200_LIB") or os.path.join(_HERE, "libfir_b200.so")   # override: A/B builds of the same library
 
 L2, CHI2, KL = 0, 1, 2
 METRICS = {"l2": L2, "chi2": CHI2, "kl": KL}

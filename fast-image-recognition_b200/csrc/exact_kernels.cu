@@ -20,6 +20,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+#ifndef FIR_DIV_UNROLL
+#define FIR_DIV_UNROLL 1
+#endif
+constexpr int kDivUnroll = FIR_DIV_UNROLL;   // k-loop unroll of the division / logf metrics (instruction-cache footprint)
 constexpr int TS = kExactTile;        // 64
 constexpr int CH = kExactChunk;       // 32
 constexpr int LDT = CH + 4;           // smem row stride in floats: 36 ⇒ LDS.128 conflict-free for 8 consecutive rows
@@ -115,7 +119,9 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
             const float* xb = xs + st * TS * LDT;
             const int kmax = min(CH, p.d_end - c * CH);
             if (kmax == CH) {
-#pragma unroll
+                // L2's 3-instruction step unrolls fully (24 KB of code); the division / logf steps are ~16-60 instructions
+                // each, so their k-loop stays rolled to fit the instruction cache (ncu: 28 % stall_no_inst when unrolled)
+#pragma unroll (METRIC == FIR_L2 ? CH / 4 : kDivUnroll)
                 for (int k4 = 0; k4 < CH / 4; ++k4) {
                     float4 qa[4], xa[4];
 #pragma unroll

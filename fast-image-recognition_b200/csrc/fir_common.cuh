@@ -140,7 +140,7 @@ __device__ const double kLogfTab[16][2] = {
 
 __device__ __forceinline__ float glibc_logf(float x) {
     uint32_t ix = __float_as_uint(x);
-    if (ix == 0x3f800000u) return 0.0f;
+    // (glibc's `x == 1 → +0` shortcut is redundant in round-to-nearest: table entry 9 is {1, 0}, so the main path gives +0)
     if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
         if (ix * 2 == 0) return -__int_as_float(0x7f800000);
         if (ix == 0x7f800000u) return x;
@@ -165,23 +165,33 @@ __device__ __forceinline__ float glibc_logf(float x) {
 
 // One step of feature_distance (qt_cpp/db_features.cpp:26,29-36): fp32, no FMA contraction,
 // IEEE round-to-nearest for every operation, in the reference's operation order.
+// The chi-square and KL steps are written branch-free: the reference's `if (l + r > 0)` / `if (l > 0)` guards become
+// selects around the same arithmetic on a safe operand (about half of ReLU-style features are exact zeros, so branching
+// diverges in nearly every warp, and a zero denominator would push the IEEE division onto its slow path).
 template <int METRIC>
 __device__ __forceinline__ void dist_step(float& acc, float l, float r) {
     if (METRIC == FIR_L2) {
         float d = __fsub_rn(l, r);
         acc = __fadd_rn(acc, __fmul_rn(d, d));
     } else if (METRIC == FIR_CHI2) {
-        float s = __fadd_rn(l, r);
-        if (s > 0.f) {
-            float d = __fsub_rn(l, r);
-            acc = __fadd_rn(acc, __fdiv_rn(__fmul_rn(d, d), s));
-        }
+        const float s = __fadd_rn(l, r);
+        const bool pos = s > 0.f;
+        const float d = __fsub_rn(l, r);
+        // masked lanes divide 1/1: a zero numerator or denominator would send the IEEE division down its slow path
+        const float q = __fdiv_rn(pos ? __fmul_rn(d, d) : 1.f, pos ? s : 1.f);
+        const float nacc = __fadd_rn(acc, q);
+        acc = pos ? nacc : acc;
     } else {
-        float s = __fadd_rn(l, r);
-        if (s > 0.f) {
-            if (l > 0.f) acc = __fadd_rn(acc, __fmul_rn(l, glibc_logf(__fdiv_rn(__fmul_rn(2.f, l), s))));
-            if (r > 0.f) acc = __fadd_rn(acc, __fmul_rn(r, glibc_logf(__fdiv_rn(__fmul_rn(2.f, r), s))));
-        }
+        const float s = __fadd_rn(l, r);
+        const bool pos = s > 0.f;
+        const float ss = pos ? s : 1.f;
+        const bool lp = pos && l > 0.f, rp = pos && r > 0.f;
+        const float tl = __fmul_rn(l, glibc_logf(__fdiv_rn(__fmul_rn(2.f, lp ? l : 1.f), ss)));
+        const float a1 = __fadd_rn(acc, tl);
+        acc = lp ? a1 : acc;
+        const float tr = __fmul_rn(r, glibc_logf(__fdiv_rn(__fmul_rn(2.f, rp ? r : 1.f), ss)));
+        const float a2 = __fadd_rn(acc, tr);
+        acc = rp ? a2 : acc;
     }
 }
 

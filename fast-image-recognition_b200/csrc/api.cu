@@ -88,6 +88,24 @@ int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_
     return FIR_OK;
 }
 
+// small-batch path: nq <= 8 queries → 8-row zero-padded query block + one streaming pass → dist[nq][n] in the workspace
+static int stream_distances(fir_gallery* g, const float* queries, int64_t nq, int memspace, int d_end, float** dist_out) {
+    const int dp = g->dp;
+    float* qbuf = (float*)g->ws.take(sizeof(float) * (size_t)kStreamMaxQueries * dp);
+    float* dist = (float*)g->ws.take(sizeof(float) * (size_t)nq * g->n);
+    if (!qbuf || !dist) return fail(FIR_ERR_INTERNAL, "workspace underestimated (stream path)");
+    FIR_CUDA_TRY(cudaMemsetAsync(qbuf, 0, sizeof(float) * (size_t)kStreamMaxQueries * dp, g->stream));
+    FIR_CUDA_TRY(cudaMemcpy2DAsync(qbuf, sizeof(float) * dp, queries, sizeof(float) * g->d, sizeof(float) * g->d, (size_t)nq,
+                                   memspace == FIR_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, g->stream));
+    auto* ev = g->prof_begin(FIR_KERNEL_STREAM_DISTANCES);
+    int st = launch_stream_distances(g->metric, (int)nq, qbuf, dp, g->rows, dp, g->n, d_end, dist, g->n, g->n_sm, g->stream);
+    g->prof_end(ev);
+    FIR_TRY(st);
+    g->stats.gpu_launches++;
+    *dist_out = dist;
+    return FIR_OK;
+}
+
 }  // namespace fir
 
 using namespace fir;
@@ -231,6 +249,31 @@ int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k,
     bool use_tensor = (path == FIR_PATH_TENSOR) || (path == FIR_PATH_AUTO && tensor_ok && nq * g->n >= (int64_t)1 << 22);
     if (use_tensor) return tensor_search_topk(g, queries, nq, k, memspace, out_idx, out_dist);
 
+    if (nq <= kStreamMaxQueries && k <= kStreamMaxK && g->n >= 4096) {
+        // latency mode: one pass over the gallery for all (<= 8) queries, then per-segment top-k + merge
+        const int nseg = (int)std::max<int64_t>(1, std::min<int64_t>(1024, g->n / 2048));
+        size_t need_s = al(sizeof(float) * (size_t)kStreamMaxQueries * g->dp) + al(sizeof(float) * (size_t)nq * g->n) +
+                        2 * al((size_t)nq * nseg * k * 4) + 2 * al((size_t)nq * k * 4) + 4096;
+        FIR_TRY(g->ws.reserve(need_s));
+        float* dist = nullptr;
+        FIR_TRY(stream_distances(g, queries, nq, memspace, d_end, &dist));
+        float* part_d = (float*)g->ws.take((size_t)nq * nseg * k * 4);
+        int32_t* part_i = (int32_t*)g->ws.take((size_t)nq * nseg * k * 4);
+        float* od = out_dist; int32_t* oi = out_idx;
+        if (memspace == FIR_HOST || !out_dist) od = (float*)g->ws.take((size_t)nq * k * 4);
+        if (memspace == FIR_HOST) oi = (int32_t*)g->ws.take((size_t)nq * k * 4);
+        if (!part_d || !part_i || !od || !oi) return fail(FIR_ERR_INTERNAL, "workspace underestimated (stream topk)");
+        FIR_TRY(launch_stream_topk(dist, g->n, g->n, (int)nq, k, nseg, part_d, part_i, g->stream));
+        FIR_TRY(launch_merge_parts(part_d, part_i, nseg, k, (int64_t)nseg * k, nq, k, g->index_offset, nullptr, nullptr, od, oi, g->stream));
+        g->stats.gpu_launches += 2;
+        g->stats.path_used = FIR_PATH_EXACT;
+        if (memspace == FIR_HOST) {
+            FIR_CUDA_TRY(cudaMemcpyAsync(out_idx, oi, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
+            if (out_dist) FIR_CUDA_TRY(cudaMemcpyAsync(out_dist, od, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
+            FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
+        }
+        return FIR_OK;
+    }
     const int nsplit = pick_nsplit(nq, g->n, g->n_sm);
     size_t need = al(sizeof(float) * (size_t)nq * g->dp) + 2 * al((size_t)nq * nsplit * k * 4) + 2 * al((size_t)nq * k * 4) + 4096;
     FIR_TRY(g->ws.reserve(need));
@@ -326,10 +369,14 @@ static int class_reduce(fir_gallery* g, const float* queries, int64_t nq, int me
     FIR_CUDA_TRY(cudaSetDevice(g->device));
     const int C = g->n_classes;
     const size_t cells = (size_t)nq * C;
+    const bool stream = nq <= kStreamMaxQueries && g->n >= 4096;
     size_t need = al(sizeof(float) * (size_t)nq * g->dp) + al(cells * 8) + al(cells * 4) * 2 + al((size_t)nq * 4) + 4096;
+    if (stream) need += al(sizeof(float) * (size_t)kStreamMaxQueries * g->dp) + al(sizeof(float) * (size_t)nq * g->n);
     FIR_TRY(g->ws.reserve(need));
     const float* dq = nullptr;
-    FIR_TRY(stage_queries(g, queries, nq, memspace, &dq));
+    float* sdist = nullptr;
+    if (stream) FIR_TRY(stream_distances(g, queries, nq, memspace, g->d, &sdist));
+    else FIR_TRY(stage_queries(g, queries, nq, memspace, &dq));
     ExactParams p{};
     p.q = dq; p.nq = nq; p.ldq = g->dp;
     p.x = g->rows; p.n = g->n; p.ldx = g->dp;
@@ -345,7 +392,8 @@ static int class_reduce(fir_gallery* g, const float* queries, int64_t nq, int me
         if (!keys || !dmin || !darg) return fail(FIR_ERR_INTERNAL, "workspace underestimated (classmin)");
         FIR_TRY(launch_fill_u64(keys, (int64_t)cells, ~0ull, g->stream));
         p.cls_key = keys;
-        FIR_TRY(launch_exact_tiles(g->metric, p, g->stream));
+        if (stream) FIR_TRY(launch_stream_class(sdist, g->n, g->n, (int)nq, g->labels, C, MODE_CLASSMIN, 0.0, keys, nullptr, g->stream));
+        else FIR_TRY(launch_exact_tiles(g->metric, p, g->stream));
         FIR_TRY(launch_classmin_finalize(keys, (int64_t)cells, g->index_offset, dmin, darg, g->stream));
         if (memspace == FIR_HOST) {
             FIR_CUDA_TRY(cudaMemcpyAsync(out_min, dmin, cells * 4, cudaMemcpyDeviceToHost, g->stream));
@@ -360,7 +408,8 @@ static int class_reduce(fir_gallery* g, const float* queries, int64_t nq, int me
         if (!sc) return fail(FIR_ERR_INTERNAL, "workspace underestimated (pnn)");
         FIR_CUDA_TRY(cudaMemsetAsync(sc, 0, cells * 8, g->stream));
         p.cls_score = sc; p.two_var = 2 * var;
-        FIR_TRY(launch_exact_tiles(g->metric, p, g->stream));
+        if (stream) FIR_TRY(launch_stream_class(sdist, g->n, g->n, (int)nq, g->labels, C, MODE_PNN, 2 * var, nullptr, sc, g->stream));
+        else FIR_TRY(launch_exact_tiles(g->metric, p, g->stream));
         FIR_TRY(launch_pnn_finalize(sc, nq, C, (double)(n_total > 0 ? n_total : g->n), lab, g->stream));
         if (memspace == FIR_HOST) {
             if (out_scores) FIR_CUDA_TRY(cudaMemcpyAsync(out_scores, sc, cells * 8, cudaMemcpyDeviceToHost, g->stream));

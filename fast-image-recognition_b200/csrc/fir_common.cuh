@@ -77,6 +77,15 @@ int launch_pair_distances(int metric, const float* q, int64_t nq, int ldq, const
 int launch_normalize_rows(float* rows, int64_t n, int d, int ld, int metric, cudaStream_t s);
 int launch_pad_rows(const float* src, int64_t n, int d, float* dst, int ld, cudaStream_t s);
 
+// ---- small-batch streaming path: stream_kernels.cu --------------------------------------------------
+int launch_stream_distances(int metric, int nq, const float* q, int ldq, const float* x, int ldx, int64_t n, int d_end, float* out,
+                            int64_t out_stride, int n_sm, cudaStream_t s);
+int launch_stream_topk(const float* dist, int64_t stride, int64_t n, int nq, int k, int nseg, float* part_d, int32_t* part_i, cudaStream_t s);
+int launch_stream_class(const float* dist, int64_t stride, int64_t n, int nq, const int32_t* labels, int n_classes, int mode, double two_var,
+                        unsigned long long* cls_key, double* cls_score, cudaStream_t s);
+constexpr int kStreamMaxQueries = 8;
+constexpr int kStreamMaxK = 16;
+
 // ---- tensor-core (tcgen05) L2 candidate path: l2_tensor.cu -------------------------------------
 struct TensorSide {              // fp16 shadow of a set of fp32 rows
     __half* h = nullptr;         // [rows_padded][dph], scaled by `scale`

@@ -109,7 +109,8 @@ typedef enum fir_kernel {
     FIR_KERNEL_L2_CANDIDATES = 0,       /* tcgen05 candidate kernel, first pass (all queries)            */
     FIR_KERNEL_EXACT_TILES = 1,
     FIR_KERNEL_DEM_LIKELIHOOD = 2,
-    FIR_KERNEL_L2_CANDIDATES_PASS2 = 3  /* same kernel, second pass over the few uncertified queries      */
+    FIR_KERNEL_L2_CANDIDATES_PASS2 = 3, /* same kernel, second pass over the few uncertified queries      */
+    FIR_KERNEL_STREAM_DISTANCES = 4     /* small-batch one-pass streaming kernel (HBM-bound)               */
 } fir_kernel;
 int fir_profile_enable(fir_gallery* g, int32_t on);
 int fir_profile_read(fir_gallery* g, int32_t kernel, double* total_ms, int32_t* launches);

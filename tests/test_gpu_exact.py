@@ -152,3 +152,27 @@ def test_error_behaviour(fir):
     idx, dist = gal.search(np.full((2, 8), 1e4, np.float32), k=1, path=fir.PATH_EXACT)   # all distances >= 1e5 ⇒ -1 (ann.cpp:115-116)
     assert (idx == -1).all()
     gal.close()
+
+
+@pytest.mark.parametrize("metric", ["l2", "chi2", "kl"])
+def test_small_batch_streaming_path(fir, port, metric):
+    """<= 8 queries take the one-pass streaming kernels (latency mode); same bits as the reference."""
+    g, gl, q, ql = make_data(port, metric, 5000, 8, 200, 12, seed=13)
+    g[4000:4100] = g[10:110]                              # ties across segments
+    gal = fir.Gallery(g, gl, metric)
+    for nq in (1, 3, 8):
+        for k in (1, 7, 16):
+            idx, dist = gal.search(q[:nq], k=k, path=fir.PATH_EXACT)
+            oi, od = port.topk(metric, g, q[:nq], k)
+            assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od)), (nq, k)
+        mn, arg = gal.class_min(q[:nq])
+        omn, oarg = port.class_min(metric, g, gl, gal.n_classes, q[:nq])
+        assert np.array_equal(arg, oarg) and np.array_equal(bits(mn), bits(omn))
+        sc, lab = gal.pnn_scores(q[:nq], 5e-4)
+        osc, olab = port.pnn_div(metric, g, gl, gal.n_classes, q[:nq], 5e-4)
+        assert np.array_equal(lab, olab)
+        np.testing.assert_allclose(sc, osc, rtol=1e-5, atol=0)
+    idx, dist = gal.search(q[:2], k=1, max_features=96, path=fir.PATH_EXACT)
+    oi, od = port.bf(metric, g, q[:2], max_features=96)
+    assert np.array_equal(idx[:, 0], oi) and np.array_equal(bits(dist[:, 0]), bits(od))
+    gal.close()

@@ -91,6 +91,7 @@ struct TensorSide {              // fp16 shadow of a set of fp32 rows
     __half* h = nullptr;         // [rows_padded][dph], scaled by `scale`
     float* norm2 = nullptr;      // ||x||^2 (fp32 of the fp64 sum), +inf for padding rows
     float* resid = nullptr;      // ||x - h/scale|| rounded up
+    float* row_scale = nullptr;  // per-row power-of-two scale (query side); the gallery side uses one global scale in meta[1]
     unsigned int* meta = nullptr; // [0] = bits of max|x|, [1] = bits of the power-of-two scale (device)
     int64_t rows = 0, rows_padded = 0;
     int64_t perm_a = 1, perm_b = 0;   // shadow row p = original row (p*perm_a + perm_b) mod rows
@@ -99,7 +100,7 @@ struct TensorSide {              // fp16 shadow of a set of fp32 rows
 
 size_t tensor_side_bytes(int64_t rows, int d, int row_tile);
 int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out,
-                     float* d_stats /*[2]: max ||x||, max resid (device)*/, bool permute, cudaStream_t s);
+                     float* d_stats /*[2]: max ||x||, max resid (device)*/, bool permute, bool per_row_scale, cudaStream_t s);
 struct TensorSearchArgs {
     const TensorSide* gal; const TensorSide* qry;
     const CUtensorMap* tmap_a; const CUtensorMap* tmap_b;

@@ -140,17 +140,24 @@ __global__ void absmax_kernel(const float* __restrict__ rows, int64_t n, int ld,
 // meta[0] = absmax bits (in), meta[1] = scale (out, float bits)
 __global__ void pack_rows_kernel(const float* __restrict__ rows, int64_t n, int64_t rows_padded, int ld, int d, int dph,
                                  __half* __restrict__ h, float* __restrict__ norm2, float* __restrict__ resid,
-                                 unsigned int* meta, unsigned int* stats_bits, int64_t perm_a, int64_t perm_b) {
+                                 unsigned int* meta, unsigned int* stats_bits, int64_t perm_a, int64_t perm_b, float* __restrict__ row_scale) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows_padded) return;
-    float amax = __uint_as_float(meta[0]);
+    // scale: a power of two bringing the largest magnitude into [0.5, 1) — one global value for the gallery (meta[0] holds
+    // its max|x|), or one per row for queries (row_scale != nullptr: no separate max pass, each epilogue thread owns a row)
+    float amax = 0.f;
+    if (row_scale) {
+        if (row < n) for (int c = lane; c < d; c += 32) amax = fmaxf(amax, fabsf(rows[row * ld + c]));
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    } else amax = __uint_as_float(meta[0]);
     float scale = 1.f;
     if (amax > 0.f && isfinite(amax)) {
         int e;
         frexpf(amax, &e);                 // amax = m * 2^e, m in [0.5,1)  ⇒  amax * 2^-e in [0.5,1)
         scale = ldexpf(1.f, -e);
     }
+    if (row_scale && lane == 0) row_scale[row] = scale;
     if (row == 0 && lane == 0) meta[1] = __float_as_uint(scale);
     __half* hr = h + row * dph;
     if (row >= n) {
@@ -193,19 +200,20 @@ static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 size_t tensor_side_bytes(int64_t rows, int d, int row_tile) {
     int64_t rp = ceil_div(rows, row_tile) * row_tile;
     int dph = round_up(d, BK);
-    return al256((size_t)rp * dph * 2) + 2 * al256((size_t)rp * 4) + 256 + 1024;
+    return al256((size_t)rp * dph * 2) + 3 * al256((size_t)rp * 4) + 256 + 1024;
 }
 
 static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
 int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out, float* d_stats,
-                     bool permute, cudaStream_t s) {
+                     bool permute, bool per_row_scale, cudaStream_t s) {
     int64_t rp = ceil_div(n, row_tile) * row_tile;
     int dph = round_up(d, BK);
     char* p = (char*)(((uintptr_t)buf + 1023) & ~(uintptr_t)1023);     // TMA global address alignment (>=16B); keep 1 KiB
     out->h = (__half*)p; p += al256((size_t)rp * dph * 2);
     out->norm2 = (float*)p; p += al256((size_t)rp * 4);
     out->resid = (float*)p; p += al256((size_t)rp * 4);
+    out->row_scale = (float*)p; p += al256((size_t)rp * 4);
     out->meta = (unsigned int*)p;
     out->rows = n; out->rows_padded = rp; out->dph = dph;
     // Gallery shadow rows are stored in a strided permutation so that rows which are neighbours in the caller's
@@ -218,11 +226,13 @@ int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, 
         out->perm_a = a % n; out->perm_b = n / 3;
     }
     FIR_CUDA_TRY(cudaMemsetAsync(out->meta, 0, 16, s));
-    int blocks = (int)std::min<int64_t>(1184, ceil_div(n * d, 256 * 8));
-    absmax_kernel<<<std::max(blocks, 1), 256, 0, s>>>(rows, n, ld, d, out->meta);
-    FIR_CUDA_TRY(cudaGetLastError());
+    if (!per_row_scale) {
+        int blocks = (int)std::min<int64_t>(1184, ceil_div(n * d, 256 * 8));
+        absmax_kernel<<<std::max(blocks, 1), 256, 0, s>>>(rows, n, ld, d, out->meta);
+        FIR_CUDA_TRY(cudaGetLastError());
+    }
     pack_rows_kernel<<<(unsigned)ceil_div(rp, 8), 256, 0, s>>>(rows, n, rp, ld, d, dph, out->h, out->norm2, out->resid, out->meta,
-                                                              (unsigned int*)d_stats, out->perm_a, out->perm_b);
+                                                              (unsigned int*)d_stats, out->perm_a, out->perm_b, per_row_scale ? out->row_scale : nullptr);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
@@ -324,7 +334,7 @@ struct CandParams {
     const float* gal_norm2;
     const float* qry_norm2;
     const unsigned int* gal_meta;
-    const unsigned int* qry_meta;
+    const float* qry_row_scale;
     float* cand_val;
     int32_t* cand_idx;
     float* slot_bound;
@@ -362,7 +372,7 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t taddr, const float* 
         uint32_t rr[32];
         tc_ld32(taddr + c0, rr);
         tc_wait_ld();
-        float vmin = __int_as_float(0x7f800000);
+        float gm[8];                                    // minimum of each group of 4 columns
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
@@ -372,31 +382,32 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t taddr, const float* 
             float v3 = fmaf(negc, __uint_as_float(rr[i + 3]), nx4.w);
             rr[i + 0] = __float_as_uint(v0); rr[i + 1] = __float_as_uint(v1);
             rr[i + 2] = __float_as_uint(v2); rr[i + 3] = __float_as_uint(v3);
-            vmin = fminf(vmin, fminf(fminf(v0, v1), fminf(v2, v3)));
+            gm[i >> 2] = fminf(fminf(v0, v1), fminf(v2, v3));
         }
+        const float vmin = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
         if (__any_sync(0xffffffffu, vmin < thr)) {
-            // Rare path.  Per-lane hit mask, then ONE replacement body shared by every column: the column index is made
-            // warp-uniform (OR-reduction of the masks) so selecting rr[i] is a uniform switch, not 32 inlined bodies.
-            uint32_t m = 0;
+            // Rare path.  Which groups of 4 columns hold a hit in ANY lane (8-bit masks OR-reduced across the warp): the group
+            // index is then warp-uniform, so fetching its 4 values is a uniform switch and the replacement body exists 4x, not 32x.
+            uint32_t hg = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m |= (__uint_as_float(rr[i]) < thr) ? (1u << i) : 0u;
-            uint32_t many = __reduce_or_sync(0xffffffffu, m);
+            for (int g = 0; g < 8; ++g) hg |= (gm[g] < thr) ? (1u << g) : 0u;
+            uint32_t many = __reduce_or_sync(0xffffffffu, hg);
 #pragma unroll 1
             while (many) {
-                const int i = __ffs(many) - 1;
+                const int g = __ffs(many) - 1;
                 many &= many - 1;
-                uint32_t bits;
-                switch (i) {
-#define FIR_CASE(I) case I: bits = rr[I]; break;
-                    FIR_CASE(0) FIR_CASE(1) FIR_CASE(2) FIR_CASE(3) FIR_CASE(4) FIR_CASE(5) FIR_CASE(6) FIR_CASE(7)
-                    FIR_CASE(8) FIR_CASE(9) FIR_CASE(10) FIR_CASE(11) FIR_CASE(12) FIR_CASE(13) FIR_CASE(14) FIR_CASE(15)
-                    FIR_CASE(16) FIR_CASE(17) FIR_CASE(18) FIR_CASE(19) FIR_CASE(20) FIR_CASE(21) FIR_CASE(22) FIR_CASE(23)
-                    FIR_CASE(24) FIR_CASE(25) FIR_CASE(26) FIR_CASE(27) FIR_CASE(28) FIR_CASE(29) FIR_CASE(30)
-                    default: bits = rr[31]; break;
+                uint32_t b0, b1, b2, b3;
+                switch (g) {
+#define FIR_CASE(G) case G: b0 = rr[4 * G]; b1 = rr[4 * G + 1]; b2 = rr[4 * G + 2]; b3 = rr[4 * G + 3]; break;
+                    FIR_CASE(0) FIR_CASE(1) FIR_CASE(2) FIR_CASE(3) FIR_CASE(4) FIR_CASE(5) FIR_CASE(6)
+                    default: b0 = rr[28]; b1 = rr[29]; b2 = rr[30]; b3 = rr[31]; break;
 #undef FIR_CASE
                 }
-                const float v = __uint_as_float(bits);
-                if (v < thr) topr_replace<R>(lv, li, thr, v, jbase + c0 + i);
+                const int j = jbase + c0 + 4 * g;
+                if (__uint_as_float(b0) < thr) topr_replace<R>(lv, li, thr, __uint_as_float(b0), j);
+                if (__uint_as_float(b1) < thr) topr_replace<R>(lv, li, thr, __uint_as_float(b1), j + 1);
+                if (__uint_as_float(b2) < thr) topr_replace<R>(lv, li, thr, __uint_as_float(b2), j + 2);
+                if (__uint_as_float(b3) < thr) topr_replace<R>(lv, li, thr, __uint_as_float(b3), j + 3);
             }
         }
     }
@@ -540,8 +551,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
         const int e = warp - 4;
         const int lg = e & 3, half = e >> 2;
         const int row = lg * 32 + lane;
-        const float sg = __uint_as_float(p.gal_meta[1]), sq = __uint_as_float(p.qry_meta[1]);
-        const float negc = -2.0f / (sg * sq);
+        const float sg = __uint_as_float(p.gal_meta[1]);
+        float negc = 0.f;                              // −2 / (gallery scale · this row's query scale), set per query block
         float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000);
         int64_t cur_qb = -1;
         int as = 0; uint32_t aphase = 0;
@@ -554,6 +565,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
                 for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = -1; }
                 thr = __int_as_float(0x7f800000);
                 cur_qb = qb;
+                { const int64_t qr = qb * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f)); }
             }
             mbar_wait(smem_u32(&nx_full[as]), aphase);
             mbar_wait(smem_u32(&tmem_full[as]), aphase);
@@ -753,8 +765,8 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         const int e = warp - 4;
         const int lg = e & 3, half = e >> 2;
         const int row = lg * 32 + lane;
-        const float sg = __uint_as_float(p.gal_meta[1]), sq = __uint_as_float(p.qry_meta[1]);
-        const float negc = -2.0f / (sg * sq);
+        const float sg = __uint_as_float(p.gal_meta[1]);
+        float negc = 0.f;                              // −2 / (gallery scale · this row's query scale), set per query block
         float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000);
         int64_t cur_qb = -1;
         int as = 0; uint32_t aphase = 0;
@@ -767,6 +779,7 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
                 for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = -1; }
                 thr = __int_as_float(0x7f800000);
                 cur_qb = qb;
+                { const int64_t qr = qb * (2 * BM) + rank * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f)); }
             }
             mbar_wait(smem_u32(&nx_full[as]), aphase);
             mbar_wait_cluster(smem_u32(&tmem_full[as]), aphase);
@@ -807,7 +820,7 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     p.nkb = a.gal->dph / BK;
     p.n_slots = a.n_slots;
     p.gal_norm2 = a.gal->norm2; p.qry_norm2 = a.qry->norm2;
-    p.gal_meta = a.gal->meta; p.qry_meta = a.qry->meta;
+    p.gal_meta = a.gal->meta; p.qry_row_scale = a.qry->row_scale;
     p.cand_val = a.cand_val; p.cand_idx = a.cand_idx; p.slot_bound = a.slot_bound;
     const bool a_res = p.nkb <= MAX_RES_KB;
     const size_t smem = a.ctas == 2 ? cand_smem_bytes_2cta(a_res) : cand_smem_bytes(a_res);
@@ -973,7 +986,7 @@ static int ensure_gallery_side(fir_gallery* g) {
     FIR_CUDA_TRY(cudaMalloc(&g->tensor_buf, bytes));
     FIR_CUDA_TRY(cudaMalloc(&g->d_stats, 64));
     FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, 64, g->stream));
-    FIR_TRY(tensor_pack_side(g->rows, g->n, g->dp, g->d, BN, g->tensor_buf, &g->tside, g->d_stats, true, g->stream));
+    FIR_TRY(tensor_pack_side(g->rows, g->n, g->dp, g->d, BN, g->tensor_buf, &g->tside, g->d_stats, true, false, g->stream));
     FIR_TRY(tensor_encode_map(&g->tmap_b, g->tside.h, g->tside.rows_padded, g->tside.dph, BN));
     FIR_TRY(tensor_encode_map(&g->tmap_b_half, g->tside.h, g->tside.rows_padded, g->tside.dph, BN / 2));
     g->tensor_ready = true;
@@ -1029,7 +1042,7 @@ bool pass_take(fir_gallery* g, int64_t nq, PassBuffers* pb) {
 int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const PassBuffers& pb, int64_t index_offset, float* od, int32_t* oi,
              int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags, float* max_bound, int prof_kind) {
     TensorSide qs;
-    FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, pb.qbuf, &qs, nullptr, false, g->stream));
+    FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, pb.qbuf, &qs, nullptr, false, true, g->stream));
     CUtensorMap tmap_a;
     FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
     const int rt = pb.n_slots * pb.R;
@@ -1043,7 +1056,7 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, pb.cand_idx, rt, 0, pb.cand_exact, g->stream));
     FIR_TRY(launch_tensor_select(pb.cand_exact, pb.cand_idx, pb.slot_bound, nq, pb.n_slots, pb.R, k, g->d, qs.norm2, qs.resid, g->d_stats, index_offset, od,
                                  oi, flagged, n_flagged, fail_flags, max_bound, g->stream));
-    g->stats.gpu_launches += 6;   // absmax, pack, candidates, prune, rerank, select
+    g->stats.gpu_launches += 5;   // pack, candidates, prune, rerank, select
     return FIR_OK;
 }
 }  // namespace
@@ -1055,7 +1068,7 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     // gallery — cheap to maintain (cost ~ R² per list).  A list that would have needed more than R of the k best makes the
     // certificate fail; those few queries get a second tensor pass with long lists, and only what even that cannot
     // certify (mass exact ties) is re-run through the exact CUDA-core kernel.  All counts stay on the device.
-    const int64_t cap2 = std::min<int64_t>(nq, 1024);                      // queries served by the second pass
+    const int64_t cap2 = std::min<int64_t>(nq, std::max<int64_t>(256, nq / 64));   // queries served by the second pass (the rest overflow to the exact re-run)
     PassBuffers p1{}, p2{};
     pass_bytes(g, nq, 4, ctas, &p1);
     pass_bytes(g, cap2, 4, ctas, &p2);

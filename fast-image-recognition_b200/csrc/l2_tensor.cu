@@ -308,6 +308,36 @@ inline Partition make_partition(int64_t nq, int64_t n, int n_sm, int ctas) {
     return P;
 }
 
+// Walks a unit's items in order with adds and compares only: the MMA issuer is ONE thread, and a 64-bit division per
+// item (what part_locate costs) is hundreds of serial instructions — enough to starve the tensor pipe between tiles.
+struct WorkIter {
+    int64_t qb, left, in_full, rem_qb0;
+    int tile, ntiles, grid, rem_tile0;
+    __device__ __forceinline__ void init(const Partition& P, int64_t u) {
+        ntiles = (int)P.ntiles; grid = P.grid;
+        in_full = P.full_rounds * P.ntiles;
+        const int64_t lo = part_rem_lo(P, u), cnt = part_rem_lo(P, u + 1) - lo;
+        const int64_t q = P.ntiles ? lo / P.ntiles : 0;
+        rem_qb0 = P.full_rounds * P.grid + q; rem_tile0 = (int)(lo - q * P.ntiles);
+        left = in_full + cnt;
+        if (in_full > 0) { qb = u; tile = 0; } else { qb = rem_qb0; tile = rem_tile0; }
+    }
+    __device__ __forceinline__ bool done() const { return left <= 0; }
+    __device__ __forceinline__ int64_t next_qb() const {          // query block of the following item, -1 if none
+        if (left <= 1) return -1;
+        if (in_full > 0) return in_full == 1 ? rem_qb0 : (tile + 1 == ntiles ? qb + grid : qb);
+        return tile + 1 == ntiles ? qb + 1 : qb;
+    }
+    __device__ __forceinline__ void advance() {
+        --left;
+        if (in_full > 0) {
+            --in_full;
+            if (in_full == 0) { qb = rem_qb0; tile = rem_tile0; }
+            else if (++tile == ntiles) { tile = 0; qb += grid; }
+        } else if (++tile == ntiles) { tile = 0; ++qb; }
+    }
+};
+
 int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots, int* min_slots) {
     const Partition P = make_partition(nq, n, n_sm, ctas);
     int slots = 1, least = P.full_rounds > 0 ? 1 : (1 << 30);
@@ -453,7 +483,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Partition P = p.part;
     const int64_t unit = blockIdx.x;
-    const int64_t n_items = part_count(P, unit);
+    WorkIter work0; work0.init(P, unit);
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();     // SWIZZLE_128B tiles need 1 KiB alignment
@@ -478,9 +508,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         int stage = 0; uint32_t phase = 0; uint32_t a_loads = 0;
         int64_t cur_qb = -1;
-        for (int64_t it = 0; it < n_items; ++it) {
-            int64_t qb, tile;
-            part_locate(P, unit, it, qb, tile);
+        for (WorkIter wi = work0; !wi.done(); wi.advance()) {
+            const int64_t qb = wi.qb; const int64_t tile = wi.tile;
             if (A_RES && qb != cur_qb) {
                 mbar_wait(smem_u32(a_empty), (a_loads & 1) ^ 1);      // every MMA that read the old A has retired
                 mbar_expect_tx(smem_u32(a_full), (uint32_t)p.nkb * A_KB_BYTES);
@@ -503,9 +532,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
         int stage = 0; uint32_t phase = 0; uint32_t a_uses = 0;
         int as = 0; uint32_t aphase = 0;
         int64_t cur_qb = -1;
-        for (int64_t it = 0; it < n_items; ++it) {
-            int64_t qb, tile_unused;
-            part_locate(P, unit, it, qb, tile_unused);
+        for (WorkIter wi = work0; !wi.done(); wi.advance()) {
+            const int64_t qb = wi.qb;
             if (A_RES && qb != cur_qb) { mbar_wait(smem_u32(a_full), a_uses & 1); ++a_uses; }
             cur_qb = qb;
             mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);         // epilogue has drained this accumulator
@@ -525,8 +553,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
             }
             tc_commit(smem_u32(&tmem_full[as]));                      // accumulator ready for the epilogue
             if (A_RES) {
-                bool last_of_qb = it + 1 == n_items;
-                if (!last_of_qb) { int64_t nqb_, nt_; part_locate(P, unit, it + 1, nqb_, nt_); last_of_qb = nqb_ != qb; }
+                const bool last_of_qb = wi.next_qb() != qb;
                 if (last_of_qb) tc_commit(smem_u32(a_empty));
             }
             as ^= 1; if (as == 0) aphase ^= 1;
@@ -534,9 +561,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
     } else if (warp == 3) {
         // ===== norm loader: stages each tile's 256 gallery norms into nx_s[as] for the epilogue warps =====
         int as = 0; uint32_t aphase = 0;
-        for (int64_t it = 0; it < n_items; ++it) {
-            int64_t qb_unused, tile;
-            part_locate(P, unit, it, qb_unused, tile);
+        for (WorkIter wi = work0; !wi.done(); wi.advance()) {
+            const int64_t tile = wi.tile;
             mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);         // epilogue finished with this buffer pair
             const float4* src = reinterpret_cast<const float4*>(p.gal_norm2 + tile * BN + lane * 8);
             const float4 v0 = src[0], v1 = src[1];
@@ -556,9 +582,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
         float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000);
         int64_t cur_qb = -1;
         int as = 0; uint32_t aphase = 0;
-        for (int64_t it = 0; it < n_items; ++it) {
-            int64_t qb, tile;
-            part_locate(P, unit, it, qb, tile);
+        for (WorkIter wi = work0; !wi.done(); wi.advance()) {
+            const int64_t qb = wi.qb; const int64_t tile = wi.tile;
             if (qb != cur_qb) {
                 if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
 #pragma unroll
@@ -663,7 +688,7 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
     const int pair = blockIdx.x >> 1;
     const Partition P = p.part;
     const int64_t unit = pair;
-    const int64_t n_items = part_count(P, unit);
+    WorkIter work0; work0.init(P, unit);
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -691,9 +716,8 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         int stage = 0; uint32_t phase = 0; uint32_t a_loads = 0;
         int64_t cur_qb = -1;
-        for (int64_t it = 0; it < n_items; ++it) {
-            int64_t qb, tile;
-            part_locate(P, unit, it, qb, tile);
+        for (WorkIter wi = work0; !wi.done(); wi.advance()) {
+            const int64_t qb = wi.qb; const int64_t tile = wi.tile;
             const int arow = (int)(qb * (2 * BM) + rank * BM);
             if (A_RES && qb != cur_qb) {
                 mbar_wait(smem_u32(a_empty), (a_loads & 1) ^ 1);
@@ -717,9 +741,8 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         int stage = 0; uint32_t phase = 0; uint32_t a_uses = 0;
         int as = 0; uint32_t aphase = 0;
         int64_t cur_qb = -1;
-        for (int64_t it = 0; it < n_items; ++it) {
-            int64_t qb, tile_unused;
-            part_locate(P, unit, it, qb, tile_unused);
+        for (WorkIter wi = work0; !wi.done(); wi.advance()) {
+            const int64_t qb = wi.qb;
             if (A_RES && qb != cur_qb) { mbar_wait_cluster(smem_u32(a_full), a_uses & 1); ++a_uses; }
             cur_qb = qb;
             mbar_wait_cluster(smem_u32(&tmem_empty[as]), aphase ^ 1);
@@ -739,8 +762,7 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
             }
             tc_commit_2sm(smem_u32(&tmem_full[as]));
             if (A_RES) {
-                bool last_of_qb = it + 1 == n_items;
-                if (!last_of_qb) { int64_t nqb_, nt_; part_locate(P, unit, it + 1, nqb_, nt_); last_of_qb = nqb_ != qb; }
+                const bool last_of_qb = wi.next_qb() != qb;
                 if (last_of_qb) tc_commit_2sm(smem_u32(a_empty));
             }
             as ^= 1; if (as == 0) aphase ^= 1;
@@ -748,9 +770,8 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
     } else if (warp == 3) {
         // ===== norm loader (per CTA) =====
         int as = 0; uint32_t aphase = 0;
-        for (int64_t it = 0; it < n_items; ++it) {
-            int64_t qb_unused, tile;
-            part_locate(P, unit, it, qb_unused, tile);
+        for (WorkIter wi = work0; !wi.done(); wi.advance()) {
+            const int64_t tile = wi.tile;
             mbar_wait(smem_u32(&nx_empty[as]), aphase ^ 1);
             const float4* src = reinterpret_cast<const float4*>(p.gal_norm2 + tile * BN + lane * 8);
             const float4 v0 = src[0], v1 = src[1];
@@ -770,9 +791,8 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000);
         int64_t cur_qb = -1;
         int as = 0; uint32_t aphase = 0;
-        for (int64_t it = 0; it < n_items; ++it) {
-            int64_t qb, tile;
-            part_locate(P, unit, it, qb, tile);
+        for (WorkIter wi = work0; !wi.done(); wi.advance()) {
+            const int64_t qb = wi.qb; const int64_t tile = wi.tile;
             if (qb != cur_qb) {
                 if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
 #pragma unroll

@@ -426,19 +426,43 @@ int launch_pair_distances(int metric, const float* q, int64_t nq, int ldq, const
 // ---------------------------------------------------------------------------------------------------
 // Loader normalisation (qt_cpp/db_features.cpp:79-101), one thread per row, sequential fp32 sums.
 // ---------------------------------------------------------------------------------------------------
-__global__ void normalize_rows_kernel(float* rows, int64_t n, int d, int ld, int metric) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    float* f = rows + r * ld;
+// One warp per 32 rows.  Pass 1: 64-dim slabs are staged coalesced into shared memory and lane r walks row r in index
+// order (the reference's sequential fp32 sum).  Pass 2: every element is re-read coalesced, zeroed / divided, written back.
+constexpr int NCH = 64, NLD = NCH + 1;
+__global__ void __launch_bounds__(128) normalize_rows_kernel(float* rows, int64_t n, int d, int ld, int metric) {
+    __shared__ float tile[4][32 * NLD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* t = tile[warp];
+    const int64_t r0 = ((int64_t)blockIdx.x * 4 + warp) * 32;
+    if (r0 >= n) return;
     float sum = 0.f;
-    for (int i = 0; i < d; ++i) {
-        float v = f[i];
-        if ((double)fabsf(v) < 0.0001) v = 0.f;                               // :85-86 (float |x| against a double literal)
-        f[i] = v;
-        sum = (metric == FIR_L2) ? __fadd_rn(sum, __fmul_rn(v, v)) : __fadd_rn(sum, v);   // :91 / :93
+    for (int c0 = 0; c0 < d; c0 += NCH) {
+        for (int r = 0; r < 32; ++r) {
+#pragma unroll
+            for (int h = 0; h < NCH / 32; ++h) {
+                const int c = c0 + lane + 32 * h;
+                t[r * NLD + lane + 32 * h] = (r0 + r < n && c < d) ? rows[(r0 + r) * ld + c] : 0.f;
+            }
+        }
+        __syncwarp();
+        const int kmax = min(NCH, d - c0);
+        for (int kk = 0; kk < kmax; ++kk) {
+            float v = t[lane * NLD + kk];
+            if ((double)fabsf(v) < 0.0001) v = 0.f;                               // :85-86 (float |x| against a double literal)
+            sum = (metric == FIR_L2) ? __fadd_rn(sum, __fmul_rn(v, v)) : __fadd_rn(sum, v);   // :91 / :93
+        }
+        __syncwarp();
     }
-    if (metric == FIR_L2) sum = __fsqrt_rn(sum);                              // :98
-    for (int i = 0; i < d; ++i) f[i] = __fdiv_rn(f[i], sum);                  // :100-101
+    if (metric == FIR_L2) sum = __fsqrt_rn(sum);                                  // :98
+    for (int r = 0; r < 32 && r0 + r < n; ++r) {
+        const float sr = __shfl_sync(0xffffffffu, sum, r);
+        float* f = rows + (r0 + r) * ld;
+        for (int c = lane; c < d; c += 32) {
+            float v = f[c];
+            if ((double)fabsf(v) < 0.0001) v = 0.f;
+            f[c] = __fdiv_rn(v, sr);                                              // :100-101
+        }
+    }
 }
 int launch_normalize_rows(float* rows, int64_t n, int d, int ld, int metric, cudaStream_t s) {
     if (n <= 0) return FIR_OK;

@@ -19,8 +19,8 @@ __device__ __forceinline__ void s_cp_async16(void* smem, const void* gmem, int s
 }
 
 constexpr int SW = 4;          // warps per block
-constexpr int SCH = 64;        // dims per slab
-constexpr int SLD = SCH + 4;   // 68 floats: LDS.128 conflict-free across 8 consecutive rows
+constexpr int SCH = 32;        // dims per slab (32: 9 KB per warp in flight ⇒ 5 blocks / 20 warps per SM)
+constexpr int SLD = SCH + 4;   // row stride in floats (36): LDS.128 conflict-free across 8 consecutive rows
 
 template <int METRIC, int NQ>
 __global__ void __launch_bounds__(SW * 32) stream_distance_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ x, int ldx, int64_t n,
@@ -42,12 +42,13 @@ __global__ void __launch_bounds__(SW * 32) stream_distance_kernel(const float* _
         const int64_t r0 = grp * 32;
         auto stage = [&](int slab, int buf) {
             float* t = wt + buf * 32 * SLD;
-            // 32 rows x 16 float4: lane handles float4 column (lane & 15) of rows (lane >> 4) + 2*i
-            const int c4 = (lane & 15) * 4, rr = lane >> 4;
+            // 32 rows x (SCH/4) float4: lane handles float4 column (lane % CPR) of rows (lane / CPR) + RPI*i
+            constexpr int CPR = SCH / 4, RPI = 32 / CPR;
+            const int c4 = (lane % CPR) * 4, rr = lane / CPR;
             const int col = slab * SCH + c4;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int r = rr + 2 * i;
+            for (int i = 0; i < 32 / RPI; ++i) {
+                const int r = rr + RPI * i;
                 const int64_t row = r0 + r;
                 const bool ok = row < n && col < ldx;
                 s_cp_async16(&t[r * SLD + c4], x + (ok ? row : 0) * ldx + (ok ? col : 0), ok ? 16 : 0);
@@ -95,7 +96,7 @@ static int launch_stream_metric(int nq, const float* q, int ldq, const float* x,
     const int dq_pad = (d_end + SCH - 1) / SCH * SCH;
     const int NQ = nq <= 1 ? 1 : (nq <= 2 ? 2 : (nq <= 4 ? 4 : 8));
     const size_t smem = sizeof(float) * ((size_t)NQ * dq_pad + (size_t)SW * 2 * 32 * SLD);
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ceil_div(n, 32), SW), (int64_t)n_sm * 3));
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ceil_div(n, 32), SW), (int64_t)n_sm * 6));
     auto go = [&](auto kern) -> int {
         FIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, SW * 32, smem, s>>>(q, ldq, x, ldx, n, d_end, out, out_stride);

@@ -25,7 +25,7 @@ LIB_PATH = os.environ.get("FIR_B200_LIB") or os.path.join(_HERE, "libfir_b200.so
 L2, CHI2, KL = 0, 1, 2
 METRICS = {"l2": L2, "chi2": CHI2, "kl": KL}
 HOST, DEVICE = 0, 1
-PATH_AUTO, PATH_EXACT, PATH_TENSOR = 0, 1, 2
+PATH_AUTO, PATH_EXACT, PATH_TENSOR, PATH_APPROX = 0, 1, 2, 3
 
 EXPORTS = [
     "fir_last_error_string", "fir_version", "fir_device_count", "fir_set_device",

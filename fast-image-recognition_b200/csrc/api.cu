@@ -184,6 +184,7 @@ int fir_gallery_destroy(fir_gallery* g) {
     if (g->labels) cudaFree(g->labels);
     if (g->tensor_buf) cudaFree(g->tensor_buf);
     if (g->d_stats) cudaFree(g->d_stats);
+    if (g->d_l1max) cudaFree(g->d_l1max);
     for (auto& e : g->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     g->ws.release();
     delete g;
@@ -248,6 +249,10 @@ int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k,
         return fail(FIR_ERR_UNSUPPORTED, "tensor path needs L2, all dimensions, k<=28 and an sm_100 device");
     bool use_tensor = (path == FIR_PATH_TENSOR) || (path == FIR_PATH_AUTO && tensor_ok && nq * g->n >= (int64_t)1 << 22);
     if (use_tensor) return tensor_search_topk(g, queries, nq, k, memspace, out_idx, out_dist);
+    const bool approx_ok = g->metric != FIR_L2 && max_features == 0 && k <= 28;
+    if (path == FIR_PATH_APPROX && !approx_ok) return fail(FIR_ERR_UNSUPPORTED, "approximate path needs chi2/KL, all dimensions and k<=28");
+    if (path == FIR_PATH_APPROX || (path == FIR_PATH_AUTO && approx_ok && nq > kStreamMaxQueries && nq * g->n >= (int64_t)1 << 22))
+        return approx_search_topk(g, queries, nq, k, memspace, out_idx, out_dist);
 
     if (nq <= kStreamMaxQueries && k <= kStreamMaxK && g->n >= 4096) {
         // latency mode: one pass over the gallery for all (<= 8) queries, then per-segment top-k + merge
@@ -319,6 +324,14 @@ int fir_profile_read(fir_gallery* g, int32_t kernel, double* total_ms, int32_t* 
 
 int fir_search_last_stats(const fir_gallery* g, fir_search_stats* stats) {
     if (!g || !stats) return fail(FIR_ERR_BAD_ARG, "null argument");
+    if (g->stats.path_used == FIR_PATH_APPROX && g->stats.n_fallback < 0 && g->d_l1max) {
+        fir_gallery* m = const_cast<fir_gallery*>(g);
+        int32_t nf = 0; float mb = 0.f;
+        FIR_CUDA_TRY(cudaStreamSynchronize(m->stream));
+        FIR_CUDA_TRY(cudaMemcpy(&nf, m->d_l1max + 4, 4, cudaMemcpyDeviceToHost));
+        FIR_CUDA_TRY(cudaMemcpy(&mb, m->d_l1max + 5, 4, cudaMemcpyDeviceToHost));
+        m->stats.n_fallback = nf; m->stats.reserved = (float)nf; m->stats.approx_err_bound = mb;
+    }
     if (g->stats.path_used == FIR_PATH_TENSOR && g->stats.n_fallback < 0 && g->d_stats) {
         fir_gallery* m = const_cast<fir_gallery*>(g);      // device-side counters are fetched on demand
         int32_t nf = 0; float mb = 0.f;

@@ -115,11 +115,24 @@ int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slo
 int tensor_cta_mode();
 int tensor_encode_map(CUtensorMap* map, const __half* base, int64_t rows_padded, int dph, int box_rows);
 int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s);
-int launch_tensor_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots,
-                         int R, int k, int d, const float* q_norm2, const float* q_resid, const float* gal_stats,
-                         int64_t index_offset, float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged,
-                         unsigned char* fail_flags, float* max_bound, cudaStream_t s);
+
 bool tensor_path_supported(int d);
+
+// How far an approximate candidate value can be from the reference's own result, per query:
+//   |approx − dist_scale·reference| ≤ E + rel·(dist_scale·reference)
+struct ErrModel {
+    int kind;                 // 0: fp16 tensor-core L2 (Cauchy–Schwarz on measured residuals); 1: relative only; 2: E from L1 norms
+    int d, nkb;
+    const float* q_norm2; const float* q_resid; const float* gal_stats;     // kind 0
+    double rel;               // relative part (kind 0: the reference's sequential-sum error (D+4)·2⁻²⁴)
+    double abs_coef;          // kind 2: E = abs_coef · (‖q‖₁ + max‖x‖₁)
+    const float* q_l1; const float* x_l1_max;                               // kind 2 (device)
+    double dist_scale;        // approx units per reference-distance unit: D on the tensor path (squared distance), 1 otherwise
+};
+int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s);
+int launch_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots, int R, int k,
+                  const ErrModel& em, int64_t index_offset, float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged,
+                  unsigned char* fail_flags, float* max_bound, cudaStream_t s);
 
 }  // namespace fir
 

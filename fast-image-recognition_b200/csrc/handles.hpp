@@ -19,6 +19,7 @@ struct fir_gallery {
     CUtensorMap tmap_b;           // box 64 x 256 rows (single-CTA kernel)
     CUtensorMap tmap_b_half;      // box 64 x 128 rows (each CTA of a pair loads half a tile)
     float* d_stats = nullptr;     // [2] max ||x||, max ||x - fp16(x)||
+    float* d_l1max = nullptr;     // chi2/KL approximate path: [0] max ||x||_1, [4] flagged count, [5] max bound
     fir::Workspace ws;
     // diagnostics: where the last tensor-path call left its candidate lists (valid until the next call)
     const float* dbg_cand_val = nullptr; const float* dbg_cand_exact = nullptr; const int32_t* dbg_cand_idx = nullptr;
@@ -41,4 +42,5 @@ int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_
                       const int32_t* n_active, float* part_d, int32_t* part_i, int nsplit, float* od, int32_t* oi,
                       int64_t active_offset = 0, int64_t active_cap = 0);
 int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
+int approx_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
 }

@@ -874,6 +874,13 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
 // certify: every non-candidate row has approx ≥ B = min over lists of the list's maximum, hence
 //         reference·D ≥ (B − E)(1 − ρ); certified when that exceeds the k-th exact distance (strictly).
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double approx_error_bound(double nq2, double rq, double NX, double RX, int nkb);
+__device__ __forceinline__ void err_bounds(const ErrModel& m, int64_t q, double& E, double& rho) {
+    rho = m.rel;
+    if (m.kind == 0) E = approx_error_bound((double)m.q_norm2[q], (double)m.q_resid[q], (double)m.gal_stats[0], (double)m.gal_stats[1], m.nkb);
+    else if (m.kind == 2) E = m.abs_coef * ((double)m.q_l1[q] + (double)*m.x_l1_max);
+    else E = 0.0;
+}
 __device__ __forceinline__ double approx_error_bound(double nq2, double rq, double NX, double RX, int nkb) {
     const double nqn = sqrt(nq2);
     const double gamma = (double)(4 * nkb + 8) * 2.384185791015625e-07;        // (#UMMA K-steps + 8) · 2⁻²²
@@ -881,8 +888,7 @@ __device__ __forceinline__ double approx_error_bound(double nq2, double rq, doub
 }
 
 __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ cand_val, int32_t* __restrict__ cand_idx, int64_t nq, int rt, int k,
-                                                           int d, int nkb, const float* __restrict__ q_norm2, const float* __restrict__ q_resid,
-                                                           const float* __restrict__ gal_stats) {
+                                                           const ErrModel em) {
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (q >= nq) return;
@@ -905,8 +911,8 @@ __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ c
         kth = best; taken += cnt;
     }
     if (taken < k) return;                                                     // keep everything
-    const double E = approx_error_bound((double)q_norm2[q], (double)q_resid[q], (double)gal_stats[0], (double)gal_stats[1], nkb);
-    const double rho = (double)(d + 4) * 5.9604644775390625e-08;
+    double E, rho;
+    err_bounds(em, q, E, rho);
     // c is dominated when (approx_c − E)(1−ρ) > (kth + E)(1+ρ): then reference(c) > reference(each of the k best-by-approx)
     const double cut = ((double)kth + E) * (1.0 + rho) / (1.0 - rho) + E;
     // compact the survivors to the front (order is irrelevant downstream)
@@ -926,9 +932,8 @@ __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ c
 }
 
 __global__ void __launch_bounds__(128) tensor_select_kernel(const float* __restrict__ cand_exact, const int32_t* __restrict__ cand_idx,
-                                                            const float* __restrict__ slot_bound, int64_t nq, int n_slots, int R, int k, int d, int nkb,
-                                                            const float* __restrict__ q_norm2, const float* __restrict__ q_resid,
-                                                            const float* __restrict__ gal_stats, int64_t index_offset, float* __restrict__ out_dist,
+                                                            const float* __restrict__ slot_bound, int64_t nq, int n_slots, int R, int k,
+                                                            const ErrModel em, int64_t index_offset, float* __restrict__ out_dist,
                                                             int32_t* __restrict__ out_idx, int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags,
                                                             float* max_bound) {
     const int lane = threadIdx.x & 31;
@@ -968,31 +973,27 @@ __global__ void __launch_bounds__(128) tensor_select_kernel(const float* __restr
         const float b = slot_bound[q * n_slots + s];
         if (b == b && (double)b < B) B = (double)b;                            // NaN = list never written = nothing excluded there
     }
-    const double E = approx_error_bound((double)q_norm2[q], (double)q_resid[q], (double)gal_stats[0], (double)gal_stats[1], nkb);
-    const double rho = (double)(d + 4) * 5.9604644775390625e-08;
+    double E, rho;
+    err_bounds(em, q, E, rho);
     bool ok;
     if (isinf(B)) ok = true;                                                   // every row of the gallery was a candidate
     else if (found < k) ok = false;
-    else ok = (B - E) * (1.0 - rho) > (double)kth * (double)d * (1.0 + rho);
+    else ok = (B - E) * (1.0 - rho) > (double)kth * em.dist_scale * (1.0 + rho);
     if (!ok) { int pos = atomicAdd(n_flagged, 1); flagged[pos] = (int32_t)q; if (fail_flags) fail_flags[q] = 1; }
     atomicMax(reinterpret_cast<unsigned int*>(max_bound), __float_as_uint((float)E));
 }
 
-int launch_tensor_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, int d, const float* q_norm2, const float* q_resid,
-                        const float* gal_stats, cudaStream_t s) {
-    const int nkb = round_up(d, BK) / BK;
-    tensor_prune_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cand_val, cand_idx, nq, rt, k, d, nkb, q_norm2, q_resid, gal_stats);
+int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s) {
+    tensor_prune_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cand_val, cand_idx, nq, rt, k, em);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
 
-int launch_tensor_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots, int R,
-                         int k, int d, const float* q_norm2, const float* q_resid, const float* gal_stats, int64_t index_offset,
-                         float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags, float* max_bound, cudaStream_t s) {
-    const int nkb = round_up(d, BK) / BK;
-    tensor_select_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, d, nkb, q_norm2,
-                                                                   q_resid, gal_stats, index_offset, out_dist, out_idx, flagged,
-                                                                   n_flagged, fail_flags, max_bound);
+int launch_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots, int R, int k,
+                  const ErrModel& em, int64_t index_offset, float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged,
+                  unsigned char* fail_flags, float* max_bound, cudaStream_t s) {
+    tensor_select_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, em, index_offset, out_dist,
+                                                                   out_idx, flagged, n_flagged, fail_flags, max_bound);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
@@ -1072,10 +1073,13 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     a.gal = &g->tside; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = ctas == 2 ? &g->tmap_b_half : &g->tmap_b; a.ctas = ctas;
     a.n_sm = g->n_sm; a.d = g->d; a.R = pb.R; a.n_slots = pb.n_slots; a.cand_val = pb.cand_val; a.cand_idx = pb.cand_idx; a.slot_bound = pb.slot_bound; a.grid = pb.grid;
     { auto* ev = g->prof_begin(prof_kind); int st_ = launch_tensor_candidates(a, g->stream); g->prof_end(ev); FIR_TRY(st_); }
-    FIR_TRY(launch_tensor_prune(pb.cand_val, pb.cand_idx, nq, rt, k, g->d, qs.norm2, qs.resid, g->d_stats, g->stream));
+    ErrModel em{};
+    em.kind = 0; em.d = g->d; em.nkb = round_up(g->d, BK) / BK; em.q_norm2 = qs.norm2; em.q_resid = qs.resid; em.gal_stats = g->d_stats;
+    em.rel = (double)(g->d + 4) * 5.9604644775390625e-08; em.dist_scale = (double)g->d;
+    FIR_TRY(launch_prune(pb.cand_val, pb.cand_idx, nq, rt, k, em, g->stream));
     FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, pb.cand_idx, rt, 0, pb.cand_exact, g->stream));
-    FIR_TRY(launch_tensor_select(pb.cand_exact, pb.cand_idx, pb.slot_bound, nq, pb.n_slots, pb.R, k, g->d, qs.norm2, qs.resid, g->d_stats, index_offset, od,
-                                 oi, flagged, n_flagged, fail_flags, max_bound, g->stream));
+    FIR_TRY(launch_select(pb.cand_exact, pb.cand_idx, pb.slot_bound, nq, pb.n_slots, pb.R, k, em, index_offset, od, oi, flagged, n_flagged, fail_flags,
+                          max_bound, g->stream));
     g->stats.gpu_launches += 5;   // pack, candidates, prune, rerank, select
     return FIR_OK;
 }

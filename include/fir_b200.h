@@ -47,9 +47,11 @@ typedef enum fir_metric { FIR_L2 = 0, FIR_CHI2 = 1, FIR_KL = 2 } fir_metric;
 typedef enum fir_memspace { FIR_HOST = 0, FIR_DEVICE = 1 } fir_memspace;
 /* which kernels serve fir_search_topk */
 typedef enum fir_path {
-    FIR_PATH_AUTO = 0,   /* L2: tensor-core candidates + exact rerank; chi2/KL: exact CUDA-core tiles */
+    FIR_PATH_AUTO = 0,   /* L2: tensor-core candidates + exact rerank; chi2/KL: approximate tiles + exact rerank;
+                            <= 8 queries: one-pass streaming kernels                                  */
     FIR_PATH_EXACT = 1,  /* exact CUDA-core tile kernel for every metric                              */
-    FIR_PATH_TENSOR = 2  /* force the tcgen05 path (L2 only)                                          */
+    FIR_PATH_TENSOR = 2, /* force the tcgen05 path (L2 only)                                          */
+    FIR_PATH_APPROX = 3  /* chi2/KL: fast-intrinsic approximate tiles + exact rerank + certificate     */
 } fir_path;
 
 typedef struct fir_gallery fir_gallery;       /* vector<ImageInfo> dbImages + its ImagesDatabase      */
@@ -110,7 +112,8 @@ typedef enum fir_kernel {
     FIR_KERNEL_EXACT_TILES = 1,
     FIR_KERNEL_DEM_LIKELIHOOD = 2,
     FIR_KERNEL_L2_CANDIDATES_PASS2 = 3, /* same kernel, second pass over the few uncertified queries      */
-    FIR_KERNEL_STREAM_DISTANCES = 4     /* small-batch one-pass streaming kernel (HBM-bound)               */
+    FIR_KERNEL_STREAM_DISTANCES = 4,    /* small-batch one-pass streaming kernel (HBM-bound)               */
+    FIR_KERNEL_APPROX_TILES = 5         /* chi2/KL approximate tile kernel                                  */
 } fir_kernel;
 int fir_profile_enable(fir_gallery* g, int32_t on);
 int fir_profile_read(fir_gallery* g, int32_t kernel, double* total_ms, int32_t* launches);

@@ -176,3 +176,18 @@ def test_small_batch_streaming_path(fir, port, metric):
     oi, od = port.bf(metric, g, q[:2], max_features=96)
     assert np.array_equal(idx[:, 0], oi) and np.array_equal(bits(dist[:, 0]), bits(od))
     gal.close()
+
+
+@pytest.mark.parametrize("metric,n,nq,d,c", [("chi2", 3000, 200, 160, 20), ("kl", 2500, 150, 96, 15), ("chi2", 777, 40, 100, 6)])
+def test_approximate_pass_with_exact_rerank(fir, port, metric, n, nq, d, c):
+    """chi2/KL batched search through the fast approximate tiles: the certificate + exact rerank must return the
+    reference's bits, also with duplicated rows (exact ties ⇒ certificate failures ⇒ exact re-run)."""
+    g, gl, q, ql = make_data(port, metric, n, nq, d, c, seed=n % 11)
+    g[n - 60:] = g[:60]
+    gal = fir.Gallery(g, gl, metric)
+    for k in (1, 10, 20):
+        idx, dist = gal.search(q, k=k, path=fir.PATH_APPROX)
+        assert gal.stats()["path_used"] == fir.PATH_APPROX
+        oi, od = port.topk(metric, g, q, k, nthreads=8)
+        assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od)), (metric, k, gal.stats())
+    gal.close()

@@ -57,43 +57,66 @@ def traffic_from_profiles():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML (sub-millisecond per sample, every 2 ms) when
+    pynvml is importable, else `nvidia-smi` (the recipe's clocks line, ~5 samples/s)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index=0):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self._stop_evt = gpu_index, [], threading.Event()
+        self.gpu, self.sm, self.max_sm, self.reasons, self._stop_evt, self.source = gpu_index, [], 0.0, set(), threading.Event(), "nvidia-smi"
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].strip().isdigit() else gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        r = [c.strip() for c in out.split(",")]
+        self.sm.append(float(r[0]))
+        self.max_sm = max(self.max_sm, float(r[1]))
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.002 if self.nvml else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        busy = sorted(s for s in sm if s > 0)
-        # median over the upper half of the samples ≈ clocks under load (idle samples bracket the region)
-        load = busy[len(busy) // 2:] if busy else []
-        med = load[len(load) // 2] if load else None
-        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(self.rows)}
+        busy = sorted(s for s in self.sm if s > 0)
+        med = busy[len(busy) // 2] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_sm or None, "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def cpu_reference_arm(g, q, k_unused, seconds_target=15.0, nthreads=None):

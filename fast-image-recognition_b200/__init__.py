@@ -32,7 +32,7 @@ EXPORTS = [
     "fir_gallery_create", "fir_gallery_destroy", "fir_gallery_set_stream", "fir_gallery_info", "fir_gallery_set_num_classes",
     "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
     "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates", "fir_profile_enable", "fir_profile_read",
-    "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn",
+    "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn", "fir_classifier_pnn_sequential",
     "fir_dem_build", "fir_dem_from_state", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
     "fir_dem_get_min_other", "fir_dem_search",
 ]
@@ -87,6 +87,7 @@ def lib():
     L.fir_classifier_destroy.argtypes = [vp]
     L.fir_classifier_knn.argtypes = [vp, vp, i64, i32, vp]
     L.fir_classifier_pnn.argtypes = [vp, vp, i64, vp, vp]
+    L.fir_classifier_pnn_sequential.argtypes = [vp, vp, i64, vp]
     L.fir_dem_build.argtypes = [vp, C.POINTER(DemParams), C.POINTER(vp)]
     L.fir_dem_from_state.argtypes = [vp, vp, i32, vp, C.c_float, C.POINTER(vp)]
     L.fir_dem_destroy.argtypes = [vp]
@@ -295,6 +296,13 @@ class Classifier:
         q = np.ascontiguousarray(queries, dtype=np.float64)
         lab = np.empty(q.shape[0], np.int32)
         _check(lib().fir_classifier_knn(self._h, _ptr(q), q.shape[0], int(K), _ptr(lab)))
+        return lab
+
+    def pnn_sequential(self, queries):
+        """PNNClassifier(bf=False): predict_sequentional."""
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        lab = np.empty(q.shape[0], np.int32)
+        _check(lib().fir_classifier_pnn_sequential(self._h, _ptr(q), q.shape[0], _ptr(lab)))
         return lab
 
     def pnn(self, queries, scores=True):

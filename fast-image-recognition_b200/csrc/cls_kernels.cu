@@ -37,25 +37,30 @@ constexpr int CLD = CK + 1;
 
 // dist[q][t] = sum_fi fl(fl(xc[t][fi] - qc[q][fi])^2), sequential in fi   (classification.cpp:127-142, 201-212)
 __global__ void __launch_bounds__(256) cls_dist_kernel(const double* __restrict__ qc, int64_t nq, const double* __restrict__ xc, int64_t n,
-                                                       int d, double* __restrict__ out) {
+                                                       int d, double* __restrict__ out, int k_lo, int k_hi, int accumulate) {
     __shared__ double qs[CT * CLD];
     __shared__ double xs[CT * CLD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int64_t q0 = (int64_t)blockIdx.y * CT, x0 = (int64_t)blockIdx.x * CT;
+    // dimensions [k_lo, k_hi); with `accumulate` the running sums continue from `out` (sequential PNN: one 32-dim chunk per
+    // call — the same additions in the same order as one uninterrupted sum)
     double acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-    for (int k0 = 0; k0 < d; k0 += CK) {
+        for (int b = 0; b < 4; ++b) {
+            const int64_t qi = q0 + ty + 16 * a, xi = x0 + tx + 16 * b;
+            acc[a][b] = (accumulate && qi < nq && xi < n) ? out[qi * n + xi] : 0.0;
+        }
+    for (int k0 = k_lo; k0 < k_hi; k0 += CK) {
         for (int i = tid; i < CT * CK; i += 256) {
             int r = i / CK, c = i - r * CK;
             int64_t qi = q0 + r, xi = x0 + r;
-            qs[r * CLD + c] = (qi < nq && k0 + c < d) ? qc[qi * d + k0 + c] : 0.0;
-            xs[r * CLD + c] = (xi < n && k0 + c < d) ? xc[xi * d + k0 + c] : 0.0;
+            qs[r * CLD + c] = (qi < nq && k0 + c < k_hi) ? qc[qi * d + k0 + c] : 0.0;
+            xs[r * CLD + c] = (xi < n && k0 + c < k_hi) ? xc[xi * d + k0 + c] : 0.0;
         }
         __syncthreads();
-        const int kmax = min(CK, d - k0);
+        const int kmax = min(CK, k_hi - k0);
         for (int kk = 0; kk < kmax; ++kk) {
             double qa[4], xa[4];
 #pragma unroll
@@ -157,6 +162,25 @@ __global__ void __launch_bounds__(128) knn_vote_kernel(const double* __restrict_
     }
 }
 
+// predict_sequentional's per-chunk decision (classification.cpp:270-292), one thread per query: arg-max over the classes
+// still checked, drop those below max/1e9 (threshold rounded to float as in the reference), stop when one class is left.
+__global__ void pnn_seq_decide_kernel(const double* __restrict__ scores, int64_t nq, int n_classes, unsigned char* __restrict__ check,
+                                      int32_t* __restrict__ best, unsigned char* __restrict__ done) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq || done[q]) return;
+    const double* sc = scores + q * n_classes;
+    unsigned char* ck = check + q * n_classes;
+    double mx = -1.7976931348623157e308; int b = best[q];
+    for (int c = 0; c < n_classes; ++c)
+        if (ck[c] && mx < sc[c]) { mx = sc[c]; b = c; }
+    best[q] = b;
+    const float thr = (float)(mx / 1000000000.0);
+    int variants = 0;
+    for (int c = 0; c < n_classes; ++c)
+        if (ck[c]) { if (sc[c] < (double)thr) ck[c] = 0; else ++variants; }
+    if (variants == 1) done[q] = 1;
+}
+
 }  // namespace fir
 
 using namespace fir;
@@ -213,7 +237,8 @@ int fir_classifier_destroy(fir_classifier* c) {
 }
 
 // shared driver: distances for a chunk of queries, then the requested reducer
-static int classify(fir_classifier* c, const double* queries, int64_t nq, int K, bool pnn, double* out_scores, int32_t* out_label) {
+static int classify(fir_classifier* c, const double* queries, int64_t nq, int K, bool pnn, double* out_scores, int32_t* out_label,
+                    bool sequential = false) {
     if (!c) return fail(FIR_ERR_BAD_ARG, "classifier is null");
     if (nq < 0 || (nq > 0 && (!queries || !out_label))) return fail(FIR_ERR_BAD_ARG, "bad arguments");
     if (!pnn && K < 1) return fail(FIR_ERR_BAD_ARG, "K must be >= 1");
@@ -223,7 +248,7 @@ static int classify(fir_classifier* c, const double* queries, int64_t nq, int K,
     const int64_t chunk = std::max<int64_t>(64, std::min<int64_t>(nq, ((int64_t)512 << 20) / (8 * n)));   // <= 512 MiB of distances
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t need = 2 * al(sizeof(double) * (size_t)chunk * d) + al(sizeof(double) * (size_t)chunk * n) + al(sizeof(double) * (size_t)chunk * C) +
-                  al(sizeof(float) * (size_t)chunk * C) + al(sizeof(int32_t) * (size_t)chunk) + 4096;
+                  al(sizeof(float) * (size_t)chunk * C) + al(sizeof(int32_t) * (size_t)chunk) + al((size_t)chunk * C) + al((size_t)chunk) + 4096;
     FIR_TRY(c->ws.reserve(need));
     double* qraw = (double*)c->ws.take(sizeof(double) * (size_t)chunk * d);
     double* qc = (double*)c->ws.take(sizeof(double) * (size_t)chunk * d);
@@ -231,6 +256,9 @@ static int classify(fir_classifier* c, const double* queries, int64_t nq, int K,
     double* sc = (double*)c->ws.take(sizeof(double) * (size_t)chunk * C);
     float* votes = (float*)c->ws.take(sizeof(float) * (size_t)chunk * C);
     int32_t* lab = (int32_t*)c->ws.take(sizeof(int32_t) * (size_t)chunk);
+    unsigned char* check = (unsigned char*)c->ws.take((size_t)chunk * C);
+    unsigned char* done = (unsigned char*)c->ws.take((size_t)chunk);
+    if (!check || !done) return fail(FIR_ERR_INTERNAL, "workspace underestimated (classifier)");
     if (!qraw || !qc || !dist || !sc || !votes || !lab) return fail(FIR_ERR_INTERNAL, "workspace underestimated (classifier)");
     double var = 0.00002;                                       // classification.cpp:190
     if (d > 2000) var /= 10;                                    // :192-193
@@ -241,8 +269,22 @@ static int classify(fir_classifier* c, const double* queries, int64_t nq, int K,
         FIR_CUDA_TRY(cudaMemcpyAsync(qraw, queries + lo * d, sizeof(double) * (size_t)m * d, cudaMemcpyHostToDevice, s));
         centre_rows_kernel<<<(unsigned)ceil_div(m * d, 256), 256, 0, s>>>(qraw, c->avg, m, d, qc);
         dim3 grid((unsigned)ceil_div(n, CT), (unsigned)ceil_div(m, CT));
-        cls_dist_kernel<<<grid, 256, 0, s>>>(qc, m, c->xc, n, d, dist);
-        if (pnn) {
+        if (!sequential) cls_dist_kernel<<<grid, 256, 0, s>>>(qc, m, c->xc, n, d, dist, 0, d, 0);
+        if (sequential) {
+            // PNNClassifier::predict_sequentional: 32-dimension chunks (delta_features_count, classification.cpp:182).  A class that
+            // is still checked gets the same score as in the reference whatever was pruned before, so every chunk is evaluated
+            // for all classes and the pruning walk is replayed per query by pnn_seq_decide_kernel.
+            FIR_CUDA_TRY(cudaMemsetAsync(check, 1, (size_t)m * C, s));
+            FIR_CUDA_TRY(cudaMemsetAsync(done, 0, (size_t)m, s));
+            FIR_CUDA_TRY(cudaMemsetAsync(lab, 0xFF, sizeof(int32_t) * (size_t)m, s));
+            for (int cur = 0; cur < d; cur += 32) {
+                const int max_fi = std::min(cur + 32, d);
+                cls_dist_kernel<<<grid, 256, 0, s>>>(qc, m, c->xc, n, d, dist, cur, max_fi, cur > 0 ? 1 : 0);
+                pnn_class_sum_kernel<<<(unsigned)ceil_div(m * C, 128), 128, 0, s>>>(dist, m, n, C, c->cls_begin, c->labels, c->class_major ? 1 : 0,
+                                                                                   (2 * var) * (double)(size_t)max_fi, (double)n, sc);
+                pnn_seq_decide_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, s>>>(sc, m, C, check, lab, done);
+            }
+        } else if (pnn) {
             pnn_class_sum_kernel<<<(unsigned)ceil_div(m * C, 128), 128, 0, s>>>(dist, m, n, C, c->cls_begin, c->labels, c->class_major ? 1 : 0, den,
                                                                                (double)n, sc);
             argmax_double_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, s>>>(sc, m, C, lab);
@@ -259,6 +301,10 @@ static int classify(fir_classifier* c, const double* queries, int64_t nq, int K,
 
 int fir_classifier_knn(fir_classifier* c, const double* queries, int64_t nq, int32_t K, int32_t* out_label) {
     return classify(c, queries, nq, K, false, nullptr, out_label);
+}
+
+int fir_classifier_pnn_sequential(fir_classifier* c, const double* queries, int64_t nq, int32_t* out_label) {
+    return classify(c, queries, nq, 0, true, nullptr, out_label, true);
 }
 
 int fir_classifier_pnn(fir_classifier* c, const double* queries, int64_t nq, double* out_scores, int32_t* out_label) {

@@ -161,6 +161,9 @@ int fir_classifier_destroy(fir_classifier* c);
 int fir_classifier_knn(fir_classifier* c, const double* queries, int64_t nq, int32_t K, int32_t* out_label);
 int fir_classifier_pnn(fir_classifier* c, const double* queries, int64_t nq, double* out_scores /* nq x C or NULL */,
                        int32_t* out_label);
+/* replaces: PNNClassifier::predict_sequentional (qt_cpp/classification.cpp:228-295; PNNClassifier(bf=false)): 32-dimension
+ * chunks, classes scoring below max/1e9 are dropped, stop when one class is left.   */
+int fir_classifier_pnn_sequential(fir_classifier* c, const double* queries, int64_t nq, int32_t* out_label);
 
 /* ---- directed enumeration ---------------------------------------------------------------------
  * replaces: DirectedEnumeration (qt_cpp/ann.h:61-100): ctor + init (qt_cpp/ann.cpp:270-348,357-386),

@@ -365,17 +365,21 @@ private:
 
 class PNNClassifier : public Classifier {                                // classification.cpp:173-226 (predict_bf)
 public:
-    PNNClassifier(fir::TrainingSet& ts, bool bf = true, std::string name = "PNN") : Classifier(name, ts) {
-        if (!bf) throw std::invalid_argument("PNNClassifier(bf=false): predict_sequentional is outside the accelerated path");
-    }
+    PNNClassifier(fir::TrainingSet& ts, bool bf = true, std::string name = "PNN") : Classifier(name + (bf ? "" : " (seq)"), ts), bruteforce(bf) {}
     std::vector<int> predict_batch(const std::vector<Feature_vector>& inputs) {
         std::vector<double> q = pack(inputs);
         std::vector<int32_t> lab(inputs.size());
+        if (!bruteforce) {                                               // predict_sequentional, classification.cpp:228-295
+            fir::check(fir_classifier_pnn_sequential(train_set.c, q.data(), (int64_t)inputs.size(), lab.data()), "fir_classifier_pnn_sequential");
+            return std::vector<int>(lab.begin(), lab.end());
+        }
         scores.assign(inputs.size() * (size_t)train_set.n_classes, 0.0);
         fir::check(fir_classifier_pnn(train_set.c, q.data(), (int64_t)inputs.size(), scores.data(), lab.data()), "fir_classifier_pnn");
         return std::vector<int>(lab.begin(), lab.end());
     }
     std::vector<double> scores;                                          // per-class outputs of the last call (locals in the reference, :194)
+private:
+    bool bruteforce;
 };
 
 // BruteForceClassifier (ImageTesting.cpp:58-71): recognize_image_bf over a dimension prefix

@@ -308,6 +308,53 @@ void fir_oracle_pnn(const double* train, const int32_t* train_label, int64_t n, 
     }
 }
 
+void fir_oracle_pnn_seq(const double* train, const int32_t* train_label, int64_t n, int d, int n_classes,
+                        const double* avg, const double* q, int64_t nq, int32_t* out_label) {
+    const int delta = 32;                                               /* delta_features_count, :182 */
+    double var = 0.00002;                                               /* :230 */
+    if (d > 2000) var /= 10;                                            /* :232-233 */
+    double* dist = (double*)malloc(sizeof(double) * (size_t)n);
+    double* outputs = (double*)malloc(sizeof(double) * (size_t)n_classes);
+    char* check = (char*)malloc((size_t)n_classes);
+    for (int64_t i = 0; i < nq; ++i) {
+        int bestClass = -1;
+        for (int64_t t = 0; t < n; ++t) dist[t] = 0;                    /* :237-240 */
+        for (int c = 0; c < n_classes; ++c) { outputs[c] = 0; check[c] = 1; }
+        const double den = (double)n;                                   /* :243 */
+        for (int cur = 0; cur < d; cur += delta) {                      /* :245 */
+            int max_fi = cur + delta;
+            if (max_fi > d) max_fi = d;
+            for (int c = 0; c < n_classes; ++c) if (check[c]) outputs[c] = 0;            /* :251 */
+            for (int64_t t = 0; t < n; ++t) {                           /* class-major ⇒ the order of :249-264 */
+                const int c = train_label[t];
+                if (!check[c]) continue;
+                for (int fi = cur; fi < max_fi; ++fi) {
+                    double diff = train[t * d + fi] - avg[fi];          /* :258 */
+                    double val = q[i * d + fi] - avg[fi];               /* :261 */
+                    diff -= val;
+                    dist[t] += diff * diff;                             /* :264 */
+                }
+                outputs[c] += exp(-dist[t] / (2 * var * (double)(size_t)max_fi));        /* :266 */
+            }
+            double max_output = -DBL_MAX;
+            for (int c = 0; c < n_classes; ++c)
+                if (check[c]) {
+                    outputs[c] = outputs[c] / den;                      /* :268 */
+                    if (max_output < outputs[c]) { max_output = outputs[c]; bestClass = c; }   /* :271-279 */
+                }
+            int variants = 0;
+            const float thr = (float)(max_output / 1000000000);         /* :282, output_dividor = 1E9 (:185) */
+            for (int c = 0; c < n_classes; ++c)
+                if (check[c]) {
+                    if (outputs[c] < thr) check[c] = 0; else ++variants;                  /* :283-289 */
+                }
+            if (variants == 1) break;                                   /* :291-292 */
+        }
+        out_label[i] = bestClass;
+    }
+    free(dist); free(outputs); free(check);
+}
+
 /* ------------------------------------------------------------------------------------------
  * DirectedEnumeration build — ann.cpp:270-348 (PIVOT branch), init :357-386, getThreshold :84-93
  * ------------------------------------------------------------------------------------------ */

@@ -46,6 +46,11 @@ void fir_oracle_knn(const double* train, const int32_t* train_label, int64_t n, 
 void fir_oracle_pnn(const double* train, const int32_t* train_label, int64_t n, int d, int n_classes,
                     const double* avg, const double* q, int64_t nq, double* out_scores, int32_t* out_label);
 
+/* PNNClassifier::predict_sequentional classification.cpp:228-295: 32-dimension chunks, classes whose score falls below
+ * max/1e9 are dropped, stop when one class is left. */
+void fir_oracle_pnn_seq(const double* train, const int32_t* train_label, int64_t n, int d, int n_classes,
+                        const double* avg, const double* q, int64_t nq, int32_t* out_label);
+
 /* DirectedEnumeration ctor + init, ann.cpp:270-348,357-386 (PIVOT build); getThreshold :84-93.
  * pivot0 replaces the first element of the reference's random_shuffle (:369).  keep_rows rows of the
  * pivot-distance matrix are written to P (keep_rows x n); np_out = max(5,(int)(n*0.015)) rows are walked. */

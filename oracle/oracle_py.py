@@ -67,6 +67,7 @@ class Port:
         L.fir_oracle_pnn_div.argtypes = [C.c_int, _f32p, _i32p, C.c_int64, C.c_int, C.c_int, _f32p, C.c_int64, C.c_double, _f64p, _i32p]
         L.fir_oracle_knn.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, _f64p, _f64p, C.c_int64, C.c_int, _i32p]
         L.fir_oracle_pnn.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, _f64p, _f64p, C.c_int64, _f64p, _i32p]
+        L.fir_oracle_pnn_seq.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, _f64p, _f64p, C.c_int64, _i32p]
         L.fir_oracle_dem_build.restype = C.c_int
         L.fir_oracle_dem_build.argtypes = [C.c_int, _f32p, _i32p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                            C.POINTER(C.c_int), _i32p, _f32p, _f32p, C.POINTER(C.c_float)]
@@ -128,6 +129,12 @@ class Port:
         lab = np.empty(q.shape[0], np.int32)
         self.L.fir_oracle_pnn(train, train_label, train.shape[0], train.shape[1], n_classes, avg, q, q.shape[0], sc, lab)
         return sc, lab
+
+    def pnn_seq(self, train, train_label, n_classes, avg, q):
+        train, q, avg, train_label = _f64(train), _f64(q), _f64(avg), _i32(train_label)
+        lab = np.empty(q.shape[0], np.int32)
+        self.L.fir_oracle_pnn_seq(train, train_label, train.shape[0], train.shape[1], n_classes, avg, q, q.shape[0], lab)
+        return lab
 
     def dem_build(self, metric, g, labels, pivot0, far=0.01, threshold=0.0, keep_rows=32):
         g, labels = _f32(g), _i32(labels)
@@ -201,6 +208,8 @@ class Ref:
             L.fir_ref_cls_knn.argtypes = [C.c_int, C.c_long, C.c_long, C.c_int, _i32p]
             L.fir_ref_cls_pnn.restype = C.c_double
             L.fir_ref_cls_pnn.argtypes = [C.c_long, C.c_long, _i32p, C.c_void_p]
+            L.fir_ref_cls_pnn_seq.restype = C.c_double
+            L.fir_ref_cls_pnn_seq.argtypes = [C.c_long, C.c_long, _i32p]
 
     def distance(self, l, r, start=0, end=None):
         l, r = _f32(l), _f32(r)
@@ -303,6 +312,11 @@ class Ref:
     def cls_knn(self, K, first, count, timing=False):
         lab = np.empty(count, np.int32)
         t = self.L.fir_ref_cls_knn(K, first, count, 1, lab)
+        return (lab, t) if timing else lab
+
+    def cls_pnn_seq(self, first, count, timing=False):
+        lab = np.empty(count, np.int32)
+        t = self.L.fir_ref_cls_pnn_seq(first, count, lab)
         return (lab, t) if timing else lab
 
     def cls_pnn(self, first, count, scores=True, timing=False):

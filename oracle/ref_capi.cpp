@@ -378,6 +378,14 @@ double fir_ref_cls_pnn(long first, long count, int* out_label, double* out_score
     }
     return std::chrono::duration<double>(t2 - t1).count();
 }
+// PNNClassifier(false): predict() dispatches to predict_sequentional (classification.cpp:228-295, 297-307)
+double fir_ref_cls_pnn_seq(long first, long count, int* out_label) {
+    PNNClassifier pnn(false);
+    auto t1 = std::chrono::high_resolution_clock::now();
+    for (long j = 0; j < count; ++j) out_label[j] = pnn.predict(tmp_dataset[test_set[first + j]]);
+    auto t2 = std::chrono::high_resolution_clock::now();
+    return std::chrono::duration<double>(t2 - t1).count();
+}
 #endif  // FIR_REF_WITH_CLASSIFICATION
 
 }  // extern "C"

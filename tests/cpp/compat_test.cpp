@@ -50,5 +50,10 @@ int main(int argc, char** argv) {
     std::printf("\nPNN");
     for (size_t i = 0; i < p.size(); ++i) std::printf(" %d", p[i]);
     std::printf("\nPNN1 %d\n", pnn.predict(q[0]));
+    PNNClassifier pnn_seq(ts, false);                                    // predict_sequentional
+    std::vector<int> ps = pnn_seq.predict_batch(q);
+    std::printf("PNNSEQ");
+    for (size_t i = 0; i < ps.size(); ++i) std::printf(" %d", ps[i]);
+    std::printf("\n");
     return 0;
 }

@@ -90,6 +90,15 @@ def main():
     for K in (1, 3):
         out["knn%d" % K] = ref.cls_knn(K, 0, len(te))
     out["pnn_label"], out["pnn_scores"] = ref.cls_pnn(0, len(te))
+    out["pnn_seq_label"] = ref.cls_pnn_seq(0, len(te))
+    # second split with a class-independent first chunk so predict_sequentional's pruning departs from predict_bf
+    rows2 = rows.copy()
+    rows2[:, :32] = np.random.default_rng(11).normal(0, 0.04, size=(len(rows2), 32))
+    rows2 /= np.linalg.norm(rows2, axis=1, keepdims=True)
+    tr2, trl2, te2, avg2 = ref.cls_setup(rows2, labels, 7, 12, seed=5)
+    out.update(rows2=rows2, train_idx2=tr2, train_labels2=trl2, test_idx2=te2, avg2=avg2)
+    out["pnn_seq_label2"] = ref.cls_pnn_seq(0, len(te2))
+    out["pnn_label2"] = ref.cls_pnn(0, len(te2))[0]
     np.savez_compressed(os.path.join(HERE, "ref_classification.npz"), **out)
     print("classification ->", len(out), "arrays")
 

@@ -42,6 +42,31 @@ def test_knn_pnn_match_port_ragged(fir, port):
     clf.close()
 
 
+def _misleading_head(rows, seed, sigma):
+    """Replace the first 32 dimensions with class-independent noise so the sequential PNN prunes on a misleading chunk."""
+    r = np.random.default_rng(seed)
+    rows = rows.copy()
+    rows[:, :32] = r.normal(0, sigma, size=(len(rows), 32))
+    return rows / np.linalg.norm(rows, axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize("n,d,c,per,head", [(900, 96, 12, 20, 0), (600, 200, 9, 15, 0), (700, 100, 10, 20, 0.04), (500, 40, 6, 25, 0.02)])
+def test_pnn_sequential_matches_reference_build(fir, port, ref_l2, n, d, c, per, head):
+    """PNNClassifier(bf=false) == predict_sequentional (classification.cpp:228-295); SURVEY §8(f) rank 1."""
+    rows, labels = _cls_problem(port, n, d, c, seed=n + d)
+    if head:
+        rows = _misleading_head(rows, seed=d, sigma=head)
+    tr, trl, te, avg = ref_l2.cls_setup(rows, labels, c, per, seed=3)
+    clf = fir.Classifier(rows[tr], trl, c, avg)
+    got = clf.pnn_sequential(rows[te])
+    want = ref_l2.cls_pnn_seq(0, len(te))
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, port.pnn_seq(rows[tr], trl, c, avg, rows[te]))
+    if head:                                                           # the pruning walk is really exercised: it differs from predict_bf
+        assert not np.array_equal(got, clf.pnn(rows[te], scores=False)[0])
+    clf.close()
+
+
 @pytest.mark.parametrize("metric", ["l2", "chi2"])
 def test_dem_build_matches_reference(fir, port, metric, request):
     ref = request.getfixturevalue("ref_" + metric)

@@ -52,3 +52,4 @@ def test_cpp_adapters_match_oracle(port, tmp_path):
     assert [int(x) for x in lines["KNN3"]] == port.knn(tr64, dbl, n_classes, avg, te64, 3).tolist()
     sc, pl = port.pnn(tr64, dbl, n_classes, avg, te64)
     assert [int(x) for x in lines["PNN"]] == pl.tolist() and int(lines["PNN1"][0]) == pl[0]
+    assert [int(x) for x in lines["PNNSEQ"]] == port.pnn_seq(tr64, dbl, n_classes, avg, te64).tolist()

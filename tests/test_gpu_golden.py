@@ -63,4 +63,9 @@ def test_classification_golden(fir):
     lab, sc = clf.pnn(rows[te])
     assert np.array_equal(lab, G["pnn_label"])
     np.testing.assert_allclose(sc, G["pnn_scores"], rtol=1e-5, atol=0)
+    assert np.array_equal(clf.pnn_sequential(rows[te]), G["pnn_seq_label"])
+    rows2, tr2, te2 = G["rows2"], G["train_idx2"], G["test_idx2"]
+    clf2 = fir.Classifier(rows2[tr2], G["train_labels2"], 7, G["avg2"])
+    assert np.array_equal(clf2.pnn_sequential(rows2[te2]), G["pnn_seq_label2"])
+    clf2.close()
     clf.close()

@@ -43,3 +43,12 @@ def test_dem_and_classifiers(port, ref_l2):
     rl, rs = ref_l2.cls_pnn(0, len(te))
     ps, pl = port.pnn(rows[tr], trl, 12, avg, rows[te])
     assert np.array_equal(rl, pl) and np.array_equal(bits(rs), bits(ps))
+    assert np.array_equal(ref_l2.cls_pnn_seq(0, len(te)), port.pnn_seq(rows[tr], trl, 12, avg, rows[te]))
+    # a misleading first 32-dimension chunk: predict_sequentional prunes the right class and departs from predict_bf
+    r = np.random.default_rng(0)
+    rows[:, :32] = r.normal(0, 0.04, size=(len(rows), 32))
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    tr, trl, te, avg = ref_l2.cls_setup(rows, labels, 12, 15, seed=2)
+    seq = ref_l2.cls_pnn_seq(0, len(te))
+    assert np.array_equal(seq, port.pnn_seq(rows[tr], trl, 12, avg, rows[te]))
+    assert not np.array_equal(seq, ref_l2.cls_pnn(0, len(te))[0])

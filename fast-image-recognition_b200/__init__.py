@@ -33,6 +33,7 @@ EXPORTS = [
     "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
     "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates", "fir_profile_enable", "fir_profile_read",
     "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn", "fir_classifier_pnn_sequential",
+    "fir_twd_conventional", "fir_twd_proposed",
     "fir_dem_build", "fir_dem_from_state", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
     "fir_dem_get_min_other", "fir_dem_search",
 ]
@@ -88,6 +89,8 @@ def lib():
     L.fir_classifier_knn.argtypes = [vp, vp, i64, i32, vp]
     L.fir_classifier_pnn.argtypes = [vp, vp, i64, vp, vp]
     L.fir_classifier_pnn_sequential.argtypes = [vp, vp, i64, vp]
+    L.fir_twd_conventional.argtypes = [vp, vp, i64, i32, C.c_double, i32, i32, i32, vp, vp, vp]
+    L.fir_twd_proposed.argtypes = [vp, vp, i64, i32, C.c_double, i32, i32, vp, vp, vp]
     L.fir_dem_build.argtypes = [vp, C.POINTER(DemParams), C.POINTER(vp)]
     L.fir_dem_from_state.argtypes = [vp, vp, i32, vp, C.c_float, C.POINTER(vp)]
     L.fir_dem_destroy.argtypes = [vp]
@@ -246,6 +249,30 @@ class Gallery:
         arg = _out((nq, self.n_classes), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
         _check(lib().fir_class_min(self._h, _ptr(q), nq, space, _ptr(mn), _ptr(arg)))
         return mn, arg
+
+    TWD_TYPES = {"posteriors": 0, "diff": 1, "ratio": 2}
+
+    def _twd_out(self, q, space):
+        nq = int(q.shape[0])
+        dev = getattr(q, "device", None)
+        return (_out((nq,), np.int32, "int32", space == DEVICE, dev), _out((nq,), np.int32, "int32", space == DEVICE, dev),
+                _out((nq,), np.uint8, "uint8", space == DEVICE, dev))
+
+    def twd_conventional(self, queries, kind, threshold, feat_count=64, last_feature=256):
+        """ConventionalTWDClassifier(cls_num, kind, threshold, feat_count).recognize → (index, class, unreliable)."""
+        q, space = _prep(queries, np.float32, "float32")
+        idx, lab, unrel = self._twd_out(q, space)
+        _check(lib().fir_twd_conventional(self._h, _ptr(q), int(q.shape[0]), self.TWD_TYPES[kind], float(threshold), int(feat_count),
+                                          int(last_feature), space, _ptr(idx), _ptr(lab), _ptr(unrel)))
+        return idx, lab, unrel
+
+    def twd_proposed(self, queries, feat_count, threshold, last_feature=256):
+        """ProposedTWDClassifier(cls_num, feat_count, threshold).recognize → (index, class, unreliable)."""
+        q, space = _prep(queries, np.float32, "float32")
+        idx, lab, unrel = self._twd_out(q, space)
+        _check(lib().fir_twd_proposed(self._h, _ptr(q), int(q.shape[0]), int(feat_count), float(threshold), int(last_feature), space,
+                                      _ptr(idx), _ptr(lab), _ptr(unrel)))
+        return idx, lab, unrel
 
     def pnn_scores(self, queries, var, n_total=0):
         q, space = _prep(queries, np.float32, "float32")

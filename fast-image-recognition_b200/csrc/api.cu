@@ -442,6 +442,57 @@ int fir_pnn_scores(fir_gallery* g, const float* queries, int64_t nq, double var,
     return class_reduce(g, queries, nq, memspace, MODE_PNN, var, n_total, nullptr, nullptr, out_scores, out_label);
 }
 
+static int twd_entry(fir_gallery* g, const float* queries, int64_t nq, int kind, int type, double threshold, int feat_count, int last_feature,
+                     int memspace, int32_t* out_index, int32_t* out_label, uint8_t* out_unreliable) {
+    if (!g) return fail(FIR_ERR_BAD_ARG, "gallery is null");
+    if (nq < 0 || (nq > 0 && !queries)) return fail(FIR_ERR_BAD_ARG, "bad query pointer");
+    if (memspace != FIR_HOST && memspace != FIR_DEVICE) return fail(FIR_ERR_BAD_ARG, "bad memspace");
+    if (feat_count < 1 || last_feature < 1) return fail(FIR_ERR_BAD_ARG, "feat_count and last_feature must be positive");
+    if (!(threshold == threshold)) return fail(FIR_ERR_BAD_ARG, "threshold is NaN");
+    if (kind == 0) {
+        if (type < 0 || type > 2) return fail(FIR_ERR_BAD_ARG, "type must be 0 (posteriors), 1 (diff) or 2 (ratio)");
+        if (feat_count >= last_feature) return fail(FIR_ERR_BAD_ARG, "feat_count must be below last_feature");
+        if (last_feature > g->d) return fail(FIR_ERR_BAD_ARG, "last_feature exceeds the gallery dimension");
+        if (type == 0 && g->n_classes < 5) return fail(FIR_ERR_UNSUPPORTED, "the posterior test sums the five largest class posteriors: needs >= 5 classes");
+    } else {
+        if (threshold == 0) return fail(FIR_ERR_BAD_ARG, "threshold must be non-zero (the classifier uses 1/threshold)");
+        // the last chunk may run past last_feature when feat_count does not divide it (ImageTesting.cpp:223,243)
+        if ((int64_t)ceil_div(last_feature, feat_count) * feat_count > g->d) return fail(FIR_ERR_BAD_ARG, "the last chunk exceeds the gallery dimension");
+    }
+    if (nq == 0) return FIR_OK;
+    FIR_CUDA_TRY(cudaSetDevice(g->device));
+    int64_t mq = 0;
+    const size_t need = al(sizeof(float) * (size_t)nq * g->dp) + twd_workspace_bytes(g, nq, &mq) + 2 * al(4 * (size_t)nq) + al((size_t)nq) + 4096;
+    FIR_TRY(g->ws.reserve(need));
+    const float* dq = nullptr;
+    FIR_TRY(stage_queries(g, queries, nq, memspace, &dq));
+    int32_t* di = out_index; int32_t* dl = out_label; unsigned char* du = out_unreliable;
+    if (memspace == FIR_HOST) {
+        di = out_index ? (int32_t*)g->ws.take(4 * (size_t)nq) : nullptr;
+        dl = out_label ? (int32_t*)g->ws.take(4 * (size_t)nq) : nullptr;
+        du = out_unreliable ? (unsigned char*)g->ws.take((size_t)nq) : nullptr;
+        if ((out_index && !di) || (out_label && !dl) || (out_unreliable && !du)) return fail(FIR_ERR_INTERNAL, "workspace underestimated (twd outputs)");
+    }
+    FIR_TRY(twd_run(g, dq, nq, mq, kind, type, threshold, feat_count, last_feature, di, dl, du));
+    if (memspace == FIR_HOST) {
+        if (out_index) FIR_CUDA_TRY(cudaMemcpyAsync(out_index, di, 4 * (size_t)nq, cudaMemcpyDeviceToHost, g->stream));
+        if (out_label) FIR_CUDA_TRY(cudaMemcpyAsync(out_label, dl, 4 * (size_t)nq, cudaMemcpyDeviceToHost, g->stream));
+        if (out_unreliable) FIR_CUDA_TRY(cudaMemcpyAsync(out_unreliable, du, (size_t)nq, cudaMemcpyDeviceToHost, g->stream));
+        FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    }
+    return FIR_OK;
+}
+
+int fir_twd_conventional(fir_gallery* g, const float* queries, int64_t nq, int32_t type, double threshold, int32_t feat_count,
+                         int32_t last_feature, int32_t memspace, int32_t* out_index, int32_t* out_label, uint8_t* out_unreliable) {
+    return twd_entry(g, queries, nq, 0, type, threshold, feat_count, last_feature, memspace, out_index, out_label, out_unreliable);
+}
+
+int fir_twd_proposed(fir_gallery* g, const float* queries, int64_t nq, int32_t feat_count, double threshold, int32_t last_feature,
+                     int32_t memspace, int32_t* out_index, int32_t* out_label, uint8_t* out_unreliable) {
+    return twd_entry(g, queries, nq, 1, 0, threshold, feat_count, last_feature, memspace, out_index, out_label, out_unreliable);
+}
+
 int fir_merge_topk(const float* parts_dist, const int32_t* parts_idx, int32_t n_parts, int64_t nq, int32_t k, float* out_dist,
                    int32_t* out_idx, void* cuda_stream) {
     if (!parts_dist || !parts_idx || !out_dist || !out_idx || n_parts < 1 || k < 1 || nq < 0) return fail(FIR_ERR_BAD_ARG, "bad arguments");

@@ -150,6 +150,21 @@ int fir_pnn_scores(fir_gallery* g, const float* queries, int64_t nq, double var,
 int fir_merge_topk(const float* parts_dist, const int32_t* parts_idx, int32_t n_parts, int64_t nq, int32_t k,
                    float* out_dist, int32_t* out_idx, void* cuda_stream);
 
+/* ---- sequential three-way decisions (TWD) ---------------------------------------------------
+ * replaces: ConventionalTWDClassifier::recognize (qt_cpp/ImageTesting.cpp:108-186) and
+ * ProposedTWDClassifier::recognize (:207-288, the CHECK_ALL_INSTANCES build) over a gallery handle (train(&dbImages), :40).
+ *   type            FIR_TWD_POSTERIORS / FIR_TWD_DIST_DIFF / FIR_TWD_DIST_RATIO  (TWD_Type, :76)
+ *   threshold       the constructor's `th` (the proposed classifier applies 1/th itself, :191)
+ *   feat_count      reduced_features_count (:77 default 64; 32 or 64 for the proposed classifier, :533-534)
+ *   last_feature    256 in the reference (:168, :221)
+ *   out_index       bestInd (global gallery index, -1 = none); out_label = its class (what recognize() returns);
+ *   out_unreliable  the query's contribution to num_of_unreliable (:33, :167, :282).  Any output may be NULL. */
+enum { FIR_TWD_POSTERIORS = 0, FIR_TWD_DIST_DIFF = 1, FIR_TWD_DIST_RATIO = 2 };
+int fir_twd_conventional(fir_gallery* g, const float* queries, int64_t nq, int32_t type, double threshold, int32_t feat_count,
+                         int32_t last_feature, int32_t memspace, int32_t* out_index, int32_t* out_label, uint8_t* out_unreliable);
+int fir_twd_proposed(fir_gallery* g, const float* queries, int64_t nq, int32_t feat_count, double threshold, int32_t last_feature,
+                     int32_t memspace, int32_t* out_index, int32_t* out_label, uint8_t* out_unreliable);
+
 /* ---- fp64 kNN / PNN ---------------------------------------------------------------------------
  * replaces: the file-scope training state of qt_cpp/classification.cpp:53-62 as left by
  * split_train_test (:942-990) — training rows in class-major order (the order predict() walks

@@ -4,6 +4,8 @@
 //                          getTrainingAndTestImages, recognize_image_bf)
 //   qt_cpp/ann.h          (ClassificationMethod, BruteForce, DirectedEnumeration)
 //   qt_cpp/classification.cpp's Classifier shape (Feature_vector, Classifier, KNNClassifier, PNNClassifier)
+//   qt_cpp/ImageTesting.cpp  (namespace image_testing: Classifier, BruteForceClassifier, ConventionalTWDClassifier,
+//                             ProposedTWDClassifier, num_of_unreliable)
 // includes this header instead and links -lfir_b200; names, argument meaning and return conventions are the
 // reference's (index -1 = no match, matcher objects borrow `std::vector<ImageInfo>&`).  Differences, all additive:
 //   * FEATURES_COUNT is a run-time value (fir::features_count()) instead of the macro in qt_cpp/db.h:86,
@@ -382,14 +384,123 @@ private:
     bool bruteforce;
 };
 
-// BruteForceClassifier (ImageTesting.cpp:58-71): recognize_image_bf over a dimension prefix
-class BruteForceClassifier {
+// ---- qt_cpp/ImageTesting.cpp: Classifier (:35-48) and its three matching classifiers ----------------------------
+// ImageTesting.cpp has its own `class Classifier` (train(&dbImages) / recognize(testImageInfo) → class); it lives in a nested
+// namespace here because classification.cpp's Classifier above has the same name.  train() packs and uploads the gallery;
+// recognize() is a batch-of-1 call and recognize_batch() hands the whole test set to the GPU.  num_of_unreliable (:33) is
+// the file-scope counter testRecognitionMethod resets and prints (:458,:473).
+namespace image_testing {
+
+inline int& num_of_unreliable() { static int n = 0; return n; }
+
+class Classifier {
 public:
-    explicit BruteForceClassifier(int max_feats = 0) : max_features(max_feats) {}
-    int recognize(std::vector<ImageInfo>& db, ImageInfo& testImageInfo) { return recognize_image_bf(db, testImageInfo, max_features); }
+    Classifier(std::string n) : pDbImages(0), pg(0), name(n) {}
+    virtual ~Classifier() { delete pg; }
+    virtual void train(std::vector<ImageInfo>* pDb) {
+        pDbImages = pDb;
+        delete pg;
+        pg = new detail::PackedGallery(*pDb, fir::metric());
+    }
+    virtual int recognize(ImageInfo& testImageInfo) {
+        std::vector<ImageInfo> one(1, testImageInfo);
+        return recognize_batch(one)[0];
+    }
+    virtual std::vector<int> recognize_batch(std::vector<ImageInfo>& testImages) = 0;
+    std::string get_name() { return name; }
+protected:
+    std::vector<ImageInfo>* pDbImages;
+    detail::PackedGallery* pg;
+    static std::string build_name(std::string prefix, int param) {
+        std::ostringstream os;
+        os << prefix << ", " << param;
+        return os.str();
+    }
+    // run one of the C-ABI classifiers over a batch; counts the unreliable ones like the reference's global does
+    template <typename Call> std::vector<int> run(std::vector<ImageInfo>& testImages, Call call) {
+        std::vector<int> out(testImages.size(), -1);
+        if (!pg || !pg->g || testImages.empty()) return out;
+        std::vector<float> q = detail::pack_queries(testImages, pg->d);
+        std::vector<int32_t> lab(testImages.size());
+        std::vector<uint8_t> unrel(testImages.size());
+        call(q.data(), (int64_t)testImages.size(), lab.data(), unrel.data());
+        for (size_t i = 0; i < out.size(); ++i) { out[i] = lab[i]; num_of_unreliable() += unrel[i]; }
+        return out;
+    }
+private:
+    std::string name;
+    Classifier(const Classifier&);
+    Classifier& operator=(const Classifier&);
+};
+
+class BruteForceClassifier : public Classifier {                         // ImageTesting.cpp:58-71
+public:
+    BruteForceClassifier(int max_feats = fir::features_count()) : Classifier(Classifier::build_name("BF", max_feats)), max_features(max_feats) {}
+    std::vector<int> recognize_batch(std::vector<ImageInfo>& testImages) {
+        std::vector<int> out(testImages.size(), -1);
+        if (!pg || !pg->g || testImages.empty()) return out;
+        std::vector<float> q = detail::pack_queries(testImages, pg->d);
+        std::vector<int32_t> idx(testImages.size());
+        // recognize_image_bf treats max_features == 0 as "all" and divides by the prefix length otherwise (db_features.cpp:319-335)
+        fir::check(fir_search_topk(pg->g, q.data(), (int64_t)testImages.size(), 1, max_features >= pg->d ? 0 : max_features, FIR_PATH_AUTO,
+                                   FIR_HOST, idx.data(), 0), "fir_search_topk");
+        for (size_t i = 0; i < out.size(); ++i) out[i] = idx[i] >= 0 ? (*pDbImages)[idx[i]].classNo : -1;
+        return out;
+    }
 private:
     int max_features;
 };
+
+class ConventionalTWDClassifier : public Classifier {                    // ImageTesting.cpp:74-186
+public:
+    enum class TWD_Type { Posteriors, DistDiff, DistRatio };
+    ConventionalTWDClassifier(int cls_num, TWD_Type t, double th, int feat_count = 64)
+        : Classifier(build_name(t, th)), num_of_classes(cls_num), reduced_features_count(feat_count), threshold(th), type(t) {}
+    void train(std::vector<ImageInfo>* pDb) {
+        Classifier::train(pDb);
+        if (pg->g) fir::check(fir_gallery_set_num_classes(pg->g, num_of_classes), "fir_gallery_set_num_classes");   // vector<double> probabs(num_of_classes), :114
+    }
+    std::vector<int> recognize_batch(std::vector<ImageInfo>& testImages) {
+        const int t = type == TWD_Type::Posteriors ? FIR_TWD_POSTERIORS : type == TWD_Type::DistDiff ? FIR_TWD_DIST_DIFF : FIR_TWD_DIST_RATIO;
+        fir_gallery* g = pg ? pg->g : 0;
+        const double th = threshold; const int fc = reduced_features_count;
+        return run(testImages, [=](const float* q, int64_t nq, int32_t* lab, uint8_t* unrel) {
+            fir::check(fir_twd_conventional(g, q, nq, t, th, fc, 256, FIR_HOST, 0, lab, unrel), "fir_twd_conventional");
+        });
+    }
+private:
+    int num_of_classes, reduced_features_count;
+    double threshold;
+    TWD_Type type;
+    static std::string build_name(TWD_Type type, double threshold) {
+        std::ostringstream os;
+        os << (type == TWD_Type::Posteriors ? "TWD posteriors" : type == TWD_Type::DistDiff ? "TWD diff" : "TWD ratio") << ", " << threshold;
+        return os.str();
+    }
+};
+
+class ProposedTWDClassifier : public Classifier {                        // ImageTesting.cpp:188-288
+public:
+    ProposedTWDClassifier(int cls_num, int feat_count, double th)
+        : Classifier(build_name(feat_count, th)), num_of_classes(cls_num), reduced_features_count(feat_count), threshold(th) {}
+    std::vector<int> recognize_batch(std::vector<ImageInfo>& testImages) {
+        fir_gallery* g = pg ? pg->g : 0;
+        const double th = threshold; const int fc = reduced_features_count;
+        return run(testImages, [=](const float* q, int64_t nq, int32_t* lab, uint8_t* unrel) {
+            fir::check(fir_twd_proposed(g, q, nq, fc, th, 256, FIR_HOST, 0, lab, unrel), "fir_twd_proposed");
+        });
+    }
+private:
+    int num_of_classes, reduced_features_count;
+    double threshold;                                                    // the reference stores 1/th (:191); the C-ABI takes th
+    static std::string build_name(int feat_count, double threshold) {
+        std::ostringstream os;
+        os << "Proposed TWD, " << feat_count << ", " << threshold;
+        return os.str();
+    }
+};
+
+}  // namespace image_testing
 
 }  // namespace fir_compat
 

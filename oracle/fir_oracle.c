@@ -356,6 +356,106 @@ void fir_oracle_pnn_seq(const double* train, const int32_t* train_label, int64_t
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Three-way-decision classifiers — ImageTesting.cpp:74-186 (conventional) and :188-288 (proposed,
+ * CHECK_ALL_INSTANCES build).  last_feature is the reference's hard-coded 256 (:168, :221).
+ * ------------------------------------------------------------------------------------------ */
+static int desc_cmp(const void* a, const void* b) {
+    double x = *(const double*)a, y = *(const double*)b;
+    return (x < y) - (x > y);
+}
+
+void fir_oracle_twd_conventional(int metric, const float* g, const int32_t* labels, int64_t n, int d, int n_classes,
+                                 const float* q, int64_t nq, int type, double threshold, int feat_count, int last_feature,
+                                 int32_t* out_idx, int32_t* out_class, uint8_t* out_unreliable) {
+    double* distances = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    double* probabs = (double*)malloc(sizeof(double) * (size_t)n_classes);
+    (void)d;
+    for (int64_t i = 0; i < nq; ++i) {
+        const float* lhs = q + i * d;
+        int bestInd = -1;
+        double bestDist = 100000, secondBestDist = 100000;          /* :111 */
+        double max_probab = 0, probab = 0;
+        for (int c = 0; c < n_classes; ++c) probabs[c] = 0;
+        for (int64_t j = 0; j < n; ++j) {                           /* :116-133 */
+            distances[j] = fir_oracle_distance(metric, lhs, g + j * d, 0, feat_count);
+            if (type == 0) {
+                probab = exp(-distances[j] * 100);                  /* DIST_WEIGHT, :113,119 */
+                if (probab > probabs[labels[j]]) probabs[labels[j]] = probab;
+            }
+            if (distances[j] < bestDist) {
+                if (bestInd != -1 && labels[bestInd] != labels[j]) secondBestDist = bestDist;   /* previous best, not the true runner-up */
+                bestDist = distances[j];
+                bestInd = (int)j;
+                if (type == 0) max_probab = probab;
+            }
+        }
+        int reliable = 0;
+        if (type == 0) {
+            /* :143-150: nth_element(…, 5, greater) then the sum of the first five = the five largest posteriors.  The order
+             * in which libstdc++ leaves them (and so the last bits of the sum) is unspecified; summed here largest first. */
+            qsort(probabs, (size_t)n_classes, sizeof(double), desc_cmp);
+            double sum = 0;
+            for (int c = 0; c < 5; ++c) sum += probabs[c];
+            max_probab /= sum;
+            reliable = max_probab > threshold;
+        } else if (type == 1) {
+            reliable = (secondBestDist - bestDist) > threshold;     /* :160 */
+        } else {
+            reliable = (bestDist / secondBestDist) < threshold;     /* :163 */
+        }
+        if (!reliable) {                                            /* :166-181 */
+            bestInd = -1;
+            bestDist = 100000;
+            for (int64_t j = 0; j < n; ++j) {
+                /* double*int + float*int: the second product is single precision (:174-175) */
+                const float rest = fir_oracle_distance(metric, lhs, g + j * d, feat_count, last_feature) * (float)(last_feature - feat_count);
+                distances[j] = (distances[j] * feat_count + rest) / last_feature;
+                if (distances[j] < bestDist) { bestDist = distances[j]; bestInd = (int)j; }
+            }
+        }
+        if (out_unreliable) out_unreliable[i] = (uint8_t)!reliable;
+        if (out_idx) out_idx[i] = bestInd;
+        if (out_class) out_class[i] = bestInd >= 0 ? labels[bestInd] : -1;
+    }
+    free(distances); free(probabs);
+}
+
+void fir_oracle_twd_proposed(int metric, const float* g, const int32_t* labels, int64_t n, int d, const float* q, int64_t nq,
+                             int feat_count, double th, int last_feature, int32_t* out_idx, int32_t* out_class, uint8_t* out_unreliable) {
+    const double threshold = 1.0 / th;                              /* ctor, :191 */
+    double* distances = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    char* check = (char*)malloc((size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < nq; ++i) {
+        const float* lhs = q + i * d;
+        int bestInd = -1;
+        uint8_t unreliable = 0;
+        for (int64_t j = 0; j < n; ++j) { distances[j] = 0; check[j] = 1; }
+        for (int cur = 0; cur < last_feature; cur += feat_count) {  /* :223 */
+            double bestDist = 100000;
+            for (int64_t j = 0; j < n; ++j) {
+                if (!check[j]) continue;
+                distances[j] += fir_oracle_distance(metric, lhs, g + j * d, cur, cur + feat_count);   /* :243 */
+                if (distances[j] < bestDist) { bestDist = distances[j]; bestInd = (int)j; }
+            }
+            int variants = 1;
+            const double dist_threshold = bestDist * threshold;     /* :256 */
+            const int bestClass = labels[bestInd];
+            for (int64_t j = 0; j < n; ++j)
+                if (check[j]) {
+                    if (distances[j] > dist_threshold) check[j] = 0;
+                    else if (labels[j] != bestClass) ++variants;
+                }
+            if (variants == 1) break;
+            if (cur == 0) unreliable = 1;                           /* :281-282 */
+        }
+        if (out_unreliable) out_unreliable[i] = unreliable;
+        if (out_idx) out_idx[i] = bestInd;
+        if (out_class) out_class[i] = bestInd >= 0 ? labels[bestInd] : -1;
+    }
+    free(distances); free(check);
+}
+
+/* ------------------------------------------------------------------------------------------
  * DirectedEnumeration build — ann.cpp:270-348 (PIVOT branch), init :357-386, getThreshold :84-93
  * ------------------------------------------------------------------------------------------ */
 static int fcmp(const void* a, const void* b) {

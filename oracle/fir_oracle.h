@@ -51,6 +51,15 @@ void fir_oracle_pnn(const double* train, const int32_t* train_label, int64_t n, 
 void fir_oracle_pnn_seq(const double* train, const int32_t* train_label, int64_t n, int d, int n_classes,
                         const double* avg, const double* q, int64_t nq, int32_t* out_label);
 
+/* ConventionalTWDClassifier::recognize ImageTesting.cpp:108-186 (type 0 Posteriors, 1 DistDiff, 2 DistRatio) and
+ * ProposedTWDClassifier::recognize :207-288; last_feature = 256 in the reference.  out_unreliable = the query's
+ * contribution to num_of_unreliable. */
+void fir_oracle_twd_conventional(int metric, const float* g, const int32_t* labels, int64_t n, int d, int n_classes,
+                                 const float* q, int64_t nq, int type, double threshold, int feat_count, int last_feature,
+                                 int32_t* out_idx, int32_t* out_class, uint8_t* out_unreliable);
+void fir_oracle_twd_proposed(int metric, const float* g, const int32_t* labels, int64_t n, int d, const float* q, int64_t nq,
+                             int feat_count, double th, int last_feature, int32_t* out_idx, int32_t* out_class, uint8_t* out_unreliable);
+
 /* DirectedEnumeration ctor + init, ann.cpp:270-348,357-386 (PIVOT build); getThreshold :84-93.
  * pivot0 replaces the first element of the reference's random_shuffle (:369).  keep_rows rows of the
  * pivot-distance matrix are written to P (keep_rows x n); np_out = max(5,(int)(n*0.015)) rows are walked. */

@@ -68,6 +68,10 @@ class Port:
         L.fir_oracle_knn.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, _f64p, _f64p, C.c_int64, C.c_int, _i32p]
         L.fir_oracle_pnn.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, _f64p, _f64p, C.c_int64, _f64p, _i32p]
         L.fir_oracle_pnn_seq.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, _f64p, _f64p, C.c_int64, _i32p]
+        L.fir_oracle_twd_conventional.argtypes = [C.c_int, _f32p, _i32p, C.c_int64, C.c_int, C.c_int, _f32p, C.c_int64, C.c_int, C.c_double,
+                                                  C.c_int, C.c_int, _i32p, _i32p, _u8p]
+        L.fir_oracle_twd_proposed.argtypes = [C.c_int, _f32p, _i32p, C.c_int64, C.c_int, _f32p, C.c_int64, C.c_int, C.c_double, C.c_int,
+                                              _i32p, _i32p, _u8p]
         L.fir_oracle_dem_build.restype = C.c_int
         L.fir_oracle_dem_build.argtypes = [C.c_int, _f32p, _i32p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                            C.POINTER(C.c_int), _i32p, _f32p, _f32p, C.POINTER(C.c_float)]
@@ -136,6 +140,24 @@ class Port:
         self.L.fir_oracle_pnn_seq(train, train_label, train.shape[0], train.shape[1], n_classes, avg, q, q.shape[0], lab)
         return lab
 
+    TWD_TYPES = {"posteriors": 0, "diff": 1, "ratio": 2}
+
+    def twd_conventional(self, metric, g, labels, n_classes, q, kind, threshold, feat_count=64, last_feature=256):
+        """ConventionalTWDClassifier::recognize → (index, class, unreliable)."""
+        g, q, labels = _f32(g), _f32(q), _i32(labels)
+        idx, cls, unrel = np.empty(len(q), np.int32), np.empty(len(q), np.int32), np.empty(len(q), np.uint8)
+        self.L.fir_oracle_twd_conventional(METRICS[metric], g, labels, g.shape[0], g.shape[1], n_classes, q, q.shape[0],
+                                           self.TWD_TYPES[kind], float(threshold), feat_count, last_feature, idx, cls, unrel)
+        return idx, cls, unrel
+
+    def twd_proposed(self, metric, g, labels, q, feat_count, th, last_feature=256):
+        """ProposedTWDClassifier::recognize → (index, class, unreliable)."""
+        g, q, labels = _f32(g), _f32(q), _i32(labels)
+        idx, cls, unrel = np.empty(len(q), np.int32), np.empty(len(q), np.int32), np.empty(len(q), np.uint8)
+        self.L.fir_oracle_twd_proposed(METRICS[metric], g, labels, g.shape[0], g.shape[1], q, q.shape[0], feat_count, float(th),
+                                       last_feature, idx, cls, unrel)
+        return idx, cls, unrel
+
     def dem_build(self, metric, g, labels, pivot0, far=0.01, threshold=0.0, keep_rows=32):
         g, labels = _f32(g), _i32(labels)
         n = g.shape[0]
@@ -199,6 +221,7 @@ class Ref:
         L.fir_ref_dem_search.restype = C.c_double
         L.fir_ref_dem_search.argtypes = [C.c_void_p, _f32p, C.c_long, C.c_int, C.c_int, _i32p, _f32p, _u8p, _i32p]
         L.fir_ref_dem_free.argtypes = [C.c_void_p]
+        L.fir_ref_twd_run.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _f32p, _i32p, C.c_int64, C.c_int, _f32p, C.c_int64, _i32p, _u8p]
         if metric == "l2":
             L.fir_ref_cls_setup.argtypes = [_f64p, _i32p, C.c_long, C.c_int, C.c_int, C.c_double, C.c_uint]
             L.fir_ref_cls_counts.restype = C.c_long
@@ -210,6 +233,16 @@ class Ref:
             L.fir_ref_cls_pnn.argtypes = [C.c_long, C.c_long, _i32p, C.c_void_p]
             L.fir_ref_cls_pnn_seq.restype = C.c_double
             L.fir_ref_cls_pnn_seq.argtypes = [C.c_long, C.c_long, _i32p]
+
+    def twd(self, kind, g, labels, n_classes, q, feat_count, th, twd_type="diff"):
+        """kind 'conventional' | 'proposed' | 'bf' through the verbatim ImageTesting.cpp classes → (class, unreliable)."""
+        g, q, labels = _f32(g), _f32(q), _i32(labels)
+        cls, unrel = np.empty(len(q), np.int32), np.empty(len(q), np.uint8)
+        k = {"conventional": 0, "proposed": 1, "bf": 2}[kind]
+        rc = self.L.fir_ref_twd_run(k, Port.TWD_TYPES[twd_type], float(th), feat_count, n_classes, g, labels, g.shape[0], g.shape[1],
+                                    q, q.shape[0], cls, unrel)
+        assert rc == 0
+        return cls, unrel
 
     def distance(self, l, r, start=0, end=None):
         l, r = _f32(l), _f32(r)

@@ -18,6 +18,10 @@ import importlib  # noqa: E402
 synth = importlib.import_module("fast-image-recognition_b200.synth")
 
 
+TWD_PROPOSED = [(32, 0.7), (64, 0.7), (32, 0.9)]
+TWD_CONVENTIONAL = [("posteriors", 0.24), ("diff", 0.003), ("ratio", 0.7), ("diff", 0.0003), ("ratio", 0.9)]
+
+
 def raw(metric, n, nq, d, c, seed):
     return synth.make_split(n, nq, d, c, metric, seed=seed)
 
@@ -101,6 +105,24 @@ def main():
     out["pnn_label2"] = ref.cls_pnn(0, len(te2))[0]
     np.savez_compressed(os.path.join(HERE, "ref_classification.npz"), **out)
     print("classification ->", len(out), "arrays")
+    # three-way-decision classifiers (ImageTesting.cpp), the verbatim classes on one fixed 256-d split per metric
+    port = oracle_py.Port()
+    out = {}
+    for metric in ("l2", "chi2", "kl"):
+        ref = oracle_py.Ref(metric)
+        g, gl, q, ql = synth.make_split(180, 60, 256, 6, metric, sigma=2.0, seed=77)
+        # inputs are stored as float16 (exactly representable, small file) and normalised with the loader restatement
+        g, q = g.astype(np.float16), q.astype(np.float16)
+        out["%s_gallery_f16" % metric], out["%s_queries_f16" % metric] = g, q
+        out["%s_gallery_labels" % metric] = gl
+        gn, qn = port.normalize_rows(metric, g.astype(np.float32)), port.normalize_rows(metric, q.astype(np.float32))
+        for fc, th in TWD_PROPOSED:
+            out["%s_prop_%d_%g_class" % (metric, fc, th)], out["%s_prop_%d_%g_unrel" % (metric, fc, th)] = ref.twd("proposed", gn, gl, 6, qn, fc, th)
+        for kind, th in TWD_CONVENTIONAL:
+            out["%s_conv_%s_%g_class" % (metric, kind, th)], out["%s_conv_%s_%g_unrel" % (metric, kind, th)] = \
+                ref.twd("conventional", gn, gl, 6, qn, 64, th, kind)
+    np.savez_compressed(os.path.join(HERE, "ref_twd.npz"), **out)
+    print("twd ->", len(out), "arrays")
 
 
 if __name__ == "__main__":

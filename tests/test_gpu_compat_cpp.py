@@ -53,3 +53,42 @@ def test_cpp_adapters_match_oracle(port, tmp_path):
     sc, pl = port.pnn(tr64, dbl, n_classes, avg, te64)
     assert [int(x) for x in lines["PNN"]] == pl.tolist() and int(lines["PNN1"][0]) == pl[0]
     assert [int(x) for x in lines["PNNSEQ"]] == port.pnn_seq(tr64, dbl, n_classes, avg, te64).tolist()
+
+
+def test_cpp_twd_adapters_match_oracle(port, tmp_path):
+    """fir_compat::image_testing (ImageTesting.cpp's Classifier family) driven like testRecognition, vs the oracle port."""
+    d, n_classes = 256, 8
+    g, gl, q, ql = synth.make_split(8 * 50, 1, d, n_classes, "l2", sigma=2.0, seed=5)
+    txt = str(tmp_path / "features.txt")
+    synth.write_features_file(txt, g, ["class_%02d" % c for c in gl])
+    exe = str(tmp_path / "twd_test")
+    pkg = os.path.join(ROOT, "fast-image-recognition_b200")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "twd_test.cpp"),
+                    "-o", exe, "-L", pkg, "-lfir_b200", "-Wl,-rpath," + pkg], check=True)
+    parsed = np.array([[np.float32(float("{:f}".format(float(v)))) for v in row] for row in g], np.float32)
+    rows = port.normalize_rows("l2", parsed)
+    db_i, te_i = [], []
+    for c in range(n_classes):
+        idx = np.flatnonzero(gl == c)
+        db_i += list(idx[:30])
+        te_i += list(idx[30:400])
+    db, test, dbl = rows[db_i], rows[te_i], gl[db_i]
+    out = subprocess.run([exe, txt, str(d)], check=True, capture_output=True, text=True).stdout
+    lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l}
+    assert [int(v) for v in lines["SIZES"]] == [n_classes, len(db), len(test)]
+    want = []
+    for mf in (0, 64, 0):                                                  # BF, BF 64, BF 256 (= all 256 dimensions)
+        want.append((dbl[port.bf("l2", db, test, max_features=mf)[0]], np.zeros(len(test), np.uint8)))
+    for kind, th in (("posteriors", 0.24), ("diff", 0.003), ("ratio", 0.7)):
+        want.append(port.twd_conventional("l2", db, dbl, n_classes, test, kind, th, 64)[1:])
+    for fc in (32, 64):
+        want.append(port.twd_proposed("l2", db, dbl, test, fc, 0.7)[1:])
+    names = ["BF, 256", "BF, 64", "BF, 256", "TWD posteriors, 0.24", "TWD diff, 0.003", "TWD ratio, 0.7", "Proposed TWD, 32, 0.7", "Proposed TWD, 64, 0.7"]
+    some_unreliable = 0
+    for c, (cls, unrel) in enumerate(want):
+        assert " ".join(lines["NAME%d" % c]) == names[c]
+        assert [int(v) for v in lines["CLS%d" % c]] == cls.tolist(), names[c]
+        assert int(lines["UNREL%d" % c][0]) == int(unrel.sum()), names[c]
+        assert [int(v) for v in lines["ONE%d" % c]] == [int(cls[1]), int(unrel[1])], names[c]
+        some_unreliable += int(unrel.sum())
+    assert some_unreliable > 0

@@ -69,3 +69,24 @@ def test_classification_golden(fir):
     assert np.array_equal(clf2.pnn_sequential(rows2[te2]), G["pnn_seq_label2"])
     clf2.close()
     clf.close()
+
+
+@pytest.mark.parametrize("metric", ["l2", "chi2", "kl"])
+def test_twd_golden(fir, metric):
+    """Three-way-decision classifiers against the frozen outputs of the reference's own classes (ImageTesting.cpp)."""
+    from test_oracle_golden import TWD_CONVENTIONAL, TWD_PROPOSED
+    G = np.load(os.path.join(GOLD, "ref_twd.npz"))
+    g = G["%s_gallery_f16" % metric].astype(np.float32)
+    q = G["%s_queries_f16" % metric].astype(np.float32)
+    fir.normalize_rows(g, metric)
+    fir.normalize_rows(q, metric)
+    gal = fir.Gallery(g, G["%s_gallery_labels" % metric], metric)
+    for fc, th in TWD_PROPOSED:
+        idx, cls, unrel = gal.twd_proposed(q, fc, th)
+        assert np.array_equal(cls, G["%s_prop_%d_%g_class" % (metric, fc, th)])
+        assert np.array_equal(unrel, G["%s_prop_%d_%g_unrel" % (metric, fc, th)])
+    for kind, th in TWD_CONVENTIONAL:
+        idx, cls, unrel = gal.twd_conventional(q, kind, th, 64)
+        assert np.array_equal(cls, G["%s_conv_%s_%g_class" % (metric, kind, th)])
+        assert np.array_equal(unrel, G["%s_conv_%s_%g_unrel" % (metric, kind, th)])
+    gal.close()

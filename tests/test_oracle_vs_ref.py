@@ -52,3 +52,26 @@ def test_dem_and_classifiers(port, ref_l2):
     seq = ref_l2.cls_pnn_seq(0, len(te))
     assert np.array_equal(seq, port.pnn_seq(rows[tr], trl, 12, avg, rows[te]))
     assert not np.array_equal(seq, ref_l2.cls_pnn(0, len(te))[0])
+
+
+@pytest.mark.parametrize("metric", ["l2", "chi2", "kl"])
+def test_twd_port_matches_reference(port, request, metric):
+    """ImageTesting.cpp's TWD classifiers: the C port against the verbatim classes (class + num_of_unreliable per query)."""
+    ref = request.getfixturevalue("ref_" + metric)
+    g, gl, q, ql = make_data(port, metric, 300, 120, 288, 8, seed=6, sigma=2.0)
+    seen = 0
+    for fc, th in ((32, 0.7), (64, 0.7), (96, 0.8), (32, 1.5)):
+        idx, cls, unrel = port.twd_proposed(metric, g, gl, q, fc, th)
+        rc, ru = ref.twd("proposed", g, gl, 8, q, fc, th)
+        assert np.array_equal(cls, rc) and np.array_equal(unrel, ru), (fc, th)
+        seen += int(unrel.sum())
+    for kind, th in (("posteriors", 0.24), ("diff", 0.003), ("ratio", 0.7), ("diff", 0.0003), ("ratio", 0.9)):
+        for fc in (64, 17):
+            idx, cls, unrel = port.twd_conventional(metric, g, gl, 8, q, kind, th, fc)
+            rc, ru = ref.twd("conventional", g, gl, 8, q, fc, th, kind)
+            assert np.array_equal(cls, rc) and np.array_equal(unrel, ru), (kind, th, fc)
+            seen += int(unrel.sum())
+    # BruteForceClassifier(max_feats) = recognize_image_bf over a prefix
+    rc, _ = ref.twd("bf", g, gl, 8, q, 64, 0)
+    assert np.array_equal(rc, gl[port.bf(metric, g, q, max_features=64)[0]])
+    assert seen > 0

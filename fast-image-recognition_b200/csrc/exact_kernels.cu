@@ -423,6 +423,81 @@ int launch_pair_distances(int metric, const float* q, int64_t nq, int ldq, const
     return fail(FIR_ERR_BAD_ARG, "unknown metric");
 }
 
+// Same arithmetic over an explicit list of (query, candidate) cells gathered from ALL queries (the survivors of the prune
+// are few per query — about k — so one warp per query would run nearly empty).  One lane = one pair; both rows of every
+// pair are staged 64 dims at a time with cp.async (two rows per instruction), then each lane walks its pair sequentially.
+constexpr int LCH = 64;          // dims per stage
+constexpr int LLD = LCH + 4;     // 68 ⇒ LDS.128 conflict-free across 8 consecutive rows
+
+template <int METRIC>
+__global__ void __launch_bounds__(PW * 32) pair_list_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ x, int ldx, int d_end,
+                                                            const uint32_t* __restrict__ cells, const int32_t* __restrict__ count, int rt,
+                                                            const int32_t* __restrict__ cand_idx, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total = *count;
+    const int64_t base = ((int64_t)blockIdx.x * PW + warp) * 32;
+    if (base >= total) return;
+    float* xs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (2 * 32 * LLD);
+    float* qs = xs + 32 * LLD;
+    const bool valid = base + lane < total;
+    const uint32_t cell = valid ? cells[base + lane] : 0u;
+    const int64_t my_q = valid ? (int64_t)(cell / (uint32_t)rt) : -1;
+    const int64_t my_x = valid ? (int64_t)cand_idx[cell] : -1;
+    const int sub = lane >> 4, l16 = lane & 15;
+    float acc = 0.f;
+    for (int c0 = 0; c0 < d_end; c0 += LCH) {
+        const int col = c0 + l16 * 4;
+#pragma unroll 4
+        for (int c = 0; c < 16; ++c) {
+            const int r = 2 * c + sub;
+            const int64_t xr = __shfl_sync(0xffffffffu, my_x, r);
+            const int64_t qr = __shfl_sync(0xffffffffu, my_q, r);
+            if (xr < 0) continue;
+            const bool okx = col < ldx, okq = col < ldq;
+            cp_async16(&xs[r * LLD + l16 * 4], x + xr * ldx + (okx ? col : 0), okx ? 16 : 0);
+            cp_async16(&qs[r * LLD + l16 * 4], q + qr * ldq + (okq ? col : 0), okq ? 16 : 0);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        if (valid) {
+            const int kmax = min(LCH, d_end - c0);
+            const float* xrow = xs + lane * LLD;
+            const float* qrow = qs + lane * LLD;
+            int kk = 0;
+            for (; kk + 4 <= kmax; kk += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(&xrow[kk]);
+                const float4 b = *reinterpret_cast<const float4*>(&qrow[kk]);
+                dist_step<METRIC>(acc, b.x, a.x); dist_step<METRIC>(acc, b.y, a.y);            // lhs = query
+                dist_step<METRIC>(acc, b.z, a.z); dist_step<METRIC>(acc, b.w, a.w);
+            }
+            for (; kk < kmax; ++kk) dist_step<METRIC>(acc, qrow[kk], xrow[kk]);
+        }
+        __syncwarp();
+    }
+    if (valid) out[cell] = __fdiv_rn(acc, (float)d_end);
+}
+
+int launch_pair_list(int metric, const float* q, int ldq, const float* x, int ldx, int d_end, const uint32_t* cells, const int32_t* count,
+                     int64_t max_cells, int rt, const int32_t* cand_idx, float* out, cudaStream_t s) {
+    if (max_cells <= 0) return FIR_OK;
+    const size_t smem = sizeof(float) * (size_t)PW * (2 * 32 * LLD);
+    const unsigned grid = (unsigned)ceil_div(max_cells, (int64_t)PW * 32);    // sized for the worst case; blocks past *count exit at once
+    auto go = [&](auto kern) -> int {
+        FIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, PW * 32, smem, s>>>(q, ldq, x, ldx, d_end, cells, count, rt, cand_idx, out);
+        FIR_CUDA_TRY(cudaGetLastError());
+        return FIR_OK;
+    };
+    switch (metric) {
+        case FIR_L2: return go(pair_list_kernel<FIR_L2>);
+        case FIR_CHI2: return go(pair_list_kernel<FIR_CHI2>);
+        case FIR_KL: return go(pair_list_kernel<FIR_KL>);
+    }
+    return fail(FIR_ERR_BAD_ARG, "unknown metric");
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Loader normalisation (qt_cpp/db_features.cpp:79-101), one thread per row, sequential fp32 sums.
 // ---------------------------------------------------------------------------------------------------

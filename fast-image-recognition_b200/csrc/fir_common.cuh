@@ -108,6 +108,9 @@ struct TensorSearchArgs {
     int n_slots;
     float* cand_val; int32_t* cand_idx;   // [nq][n_slots][R]
     float* slot_bound;                    // [nq][n_slots]
+    const float* seed_thr;                // optional [nq] seed thresholds (approximate squared distances)
+    const int32_t* skip_if_zero;          // optional device counter: the launch does nothing when it reads 0
+    int mins_only;                        // seed pass: per-slot column-group minima instead of top-R lists (R must be 4)
     int grid; int n_sm;
     int ctas;                     // 1: cta_group::1 kernel, 2: CTA-pair kernel (grid counts pairs)
 };
@@ -129,10 +132,14 @@ struct ErrModel {
     const float* q_l1; const float* x_l1_max;                               // kind 2 (device)
     double dist_scale;        // approx units per reference-distance unit: D on the tensor path (squared distance), 1 otherwise
 };
-int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s);
+int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s, const int32_t* n_active = nullptr,
+                 uint32_t* pair_cells = nullptr, int32_t* pair_count = nullptr);
+// exact distances of the listed (query, candidate) cells: cell = q * rt + position in the query's candidate list
+int launch_pair_list(int metric, const float* q, int ldq, const float* x, int ldx, int d_end, const uint32_t* cells, const int32_t* count,
+                     int64_t max_cells, int rt, const int32_t* cand_idx, float* out, cudaStream_t s);
 int launch_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots, int R, int k,
                   const ErrModel& em, int64_t index_offset, float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged,
-                  unsigned char* fail_flags, float* max_bound, cudaStream_t s);
+                  unsigned char* fail_flags, float* max_bound, cudaStream_t s, const int32_t* n_active = nullptr, float* seed_out = nullptr);
 
 }  // namespace fir
 

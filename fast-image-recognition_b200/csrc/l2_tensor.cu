@@ -368,17 +368,21 @@ struct CandParams {
     float* cand_val;
     int32_t* cand_idx;
     float* slot_bound;
+    const int32_t* skip_if_zero; // optional device counter: nothing to do when it reads 0 (second pass without flagged queries)
+    int mins_only;              // seed pass (R = 4): the four slots are plain minima over the four 32-column groups, no lists
+    const float* seed_thr;      // optional [nq]: approximate squared distance above which a row cannot matter (see seed pass)
 };
 
-// Running top-R of one query row, UNSORTED, in registers: thr is the current maximum (+inf until the list is full).
+// Running top-R of one query row, UNSORTED, in registers: mx is the current maximum (+inf until the list is full) and
+// thr = min(mx, tau) is what a new value has to beat; tau is the query's seed threshold (+inf when there is none).
 // A better value replaces one slot holding the maximum, then the maximum is recomputed — 5R mostly independent
 // instructions (a sorted insert is a 5R-deep dependent chain, and this code runs with a single warp per scheduler).
 template <int R>
-__device__ __forceinline__ void topr_replace(float (&lv)[R], int (&li)[R], float& thr, float v, int j) {
+__device__ __forceinline__ void topr_replace(float (&lv)[R], int (&li)[R], float& mx, float& thr, float tau, float v, int j) {
     bool placed = false;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const bool hit = !placed && (lv[r] == thr);
+        const bool hit = !placed && (lv[r] == mx);
         lv[r] = hit ? v : lv[r];
         li[r] = hit ? j : li[r];
         placed = placed || hit;
@@ -386,7 +390,8 @@ __device__ __forceinline__ void topr_replace(float (&lv)[R], int (&li)[R], float
     float m = lv[0];
 #pragma unroll
     for (int r = 1; r < R; ++r) m = fmaxf(m, lv[r]);
-    thr = m;
+    mx = m;
+    thr = fminf(m, tau);
 }
 
 constexpr int EPI_WARPS = 8;                 // 2 per scheduler: warp e owns TMEM lanes 32*(e%4).. and columns 128*(e/4)..
@@ -396,7 +401,7 @@ constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
 // One accumulator tile (this warp's 32 rows x EPI_COLS columns): v = ‖x‖² − 2·s·acc, keep each row's R smallest.
 template <int R>
 __device__ __forceinline__ void epilogue_scan_tile(uint32_t taddr, const float* __restrict__ nxs, int jbase, float negc,
-                                                   float (&lv)[R], int (&li)[R], float& thr) {
+                                                   float (&lv)[R], int (&li)[R], float& mx, float& thr, float tau) {
 #pragma unroll 1
     for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
         uint32_t rr[32];
@@ -434,12 +439,31 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t taddr, const float* 
 #undef FIR_CASE
                 }
                 const int j = jbase + c0 + 4 * g;
-                if (__uint_as_float(b0) < thr) topr_replace<R>(lv, li, thr, __uint_as_float(b0), j);
-                if (__uint_as_float(b1) < thr) topr_replace<R>(lv, li, thr, __uint_as_float(b1), j + 1);
-                if (__uint_as_float(b2) < thr) topr_replace<R>(lv, li, thr, __uint_as_float(b2), j + 2);
-                if (__uint_as_float(b3) < thr) topr_replace<R>(lv, li, thr, __uint_as_float(b3), j + 3);
+                if (__uint_as_float(b0) < thr) topr_replace<R>(lv, li, mx, thr, tau, __uint_as_float(b0), j);
+                if (__uint_as_float(b1) < thr) topr_replace<R>(lv, li, mx, thr, tau, __uint_as_float(b1), j + 1);
+                if (__uint_as_float(b2) < thr) topr_replace<R>(lv, li, mx, thr, tau, __uint_as_float(b2), j + 2);
+                if (__uint_as_float(b3) < thr) topr_replace<R>(lv, li, mx, thr, tau, __uint_as_float(b3), j + 3);
             }
         }
+    }
+}
+
+// Seed pass: no lists, no indices — slot g of the row keeps the minimum over column group g (32 columns) of every tile this
+// thread sees.  Branch-free, so a short scan is not dominated by list warm-up the way a top-R scan of a few tiles is.
+__device__ __forceinline__ void epilogue_scan_tile_mins(uint32_t taddr, const float* __restrict__ nxs, float negc, float (&lv)[4]) {
+#pragma unroll
+    for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
+        uint32_t rr[32];
+        tc_ld32(taddr + c0, rr);
+        tc_wait_ld();
+        float m = lv[c0 >> 5];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
+            m = fminf(m, fminf(fminf(fmaf(negc, __uint_as_float(rr[i + 0]), nx4.x), fmaf(negc, __uint_as_float(rr[i + 1]), nx4.y)),
+                               fminf(fmaf(negc, __uint_as_float(rr[i + 2]), nx4.z), fmaf(negc, __uint_as_float(rr[i + 3]), nx4.w))));
+        }
+        lv[c0 >> 5] = m;
     }
 }
 
@@ -449,15 +473,13 @@ __device__ __forceinline__ void epilogue_flush(const CandParams& p, int64_t qrow
     if (qrow >= p.nq) return;
     const float nqv = p.qry_norm2[qrow];
     const int64_t o = (qrow * p.n_slots + slot) * R;
-    bool full = true;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         p.cand_val[o + r] = lv[r] + nqv;
         // shadow position -> original gallery row (the fp16 copy is stored in a strided permutation)
         p.cand_idx[o + r] = li[r] < 0 ? -1 : (int32_t)(((int64_t)li[r] * p.perm_a + p.perm_b) % p.n);
-        full = full && (li[r] >= 0);
     }
-    p.slot_bound[qrow * p.n_slots + slot] = full ? thr + nqv : __int_as_float(0x7f800000);
+    p.slot_bound[qrow * p.n_slots + slot] = thr + nqv;      // thr = min(list maximum or +inf while not full, seed threshold)
 }
 
 template <int R, bool A_RES>
@@ -480,6 +502,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
     uint64_t* nx_full = tmem_empty + 2;           // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(nx_full + 2);
 
+    if (p.skip_if_zero && *p.skip_if_zero == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Partition P = p.part;
     const int64_t unit = blockIdx.x;
@@ -579,7 +602,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
         const int row = lg * 32 + lane;
         const float sg = __uint_as_float(p.gal_meta[1]);
         float negc = 0.f;                              // −2 / (gallery scale · this row's query scale), set per query block
-        float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000);
+        float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000), mx = thr, tau = thr;
         int64_t cur_qb = -1;
         int as = 0; uint32_t aphase = 0;
         for (WorkIter wi = work0; !wi.done(); wi.advance()) {
@@ -587,16 +610,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
             if (qb != cur_qb) {
                 if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
 #pragma unroll
-                for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = -1; }
-                thr = __int_as_float(0x7f800000);
+                for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = p.mins_only ? 0 : -1; }
+                mx = __int_as_float(0x7f800000);
                 cur_qb = qb;
-                { const int64_t qr = qb * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f)); }
+                { const int64_t qr = qb * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f));
+                  tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx; thr = tau; }
             }
             mbar_wait(smem_u32(&nx_full[as]), aphase);
             mbar_wait(smem_u32(&tmem_full[as]), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + half * EPI_COLS);
-            epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, thr);
+            if constexpr (R == 4) {
+                if (p.mins_only) epilogue_scan_tile_mins(taddr, nx_s + as * BN + half * EPI_COLS, negc, lv);
+                else epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, mx, thr, tau);
+            } else {
+                epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, mx, thr, tau);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(smem_u32(&tmem_empty[as])); }
@@ -682,6 +711,7 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
     uint64_t* nx_empty = nx_full + 2;             // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(nx_empty + 2);
 
+    if (p.skip_if_zero && *p.skip_if_zero == 0) return;     // same answer in both CTAs of the pair: nobody waits for a peer
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -788,7 +818,7 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         const int row = lg * 32 + lane;
         const float sg = __uint_as_float(p.gal_meta[1]);
         float negc = 0.f;                              // −2 / (gallery scale · this row's query scale), set per query block
-        float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000);
+        float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000), mx = thr, tau = thr;
         int64_t cur_qb = -1;
         int as = 0; uint32_t aphase = 0;
         for (WorkIter wi = work0; !wi.done(); wi.advance()) {
@@ -796,16 +826,22 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
             if (qb != cur_qb) {
                 if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
 #pragma unroll
-                for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = -1; }
-                thr = __int_as_float(0x7f800000);
+                for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = p.mins_only ? 0 : -1; }
+                mx = __int_as_float(0x7f800000);
                 cur_qb = qb;
-                { const int64_t qr = qb * (2 * BM) + rank * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f)); }
+                { const int64_t qr = qb * (2 * BM) + rank * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f));
+                  tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx; thr = tau; }
             }
             mbar_wait(smem_u32(&nx_full[as]), aphase);
             mbar_wait_cluster(smem_u32(&tmem_full[as]), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + half * EPI_COLS);
-            epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, thr);
+            if constexpr (R == 4) {
+                if (p.mins_only) epilogue_scan_tile_mins(taddr, nx_s + as * BN + half * EPI_COLS, negc, lv);
+                else epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, mx, thr, tau);
+            } else {
+                epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, mx, thr, tau);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(smem_u32(&nx_empty[as])); if (leader) mbar_arrive(smem_u32(&tmem_empty[as])); else mbar_arrive_leader(smem_u32(&tmem_empty[as])); }
@@ -841,7 +877,7 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     p.n_slots = a.n_slots;
     p.gal_norm2 = a.gal->norm2; p.qry_norm2 = a.qry->norm2;
     p.gal_meta = a.gal->meta; p.qry_row_scale = a.qry->row_scale;
-    p.cand_val = a.cand_val; p.cand_idx = a.cand_idx; p.slot_bound = a.slot_bound;
+    p.cand_val = a.cand_val; p.cand_idx = a.cand_idx; p.slot_bound = a.slot_bound; p.seed_thr = a.seed_thr; p.skip_if_zero = a.skip_if_zero; p.mins_only = a.mins_only;
     const bool a_res = p.nkb <= MAX_RES_KB;
     const size_t smem = a.ctas == 2 ? cand_smem_bytes_2cta(a_res) : cand_smem_bytes(a_res);
     auto go = [&](auto kern) -> int {
@@ -887,40 +923,69 @@ __device__ __forceinline__ double approx_error_bound(double nq2, double rq, doub
     return 2.0 * (rq * (NX + RX) + nqn * RX) + 2.0 * gamma * nqn * NX + 1e-6 * (nq2 + NX * NX + 2.0 * nqn * NX);
 }
 
+constexpr int PRUNE_STAGE_MAX = 1024;   // valid candidates per query staged in shared memory (4 warps x 8 KiB)
+
 __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ cand_val, int32_t* __restrict__ cand_idx, int64_t nq, int rt, int k,
-                                                           const ErrModel em) {
-    const int lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+                                                           const ErrModel em, const int32_t* __restrict__ n_active,
+                                                           uint32_t* __restrict__ pair_cells, int32_t* __restrict__ pair_count) {
+    extern __shared__ __align__(16) unsigned char prune_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * 4 + warp;
     if (q >= nq) return;
     float* cv = cand_val + q * rt;
     int32_t* ci = cand_idx + q * rt;
+    if (n_active && q >= *n_active) {                                          // second pass: rows past the flagged count are padding
+        for (int c = lane; c < rt; c += 32) ci[c] = -1;
+        return;
+    }
+    // Stage the VALID candidates compacted into shared memory first: one round trip to global memory instead of one per
+    // selection round (a warp serves one query, so nothing else hides that latency when only a few queries are active).
+    // (Seeded lists are mostly empty, so the capacity is counted in valid entries; a row with more takes the global path.)
+    const int cap = min(rt, PRUNE_STAGE_MAX);
+    float* sv = reinterpret_cast<float*>(prune_smem) + (size_t)warp * 2 * cap;
+    int32_t* si = reinterpret_cast<int32_t*>(sv + cap);
+    int nv = 0;
+#pragma unroll 4
+    for (int c0 = 0; c0 < rt; c0 += 32) {
+        const int c = c0 + lane;
+        const int32_t idx = c < rt ? ci[c] : -1;
+        const float v = c < rt ? cv[c] : 0.f;
+        const uint32_t m = __ballot_sync(0xffffffffu, idx >= 0);
+        const int o = nv + __popc(m & ((1u << lane) - 1));
+        if (idx >= 0 && o < cap) { sv[o] = v; si[o] = idx; }
+        nv += __popc(m);
+    }
+    __syncwarp();
+    const float* rv = sv; const int32_t* ri = si;                              // what the rounds read
+    if (nv > cap) { rv = cv; ri = ci; nv = rt; }
     // k-th smallest approx among valid candidates: k rounds of "smallest value greater than the previous" (duplicates counted)
     float kth = -__int_as_float(0x7f800000);
     int taken = 0;
     while (taken < k) {
         float best = __int_as_float(0x7f800000); int cnt = 0;
-        for (int c = lane; c < rt; c += 32) {
-            if (ci[c] < 0) continue;
-            const float v = cv[c];
+        for (int c = lane; c < nv; c += 32) {
+            if (ri[c] < 0) continue;
+            const float v = rv[c];
             if (v > kth && v < best) best = v;
         }
         for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
         if (!(best < __int_as_float(0x7f800000))) break;                       // fewer than k valid candidates
-        for (int c = lane; c < rt; c += 32) cnt += (ci[c] >= 0 && cv[c] == best) ? 1 : 0;
+        for (int c = lane; c < nv; c += 32) cnt += (ri[c] >= 0 && rv[c] == best) ? 1 : 0;
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         kth = best; taken += cnt;
     }
-    if (taken < k) return;                                                     // keep everything
     double E, rho;
     err_bounds(em, q, E, rho);
     // c is dominated when (approx_c − E)(1−ρ) > (kth + E)(1+ρ): then reference(c) > reference(each of the k best-by-approx)
-    const double cut = ((double)kth + E) * (1.0 + rho) / (1.0 - rho) + E;
-    // compact the survivors to the front (order is irrelevant downstream)
+    // (fewer than k valid candidates: keep everything)
+    const double cut = taken < k ? __longlong_as_double(0x7ff0000000000000LL) : ((double)kth + E) * (1.0 + rho) / (1.0 - rho) + E;
+    // compact the survivors to the front of the query's row (order is irrelevant downstream; tensor_select_kernel and the
+    // rerank rely on the survivors being a prefix)
     int base = 0;
-    for (int c0 = 0; c0 < rt; c0 += 32) {
+    for (int c0 = 0; c0 < nv; c0 += 32) {
         const int c = c0 + lane;
         int32_t idx = -1; float v = 0.f;
-        if (c < rt) { idx = ci[c]; v = cv[c]; }
+        if (c < nv) { idx = ri[c]; v = rv[c]; }
         const bool keep = idx >= 0 && !((double)v > cut);
         const uint32_t m = __ballot_sync(0xffffffffu, keep);
         __syncwarp();
@@ -929,16 +994,23 @@ __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ c
     }
     __syncwarp();
     for (int c = base + lane; c < rt; c += 32) ci[c] = -1;
+    if (pair_cells && base > 0) {
+        // the survivors of all queries go on one list so that the rerank's warps are full: cell = q * rt + position
+        int off = 0;
+        if (lane == 0) off = atomicAdd(pair_count, base);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        for (int c = lane; c < base; c += 32) pair_cells[off + c] = (uint32_t)(q * rt + c);
+    }
 }
 
 __global__ void __launch_bounds__(128) tensor_select_kernel(const float* __restrict__ cand_exact, const int32_t* __restrict__ cand_idx,
                                                             const float* __restrict__ slot_bound, int64_t nq, int n_slots, int R, int k,
                                                             const ErrModel em, int64_t index_offset, float* __restrict__ out_dist,
                                                             int32_t* __restrict__ out_idx, int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags,
-                                                            float* max_bound) {
+                                                            float* max_bound, const int32_t* __restrict__ n_active, float* __restrict__ seed_out) {
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (q >= nq) return;
+    if (q >= nq || (n_active && q >= *n_active)) return;
     const int rt = n_slots * R;
     const float* ce = cand_exact + q * rt;
     const int32_t* ci = cand_idx + q * rt;
@@ -947,8 +1019,10 @@ __global__ void __launch_bounds__(128) tensor_select_kernel(const float* __restr
     float kth = 0.f;
     for (int r = 0; r < k; ++r) {
         float bd = __int_as_float(0x7f800000); int bi = 0x7fffffff;
-        for (int c = lane; c < rt; c += 32) {
-            const int i = ci[c];
+        for (int c0 = 0; c0 < rt; c0 += 32) {
+            const int c = c0 + lane;
+            const int i = c < rt ? ci[c] : -1;
+            if (__all_sync(0xffffffffu, i < 0)) break;                         // survivors are a prefix (tensor_prune_kernel)
             if (i < 0) continue;
             const float dd = ce[c];
             if (!(dd < 100000.0f)) continue;                                   // ann.cpp:116: nothing ≥ 100000 is ever accepted
@@ -979,21 +1053,30 @@ __global__ void __launch_bounds__(128) tensor_select_kernel(const float* __restr
     if (isinf(B)) ok = true;                                                   // every row of the gallery was a candidate
     else if (found < k) ok = false;
     else ok = (B - E) * (1.0 - rho) > (double)kth * em.dist_scale * (1.0 + rho);
-    if (!ok) { int pos = atomicAdd(n_flagged, 1); flagged[pos] = (int32_t)q; if (fail_flags) fail_flags[q] = 1; }
+    if (!ok) {
+        int pos = atomicAdd(n_flagged, 1); flagged[pos] = (int32_t)q; if (fail_flags) fail_flags[q] = 1;
+        // threshold for the second pass: the k-th best found so far bounds the true k-th best from above, so no row whose
+        // approximate value exceeds it by the error margins can matter; with this seed the second pass certifies
+        // ((B − E)(1 − ρ) > kth(1 + ρ) holds with B = seed) unless one of its lists overflows
+        if (seed_out) seed_out[pos] = found >= k ? __double2float_ru((double)kth * em.dist_scale * (1.0 + rho) / (1.0 - rho) + 2.0 * E)
+                                                 : __int_as_float(0x7f800000);
+    }
     atomicMax(reinterpret_cast<unsigned int*>(max_bound), __float_as_uint((float)E));
 }
 
-int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s) {
-    tensor_prune_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cand_val, cand_idx, nq, rt, k, em);
+int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s, const int32_t* n_active,
+                 uint32_t* pair_cells, int32_t* pair_count) {
+    const size_t smem = (size_t)4 * 2 * std::min(rt, PRUNE_STAGE_MAX) * 4;
+    tensor_prune_kernel<<<(unsigned)ceil_div(nq, 4), 128, smem, s>>>(cand_val, cand_idx, nq, rt, k, em, n_active, pair_cells, pair_count);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
 
 int launch_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots, int R, int k,
                   const ErrModel& em, int64_t index_offset, float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged,
-                  unsigned char* fail_flags, float* max_bound, cudaStream_t s) {
+                  unsigned char* fail_flags, float* max_bound, cudaStream_t s, const int32_t* n_active, float* seed_out) {
     tensor_select_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, em, index_offset, out_dist,
-                                                                   out_idx, flagged, n_flagged, fail_flags, max_bound);
+                                                                   out_idx, flagged, n_flagged, fail_flags, max_bound, n_active, seed_out);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
@@ -1039,8 +1122,74 @@ __global__ void escalation_scatter_kernel(const int32_t* __restrict__ flagged, c
     }
 }
 
+// Seed thresholds.  A list that starts empty accepts everything until it is full and then tightens like R/i: the first
+// tiles of every query block are a burst of replacements that outruns the tensor pipe (the accumulator is only double
+// buffered).  So the candidate kernel is first run over a SAMPLE of the gallery (the first S rows of the shadow, which is
+// stored in a pseudo-random strided order), keeping only the minimum of every (work unit, 32-column group) — a branch-free
+// scan — and each query's m-th smallest group minimum becomes the threshold all of its lists start from: only about
+// m·N/S rows of the whole gallery fall below it, spread evenly over the scan.  The seed needs no
+// guarantee — slot_bound reports min(seed, list maximum), so a seed that turns out too small fails the certificate and the
+// query takes the second pass like any other uncertified one.
+struct SeedPlan { int64_t S; int m, R, n_slots, grid; float* cand_val; int32_t* cand_idx; float* slot_bound; float* seed; };
+
+static bool seed_enabled() {
+    static int on = [] { const char* e = getenv("FIR_TENSOR_SEED"); return e ? atoi(e) : 1; }();
+    return on != 0;
+}
+
+static size_t seed_plan(fir_gallery* g, int64_t nq, int k, int ctas, SeedPlan* sp) {
+    *sp = SeedPlan{};
+    static const int div = [] { const char* e = getenv("FIR_TENSOR_SEED_DIV"); int v = e ? atoi(e) : 50; return v > 0 ? v : 50; }();
+    static const int m_override = [] { const char* e = getenv("FIR_TENSOR_SEED_M"); return e ? atoi(e) : 0; }();
+    const int64_t S = g->n / div / BN * BN;               // 2 % of the gallery, whole tiles
+    if (!seed_enabled() || S < 4 * BN || nq < 4 * BM) return 0;
+    sp->S = S;
+    // m >= k would make a too-small seed impossible; 0.6 k leaves about one query in 10^7 to the second pass
+    sp->m = m_override > 0 ? m_override : std::max(2, (3 * k + 4) / 5);
+    sp->R = 4;                                            // four column-group minima per (slot, half): see epilogue_scan_tile_mins
+    int least = 1;
+    tensor_plan(nq, S, g->n_sm, ctas, &sp->grid, &sp->n_slots, &least);
+    sp->n_slots *= EPI_WARPS / 4;
+    return 2 * al256((size_t)nq * sp->n_slots * sp->R * 4) + al256((size_t)nq * sp->n_slots * 4) + al256((size_t)nq * 4) + 1024;
+}
+
+static bool seed_take(fir_gallery* g, int64_t nq, SeedPlan* sp) {
+    if (!sp->S) return true;
+    const size_t cells = (size_t)nq * sp->n_slots * sp->R;
+    sp->cand_val = (float*)g->ws.take(cells * 4);
+    sp->cand_idx = (int32_t*)g->ws.take(cells * 4);
+    sp->slot_bound = (float*)g->ws.take((size_t)nq * sp->n_slots * 4);
+    sp->seed = (float*)g->ws.take((size_t)nq * 4);
+    return sp->cand_val && sp->cand_idx && sp->slot_bound && sp->seed;
+}
+
+// seed[q] = m-th smallest distinct group minimum of query q's sample pass (+inf when there are fewer groups); warp per query
+__global__ void __launch_bounds__(128) seed_select_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, int64_t nq, int rt,
+                                                          int m, float* __restrict__ seed) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const float* cv = cand_val + q * rt;
+    const int32_t* ci = cand_idx + q * rt;
+    const float inf = __int_as_float(0x7f800000);
+    float last = -inf;
+    for (int r = 0; r < m; ++r) {
+        float b = inf;
+        for (int c = lane; c < rt; c += 32) {
+            const float v = cv[c];
+            if (ci[c] >= 0 && v > last && v < b) b = v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        last = b;
+        if (b == inf) break;
+    }
+    if (lane == 0) seed[q] = last;
+}
+
 namespace {
-struct PassBuffers { void* qbuf; float* cand_val; int32_t* cand_idx; float* cand_exact; float* slot_bound; int n_slots, min_lists, grid, R; size_t qside; };
+struct PassBuffers { void* qbuf; float* cand_val; int32_t* cand_idx; float* cand_exact; float* slot_bound; uint32_t* pair_cells; int32_t* pair_count;
+                     int n_slots, min_lists, grid, R; size_t qside; };
 
 size_t pass_bytes(fir_gallery* g, int64_t nq, int R, int ctas, PassBuffers* pb) {
     int grid = 0, n_slots = 1, least = 1;
@@ -1048,7 +1197,7 @@ size_t pass_bytes(fir_gallery* g, int64_t nq, int R, int ctas, PassBuffers* pb) 
     n_slots *= EPI_WARPS / 4;                           // one list per (CTA slot, column half)
     pb->n_slots = n_slots; pb->min_lists = least * (EPI_WARPS / 4); pb->grid = grid; pb->R = R;
     pb->qside = tensor_side_bytes(nq, g->d, BM);
-    return pb->qside + 3 * al256((size_t)nq * n_slots * R * 4) + al256((size_t)nq * n_slots * 4) + 2048;
+    return pb->qside + 4 * al256((size_t)nq * n_slots * R * 4) + al256((size_t)nq * n_slots * 4) + 4096;
 }
 bool pass_take(fir_gallery* g, int64_t nq, PassBuffers* pb) {
     const size_t cells = (size_t)nq * pb->n_slots * pb->R;
@@ -1057,29 +1206,62 @@ bool pass_take(fir_gallery* g, int64_t nq, PassBuffers* pb) {
     pb->cand_idx = (int32_t*)g->ws.take(cells * 4);
     pb->cand_exact = (float*)g->ws.take(cells * 4);
     pb->slot_bound = (float*)g->ws.take((size_t)nq * pb->n_slots * 4);
-    return pb->qbuf && pb->cand_val && pb->cand_idx && pb->cand_exact && pb->slot_bound;
+    pb->pair_cells = (uint32_t*)g->ws.take(cells * 4);
+    pb->pair_count = (int32_t*)g->ws.take(256);
+    return pb->qbuf && pb->cand_val && pb->cand_idx && pb->cand_exact && pb->slot_bound && pb->pair_cells && pb->pair_count;
 }
 // pack → tcgen05 candidates → exact rerank → select + certificate, for nq device-resident fp32 queries
 int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const PassBuffers& pb, int64_t index_offset, float* od, int32_t* oi,
-             int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags, float* max_bound, int prof_kind) {
+             int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags, float* max_bound, int prof_kind, const SeedPlan* sp = nullptr,
+             const int32_t* n_rows = nullptr, float* seed_out = nullptr, const float* seed_in = nullptr) {
     TensorSide qs;
+    const bool first = prof_kind == FIR_KERNEL_L2_CANDIDATES;
+    auto* ev_pack = first ? g->prof_begin(FIR_PHASE_PACK_QUERIES) : nullptr;
     FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, pb.qbuf, &qs, nullptr, false, true, g->stream));
     CUtensorMap tmap_a;
     FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
     const int rt = pb.n_slots * pb.R;
     FIR_CUDA_TRY(cudaMemsetAsync(pb.cand_idx, 0xFF, (size_t)nq * rt * 4, g->stream));
     FIR_CUDA_TRY(cudaMemsetAsync(pb.slot_bound, 0xFF, (size_t)nq * pb.n_slots * 4, g->stream));
+    g->prof_end(ev_pack);
     TensorSearchArgs a{};
+    a.skip_if_zero = n_rows;
+    a.seed_thr = seed_in;
     a.gal = &g->tside; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = ctas == 2 ? &g->tmap_b_half : &g->tmap_b; a.ctas = ctas;
     a.n_sm = g->n_sm; a.d = g->d; a.R = pb.R; a.n_slots = pb.n_slots; a.cand_val = pb.cand_val; a.cand_idx = pb.cand_idx; a.slot_bound = pb.slot_bound; a.grid = pb.grid;
+    if (sp && sp->S) {
+        auto* evs = g->prof_begin(FIR_PHASE_SEED);
+        TensorSide sample = g->tside;
+        sample.rows = sp->S; sample.rows_padded = sp->S;
+        const int srt = sp->n_slots * sp->R;
+        FIR_CUDA_TRY(cudaMemsetAsync(sp->cand_idx, 0xFF, (size_t)nq * srt * 4, g->stream));
+        TensorSearchArgs sa = a;
+        sa.gal = &sample; sa.R = sp->R; sa.n_slots = sp->n_slots; sa.cand_val = sp->cand_val; sa.cand_idx = sp->cand_idx;
+        sa.slot_bound = sp->slot_bound; sa.grid = sp->grid; sa.seed_thr = nullptr; sa.mins_only = 1;
+        FIR_TRY(launch_tensor_candidates(sa, g->stream));
+        seed_select_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, g->stream>>>(sp->cand_val, sp->cand_idx, nq, srt, sp->m, sp->seed);
+        FIR_CUDA_TRY(cudaGetLastError());
+        g->prof_end(evs);
+        g->stats.gpu_launches += 2;
+        a.seed_thr = sp->seed;
+    }
     { auto* ev = g->prof_begin(prof_kind); int st_ = launch_tensor_candidates(a, g->stream); g->prof_end(ev); FIR_TRY(st_); }
     ErrModel em{};
     em.kind = 0; em.d = g->d; em.nkb = round_up(g->d, BK) / BK; em.q_norm2 = qs.norm2; em.q_resid = qs.resid; em.gal_stats = g->d_stats;
     em.rel = (double)(g->d + 4) * 5.9604644775390625e-08; em.dist_scale = (double)g->d;
-    FIR_TRY(launch_prune(pb.cand_val, pb.cand_idx, nq, rt, k, em, g->stream));
-    FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, pb.cand_idx, rt, 0, pb.cand_exact, g->stream));
+    auto* ev1 = first ? g->prof_begin(FIR_PHASE_PRUNE) : nullptr;
+    const bool listed = (uint64_t)nq * (uint64_t)rt < 0xffffffffull;          // cells are 32-bit
+    if (listed) FIR_CUDA_TRY(cudaMemsetAsync(pb.pair_count, 0, 4, g->stream));
+    FIR_TRY(launch_prune(pb.cand_val, pb.cand_idx, nq, rt, k, em, g->stream, n_rows, listed ? pb.pair_cells : nullptr, pb.pair_count));
+    g->prof_end(ev1);
+    auto* ev2 = first ? g->prof_begin(FIR_PHASE_RERANK) : nullptr;
+    if (listed) FIR_TRY(launch_pair_list(FIR_L2, dq, g->dp, g->rows, g->dp, g->d, pb.pair_cells, pb.pair_count, (int64_t)nq * rt, rt, pb.cand_idx, pb.cand_exact, g->stream));
+    else FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, pb.cand_idx, rt, 0, pb.cand_exact, g->stream));
+    g->prof_end(ev2);
+    auto* ev3 = first ? g->prof_begin(FIR_PHASE_SELECT) : nullptr;
     FIR_TRY(launch_select(pb.cand_exact, pb.cand_idx, pb.slot_bound, nq, pb.n_slots, pb.R, k, em, index_offset, od, oi, flagged, n_flagged, fail_flags,
-                          max_bound, g->stream));
+                          max_bound, g->stream, n_rows, seed_out));
+    g->prof_end(ev3);
     g->stats.gpu_launches += 5;   // pack, candidates, prune, rerank, select
     return FIR_OK;
 }
@@ -1100,8 +1282,12 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     auto pick_R = [&](int lists, int extra) { int want = (2 * k + lists - 1) / lists + 2 + extra; return want <= 4 ? 4 : (want <= 8 ? 8 : (want <= 16 ? 16 : 32)); };
     // (sized for the queries spread over the FEWEST lists: a full-round query block has one slot, i.e. two lists)
     const int R1 = pick_R(p1.min_lists, 0);
-    const int R2 = pick_R(p2.min_lists, p2.min_lists > p1.min_lists ? 0 : 8);    // same list structure ⇒ longer lists, else a re-deal is enough
+    // the second pass starts every list from the query's own bound (k-th best found in pass 1 plus the error margins, see
+    // tensor_select_kernel), so its lists only ever hold rows that can matter and can be long at no cost
+    const int R2 = std::max(16, pick_R(p2.min_lists, 8));
     const bool second = true;
+    SeedPlan sp{};
+    const size_t seed_bytes = seed_plan(g, nq, k, ctas, &sp);
     // Exact re-run of what two tensor passes could not certify (mass exact ties; normally nothing): the first kFbFast
     // queries of the device-side list are spread over up to 1024 gallery splits each (one or two 64-row tiles per block, so
     // even a single query is served by the whole machine); a second launch covers any overflow with coarse splits.  Both
@@ -1110,8 +1296,8 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     const int nsplit_fast = (int)std::max<int64_t>(1, std::min<int64_t>(1024, ceil_div(g->n, 64)));
     const int nsplit_slow = (int)std::max<int64_t>(1, std::min<int64_t>(16, ceil_div(g->n, 64 * 8)));
     const size_t fb_cells = std::max<size_t>((size_t)kFbFast * nsplit_fast, (size_t)nq * nsplit_slow) * k;
-    size_t need = al256(sizeof(float) * (size_t)nq * g->dp) + pass_bytes(g, nq, R1, ctas, &p1) + 3 * al256((size_t)nq * 4) +
-                  2 * al256((size_t)nq * k * 4) + 2 * al256(fb_cells * 4) + 16384;
+    size_t need = al256(sizeof(float) * (size_t)nq * g->dp) + pass_bytes(g, nq, R1, ctas, &p1) + 4 * al256((size_t)nq * 4) +
+                  2 * al256((size_t)nq * k * 4) + 2 * al256(fb_cells * 4) + seed_bytes + 16384;
     if (second) need += pass_bytes(g, cap2, R2, ctas, &p2) + al256(sizeof(float) * (size_t)cap2 * g->dp) + 2 * al256((size_t)cap2 * k * 4) + 2 * al256((size_t)cap2 * 4);
     FIR_TRY(g->ws.reserve(need));
     // fp32 queries, zero padded (for the exact rerank and the certificate fallback)
@@ -1134,13 +1320,14 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
         }
     }
     int32_t* flagged = (int32_t*)g->ws.take((size_t)nq * 4);
+    float* seed2 = (float*)g->ws.take((size_t)nq * 4);     // by position on the flagged list; NaN = padding row, accepts nothing
     int32_t* final_list = (int32_t*)g->ws.take((size_t)nq * 4);
     float* od = out_dist; int32_t* oi = out_idx;
     if (memspace == FIR_HOST || !out_dist) od = (float*)g->ws.take((size_t)nq * k * 4);
     if (memspace == FIR_HOST) oi = (int32_t*)g->ws.take((size_t)nq * k * 4);
     float* part_d = (float*)g->ws.take(fb_cells * 4);
     int32_t* part_i = (int32_t*)g->ws.take(fb_cells * 4);
-    if (!pass_take(g, nq, &p1) || !flagged || !final_list || !od || !oi || !part_d || !part_i)
+    if (!pass_take(g, nq, &p1) || !seed_take(g, nq, &sp) || !seed2 || !flagged || !final_list || !od || !oi || !part_d || !part_i)
         return fail(FIR_ERR_INTERNAL, "workspace underestimated (tensor path)");
     // device counters: [4] flagged after pass 1, [5] max bound, [6] flagged inside pass 2 (unused list), [7] final exact re-runs
     int32_t* n_flagged = reinterpret_cast<int32_t*>(g->d_stats + 4);
@@ -1148,8 +1335,9 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     int32_t* n_flagged2 = reinterpret_cast<int32_t*>(g->d_stats + 6);
     int32_t* n_final = reinterpret_cast<int32_t*>(g->d_stats + 7);
     FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats + 4, 0, 16, g->stream));
+    FIR_CUDA_TRY(cudaMemsetAsync(seed2, 0xFF, (size_t)nq * 4, g->stream));
 
-    FIR_TRY(run_pass(g, dq, nq, k, ctas, p1, g->index_offset, od, oi, flagged, n_flagged, nullptr, max_bound, FIR_KERNEL_L2_CANDIDATES));
+    FIR_TRY(run_pass(g, dq, nq, k, ctas, p1, g->index_offset, od, oi, flagged, n_flagged, nullptr, max_bound, FIR_KERNEL_L2_CANDIDATES, &sp, nullptr, seed2, nullptr));
     const int32_t* exact_list = flagged; const int32_t* exact_count = n_flagged;
     if (second) {
         float* dq2 = (float*)g->ws.take(sizeof(float) * (size_t)cap2 * g->dp);
@@ -1158,18 +1346,22 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
         int32_t* flagged2 = (int32_t*)g->ws.take((size_t)cap2 * 4);
         unsigned char* fail2 = (unsigned char*)g->ws.take((size_t)cap2);
         if (!pass_take(g, cap2, &p2) || !dq2 || !od2 || !oi2 || !flagged2 || !fail2) return fail(FIR_ERR_INTERNAL, "workspace underestimated (second pass)");
+        auto* evp2 = g->prof_begin(FIR_PHASE_PASS2);
         gather_flagged_rows_kernel<<<(unsigned)cap2, 128, 0, g->stream>>>(dq, g->dp, flagged, n_flagged, cap2, dq2);
         FIR_CUDA_TRY(cudaMemsetAsync(fail2, 0, (size_t)cap2, g->stream));
-        FIR_TRY(run_pass(g, dq2, cap2, k, ctas, p2, g->index_offset, od2, oi2, flagged2, n_flagged2, fail2, max_bound, FIR_KERNEL_L2_CANDIDATES_PASS2));
+        FIR_TRY(run_pass(g, dq2, cap2, k, ctas, p2, g->index_offset, od2, oi2, flagged2, n_flagged2, fail2, max_bound, FIR_KERNEL_L2_CANDIDATES_PASS2, nullptr, n_flagged, nullptr, seed2));
         escalation_scatter_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, g->stream>>>(flagged, n_flagged, cap2, fail2, od2, oi2, k, od, oi, final_list, n_final);
+        g->prof_end(evp2);
         FIR_CUDA_TRY(cudaGetLastError());
         g->stats.gpu_launches += 2;
         exact_list = final_list; exact_count = n_final;
     }
     // what is still uncertified: exact CUDA-core re-run (device-side count; see above)
+    auto* evx = g->prof_begin(FIR_PHASE_EXACT_RERUN);
     FIR_TRY(exact_topk_device(g, dq, nq, k, g->d, exact_list, exact_count, part_d, part_i, nsplit_fast, od, oi, 0, kFbFast));
     if (nq > kFbFast)
         FIR_TRY(exact_topk_device(g, dq, nq, k, g->d, exact_list, exact_count, part_d, part_i, nsplit_slow, od, oi, kFbFast, nq - kFbFast));
+    g->prof_end(evx);
     g->stats.path_used = FIR_PATH_TENSOR;
     g->stats.n_candidates = p1.n_slots * p1.R;
     g->stats.n_fallback = -1;     // resolved lazily by fir_search_last_stats

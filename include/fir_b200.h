@@ -113,7 +113,15 @@ typedef enum fir_kernel {
     FIR_KERNEL_DEM_LIKELIHOOD = 2,
     FIR_KERNEL_L2_CANDIDATES_PASS2 = 3, /* same kernel, second pass over the few uncertified queries      */
     FIR_KERNEL_STREAM_DISTANCES = 4,    /* small-batch one-pass streaming kernel (HBM-bound)               */
-    FIR_KERNEL_APPROX_TILES = 5         /* chi2/KL approximate tile kernel                                  */
+    FIR_KERNEL_APPROX_TILES = 5,        /* chi2/KL approximate tile kernel                                  */
+    /* phases of the tensor path around the candidate kernel (first pass unless noted) */
+    FIR_PHASE_PACK_QUERIES = 6,         /* fp16 shadow + norms + residuals of the query block               */
+    FIR_PHASE_PRUNE = 7,
+    FIR_PHASE_RERANK = 8,               /* exact fp32 distances of the surviving candidates                 */
+    FIR_PHASE_SELECT = 9,               /* top-k + certificate                                              */
+    FIR_PHASE_PASS2 = 10,               /* the whole second pass (gather, pack, kernel, prune, rerank, select, scatter) */
+    FIR_PHASE_EXACT_RERUN = 11,         /* exact CUDA-core windows for what no pass certified (normally empty) */
+    FIR_PHASE_SEED = 12                 /* sample pass that seeds the first pass's list thresholds          */
 } fir_kernel;
 int fir_profile_enable(fir_gallery* g, int32_t on);
 int fir_profile_read(fir_gallery* g, int32_t kernel, double* total_ms, int32_t* launches);

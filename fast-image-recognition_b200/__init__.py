@@ -35,7 +35,7 @@ EXPORTS = [
     "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn", "fir_classifier_pnn_sequential",
     "fir_twd_conventional", "fir_twd_proposed",
     "fir_dem_build", "fir_dem_from_state", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
-    "fir_dem_get_min_other", "fir_dem_search",
+    "fir_dem_get_min_other", "fir_dem_search", "fir_index_save", "fir_index_load",
 ]
 
 
@@ -92,6 +92,8 @@ def lib():
     L.fir_twd_conventional.argtypes = [vp, vp, i64, i32, C.c_double, i32, i32, i32, vp, vp, vp]
     L.fir_twd_proposed.argtypes = [vp, vp, i64, i32, C.c_double, i32, i32, vp, vp, vp]
     L.fir_dem_build.argtypes = [vp, C.POINTER(DemParams), C.POINTER(vp)]
+    L.fir_index_save.argtypes = [vp, vp, C.c_char_p]
+    L.fir_index_load.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(vp)]
     L.fir_dem_from_state.argtypes = [vp, vp, i32, vp, C.c_float, C.POINTER(vp)]
     L.fir_dem_destroy.argtypes = [vp]
     L.fir_dem_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float)]
@@ -159,6 +161,19 @@ def normalize_rows(rows, metric="l2", stream=None):
 
 
 class Gallery:
+    @classmethod
+    def _adopt(cls, handle):
+        """Wrap a handle created by the library (fir_index_load)."""
+        self = cls.__new__(cls)
+        self._h = handle
+        n, d, m, nc = C.c_int64(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _check(lib().fir_gallery_info(self._h, C.byref(n), C.byref(d), C.byref(m), C.byref(nc)))
+        self.n, self.d, self.n_classes = n.value, d.value, nc.value
+        self.metric_name = {v: k for k, v in METRICS.items()}[m.value]
+        self.index_offset = 0
+        self._device = None
+        return self
+
     def __init__(self, rows, labels=None, metric="l2", index_offset=0, stream=None):
         self.metric_name = metric if isinstance(metric, str) else {v: k for k, v in METRICS.items()}[metric]
         m = METRICS[metric] if isinstance(metric, str) else metric
@@ -283,6 +298,19 @@ class Gallery:
         return sc, lab
 
 
+def save_index(path, gallery, dem=None):
+    """Gallery (+ optional DirectedEnumeration state) → one binary file."""
+    _check(lib().fir_index_save(gallery._h, dem._h if dem is not None else None, os.fsencode(path)))
+
+
+def load_index(path):
+    """→ (Gallery, Dem or None)"""
+    g, d = C.c_void_p(None), C.c_void_p(None)
+    _check(lib().fir_index_load(os.fsencode(path), C.byref(g), C.byref(d)))
+    gal = Gallery._adopt(g)
+    return gal, (Dem._adopt(gal, d) if d.value else None)
+
+
 def merge_topk(parts_dist, parts_idx, stream=None):
     """k-way (dist, idx) merge of per-shard lists: CUDA tensors [n_parts, nq, k] → ([nq,k], [nq,k])."""
     import torch
@@ -343,6 +371,18 @@ class Classifier:
 class Dem:
     """DirectedEnumeration over a Gallery (kept alive by this object)."""
 
+    @classmethod
+    def _adopt(cls, gallery, handle):
+        self = cls.__new__(cls)
+        self.gallery, self._h = gallery, handle
+        self._read_info()
+        return self
+
+    def _read_info(self):
+        a, b, t = C.c_int32(0), C.c_int32(0), C.c_float(0)
+        _check(lib().fir_dem_info(self._h, C.byref(a), C.byref(b), C.byref(t)))
+        self.n_pivots, self.chain_rows, self.threshold = a.value, b.value, np.float32(t.value)
+
     def __init__(self, gallery, pivot0=-1, seed=0, false_accept_rate=0.01, threshold=0.0, max_chain=0, max_pivots=0, state=None):
         self.gallery = gallery
         h = C.c_void_p(None)
@@ -354,9 +394,7 @@ class Dem:
             p = DemParams(int(pivot0), int(seed), float(false_accept_rate), float(threshold), int(max_chain), int(max_pivots))
             _check(lib().fir_dem_build(gallery._h, C.byref(p), C.byref(h)))
         self._h = h
-        a, b, t = C.c_int32(0), C.c_int32(0), C.c_float(0)
-        _check(lib().fir_dem_info(self._h, C.byref(a), C.byref(b), C.byref(t)))
-        self.n_pivots, self.chain_rows, self.threshold = a.value, b.value, np.float32(t.value)
+        self._read_info()
 
     def close(self):
         if getattr(self, "_h", None):

@@ -37,6 +37,8 @@ struct fir_dem {
 
 namespace fir {
 
+const fir_gallery* dem_gallery(const fir_dem* dem) { return dem ? dem->g : nullptr; }
+
 // ---------------------------------------------------------------------------------------------------
 // build
 // ---------------------------------------------------------------------------------------------------

@@ -43,6 +43,7 @@ int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_
                       int64_t active_offset = 0, int64_t active_cap = 0);
 int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
 int approx_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
+const fir_gallery* dem_gallery(const fir_dem* dem);      // the gallery a DEM handle was built over
 size_t twd_workspace_bytes(const fir_gallery* g, int64_t nq, int64_t* mq_out);
 int twd_run(fir_gallery* g, const float* dq, int64_t nq, int64_t mq, int kind, int type, double threshold, int feat_count, int last_feature,
             int32_t* d_index, int32_t* d_label, unsigned char* d_unrel);

@@ -215,6 +215,16 @@ int fir_dem_get_min_other(const fir_dem* dem, float* out /* chain_rows, host */)
 int fir_dem_search(fir_dem* dem, const float* queries, int64_t nq, int32_t count_to_check, int32_t memspace,
                    int32_t* out_idx, float* out_dist, uint8_t* out_below, int32_t* out_evals);
 
+/* ---- persisted index --------------------------------------------------
+ * The reference keeps nothing on disk between runs: the gallery is re-parsed from the text features file
+ * (qt_cpp/db_features.cpp:44-116) and DirectedEnumeration is rebuilt by its constructor (qt_cpp/ann.cpp:270-348).
+ * One binary file holds the packed gallery (rows, labels, metric, class count, index offset) and, when `dem` is given,
+ * its pivots, pivot-distance rows and threshold; a checksum guards the payload.  fir_index_load returns new handles
+ * (the DEM handle borrows the gallery handle: destroy it first); *out_dem is NULL when the file carries no DEM state
+ * or out_dem itself is NULL. */
+int fir_index_save(const fir_gallery* g, const fir_dem* dem /* or NULL */, const char* path);
+int fir_index_load(const char* path, fir_gallery** out_gallery, fir_dem** out_dem /* or NULL */);
+
 #ifdef __cplusplus
 }
 #endif

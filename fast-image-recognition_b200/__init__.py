@@ -33,7 +33,8 @@ EXPORTS = [
     "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
     "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates", "fir_profile_enable", "fir_profile_read",
     "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn", "fir_classifier_pnn_sequential",
-    "fir_twd_conventional", "fir_twd_proposed",
+    "fir_twd_conventional", "fir_twd_proposed", "fir_kmedoids_select", "fir_classifier_set_total",
+    "fir_fpnn_create", "fir_fpnn_destroy", "fir_fpnn_info", "fir_fpnn_get_coefficients", "fir_fpnn_predict",
     "fir_dem_build", "fir_dem_from_state", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
     "fir_dem_get_min_other", "fir_dem_search", "fir_index_save", "fir_index_load",
 ]
@@ -89,6 +90,13 @@ def lib():
     L.fir_classifier_knn.argtypes = [vp, vp, i64, i32, vp]
     L.fir_classifier_pnn.argtypes = [vp, vp, i64, vp, vp]
     L.fir_classifier_pnn_sequential.argtypes = [vp, vp, i64, vp]
+    L.fir_kmedoids_select.argtypes = [vp, vp, i64, i32, i32, i32, vp, C.POINTER(i64)]
+    L.fir_classifier_set_total.argtypes = [vp, i64]
+    L.fir_fpnn_create.argtypes = [vp, vp, i64, i32, i32, vp, vp, f64, C.POINTER(vp)]
+    L.fir_fpnn_destroy.argtypes = [vp]
+    L.fir_fpnn_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64)]
+    L.fir_fpnn_get_coefficients.argtypes = [vp, vp]
+    L.fir_fpnn_predict.argtypes = [vp, vp, i64, i32, C.c_float, vp]
     L.fir_twd_conventional.argtypes = [vp, vp, i64, i32, C.c_double, i32, i32, i32, vp, vp, vp]
     L.fir_twd_proposed.argtypes = [vp, vp, i64, i32, C.c_double, i32, i32, vp, vp, vp]
     L.fir_dem_build.argtypes = [vp, C.POINTER(DemParams), C.POINTER(vp)]
@@ -353,6 +361,10 @@ class Classifier:
         _check(lib().fir_classifier_knn(self._h, _ptr(q), q.shape[0], int(K), _ptr(lab)))
         return lab
 
+    def set_total(self, n_total):
+        """PNN denominator when the rows are a reduced (clustered) training set."""
+        _check(lib().fir_classifier_set_total(self._h, int(n_total)))
+
     def pnn_sequential(self, queries):
         """PNNClassifier(bf=False): predict_sequentional."""
         q = np.ascontiguousarray(queries, dtype=np.float64)
@@ -366,6 +378,54 @@ class Classifier:
         sc = np.empty((q.shape[0], self.n_classes), np.float64) if scores else None
         _check(lib().fir_classifier_pnn(self._h, _ptr(q), q.shape[0], _ptr(sc), _ptr(lab)))
         return lab, sc
+
+
+def kmedoids_select(train_rows, train_labels, n_classes, num_clusters):
+    """PNNwithClusteringClassifier::train: positions (in the given class-major order) of the rows kept per class."""
+    rows = np.ascontiguousarray(train_rows, dtype=np.float64)
+    lab = np.ascontiguousarray(train_labels, dtype=np.int32)
+    sel = np.empty(rows.shape[0], np.int64)
+    cnt = C.c_int64(0)
+    _check(lib().fir_kmedoids_select(_ptr(rows), _ptr(lab), rows.shape[0], rows.shape[1], int(n_classes), int(num_clusters), _ptr(sel), C.byref(cnt)))
+    return sel[:cnt.value].copy()
+
+
+class Fpnn:
+    """FPNNClassifier (orthogonal-series PNN): trained at construction from RAW class-major rows."""
+
+    def __init__(self, train_rows, train_labels, n_classes, avg, std, scale=1.0):
+        rows = np.ascontiguousarray(train_rows, dtype=np.float64)
+        lab = np.ascontiguousarray(train_labels, dtype=np.int32)
+        avg, std = np.ascontiguousarray(avg, dtype=np.float64), np.ascontiguousarray(std, dtype=np.float64)
+        h = C.c_void_p(None)
+        _check(lib().fir_fpnn_create(_ptr(rows), _ptr(lab), rows.shape[0], rows.shape[1], int(n_classes), _ptr(avg), _ptr(std), float(scale), C.byref(h)))
+        self._h = h
+        J, na = C.c_int32(0), C.c_int64(0)
+        _check(lib().fir_fpnn_info(self._h, C.byref(J), C.byref(na)))
+        self.J, self.n_coefficients = J.value, na.value
+
+    @property
+    def coefficients(self):
+        a = np.empty(self.n_coefficients, np.float64)
+        _check(lib().fir_fpnn_get_coefficients(self._h, _ptr(a)))
+        return a
+
+    def predict(self, queries, sequential=False, output_ratio=0.9):
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        lab = np.empty(q.shape[0], np.int32)
+        _check(lib().fir_fpnn_predict(self._h, _ptr(q), q.shape[0], int(bool(sequential)), float(output_ratio), _ptr(lab)))
+        return lab
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fir_fpnn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Dem:

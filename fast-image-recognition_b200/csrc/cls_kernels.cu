@@ -14,6 +14,7 @@ struct fir_classifier {
     int device = 0;
     cudaStream_t stream = 0;
     int64_t n = 0;
+    int64_t n_total = 0;         // PNN denominator: n, or the full training-set size when the rows are a reduced set (:393)
     int d = 0, n_classes = 0;
     double* xc = nullptr;        // [n][d] training rows, already centred: fl(x - avg)
     double* avg = nullptr;       // [d]
@@ -225,6 +226,12 @@ int fir_classifier_create(const double* train_rows, const int32_t* train_labels,
     return FIR_OK;
 }
 
+int fir_classifier_set_total(fir_classifier* c, int64_t n_total) {
+    if (!c || n_total < 0) return fail(FIR_ERR_BAD_ARG, "bad arguments");
+    c->n_total = n_total;
+    return FIR_OK;
+}
+
 int fir_classifier_destroy(fir_classifier* c) {
     if (!c) return FIR_OK;
     if (c->xc) cudaFree(c->xc);
@@ -281,12 +288,12 @@ static int classify(fir_classifier* c, const double* queries, int64_t nq, int K,
                 const int max_fi = std::min(cur + 32, d);
                 cls_dist_kernel<<<grid, 256, 0, s>>>(qc, m, c->xc, n, d, dist, cur, max_fi, cur > 0 ? 1 : 0);
                 pnn_class_sum_kernel<<<(unsigned)ceil_div(m * C, 128), 128, 0, s>>>(dist, m, n, C, c->cls_begin, c->labels, c->class_major ? 1 : 0,
-                                                                                   (2 * var) * (double)(size_t)max_fi, (double)n, sc);
+                                                                                   (2 * var) * (double)(size_t)max_fi, (double)(c->n_total > 0 ? c->n_total : n), sc);
                 pnn_seq_decide_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, s>>>(sc, m, C, check, lab, done);
             }
         } else if (pnn) {
             pnn_class_sum_kernel<<<(unsigned)ceil_div(m * C, 128), 128, 0, s>>>(dist, m, n, C, c->cls_begin, c->labels, c->class_major ? 1 : 0, den,
-                                                                               (double)n, sc);
+                                                                               (double)(c->n_total > 0 ? c->n_total : n), sc);
             argmax_double_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, s>>>(sc, m, C, lab);
             if (out_scores) FIR_CUDA_TRY(cudaMemcpyAsync(out_scores + lo * C, sc, sizeof(double) * (size_t)m * C, cudaMemcpyDeviceToHost, s));
         } else {

@@ -215,6 +215,26 @@ int fir_dem_get_min_other(const fir_dem* dem, float* out /* chain_rows, host */)
 int fir_dem_search(fir_dem* dem, const float* queries, int64_t nq, int32_t count_to_check, int32_t memspace,
                    int32_t* out_idx, float* out_dist, uint8_t* out_below, int32_t* out_evals);
 
+/* replaces: PNNwithClusteringClassifier (qt_cpp/classification.cpp:311-428).  train() (:321-388, per-class k-medoids over the
+ * RAW training rows, class-major) is fir_kmedoids_select: out_selected receives the kept rows as positions in the given
+ * order (at most n), *out_count how many.  predict() (:389-428) is the Parzen PNN over the kept rows divided by the FULL
+ * training-set size: fir_classifier_create over the selected rows, fir_classifier_set_total(c, n), fir_classifier_pnn. */
+int fir_kmedoids_select(const double* train_rows, const int32_t* train_labels, int64_t n, int32_t d, int32_t n_classes,
+                        int32_t num_clusters, int64_t* out_selected, int64_t* out_count);
+int fir_classifier_set_total(fir_classifier* c, int64_t n_total);
+
+/* ---- FPNN: orthogonal-series PNN -------------------------------------------------------------
+ * replaces: FPNNClassifier (qt_cpp/classification.cpp:618-791): train() (:658-695) at creation, predict_bf (:697-735) and
+ * predict_sequentional (:736-791).  train_rows: RAW rows in class-major order; avg / std: avgValues / stdValues of
+ * split_train_test (:969-989); features_scale and output_ratio are the constructor's arguments (:620). */
+typedef struct fir_fpnn fir_fpnn;
+int fir_fpnn_create(const double* train_rows, const int32_t* train_labels, int64_t n, int32_t d, int32_t n_classes,
+                    const double* avg, const double* std, double features_scale, fir_fpnn** out);
+int fir_fpnn_destroy(fir_fpnn* f);
+int fir_fpnn_info(const fir_fpnn* f, int32_t* J, int64_t* n_coefficients);
+int fir_fpnn_get_coefficients(const fir_fpnn* f, double* out_a /* d x C x (2J+1), host */);
+int fir_fpnn_predict(fir_fpnn* f, const double* queries, int64_t nq, int32_t sequential, float output_ratio, int32_t* out_label);
+
 /* ---- persisted index --------------------------------------------------
  * The reference keeps nothing on disk between runs: the gallery is re-parsed from the text features file
  * (qt_cpp/db_features.cpp:44-116) and DirectedEnumeration is rebuilt by its constructor (qt_cpp/ann.cpp:270-348).

@@ -303,11 +303,13 @@ namespace fir {
 struct TrainingSet {
     fir_classifier* c;
     int n_classes, d;
+    std::vector<double> packed, avg, stddev;                             // raw training rows (class-major), avgValues, stdValues
+    std::vector<int32_t> labels;
     TrainingSet(const std::vector<fir_compat::Feature_vector>& rows, const std::vector<std::vector<size_t> >& training_set) : c(0) {
         n_classes = (int)training_set.size();
         d = rows.empty() ? 0 : (int)rows[0].features.size();
-        std::vector<double> packed, avg((size_t)d, 0.0);
-        std::vector<int32_t> labels;
+        avg.assign((size_t)d, 0.0);
+        stddev.assign((size_t)d, 0.0);
         size_t count = 0;
         for (size_t k = 0; k < training_set.size(); ++k)
             for (size_t t = 0; t < training_set[k].size(); ++t) {
@@ -317,9 +319,10 @@ struct TrainingSet {
                 ++count;
             }
         for (int fi = 0; fi < d; ++fi) {                                 // avgValues, classification.cpp:969-987 (same summation order)
-            double s = 0;
-            for (size_t r = 0; r < count; ++r) s += packed[r * (size_t)d + fi];
+            double s = 0, s2 = 0;
+            for (size_t r = 0; r < count; ++r) { const double f = packed[r * (size_t)d + fi]; s += f; s2 += f * f; }
             avg[fi] = s / (int)count;
+            stddev[fi] = std::sqrt((s2 - avg[fi] * avg[fi] * (int)count) / ((int)count - 1));      // stdValues, :988
         }
         check(fir_classifier_create(packed.data(), labels.data(), (int64_t)count, d, n_classes, avg.data(), &c), "fir_classifier_create");
     }
@@ -382,6 +385,64 @@ public:
     std::vector<double> scores;                                          // per-class outputs of the last call (locals in the reference, :194)
 private:
     bool bruteforce;
+};
+
+class PNNwithClusteringClassifier : public Classifier {                  // classification.cpp:311-428
+public:
+    PNNwithClusteringClassifier(fir::TrainingSet& ts, int no_clusters) : Classifier(label("PNN with clustering", no_clusters), ts), num_clusters(no_clusters), reduced(0) {}
+    ~PNNwithClusteringClassifier() { fir_classifier_destroy(reduced); }
+    void train() {                                                       // per-class k-medoids (:321-388), then the reduced Parzen set
+        const int64_t n = (int64_t)train_set.labels.size();
+        std::vector<int64_t> sel((size_t)n);
+        int64_t cnt = 0;
+        fir::check(fir_kmedoids_select(train_set.packed.data(), train_set.labels.data(), n, train_set.d, train_set.n_classes, num_clusters, sel.data(), &cnt),
+                   "fir_kmedoids_select");
+        std::vector<double> rows;
+        std::vector<int32_t> lab;
+        for (int64_t i = 0; i < cnt; ++i) {
+            rows.insert(rows.end(), train_set.packed.begin() + sel[i] * train_set.d, train_set.packed.begin() + (sel[i] + 1) * train_set.d);
+            lab.push_back(train_set.labels[sel[i]]);
+        }
+        fir_classifier_destroy(reduced); reduced = 0;
+        fir::check(fir_classifier_create(rows.data(), lab.data(), cnt, train_set.d, train_set.n_classes, train_set.avg.data(), &reduced), "fir_classifier_create");
+        fir::check(fir_classifier_set_total(reduced, n), "fir_classifier_set_total");      // den = total_training_size (:393)
+    }
+    std::vector<int> predict_batch(const std::vector<Feature_vector>& inputs) {
+        if (!reduced) train();
+        std::vector<double> q = pack(inputs);
+        std::vector<int32_t> lab(inputs.size());
+        fir::check(fir_classifier_pnn(reduced, q.data(), (int64_t)inputs.size(), 0, lab.data()), "fir_classifier_pnn");
+        return std::vector<int>(lab.begin(), lab.end());
+    }
+private:
+    static std::string label(const char* prefix, int v) { std::ostringstream os; os << prefix << ", " << v; return os.str(); }
+    int num_clusters;
+    fir_classifier* reduced;
+};
+
+class FPNNClassifier : public Classifier {                               // classification.cpp:618-791
+public:
+    FPNNClassifier(fir::TrainingSet& ts, double scale = 1.0, bool bf = true, float output_ratio = 0.9f)
+        : Classifier(label(scale) + (bf ? "" : " (seq)"), ts), features_scale(scale), bruteforce(bf), ratio(output_ratio), f(0) {}
+    ~FPNNClassifier() { fir_fpnn_destroy(f); }
+    void train() {                                                       // :658-695
+        fir_fpnn_destroy(f); f = 0;
+        fir::check(fir_fpnn_create(train_set.packed.data(), train_set.labels.data(), (int64_t)train_set.labels.size(), train_set.d, train_set.n_classes,
+                                   train_set.avg.data(), train_set.stddev.data(), features_scale, &f), "fir_fpnn_create");
+    }
+    std::vector<int> predict_batch(const std::vector<Feature_vector>& inputs) {
+        if (!f) train();
+        std::vector<double> q = pack(inputs);
+        std::vector<int32_t> lab(inputs.size());
+        fir::check(fir_fpnn_predict(f, q.data(), (int64_t)inputs.size(), bruteforce ? 0 : 1, ratio, lab.data()), "fir_fpnn_predict");
+        return std::vector<int>(lab.begin(), lab.end());
+    }
+private:
+    static std::string label(double v) { std::ostringstream os; os << "FPNN" << ", " << v; return os.str(); }
+    double features_scale;
+    bool bruteforce;
+    float ratio;
+    fir_fpnn* f;
 };
 
 // ---- qt_cpp/ImageTesting.cpp: Classifier (:35-48) and its three matching classifiers ----------------------------

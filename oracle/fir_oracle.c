@@ -356,6 +356,169 @@ void fir_oracle_pnn_seq(const double* train, const int32_t* train_label, int64_t
 }
 
 /* ------------------------------------------------------------------------------------------
+ * FPNN — orthogonal-series PNN, classification.cpp:618-791; fasterlog2 :64-73
+ * ------------------------------------------------------------------------------------------ */
+float fir_oracle_fasterlog2(float x) {
+    union { float f; uint32_t i; } vx = { x };
+    union { uint32_t i; float f; } mx = { (vx.i & 0x007FFFFF) | (0x7e << 23) };
+    float y = vx.i;
+    y *= 1.0 / (1 << 23);
+    return y - 124.22544637f - 1.498030302f * mx.f - 1.72587999f / (0.3520887068f + mx.f);
+}
+
+static double fpnn_normalize(double x, double avg, double sd, double scale) {     /* :633-654 */
+    double val = (sd != 0) ? scale * (x - avg) / sd : 0;
+    const double max_val = 0.5;
+    if (val < -max_val) val = -max_val;
+    else if (val > max_val) val = max_val;
+    return val;
+}
+
+int fir_oracle_fpnn_J(int64_t n_train, int n_classes) {                            /* :666-673 */
+    int J = (int)ceil(pow(1.0 * n_train / n_classes, 1.0 / 3));
+    if (J <= 3) J = 3;
+    return J;
+}
+
+/* train(): a[(fi*C + i)*(2J+1) + ...]; train rows are class-major (labels ascending) */
+void fir_oracle_fpnn_train(const double* train, const int32_t* train_label, int64_t n, int d, int n_classes, const double* avg,
+                           const double* sd, double scale, int J, double* a) {
+    const double PI = atan(1.0) * 4;                                               /* :656 */
+    int64_t* cls_begin = (int64_t*)calloc((size_t)n_classes + 1, sizeof(int64_t));
+    for (int64_t t = 0; t < n; ++t) cls_begin[train_label[t] + 1]++;
+    for (int c = 0; c < n_classes; ++c) cls_begin[c + 1] += cls_begin[c];
+    const size_t J1 = (size_t)(2 * J + 1);
+    for (size_t i = 0; i < (size_t)n_classes * d * J1; ++i) a[i] = 0;
+    const size_t Jz = (size_t)J;
+    for (int fi = 0; fi < d; ++fi)
+        for (int i = 0; i < n_classes; ++i) {
+            const size_t model_ind = ((size_t)fi * n_classes + i) * J1;
+            a[model_ind] = 0.5;
+            const int64_t cnt = cls_begin[i + 1] - cls_begin[i];
+            const double cur_mult = 1.0 / cnt;
+            for (int64_t t = cls_begin[i]; t < cls_begin[i + 1]; ++t) {
+                const double val = fpnn_normalize(train[t * d + fi], avg[fi], sd[fi], scale);
+                for (size_t j = 0; j < Jz; ++j) {
+                    a[model_ind + 2 * j + 1] += cos(PI * (j + 1) * val) * cur_mult * (Jz - j) / (Jz * (Jz + 1));      /* :687 */
+                    a[model_ind + 2 * j + 2] += sin(PI * (j + 1) * val) * cur_mult * (Jz - j) / (Jz * (Jz + 1));      /* :688 */
+                }
+            }
+        }
+    free(cls_begin);
+}
+
+/* predict_bf (:697-735) when sequential == 0, predict_sequentional (:736-791) otherwise */
+void fir_oracle_fpnn_predict(const double* a, int J, int d, int n_classes, const double* avg, const double* sd, double scale,
+                             const double* q, int64_t nq, int sequential, float output_ratio, int32_t* out_label) {
+    const double PI = atan(1.0) * 4;
+    const size_t J1 = (size_t)(2 * J + 1);
+    const float output_delta = fir_oracle_fasterlog2(output_ratio);                /* ctor, :621 */
+    float* outputs = (float*)malloc(sizeof(float) * (size_t)n_classes);
+    int* check = (int*)malloc(sizeof(int) * (size_t)n_classes);
+    double* cos_vals = (double*)malloc(sizeof(double) * (size_t)J);
+    double* sin_vals = (double*)malloc(sizeof(double) * (size_t)J);
+    for (int64_t qi = 0; qi < nq; ++qi) {
+        const double* x = q + qi * d;
+        int bestClass = -1;
+        for (int i = 0; i < n_classes; ++i) { outputs[i] = 0; check[i] = 1; }
+        const int delta = sequential ? 32 : d;                                     /* delta_features_count, :182 */
+        for (int cur = 0; cur < d; cur += delta) {
+            int max_fi = cur + delta;
+            if (max_fi > d) max_fi = d;
+            for (int fi = cur; fi < max_fi; ++fi) {
+                const double val = fpnn_normalize(x[fi], avg[fi], sd[fi], scale);
+                cos_vals[0] = cos(PI * val);
+                sin_vals[0] = sin(PI * val);
+                for (int j = 1; j < J; ++j) {
+                    cos_vals[j] = cos_vals[j - 1] * cos_vals[0] - sin_vals[j - 1] * sin_vals[0];
+                    sin_vals[j] = cos_vals[j - 1] * sin_vals[0] + sin_vals[j - 1] * cos_vals[0];
+                }
+                for (int i = 0; i < n_classes; ++i) {
+                    if (!check[i]) continue;
+                    const size_t model_ind = ((size_t)fi * n_classes + i) * J1;
+                    double probab = a[model_ind];
+                    for (int j = 0; j < J; ++j) probab += (a[model_ind + 2 * j + 1] * cos_vals[j] + a[model_ind + 2 * j + 2] * sin_vals[j]);
+                    outputs[i] += fir_oracle_fasterlog2(probab);
+                }
+            }
+            float max_output = -FLT_MAX;
+            for (int i = 0; i < n_classes; ++i)
+                if (check[i] && max_output < outputs[i]) { max_output = outputs[i]; bestClass = i; }
+            if (!sequential) break;
+            int variants = 0;
+            const float thr = max_output + output_delta * max_fi;                  /* :777 */
+            for (int i = 0; i < n_classes; ++i) {                                  /* :779-784: dropped classes are re-counted on stale outputs */
+                if (outputs[i] < thr) check[i] = 0;
+                else ++variants;
+            }
+            if (variants == 1) break;
+        }
+        out_label[qi] = bestClass;
+    }
+    free(outputs); free(check); free(cos_vals); free(sin_vals);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * PNN with clustering — per-class k-medoids, classification.cpp:321-388 (100 steps, medoid = the member with the smallest
+ * summed distance to its cluster, distances on the RAW rows).  out_selected: positions in the class-major training order.
+ * Returns the number selected, or -1 when a cluster runs empty (the reference then indexes with (size_t)-1).
+ * ------------------------------------------------------------------------------------------ */
+int64_t fir_oracle_kmedoids(const double* train, const int32_t* train_label, int64_t n, int d, int n_classes, int num_clusters,
+                            int64_t* out_selected) {
+    int64_t* cls_begin = (int64_t*)calloc((size_t)n_classes + 1, sizeof(int64_t));
+    for (int64_t t = 0; t < n; ++t) cls_begin[train_label[t] + 1]++;
+    for (int c = 0; c < n_classes; ++c) cls_begin[c + 1] += cls_begin[c];
+    int64_t total = 0;
+    for (int i = 0; i < n_classes; ++i) {
+        const int64_t m = cls_begin[i + 1] - cls_begin[i];
+        const double* rows = train + cls_begin[i] * d;
+        if (m <= num_clusters) {                                                   /* :381-386 */
+            for (int64_t j = 0; j < m; ++j) out_selected[total++] = cls_begin[i] + j;
+            continue;
+        }
+        double* M = (double*)malloc(sizeof(double) * (size_t)m * m);
+        for (int64_t u = 0; u < m; ++u)
+            for (int64_t v = 0; v < m; ++v) {
+                double dist = 0;
+                for (int fi = 0; fi < d; ++fi) dist += (rows[u * d + fi] - rows[v * d + fi]) * (rows[u * d + fi] - rows[v * d + fi]);
+                M[u * m + v] = dist / d;
+            }
+        int64_t* best = (int64_t*)malloc(sizeof(int64_t) * (size_t)m);
+        int64_t* cent = (int64_t*)malloc(sizeof(int64_t) * (size_t)num_clusters);
+        for (int c = 0; c < num_clusters; ++c) cent[c] = c;
+        int dead = 0;
+        for (int step = 0; step < 100 && !dead; ++step) {
+            for (int64_t t = 0; t < m; ++t) {                                      /* :333-352 */
+                best[t] = -1;
+                double bestDist = DBL_MAX;
+                for (int c = 0; c < num_clusters; ++c) {
+                    const double dist = M[cent[c] * m + t];
+                    if (dist < bestDist) { bestDist = dist; best[t] = c; }
+                }
+            }
+            for (int c = 0; c < num_clusters; ++c) {                               /* :353-375 */
+                double bestClustDist = DBL_MAX;
+                cent[c] = -1;
+                for (int64_t t = 0; t < m; ++t)
+                    if (best[t] == c) {
+                        double clustDist = 0;
+                        for (int64_t t1 = 0; t1 < m; ++t1)
+                            if (best[t1] == c) clustDist += M[t * m + t1];
+                        if (clustDist < bestClustDist) { bestClustDist = clustDist; cent[c] = t; }
+                    }
+                if (cent[c] < 0) dead = 1;
+            }
+        }
+        if (!dead)
+            for (int c = 0; c < num_clusters; ++c) out_selected[total++] = cls_begin[i] + cent[c];
+        free(M); free(best); free(cent);
+        if (dead) { free(cls_begin); return -1; }
+    }
+    free(cls_begin);
+    return total;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Three-way-decision classifiers — ImageTesting.cpp:74-186 (conventional) and :188-288 (proposed,
  * CHECK_ALL_INSTANCES build).  last_feature is the reference's hard-coded 256 (:168, :221).
  * ------------------------------------------------------------------------------------------ */

@@ -51,6 +51,19 @@ void fir_oracle_pnn(const double* train, const int32_t* train_label, int64_t n, 
 void fir_oracle_pnn_seq(const double* train, const int32_t* train_label, int64_t n, int d, int n_classes,
                         const double* avg, const double* q, int64_t nq, int32_t* out_label);
 
+/* FPNNClassifier (orthogonal-series PNN) classification.cpp:618-791, fasterlog2 :64-73.  train rows are the RAW rows in
+ * class-major order; avg / sd = avgValues / stdValues of split_train_test (:969-989).  a has d*C*(2J+1) entries. */
+float fir_oracle_fasterlog2(float x);
+int fir_oracle_fpnn_J(int64_t n_train, int n_classes);
+void fir_oracle_fpnn_train(const double* train, const int32_t* train_label, int64_t n, int d, int n_classes, const double* avg,
+                           const double* sd, double scale, int J, double* a);
+void fir_oracle_fpnn_predict(const double* a, int J, int d, int n_classes, const double* avg, const double* sd, double scale,
+                             const double* q, int64_t nq, int sequential, float output_ratio, int32_t* out_label);
+/* PNNwithClusteringClassifier::train classification.cpp:321-388: per-class k-medoids on the raw rows; positions in the
+ * class-major training order; -1 when a cluster runs empty (undefined behaviour in the reference). */
+int64_t fir_oracle_kmedoids(const double* train, const int32_t* train_label, int64_t n, int d, int n_classes, int num_clusters,
+                            int64_t* out_selected);
+
 /* ConventionalTWDClassifier::recognize ImageTesting.cpp:108-186 (type 0 Posteriors, 1 DistDiff, 2 DistRatio) and
  * ProposedTWDClassifier::recognize :207-288; last_feature = 256 in the reference.  out_unreliable = the query's
  * contribution to num_of_unreliable. */

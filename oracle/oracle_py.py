@@ -68,6 +68,13 @@ class Port:
         L.fir_oracle_knn.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, _f64p, _f64p, C.c_int64, C.c_int, _i32p]
         L.fir_oracle_pnn.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, _f64p, _f64p, C.c_int64, _f64p, _i32p]
         L.fir_oracle_pnn_seq.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, _f64p, _f64p, C.c_int64, _i32p]
+        L.fir_oracle_fasterlog2.restype = C.c_float
+        L.fir_oracle_fasterlog2.argtypes = [C.c_float]
+        L.fir_oracle_fpnn_J.argtypes = [C.c_int64, C.c_int]
+        L.fir_oracle_fpnn_train.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, _f64p, _f64p, C.c_double, C.c_int, _f64p]
+        L.fir_oracle_fpnn_predict.argtypes = [_f64p, C.c_int, C.c_int, C.c_int, _f64p, _f64p, C.c_double, _f64p, C.c_int64, C.c_int, C.c_float, _i32p]
+        L.fir_oracle_kmedoids.restype = C.c_int64
+        L.fir_oracle_kmedoids.argtypes = [_f64p, _i32p, C.c_int64, C.c_int, C.c_int, C.c_int, _i64p]
         L.fir_oracle_twd_conventional.argtypes = [C.c_int, _f32p, _i32p, C.c_int64, C.c_int, C.c_int, _f32p, C.c_int64, C.c_int, C.c_double,
                                                   C.c_int, C.c_int, _i32p, _i32p, _u8p]
         L.fir_oracle_twd_proposed.argtypes = [C.c_int, _f32p, _i32p, C.c_int64, C.c_int, _f32p, C.c_int64, C.c_int, C.c_double, C.c_int,
@@ -139,6 +146,27 @@ class Port:
         lab = np.empty(q.shape[0], np.int32)
         self.L.fir_oracle_pnn_seq(train, train_label, train.shape[0], train.shape[1], n_classes, avg, q, q.shape[0], lab)
         return lab
+
+    def fpnn_train(self, train, train_label, n_classes, avg, sd, scale=1.0):
+        train, avg, sd, train_label = _f64(train), _f64(avg), _f64(sd), _i32(train_label)
+        J = self.L.fir_oracle_fpnn_J(train.shape[0], n_classes)
+        a = np.zeros(train.shape[1] * n_classes * (2 * J + 1), np.float64)
+        self.L.fir_oracle_fpnn_train(train, train_label, train.shape[0], train.shape[1], n_classes, avg, sd, float(scale), J, a)
+        return a, J
+
+    def fpnn_predict(self, a, J, n_classes, avg, sd, q, scale=1.0, sequential=False, output_ratio=0.9):
+        q, avg, sd = _f64(q), _f64(avg), _f64(sd)
+        lab = np.empty(q.shape[0], np.int32)
+        self.L.fir_oracle_fpnn_predict(_f64(a), J, q.shape[1], n_classes, avg, sd, float(scale), q, q.shape[0], int(sequential), float(output_ratio), lab)
+        return lab
+
+    def kmedoids(self, train, train_label, n_classes, num_clusters):
+        train, train_label = _f64(train), _i32(train_label)
+        sel = np.empty(train.shape[0], np.int64)
+        cnt = self.L.fir_oracle_kmedoids(train, train_label, train.shape[0], train.shape[1], n_classes, int(num_clusters), sel)
+        if cnt < 0:
+            raise ValueError("a cluster ran empty (undefined behaviour in the reference)")
+        return sel[:cnt].copy()
 
     TWD_TYPES = {"posteriors": 0, "diff": 1, "ratio": 2}
 
@@ -231,6 +259,9 @@ class Ref:
             L.fir_ref_cls_knn.argtypes = [C.c_int, C.c_long, C.c_long, C.c_int, _i32p]
             L.fir_ref_cls_pnn.restype = C.c_double
             L.fir_ref_cls_pnn.argtypes = [C.c_long, C.c_long, _i32p, C.c_void_p]
+            L.fir_ref_cls_get_std.argtypes = [_f64p]
+            L.fir_ref_cls_fpnn.argtypes = [C.c_double, C.c_int, C.c_float, C.c_long, C.c_long, _i32p, C.c_void_p, C.POINTER(C.c_int)]
+            L.fir_ref_cls_pnn_clustered.argtypes = [C.c_int, C.c_long, C.c_long, _i32p, _i64p]
             L.fir_ref_cls_pnn_seq.restype = C.c_double
             L.fir_ref_cls_pnn_seq.argtypes = [C.c_long, C.c_long, _i32p]
 
@@ -335,6 +366,7 @@ class Ref:
         self._cls_d, self._cls_c = rows.shape[1], n_classes
         self.L.fir_ref_cls_setup(rows, labels, rows.shape[0], rows.shape[1], n_classes, float(fraction), seed)
         ntr, nte = self.L.fir_ref_cls_counts(0), self.L.fir_ref_cls_counts(1)
+        self._cls_ntrain = ntr
         tr = np.empty(ntr, np.int64)
         trl = np.empty(ntr, np.int32)
         te = np.empty(nte, np.int64)
@@ -346,6 +378,25 @@ class Ref:
         lab = np.empty(count, np.int32)
         t = self.L.fir_ref_cls_knn(K, first, count, 1, lab)
         return (lab, t) if timing else lab
+
+    def cls_std(self):
+        sd = np.empty(self._cls_d, np.float64)
+        self.L.fir_ref_cls_get_std(sd)
+        return sd
+
+    def cls_fpnn(self, first, count, scale=1.0, bf=True, output_ratio=0.9, coefficients=False):
+        lab = np.empty(count, np.int32)
+        J = C.c_int(0)
+        size = self.L.fir_ref_cls_fpnn(float(scale), int(bf), float(output_ratio), 0, 0, lab[:0].copy(), None, C.byref(J))
+        a = np.empty(size, np.float64) if coefficients else None
+        self.L.fir_ref_cls_fpnn(float(scale), int(bf), float(output_ratio), first, count, lab, a.ctypes.data if coefficients else None, C.byref(J))
+        return (lab, a, J.value) if coefficients else lab
+
+    def cls_pnn_clustered(self, num_clusters, first, count):
+        lab = np.empty(count, np.int32)
+        med = np.empty(self._cls_ntrain, np.int64)
+        cnt = self.L.fir_ref_cls_pnn_clustered(int(num_clusters), first, count, lab, med)
+        return lab, med[:cnt].copy()
 
     def cls_pnn_seq(self, first, count, timing=False):
         lab = np.empty(count, np.int32)

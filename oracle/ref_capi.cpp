@@ -34,7 +34,11 @@
 // (:53-62), so that file is textually included here (only in the L2 variant; it has no metric).
 #ifdef FIR_REF_WITH_CLASSIFICATION
 #define main fir_ref_unused_main
+#define private public      /* FPNNClassifier::a / J and PNNwithClusteringClassifier::clustered_training_set are read below */
+#define protected public
 #include "classification.cpp"
+#undef private
+#undef protected
 #undef main
 #endif
 
@@ -385,6 +389,41 @@ double fir_ref_cls_pnn_seq(long first, long count, int* out_label) {
     for (long j = 0; j < count; ++j) out_label[j] = pnn.predict(tmp_dataset[test_set[first + j]]);
     auto t2 = std::chrono::high_resolution_clock::now();
     return std::chrono::duration<double>(t2 - t1).count();
+}
+void fir_ref_cls_get_std(double* out_std) {
+    for (size_t fi = 0; fi < num_of_cont_features; ++fi) out_std[fi] = stdValues[fi];
+}
+// FPNNClassifier(scale, bf, output_ratio): train() + predict() (classification.cpp:618-791); optionally the trained series
+// coefficients a[(fi * C + i) * (2J + 1) ..] and J
+int fir_ref_cls_fpnn(double scale, int bf, float output_ratio, long first, long count, int* out_label, double* out_a, int* out_J) {
+    Silence s;
+    FPNNClassifier f(scale, bf != 0, output_ratio);
+    f.train();
+    if (out_J) *out_J = (int)f.J;
+    if (out_a) std::copy(f.a.begin(), f.a.end(), out_a);
+    for (long j = 0; j < count; ++j) out_label[j] = f.predict(tmp_dataset[test_set[first + j]]);
+    return (int)f.a.size();
+}
+// PNNwithClusteringClassifier(no_clusters): train() (per-class k-medoids, :321-388) + predict() (:389-428); the medoids are
+// returned as positions in the class-major training order of fir_ref_cls_get_split
+int fir_ref_cls_pnn_clustered(int no_clusters, long first, long count, int* out_label, long* out_medoids) {
+    Silence s;
+    PNNwithClusteringClassifier c(no_clusters);
+    c.train();
+    int total = 0;
+    size_t class_start = 0;
+    for (size_t i = 0; i < num_of_classes; ++i) {
+        for (size_t m = 0; m < c.clustered_training_set[i].size(); ++m) {
+            const size_t row = c.clustered_training_set[i][m];
+            size_t pos = 0;
+            while (training_set[i][pos] != row) ++pos;
+            if (out_medoids) out_medoids[total] = (long)(class_start + pos);
+            ++total;
+        }
+        class_start += training_set[i].size();
+    }
+    for (long j = 0; j < count; ++j) out_label[j] = c.predict(tmp_dataset[test_set[first + j]]);
+    return total;
 }
 #endif  // FIR_REF_WITH_CLASSIFICATION
 

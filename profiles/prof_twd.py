@@ -73,8 +73,30 @@ if n <= 20000:
     res = []
     for name, fn, pf in (("PNN", lambda: clf.pnn(te, scores=False)[0], lambda x: port.pnn(tr, trl, n_classes, avg, x)[1]),
                          ("PNN (seq)", lambda: clf.pnn_sequential(te), lambda x: port.pnn_seq(tr, trl, n_classes, avg, x))):
-        fn(); t0 = time.perf_counter(); lab = fn(); t = time.perf_counter() - t0          # host fp64 queries in, labels out
+        fn(); t0 = time.perf_counter(); lab = fn(); t = time.perf_counter() - t0          # host fp64 queries in, labels out (second call: workspace in place)
         t1 = time.perf_counter(); pl = pf(te[:cpu_sample]); tc = time.perf_counter() - t1
         res.append({"classifier": name, "gpu_e2e_ms": 1e3 * t, "gpu_us_per_query": 1e6 * t / nq, "cpu_port_us_per_query": 1e6 * tc / cpu_sample,
                     "matches_port_on_sample": bool(np.array_equal(pl, lab[:cpu_sample])), "accuracy_pct": 100.0 * float((lab == ql.cpu().numpy()).mean())})
     print(json.dumps({"workload": "pnn_fp64", "train": n, "queries": nq, "d": d, "classes": n_classes, "rows": res}))
+    # FPNN (orthogonal-series PNN) and PNN with clustering (classification.cpp:618-791, 311-428)
+    sd = tr.std(axis=0, ddof=1)
+    res = []
+    fir_b200.Fpnn(tr, trl, n_classes, avg, sd, 1.0).close()           # first call loads the kernels (lazy module loading); time the second
+    t0 = time.perf_counter(); f = fir_b200.Fpnn(tr, trl, n_classes, avg, sd, 1.0); t_train = time.perf_counter() - t0
+    t0 = time.perf_counter(); pa, pJ = port.fpnn_train(tr, trl, n_classes, avg, sd, 1.0); t_ptrain = time.perf_counter() - t0
+    for name, seq in (("FPNN", False), ("FPNN (seq)", True)):
+        f.predict(te, sequential=seq); t0 = time.perf_counter(); lab = f.predict(te, sequential=seq); t = time.perf_counter() - t0
+        t1 = time.perf_counter(); pl = port.fpnn_predict(pa, pJ, n_classes, avg, sd, te[:cpu_sample], 1.0, sequential=seq); tc = time.perf_counter() - t1
+        res.append({"classifier": name, "J": f.J, "gpu_train_ms": 1e3 * t_train, "cpu_port_train_ms": 1e3 * t_ptrain, "gpu_e2e_ms": 1e3 * t,
+                    "gpu_us_per_query": 1e6 * t / nq, "cpu_port_us_per_query": 1e6 * tc / cpu_sample,
+                    "matches_port_on_sample": bool(np.array_equal(pl, lab[:cpu_sample])), "accuracy_pct": 100.0 * float((lab == ql.cpu().numpy()).mean())})
+    clusters = 5
+    fir_b200.kmedoids_select(tr, trl, n_classes, clusters)
+    t0 = time.perf_counter(); sel = fir_b200.kmedoids_select(tr, trl, n_classes, clusters); t_sel = time.perf_counter() - t0
+    t0 = time.perf_counter(); psel = port.kmedoids(tr, trl, n_classes, clusters); t_psel = time.perf_counter() - t0
+    red = fir_b200.Classifier(tr[sel], trl[sel], n_classes, avg); red.set_total(len(tr))
+    red.pnn(te, scores=False); t0 = time.perf_counter(); lab = red.pnn(te, scores=False)[0]; t = time.perf_counter() - t0
+    res.append({"classifier": "PNN with clustering, %d" % clusters, "kept_rows": int(len(sel)), "gpu_kmedoids_ms": 1e3 * t_sel, "cpu_port_kmedoids_ms": 1e3 * t_psel,
+                "medoids_match_port": bool(np.array_equal(sel, psel)), "gpu_e2e_ms": 1e3 * t, "gpu_us_per_query": 1e6 * t / nq,
+                "accuracy_pct": 100.0 * float((lab == ql.cpu().numpy()).mean())})
+    print(json.dumps({"workload": "fpnn_and_clustering", "train": n, "queries": nq, "d": d, "classes": n_classes, "rows": res}))

@@ -55,5 +55,17 @@ int main(int argc, char** argv) {
     std::printf("PNNSEQ");
     for (size_t i = 0; i < ps.size(); ++i) std::printf(" %d", ps[i]);
     std::printf("\n");
+    // classification.cpp:1002-1011 — the orthogonal-series PNN and the k-medoids-reduced PNN over the same split
+    FPNNClassifier fpnn(ts, 1.0, true), fpnn_seq(ts, 0.33, false, 0.9f);
+    PNNwithClusteringClassifier pnn_clust(ts, 4);
+    fpnn.train(); fpnn_seq.train(); pnn_clust.train();
+    std::vector<int> f1 = fpnn.predict_batch(q), f2 = fpnn_seq.predict_batch(q), f3 = pnn_clust.predict_batch(q);
+    std::printf("FPNN");
+    for (size_t i = 0; i < f1.size(); ++i) std::printf(" %d", f1[i]);
+    std::printf("\nFPNNSEQ");
+    for (size_t i = 0; i < f2.size(); ++i) std::printf(" %d", f2[i]);
+    std::printf("\nPNNCLUST");
+    for (size_t i = 0; i < f3.size(); ++i) std::printf(" %d", f3[i]);
+    std::printf("\nNAMES %s|%s|%s\n", fpnn.get_name().c_str(), fpnn_seq.get_name().c_str(), pnn_clust.get_name().c_str());
     return 0;
 }

@@ -95,6 +95,14 @@ def main():
         out["knn%d" % K] = ref.cls_knn(K, 0, len(te))
     out["pnn_label"], out["pnn_scores"] = ref.cls_pnn(0, len(te))
     out["pnn_seq_label"] = ref.cls_pnn_seq(0, len(te))
+    # FPNN (orthogonal-series PNN) and PNN with clustering on the same split
+    out["std"] = ref.cls_std()
+    for scale in (1.0, 0.33):
+        lab, a, J = ref.cls_fpnn(0, len(te), scale=scale, bf=True, coefficients=True)
+        out["fpnn_%g_label" % scale], out["fpnn_%g_J" % scale] = lab, np.int32(J)
+        out["fpnn_%g_a_digest" % scale] = np.array([a.sum(), np.abs(a).sum(), a[::97].sum()])
+        out["fpnn_%g_seq_label" % scale] = ref.cls_fpnn(0, len(te), scale=scale, bf=False, output_ratio=0.9)
+    out["pnn_clustered_label"], out["pnn_clustered_medoids"] = ref.cls_pnn_clustered(4, 0, len(te))
     # second split with a class-independent first chunk so predict_sequentional's pruning departs from predict_bf
     rows2 = rows.copy()
     rows2[:, :32] = np.random.default_rng(11).normal(0, 0.04, size=(len(rows2), 32))

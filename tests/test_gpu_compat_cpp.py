@@ -53,6 +53,15 @@ def test_cpp_adapters_match_oracle(port, tmp_path):
     sc, pl = port.pnn(tr64, dbl, n_classes, avg, te64)
     assert [int(x) for x in lines["PNN"]] == pl.tolist() and int(lines["PNN1"][0]) == pl[0]
     assert [int(x) for x in lines["PNNSEQ"]] == port.pnn_seq(tr64, dbl, n_classes, avg, te64).tolist()
+    sq = np.array([sum((tr64[:, f] * tr64[:, f]).tolist()) for f in range(d)])
+    sd = np.sqrt((sq - avg * avg * len(tr64)) / (len(tr64) - 1))                      # stdValues, classification.cpp:988
+    a, J = port.fpnn_train(tr64, dbl, n_classes, avg, sd, 1.0)
+    assert [int(x) for x in lines["FPNN"]] == port.fpnn_predict(a, J, n_classes, avg, sd, te64, 1.0).tolist()
+    a, J = port.fpnn_train(tr64, dbl, n_classes, avg, sd, 0.33)
+    assert [int(x) for x in lines["FPNNSEQ"]] == port.fpnn_predict(a, J, n_classes, avg, sd, te64, 0.33, sequential=True, output_ratio=0.9).tolist()
+    sel = port.kmedoids(tr64, dbl, n_classes, 4)
+    assert [int(x) for x in lines["PNNCLUST"]] == port.pnn(tr64[sel], dbl[sel], n_classes, avg, te64)[1].tolist()
+    assert " ".join(lines["NAMES"]) == "FPNN, 1|FPNN, 0.33 (seq)|PNN with clustering, 4"
 
 
 def test_cpp_twd_adapters_match_oracle(port, tmp_path):

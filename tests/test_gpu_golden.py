@@ -64,6 +64,20 @@ def test_classification_golden(fir):
     assert np.array_equal(lab, G["pnn_label"])
     np.testing.assert_allclose(sc, G["pnn_scores"], rtol=1e-5, atol=0)
     assert np.array_equal(clf.pnn_sequential(rows[te]), G["pnn_seq_label"])
+    for scale in (1.0, 0.33):
+        f = fir.Fpnn(rows[tr], G["train_labels"], 7, G["avg"], G["std"], scale)
+        assert f.J == int(G["fpnn_%g_J" % scale])
+        a = f.coefficients
+        np.testing.assert_allclose(np.array([a.sum(), np.abs(a).sum(), a[::97].sum()]), G["fpnn_%g_a_digest" % scale], rtol=1e-12)
+        assert np.array_equal(f.predict(rows[te]), G["fpnn_%g_label" % scale])
+        assert np.array_equal(f.predict(rows[te], sequential=True, output_ratio=0.9), G["fpnn_%g_seq_label" % scale])
+        f.close()
+    sel = fir.kmedoids_select(rows[tr], G["train_labels"], 7, 4)
+    assert np.array_equal(sel, G["pnn_clustered_medoids"])
+    red = fir.Classifier(rows[tr][sel], G["train_labels"][sel], 7, G["avg"])
+    red.set_total(len(tr))
+    assert np.array_equal(red.pnn(rows[te], scores=False)[0], G["pnn_clustered_label"])
+    red.close()
     rows2, tr2, te2 = G["rows2"], G["train_idx2"], G["test_idx2"]
     clf2 = fir.Classifier(rows2[tr2], G["train_labels2"], 7, G["avg2"])
     assert np.array_equal(clf2.pnn_sequential(rows2[te2]), G["pnn_seq_label2"])

@@ -75,3 +75,30 @@ def test_twd_port_matches_reference(port, request, metric):
     rc, _ = ref.twd("bf", g, gl, 8, q, 64, 0)
     assert np.array_equal(rc, gl[port.bf(metric, g, q, max_features=64)[0]])
     assert seen > 0
+
+
+def test_fpnn_and_clustering_port_matches_reference(port, ref_l2):
+    """FPNNClassifier / PNNwithClusteringClassifier: coefficients bit-identical (same libm), labels and medoids identical."""
+    g, gl, q, ql = make_data(port, "l2", 700, 230, 100, 10, seed=800, sigma=2.0)
+    rows = np.concatenate([g, q]).astype(np.float64)
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    labels = np.concatenate([gl, ql]).astype(np.int32)
+    tr, trl, te, avg = ref_l2.cls_setup(rows, labels, 10, 30, seed=3)
+    sd = ref_l2.cls_std()
+    x = rows[tr]
+    assert np.allclose(sd, x.std(axis=0, ddof=1), rtol=1e-9)
+    for scale in (1.0, 0.33):
+        lab, a, J = ref_l2.cls_fpnn(0, len(te), scale=scale, bf=True, coefficients=True)
+        pa, pJ = port.fpnn_train(x, trl, 10, avg, sd, scale)
+        assert pJ == J and np.array_equal(bits64(pa), bits64(a))
+        assert np.array_equal(port.fpnn_predict(pa, pJ, 10, avg, sd, rows[te], scale), lab)
+        for ratio in (0.9, 0.99):
+            seq = ref_l2.cls_fpnn(0, len(te), scale=scale, bf=False, output_ratio=ratio)
+            assert np.array_equal(port.fpnn_predict(pa, pJ, 10, avg, sd, rows[te], scale, sequential=True, output_ratio=ratio), seq)
+    for clusters in (3, 5):
+        lab, med = ref_l2.cls_pnn_clustered(clusters, 0, len(te))
+        assert np.array_equal(port.kmedoids(x, trl, 10, clusters), med)
+
+
+def bits64(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.int64)

@@ -218,6 +218,7 @@ int fir_gallery_set_num_classes(fir_gallery* g, int32_t n_classes) {
 
 int fir_normalize_rows(float* rows, int64_t n, int32_t d, int32_t metric, int32_t memspace, void* cuda_stream) {
     if (!rows || n < 0 || d <= 0) return fail(FIR_ERR_BAD_ARG, "bad rows");
+    if (metric < FIR_L2 || metric > FIR_NORM_VIDEO_SUMSQ) return fail(FIR_ERR_BAD_ARG, "unknown normalisation");
     if (n == 0) return FIR_OK;
     cudaStream_t s = (cudaStream_t)cuda_stream;
     if (memspace == FIR_DEVICE) return launch_normalize_rows(rows, n, d, d, metric, s);

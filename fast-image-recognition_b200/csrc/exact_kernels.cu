@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(128) normalize_rows_kernel(float* rows, int64_
         for (int kk = 0; kk < kmax; ++kk) {
             float v = t[lane * NLD + kk];
             if ((double)fabsf(v) < 0.0001) v = 0.f;                               // :85-86 (float |x| against a double literal)
-            sum = (metric == FIR_L2) ? __fadd_rn(sum, __fmul_rn(v, v)) : __fadd_rn(sum, v);   // :91 / :93
+            sum = (metric == FIR_L2 || metric == FIR_NORM_VIDEO_SUMSQ) ? __fadd_rn(sum, __fmul_rn(v, v)) : __fadd_rn(sum, v);   // :91 / :93; video.cpp:77
         }
         __syncwarp();
     }

@@ -66,3 +66,16 @@ def write_features_file(path, rows, class_names, file_names=None):
             f.write((file_names[i] if file_names else "img_%06d.jpg" % i) + "\n")
             f.write(str(class_names[i]) + "\n")
             f.write("".join("{:f} ".format(float(v)) for v in row) + "\n")
+
+
+def write_video_file(path, people):
+    """The reference's video-features text format (qt_cpp/video.cpp:38-86): per person a name line and the number of
+    videos; per video its frame count; per frame a file-name line and D floats.  people: {name: [frames x D array, ...]}."""
+    with open(path, "w") as f:
+        for name, videos in people.items():
+            f.write(name + "\n%d\n" % len(videos))
+            for v, frames in enumerate(videos):
+                f.write("%d\n" % len(frames))
+                for j, row in enumerate(frames):
+                    f.write("%s_v%d_f%04d.jpg\n" % (name, v, j))
+                    f.write("".join("{:f} ".format(float(x)) for x in row) + "\n")

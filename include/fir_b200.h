@@ -89,7 +89,10 @@ int fir_gallery_info(const fir_gallery* g, int64_t* n, int32_t* d, int32_t* metr
 int fir_gallery_set_num_classes(fir_gallery* g, int32_t n_classes);
 
 /* replaces: the normalisation loop of loadImages (qt_cpp/db_features.cpp:79-101): zero |x|<1e-4,
- * then x /= sqrtf(sum x*x) (L2) or x /= sum x (chi2/KL), fp32, sequential.  In place. */
+ * then x /= sqrtf(sum x*x) (L2) or x /= sum x (chi2/KL), fp32, sequential.  In place.
+ * loadVideos (qt_cpp/video.cpp:64-84) is the same loop, except that its non-L2 build divides by sum x*x (no square root):
+ * pass FIR_NORM_VIDEO_SUMSQ as `metric` for that variant. */
+enum { FIR_NORM_VIDEO_SUMSQ = 3 };
 int fir_normalize_rows(float* rows, int64_t n, int32_t d, int32_t metric, int32_t memspace, void* cuda_stream);
 
 /* ---- brute force ------------------------------------------------------------------------------

@@ -23,6 +23,8 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <iterator>
+#include <map>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -130,6 +132,10 @@ inline int loadImages(ImagesDatabase& imagesDb, std::string features_file, std::
     imagesDb.resize(person2indexMap.size());
     for (int i = 0; i < total; ++i)
         imagesDb[cls[i]].push_back(FeaturesVector(packed.begin() + (size_t)i * d, packed.begin() + (size_t)(i + 1) * d));
+    double avg_count = 0;                                                // db_features.cpp:107-112
+    for (size_t i = 0; i < imagesDb.size(); ++i) avg_count += imagesDb[i].size();
+    avg_count /= imagesDb.size();
+    std::cout << "total size=" << imagesDb.size() << " totalImages=" << total << " avg_count=" << avg_count << std::endl;
     return total;
 }
 
@@ -444,6 +450,88 @@ private:
     float ratio;
     fir_fpnn* f;
 };
+
+// ---- qt_cpp/video.cpp: the YouTube-Faces experiment, a second caller of the same matching path ------------------
+typedef std::map<std::string, std::vector<std::vector<FeaturesVector> > > MapOfVideos;       // video.cpp:22
+
+// loadVideos (video.cpp:35-95): per person a name line and a video count; per video a frame count; per frame a file-name
+// line and D floats.  The zeroing + normalisation of every frame (:64-84) runs on the GPU in one call.
+inline void loadVideos(MapOfVideos& dbVideos, const std::string& video_features_file) {
+    std::ifstream ifs(video_features_file.c_str());
+    if (!ifs) return;
+    const int d = fir::features_count();
+    std::vector<float> packed;                                           // every frame of the file, in file order
+    struct Slot { std::string person; int video, frame; };
+    std::vector<Slot> slots;
+    int total_videos = 0;
+    while (ifs) {
+        std::string fileName, personName, feat_str;
+        if (!std::getline(ifs, personName)) break;
+        personName.erase(0, personName.find_first_not_of(" \t\n\r\f\v\r\n"));
+        int videos_count = 0;
+        ifs >> videos_count;
+        dbVideos.insert(std::make_pair(personName, std::vector<std::vector<FeaturesVector> >()));
+        std::vector<std::vector<FeaturesVector> >& person_videos = dbVideos[personName];
+        person_videos.resize(videos_count);
+        for (int i = 0; i < videos_count; ++i) {
+            int frames_count = 0;
+            ifs >> frames_count;
+            person_videos[i].resize(frames_count);
+            if (!std::getline(ifs, fileName)) break;                     // rest of the count line
+            for (int j = 0; j < frames_count; ++j) {
+                if (!std::getline(ifs, fileName)) break;
+                if (!std::getline(ifs, feat_str)) break;
+                std::istringstream iss(feat_str);
+                float v = 0.f;
+                for (int k = 0; k < d; ++k) { iss >> v; packed.push_back(v); }
+                Slot s; s.person = personName; s.video = i; s.frame = j;
+                slots.push_back(s);
+            }
+        }
+        total_videos += videos_count;
+    }
+    if (!slots.empty())
+        fir::check(fir_normalize_rows(packed.data(), (int64_t)slots.size(), d, fir::metric() == FIR_L2 ? (int)FIR_L2 : (int)FIR_NORM_VIDEO_SUMSQ, FIR_HOST, 0),
+                   "fir_normalize_rows");
+    for (size_t i = 0; i < slots.size(); ++i)
+        dbVideos[slots[i].person][slots[i].video][slots[i].frame].assign(packed.begin() + i * (size_t)d, packed.begin() + (i + 1) * (size_t)d);
+    std::cout << "total size=" << dbVideos.size() << " totalVideos=" << total_videos << " totalImages=" << slots.size() << std::endl;
+}
+
+// The split of testYTFRecognition (video.cpp:167-236): people present in both sets, every 10th frame of every video as a
+// query, the still images as the gallery (in the iteration order of the surviving person2indexMap, like the reference).
+inline void buildYTFSplit(ImagesDatabase& totalImages, std::unordered_map<std::string, int>& person2indexMap, MapOfVideos& videos,
+                          std::vector<ImageInfo>& dbImages, std::vector<ImageInfo>& testImages) {
+    std::vector<std::string> dbNames, videoNames;
+    for (std::unordered_map<std::string, int>::iterator it = person2indexMap.begin(); it != person2indexMap.end(); ++it) dbNames.push_back(it->first);
+    for (MapOfVideos::iterator it = videos.begin(); it != videos.end(); ++it) videoNames.push_back(it->first);
+    std::sort(videoNames.begin(), videoNames.end());
+    std::sort(dbNames.begin(), dbNames.end());
+    std::vector<std::string> commonNames(videos.size());
+    commonNames.resize(std::set_intersection(videoNames.begin(), videoNames.end(), dbNames.begin(), dbNames.end(), commonNames.begin()) - commonNames.begin());
+    std::cout << "lfw names size=" << dbNames.size() << " YTF names size=" << videoNames.size() << " common names size=" << commonNames.size() << std::endl;
+    std::vector<std::string> listToRemove;
+    std::set_symmetric_difference(videoNames.begin(), videoNames.end(), dbNames.begin(), dbNames.end(), std::back_inserter(listToRemove));
+    for (size_t i = 0; i < listToRemove.size(); ++i) { person2indexMap.erase(listToRemove[i]); videos.erase(listToRemove[i]); }
+    std::unordered_map<std::string, int> person2indexMapNew;
+    int class_index = 0;
+    for (MapOfVideos::iterator iter = videos.begin(); iter != videos.end(); ++iter) {
+        person2indexMapNew.insert(std::make_pair(iter->first, class_index));
+        for (size_t v = 0; v < iter->second.size(); ++v)
+            for (int ind = 0; ind < (int)iter->second[v].size(); ind += 10)            // :216
+                testImages.push_back(ImageInfo(class_index, ind, iter->second[v][ind]));
+        ++class_index;
+    }
+    int lfw_size = 0;
+    for (std::unordered_map<std::string, int>::iterator pi = person2indexMap.begin(); pi != person2indexMap.end(); ++pi) {
+        const int new_class_ind = person2indexMapNew[pi->first];
+        const int class_ind = pi->second;
+        for (int ind = 0; ind < (int)totalImages[class_ind].size(); ++ind) dbImages.push_back(ImageInfo(new_class_ind, ind, totalImages[class_ind][ind]));
+        ++lfw_size;
+    }
+    std::cout << "lfw names size=" << lfw_size << " YTF names size=" << videos.size() << " removed=" << listToRemove.size() << std::endl;
+    std::cout << "dbSize=" << dbImages.size() << " testSize=" << testImages.size() << std::endl;
+}
 
 // ---- qt_cpp/ImageTesting.cpp: Classifier (:35-48) and its three matching classifiers ----------------------------
 // ImageTesting.cpp has its own `class Classifier` (train(&dbImages) / recognize(testImageInfo) → class); it lives in a nested

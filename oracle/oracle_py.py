@@ -249,6 +249,13 @@ class Ref:
         L.fir_ref_dem_search.restype = C.c_double
         L.fir_ref_dem_search.argtypes = [C.c_void_p, _f32p, C.c_long, C.c_int, C.c_int, _i32p, _f32p, _u8p, _i32p]
         L.fir_ref_dem_free.argtypes = [C.c_void_p]
+        L.fir_ref_videos_load.restype = C.c_void_p
+        L.fir_ref_videos_load.argtypes = [C.c_char_p, C.c_int]
+        L.fir_ref_videos_counts.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]
+        L.fir_ref_videos_get.argtypes = [C.c_void_p, _f32p, _i32p, _i32p, _i32p, C.c_char_p, C.c_long]
+        L.fir_ref_videos_free.argtypes = [C.c_void_p]
+        L.fir_ref_ytf_run.restype = C.c_long
+        L.fir_ref_ytf_run.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_long]
         L.fir_ref_twd_run.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _f32p, _i32p, C.c_int64, C.c_int, _f32p, C.c_int64, _i32p, _u8p]
         if metric == "l2":
             L.fir_ref_cls_setup.argtypes = [_f64p, _i32p, C.c_long, C.c_int, C.c_int, C.c_double, C.c_uint]
@@ -264,6 +271,28 @@ class Ref:
             L.fir_ref_cls_pnn_clustered.argtypes = [C.c_int, C.c_long, C.c_long, _i32p, _i64p]
             L.fir_ref_cls_pnn_seq.restype = C.c_double
             L.fir_ref_cls_pnn_seq.argtypes = [C.c_long, C.c_long, _i32p]
+
+    VIDEO_FILE, TRAIN_FILE = "vgg_mean_dnn_features.txt", "dnn_vgg_features_all_mean.txt"      # video.cpp:30-33
+
+    def videos_load(self, directory, d):
+        """The verbatim loadVideos() on <directory>/VIDEO_FILE → (names, frames [F,d], person, video, frame)."""
+        h = self.L.fir_ref_videos_load(os.fsencode(directory), d)
+        assert h
+        a, b, c = C.c_long(0), C.c_long(0), C.c_long(0)
+        self.L.fir_ref_videos_counts(h, C.byref(a), C.byref(b), C.byref(c))
+        frames = np.empty((c.value, d), np.float32)
+        person, video, frame = (np.empty(c.value, np.int32) for _ in range(3))
+        names = C.create_string_buffer(1 << 20)
+        self.L.fir_ref_videos_get(h, frames, person, video, frame, names, len(names))
+        self.L.fir_ref_videos_free(h)
+        return names.value.decode().split("\n")[:-1], frames, person, video, frame
+
+    def ytf_run(self, directory, d):
+        """The verbatim testYTFRecognition() inside <directory>; returns what it printed."""
+        buf = C.create_string_buffer(1 << 20)
+        n = self.L.fir_ref_ytf_run(os.fsencode(directory), d, buf, len(buf))
+        assert n >= 0
+        return buf.value.decode()
 
     def twd(self, kind, g, labels, n_classes, q, feat_count, th, twd_type="diff"):
         """kind 'conventional' | 'proposed' | 'bf' through the verbatim ImageTesting.cpp classes → (class, unreliable)."""

@@ -428,3 +428,69 @@ int fir_ref_cls_pnn_clustered(int no_clusters, long first, long count, int* out_
 #endif  // FIR_REF_WITH_CLASSIFICATION
 
 }  // extern "C"
+
+// ---- video.cpp (YouTube-Faces experiment): the verbatim loader and driver, compiled from where they lie --------------
+#include <unistd.h>
+typedef std::map<std::string, std::vector<std::vector<FeaturesVector> > > MapOfVideos;      // video.cpp:22
+void loadVideos(MapOfVideos& dbVideos);                                                     // video.cpp:35 (reads VIDEO_FEATURES_FILE in the cwd)
+void testYTFRecognition();                                                                  // video.cpp:156
+
+namespace {
+struct Cwd {
+    char old[4096];
+    bool ok;
+    explicit Cwd(const char* dir) { ok = getcwd(old, sizeof(old)) != 0 && chdir(dir) == 0; }
+    ~Cwd() { if (ok) { int r = chdir(old); (void)r; } }
+};
+}
+
+extern "C" {
+
+struct fir_ref_videos { MapOfVideos v; int d; };
+// loadVideos() run inside `dir`, which must hold the file under the name the reference hard-codes (video.cpp:24-33)
+fir_ref_videos* fir_ref_videos_load(const char* dir, int d) {
+    Silence s;
+    fir_ref_set_dim(d);
+    Cwd c(dir);
+    if (!c.ok) return 0;
+    fir_ref_videos* h = new fir_ref_videos();
+    h->d = d;
+    loadVideos(h->v);
+    return h;
+}
+void fir_ref_videos_counts(fir_ref_videos* h, long* people, long* videos, long* frames) {
+    long nv = 0, nf = 0;
+    for (auto& kv : h->v) { nv += (long)kv.second.size(); for (auto& vid : kv.second) nf += (long)vid.size(); }
+    *people = (long)h->v.size(); *videos = nv; *frames = nf;
+}
+// frames flattened in map (name) order; person/video/frame index of each; names joined with '\n'
+void fir_ref_videos_get(fir_ref_videos* h, float* frames, int* person, int* video, int* frame, char* names, long names_cap) {
+    long r = 0; int p = 0; std::string joined;
+    for (auto& kv : h->v) {
+        joined += kv.first; joined += '\n';
+        for (size_t i = 0; i < kv.second.size(); ++i)
+            for (size_t j = 0; j < kv.second[i].size(); ++j) {
+                std::memcpy(frames + r * (long)h->d, kv.second[i][j].data(), sizeof(float) * h->d);
+                person[r] = p; video[r] = (int)i; frame[r] = (int)j; ++r;
+            }
+        ++p;
+    }
+    if (names && names_cap > 0) { std::strncpy(names, joined.c_str(), (size_t)names_cap - 1); names[names_cap - 1] = 0; }
+}
+void fir_ref_videos_free(fir_ref_videos* h) { delete h; }
+
+// the whole testYTFRecognition() inside `dir` (both hard-coded file names must exist there); what it prints is returned
+long fir_ref_ytf_run(const char* dir, int d, char* out, long cap) {
+    fir_ref_set_dim(d);
+    Cwd c(dir);
+    if (!c.ok) return -1;
+    std::ostringstream sink;
+    std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+    testYTFRecognition();
+    std::cout.rdbuf(old);
+    const std::string text = sink.str();
+    if (out && cap > 0) { std::strncpy(out, text.c_str(), (size_t)cap - 1); out[cap - 1] = 0; }
+    return (long)text.size();
+}
+
+}  // extern "C"

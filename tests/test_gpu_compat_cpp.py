@@ -101,3 +101,68 @@ def test_cpp_twd_adapters_match_oracle(port, tmp_path):
         assert [int(v) for v in lines["ONE%d" % c]] == [int(cls[1]), int(unrel[1])], names[c]
         some_unreliable += int(unrel.sum())
     assert some_unreliable > 0
+
+
+def _ytf_files(tmp_path, d, n_people, sigma, seed):
+    """Still images of people 0..n-2 (plus nobody from the last one), videos of people 1..n-1: two videos each."""
+    from oracle import oracle_py
+    g, gl, q, ql = synth.make_split(n_people * 12, n_people * 60, d, n_people, "l2", sigma=sigma, seed=seed)
+    names = ["person_%02d" % c for c in range(n_people)]
+    keep = np.flatnonzero(gl < n_people - 1)
+    synth.write_features_file(str(tmp_path / oracle_py.Ref.TRAIN_FILE), g[keep], [names[c] for c in gl[keep]])
+    people = {}
+    for c in range(1, n_people):
+        rows = q[ql == c]
+        cut = len(rows) // 2 - 3
+        people[names[c]] = [rows[:cut], rows[cut:]]
+    synth.write_video_file(str(tmp_path / oracle_py.Ref.VIDEO_FILE), people)
+    return g[keep], gl[keep], people, names
+
+
+def test_cpp_video_adapters_match_reference(port, ref_l2, tmp_path):
+    """fir_compat::loadVideos / buildYTFSplit + BruteForce / DirectedEnumeration, driven like testYTFRecognition (video.cpp),
+    against the verbatim testYTFRecognition() run by oracle/_ref on the same two files."""
+    d, n_people = 64, 9
+    stills, still_labels, people, names = _ytf_files(tmp_path, d, n_people, sigma=3.0, seed=8)
+    exe = str(tmp_path / "ytf_test")
+    pkg = os.path.join(ROOT, "fast-image-recognition_b200")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "ytf_test.cpp"),
+                    "-o", exe, "-L", pkg, "-lfir_b200", "-Wl,-rpath," + pkg], check=True)
+    out = subprocess.run([exe, str(tmp_path), str(d), "3"], check=True, capture_output=True, text=True).stdout.splitlines()
+    want = ref_l2.ytf_run(str(tmp_path), d).splitlines()
+    for prefix in ("total size=", "lfw names size=", "dbSize="):           # loader + split bookkeeping lines, verbatim
+        assert [l for l in out if l.startswith(prefix)] == [l for l in want if l.startswith(prefix)], prefix
+    bf_err = [l.split("%")[0] for l in out if l.startswith("BF error=")]
+    assert bf_err == [l.split("%")[0] for l in want if l.startswith("BF error=")] and float(bf_err[0].split("=")[1]) > 0
+    # every frame the reference loads, bit for bit: the queries are every 10th frame of every video in name order
+    rnames, frames, person, video, frame = ref_l2.videos_load(str(tmp_path), d)
+    common = [n for n in rnames if n in names[:n_people - 1]]
+    sel = np.array([i for i in range(len(frames)) if rnames[person[i]] in common and frame[i] % 10 == 0])
+    test = frames[sel]
+    lines = {l.split()[0]: l.split()[1:] for l in out if l and l.split()[0].isupper()}
+    assert int(lines["TESTBITS"][0]) == int(test.view(np.uint32).astype(np.uint64).sum())
+    test_class = np.array([common.index(rnames[person[i]]) for i in sel])
+    assert [int(x) for x in lines["TESTCLASS"]] == test_class.tolist()
+    # gallery: the stills of the common people through the loader restatement; classes are positions in `common`
+    parsed = np.array([[np.float32(float("{:f}".format(float(v)))) for v in row] for row in stills], np.float32)
+    rows = port.normalize_rows("l2", parsed)
+    gsel = np.array([i for i in range(len(rows)) if names[still_labels[i]] in common])
+    gallery, gclass = rows[gsel], np.array([common.index(names[still_labels[i]]) for i in gsel])
+    bi, bd = port.bf("l2", gallery, test)
+    assert [int(x) for x in lines["BFCLASS"]] == gclass[bi].tolist()
+    assert abs(100.0 * np.mean(gclass[bi] != test_class) - float(bf_err[0].split("=")[1])) < 1e-3
+    dem_err = [float(l.split("%")[0].split("=")[1]) for l in out if l.startswith("dem error=")]
+    assert len(dem_err) == 7 and dem_err[-1] <= dem_err[0] + 1e-9          # more candidates never hurt
+
+
+def test_video_loader_normalisation_variants(fir, ref_l2, ref_chi2, tmp_path):
+    """loadVideos' normalisation (video.cpp:64-84) on the GPU: the L2 build divides by sqrt(sum x^2), the other builds by
+    sum x^2 (FIR_NORM_VIDEO_SUMSQ) — both against the frames the verbatim loader produces."""
+    d = 48
+    stills, still_labels, people, names = _ytf_files(tmp_path, d, 5, sigma=1.0, seed=2)
+    raw = np.concatenate([np.concatenate(v) for k, v in sorted(people.items())])
+    parsed = np.array([[np.float32(float("{:f}".format(float(v)))) for v in row] for row in raw], np.float32)
+    for ref, mode in ((ref_l2, "l2"), (ref_chi2, 3)):
+        rnames, frames, person, video, frame = ref.videos_load(str(tmp_path), d)
+        got = fir.normalize_rows(parsed.copy(), mode)
+        assert np.array_equal(bits(got), bits(frames))

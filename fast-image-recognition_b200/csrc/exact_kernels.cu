@@ -41,7 +41,10 @@ static size_t exact_smem_bytes(int k, int mode) {
 // 2-stage cp.async ring; after the last chunk the 64x64 distances go to shared memory and one thread
 // per query folds them, in gallery order, into its running reduction.
 // ---------------------------------------------------------------------------------------------------
-template <int METRIC>
+// THIN: the launch serves a device-side list of queries that is usually nearly empty (the certificate fallback of the
+// tensor / approximate paths).  A warp owns query rows {2w, 2w+1} + 16a of the tile; with THIN it skips the arithmetic of
+// the rows past the active count, so one stray query costs a pass over the gallery, not 64 queries' worth of FLOPs.
+template <int METRIC, bool THIN>
 __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* qs = reinterpret_cast<float*>(smem_raw);   // [2][TS][LDT]
@@ -57,6 +60,8 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
     if (p.n_active) { n_active = max((int64_t)0, n_active - p.active_offset); if (p.active_cap > 0) n_active = min(n_active, p.active_cap); }
     const int64_t q0 = (int64_t)blockIdx.x * TS;
     if (q0 >= n_active) return;
+    const int rows_live = (int)min((int64_t)TS, n_active - q0);      // query rows of this tile that exist
+    const int wrow = (tid >> 5) * 2;                                  // first query row of this warp (a = 0)
     const int64_t ntiles = (p.n + TS - 1) / TS;
     const int64_t t_lo = (int64_t)blockIdx.y * p.tiles_per_split;
     const int64_t t_hi = min(ntiles, t_lo + p.tiles_per_split);
@@ -124,12 +129,14 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
 #pragma unroll (METRIC == FIR_L2 ? CH / 4 : kDivUnroll)
                 for (int k4 = 0; k4 < CH / 4; ++k4) {
                     float4 qa[4], xa[4];
+                    if (THIN && wrow >= rows_live) continue;                       // warp-uniform: none of this warp's rows exist
 #pragma unroll
                     for (int a = 0; a < 4; ++a) qa[a] = *reinterpret_cast<const float4*>(&qb[(ty + 16 * a) * LDT + k4 * 4]);
 #pragma unroll
                     for (int b = 0; b < 4; ++b) xa[b] = *reinterpret_cast<const float4*>(&xb[(tx + 16 * b) * LDT + k4 * 4]);
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                    for (int a = 0; a < 4; ++a) {
+                        if (THIN && wrow + 16 * a >= rows_live) continue;          // warp-uniform
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
                             dist_step<METRIC>(acc[a][b], qa[a].x, xa[b].x);
@@ -137,14 +144,17 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
                             dist_step<METRIC>(acc[a][b], qa[a].z, xa[b].z);
                             dist_step<METRIC>(acc[a][b], qa[a].w, xa[b].w);
                         }
+                    }
                 }
             } else {
                 for (int kk = 0; kk < kmax; ++kk) {
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                    for (int a = 0; a < 4; ++a) {
+                        if (THIN && wrow + 16 * a >= rows_live) continue;
 #pragma unroll
                         for (int b = 0; b < 4; ++b)
                             dist_step<METRIC>(acc[a][b], qb[(ty + 16 * a) * LDT + kk], xb[(tx + 16 * b) * LDT + kk]);
+                    }
                 }
             }
             __syncthreads();
@@ -226,10 +236,11 @@ int launch_exact_tiles(int metric, const ExactParams& p, cudaStream_t s) {
         FIR_CUDA_TRY(cudaGetLastError());
         return FIR_OK;
     };
+    const bool thin = p.n_active != nullptr;      // device-side query list: the certificate fallback, usually (nearly) empty
     switch (metric) {
-        case FIR_L2: return go(exact_tile_kernel<FIR_L2>);
-        case FIR_CHI2: return go(exact_tile_kernel<FIR_CHI2>);
-        case FIR_KL: return go(exact_tile_kernel<FIR_KL>);
+        case FIR_L2: return thin ? go(exact_tile_kernel<FIR_L2, true>) : go(exact_tile_kernel<FIR_L2, false>);
+        case FIR_CHI2: return thin ? go(exact_tile_kernel<FIR_CHI2, true>) : go(exact_tile_kernel<FIR_CHI2, false>);
+        case FIR_KL: return thin ? go(exact_tile_kernel<FIR_KL, true>) : go(exact_tile_kernel<FIR_KL, false>);
     }
     return fail(FIR_ERR_BAD_ARG, "unknown metric");
 }

@@ -369,6 +369,7 @@ struct CandParams {
     int32_t* cand_idx;
     float* slot_bound;
     const int32_t* skip_if_zero; // optional device counter: nothing to do when it reads 0 (second pass without flagged queries)
+    int debug_nolist;           // measurement aid (FIR_TENSOR_DEBUG_NOLIST=1): thresholds at -inf, nothing is ever listed — WRONG results
     int mins_only;              // seed pass (R = 4): the four slots are plain minima over the four 32-column groups, no lists
     const float* seed_thr;      // optional [nq]: approximate squared distance above which a row cannot matter (see seed pass)
 };
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
                 mx = __int_as_float(0x7f800000);
                 cur_qb = qb;
                 { const int64_t qr = qb * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f));
-                  tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx; thr = tau; }
+                  tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx; if (p.debug_nolist) tau = -mx; thr = tau; }
             }
             mbar_wait(smem_u32(&nx_full[as]), aphase);
             mbar_wait(smem_u32(&tmem_full[as]), aphase);
@@ -830,7 +831,7 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
                 mx = __int_as_float(0x7f800000);
                 cur_qb = qb;
                 { const int64_t qr = qb * (2 * BM) + rank * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f));
-                  tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx; thr = tau; }
+                  tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx; if (p.debug_nolist) tau = -mx; thr = tau; }
             }
             mbar_wait(smem_u32(&nx_full[as]), aphase);
             mbar_wait_cluster(smem_u32(&tmem_full[as]), aphase);
@@ -878,6 +879,7 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     p.gal_norm2 = a.gal->norm2; p.qry_norm2 = a.qry->norm2;
     p.gal_meta = a.gal->meta; p.qry_row_scale = a.qry->row_scale;
     p.cand_val = a.cand_val; p.cand_idx = a.cand_idx; p.slot_bound = a.slot_bound; p.seed_thr = a.seed_thr; p.skip_if_zero = a.skip_if_zero; p.mins_only = a.mins_only;
+    { static const int nolist = [] { const char* e = getenv("FIR_TENSOR_DEBUG_NOLIST"); return e ? atoi(e) : 0; }(); p.debug_nolist = nolist; }
     const bool a_res = p.nkb <= MAX_RES_KB;
     const size_t smem = a.ctas == 2 ? cand_smem_bytes_2cta(a_res) : cand_smem_bytes(a_res);
     auto go = [&](auto kern) -> int {
@@ -1144,8 +1146,10 @@ static size_t seed_plan(fir_gallery* g, int64_t nq, int k, int ctas, SeedPlan* s
     const int64_t S = g->n / div / BN * BN;               // 2 % of the gallery, whole tiles
     if (!seed_enabled() || S < 4 * BN || nq < 4 * BM) return 0;
     sp->S = S;
-    // m >= k would make a too-small seed impossible; 0.6 k leaves about one query in 10^7 to the second pass
-    sp->m = m_override > 0 ? m_override : std::max(2, (3 * k + 4) / 5);
+    // m >= k would make a too-small seed impossible, but every step down in m removes list replacements from the first
+    // pass (C2, k = 10, kernel ms: m=8 0.86, 6 0.84, 4 0.81, 3 0.79, 2 0.77); at 0.3 k a few queries in 10^4 take the
+    // second pass on top of the ones the certificate sends there anyway, at 0.2 k several times more
+    sp->m = m_override > 0 ? m_override : std::max(2, (3 * k + 9) / 10);
     sp->R = 4;                                            // four column-group minima per (slot, half): see epilogue_scan_tile_mins
     int least = 1;
     tensor_plan(nq, S, g->n_sm, ctas, &sp->grid, &sp->n_slots, &least);

@@ -1,5 +1,7 @@
 """GPU parity: the tcgen05/TMA tensor-core L2 path (candidates + exact rerank + certificate) against the
 oracle, through the C-ABI.  Indices and distances must be bit-identical to the reference argmin / top-k."""
+import os
+
 import numpy as np
 import pytest
 
@@ -90,3 +92,33 @@ def test_tensor_device_pointers(fir, port):
     oi, od = port.topk("l2", g, q, 10, nthreads=8)
     assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(bits(dist.cpu().numpy()), bits(od))
     gal.close()
+
+
+@pytest.mark.parametrize("env", [{"FIR_TENSOR_SEED": "0"}, {"FIR_TENSOR_SEED_M": "1"}, {"FIR_TENSOR_CTAS": "1"}])
+def test_tensor_path_variants_stay_exact(env):
+    """The list seeds are an optimisation, never a correctness input: with the sample pass switched off, with a seed rank that
+    is deliberately too small (most queries then fail the first certificate and take the second pass / the exact re-run), and
+    with the single-CTA kernel, the tensor path still returns the exact kernel's answer bit for bit.  (The switches are read
+    once per process, hence the subprocess.)"""
+    import subprocess
+    import sys
+    code = r'''
+import importlib, sys, numpy as np, torch
+sys.path.insert(0, %r)
+import fir_b200
+synth = importlib.import_module("fast-image-recognition_b200.synth")
+g, gl, q, ql = synth.make_split(60000, 1536, 512, 300, "l2", seed=4)
+dev = torch.device("cuda", 0)
+gd, qd = torch.from_numpy(g).to(dev), torch.from_numpy(q).to(dev)
+fir_b200.normalize_rows(gd, "l2"); fir_b200.normalize_rows(qd, "l2")
+gal = fir_b200.Gallery(gd, torch.from_numpy(gl).to(dev), "l2")
+for k in (1, 10):
+    ti, td = gal.search(qd, k=k, path=fir_b200.PATH_TENSOR)
+    st = gal.stats()
+    ei, ed = gal.search(qd, k=k, path=fir_b200.PATH_EXACT)
+    assert torch.equal(ti, ei) and torch.equal(td.view(torch.int32), ed.view(torch.int32)), k
+    print("k", k, "flagged", st["n_fallback"], "exact", st["reserved"])
+print("OK")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr

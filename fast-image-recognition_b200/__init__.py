@@ -221,12 +221,15 @@ class Gallery:
         except Exception:
             pass
 
-    def search(self, queries, k=1, max_features=0, path=PATH_AUTO):
-        """k smallest (feature_distance, index) per query; k=1 is BruteForce::recognize."""
+    def search(self, queries, k=1, max_features=0, path=PATH_AUTO, out=None):
+        """k smallest (feature_distance, index) per query; k=1 is BruteForce::recognize.  out=(idx, dist) reuses result buffers."""
         q, space = _prep(queries, np.float32, "float32")
         nq = int(q.shape[0])
-        idx = _out((nq, k), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
-        dist = _out((nq, k), np.float32, "float32", space == DEVICE, getattr(q, "device", None))
+        if out is not None:
+            idx, dist = out
+        else:
+            idx = _out((nq, k), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
+            dist = _out((nq, k), np.float32, "float32", space == DEVICE, getattr(q, "device", None))
         _check(lib().fir_search_topk(self._h, _ptr(q), nq, k, max_features, path, space, _ptr(idx), _ptr(dist)))
         return idx, dist
 

@@ -82,3 +82,27 @@ def test_twd_argument_errors(fir, port):
     idx, lab, unrel = gal.twd_proposed(q, 32, 0.7, last_feature=128)
     assert np.array_equal(idx, port.twd_proposed("l2", g, gl, q, 32, 0.7, last_feature=128)[0])
     gal.close()
+
+
+def test_twd_larger_gallery_matches_port_on_a_query_sample(fir, port):
+    """20k x 320 gallery, 3k queries on the device (several 64-query tiles, compaction across chunks); the port checks a
+    sample of the queries, the rest through properties: unreliable => more than one chunk was needed, decided class = class of
+    the returned row."""
+    import torch
+    g, gl, q, ql = make_data(port, "l2", 20000, 3000, 320, 200, seed=21, sigma=2.0)
+    dev = torch.device("cuda", 0)
+    gal = fir.Gallery(torch.from_numpy(g).to(dev), torch.from_numpy(gl).to(dev), "l2")
+    qd = torch.from_numpy(q).to(dev)
+    sample = np.arange(0, 3000, 47)
+    for fc, th in ((32, 0.7), (64, 0.8)):
+        idx, lab, unrel = (t.cpu().numpy() for t in gal.twd_proposed(qd, fc, th))
+        pi, pc, pu = port.twd_proposed("l2", g, gl, q[sample], fc, th)
+        assert np.array_equal(idx[sample], pi) and np.array_equal(lab[sample], pc) and np.array_equal(unrel[sample], pu)
+        assert np.array_equal(lab, gl[idx]) and idx.min() >= 0
+    for kind, th in (("ratio", 0.8), ("diff", 0.0005), ("posteriors", 0.22)):
+        idx, lab, unrel = (t.cpu().numpy() for t in gal.twd_conventional(qd, kind, th, 64))
+        pi, pc, pu = port.twd_conventional("l2", g, gl, 200, q[sample], kind, th, 64)
+        assert np.array_equal(idx[sample], pi) and np.array_equal(unrel[sample], pu), kind
+        assert np.array_equal(lab, gl[idx])
+        assert 0 < unrel.mean() < 1, kind                  # both branches of the decision are exercised
+    gal.close()

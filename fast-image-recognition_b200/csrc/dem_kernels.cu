@@ -141,27 +141,30 @@ __global__ void dem_pivot_phase_kernel(const float* __restrict__ pd, int64_t nq,
     st[q] = s;
 }
 
-// likelihood[q][ν] = Σ_i fl((d_i − P[i][ν])²) over the steps whose P entry is ≥ 0 (ann.cpp:453-461); +inf outside the tail
+// likelihood[q][ν] = Σ_i fl((d_i − P[i][ν])²) over the steps whose P entry is ≥ 0 (ann.cpp:453-461); +inf outside the tail.
+// One thread owns one gallery row and QPT queries: every P element read from HBM is used QPT times (the pass is bound by
+// that read — S·N·4 bytes per group of QPT queries — and by the N·4-byte likelihood row it writes per query).
+template <int QPT>
 __global__ void __launch_bounds__(256) dem_likelihood_kernel(const float* __restrict__ pd, const int32_t* __restrict__ qlist, int nqc, int S,
                                                              const float* __restrict__ P, int64_t n, const unsigned char* __restrict__ in_tail,
                                                              float* __restrict__ lik) {
-    __shared__ float dq[8][32];
-    const int q0 = blockIdx.y * 8;
-    if (threadIdx.x < 8 * 32) {
-        int qq = threadIdx.x >> 5, i = threadIdx.x & 31;
+    __shared__ float dq[QPT][32];
+    const int q0 = blockIdx.y * QPT;
+    for (int t = threadIdx.x; t < QPT * 32; t += 256) {
+        const int qq = t >> 5, i = t & 31;
         dq[qq][i] = (q0 + qq < nqc && i < S) ? pd[(int64_t)qlist[q0 + qq] * S + i] : 0.f;
     }
     __syncthreads();
     const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (v >= n) return;
-    float acc[8];
+    float acc[QPT];
 #pragma unroll
-    for (int qq = 0; qq < 8; ++qq) acc[qq] = 0.f;
+    for (int qq = 0; qq < QPT; ++qq) acc[qq] = 0.f;
     for (int i = 0; i < S; ++i) {
         const float m = P[(int64_t)i * n + v];
         if (m >= 0.f) {                                                         // :456
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq) {
+            for (int qq = 0; qq < QPT; ++qq) {
                 const float t = __fsub_rn(dq[qq][i], m);                        // :457
                 acc[qq] = __fadd_rn(acc[qq], __fmul_rn(t, t));                  // :458
             }
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(256) dem_likelihood_kernel(const float* __rest
     }
     const bool tail = in_tail[v] != 0;
 #pragma unroll
-    for (int qq = 0; qq < 8; ++qq)
+    for (int qq = 0; qq < QPT; ++qq)
         if (q0 + qq < nqc) lik[(int64_t)(q0 + qq) * n + v] = tail ? acc[qq] : __int_as_float(0x7f800000);
 }
 
@@ -700,9 +703,9 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
     for (int lo = 0; lo < n_act; lo += QC) {
         const int nqc = std::min(QC, n_act - lo);
         const int32_t* ql = active + lo;
-        dim3 lg((unsigned)ceil_div(n, 256), (unsigned)ceil_div(nqc, 8));
         { auto* ev = g->prof_begin(FIR_KERNEL_DEM_LIKELIHOOD);
-          dem_likelihood_kernel<<<lg, 256, 0, s>>>(pd, ql, nqc, S, dm->P_search, n, dm->in_tail, lik);
+          if (nqc >= 24) dem_likelihood_kernel<32><<<dim3((unsigned)ceil_div(n, 256), (unsigned)ceil_div(nqc, 32)), 256, 0, s>>>(pd, ql, nqc, S, dm->P_search, n, dm->in_tail, lik);
+          else dem_likelihood_kernel<8><<<dim3((unsigned)ceil_div(n, 256), (unsigned)ceil_div(nqc, 8)), 256, 0, s>>>(pd, ql, nqc, S, dm->P_search, n, dm->in_tail, lik);
           g->prof_end(ev); }
         int round_size = 256;
         int remaining = nqc;

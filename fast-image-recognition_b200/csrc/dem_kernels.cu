@@ -639,7 +639,7 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
     // (the reference has undefined behaviour for M < S — partial_sort with middle < first, ann.cpp:469; here the
     //  candidate phase simply does not run, which is also what its while-loop at :472 does.)
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const int QC = (int)std::max<int64_t>(8, std::min<int64_t>(std::min<int64_t>(nq, 1024), ((int64_t)1 << 30) / (4 * n)));   // lik chunk ≤ 1 GiB
+    const int QC = (int)std::max<int64_t>(8, std::min<int64_t>(std::min<int64_t>(nq, 2048), ((int64_t)4 << 30) / (4 * n)));   // lik chunk ≤ 4 GiB
     const int cap_max = (int)std::min<int64_t>(n, std::max<int64_t>(256, ((int64_t)256 << 20) / ((int64_t)QC * 12)));
     size_t need = al(4 * (size_t)nq * g->dp) + 2 * al(4 * (size_t)nq * S) + al(sizeof(QState) * (size_t)nq) + al(4 * (size_t)nq) +
                   al(4 * (size_t)QC * n) + al(4 * (size_t)QC * 2048) + 3 * al(4 * (size_t)QC * cap_max) + 14 * al(4 * (size_t)QC) + al(4 * (size_t)QC * TIE_CAP) +

@@ -1287,8 +1287,9 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     // (sized for the queries spread over the FEWEST lists: a full-round query block has one slot, i.e. two lists)
     const int R1 = pick_R(p1.min_lists, 0);
     // the second pass starts every list from the query's own bound (k-th best found in pass 1 plus the error margins, see
-    // tensor_select_kernel), so its lists only ever hold rows that can matter and can be long at no cost
-    const int R2 = std::max(16, pick_R(p2.min_lists, 8));
+    // tensor_select_kernel), so its lists only ever hold rows that can matter: k plus the rows within the error margin of the
+    // k-th best, spread over all the lists of the query — 8 per list overflows only on mass ties (-> exact re-run)
+    const int R2 = std::max(8, pick_R(p2.min_lists, 0));
     const bool second = true;
     SeedPlan sp{};
     const size_t seed_bytes = seed_plan(g, nq, k, ctas, &sp);

@@ -20,7 +20,7 @@ namespace fir {
 
 constexpr int TT = 64;      // tile: 64 queries x 64 gallery rows
 constexpr int TK = 32;      // dims staged per slab
-constexpr int TLD = TK + 1;
+constexpr int TLD = TK + 4;  // 36 ⇒ LDS.128 conflict-free across 8 consecutive rows
 enum { TWD_SET = 0, TWD_ACC = 1, TWD_MIX = 2 };
 
 // D[q][j] (op)= feature_distance(query q, row j, lo, hi) for the queries on the active list
@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(256) twd_range_kernel(const float* __restrict_
     const int na = *n_active;
     const int p0 = blockIdx.y * TT;
     if (p0 >= na) return;
-    __shared__ float qs[TT * TLD];
-    __shared__ float xs[TT * TLD];
+    __shared__ __align__(16) float qs[TT * TLD];
+    __shared__ __align__(16) float xs[TT * TLD];
     __shared__ int32_t qid[TT];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int64_t x0 = (int64_t)blockIdx.x * TT;
@@ -53,16 +53,28 @@ __global__ void __launch_bounds__(256) twd_range_kernel(const float* __restrict_
         }
         __syncthreads();
         const int kmax = min(TK, hi - k0);
-        for (int kk = 0; kk < kmax; ++kk) {
-            float qa[4], xa[4];
+        int kk = 0;
+        for (; kk + 4 <= kmax; kk += 4) {
+            float4 qa[4], xa[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) qa[a] = qs[(ty + 16 * a) * TLD + kk];
+            for (int a = 0; a < 4; ++a) qa[a] = *reinterpret_cast<const float4*>(&qs[(ty + 16 * a) * TLD + kk]);
 #pragma unroll
-            for (int b = 0; b < 4; ++b) xa[b] = xs[(tx + 16 * b) * TLD + kk];
+            for (int b = 0; b < 4; ++b) xa[b] = *reinterpret_cast<const float4*>(&xs[(tx + 16 * b) * TLD + kk]);
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) dist_step<METRIC>(acc[a][b], qa[a], xa[b]);      // lhs = query (ImageTesting.cpp:117,243)
+                for (int b = 0; b < 4; ++b) {                                               // lhs = query (ImageTesting.cpp:117,243)
+                    dist_step<METRIC>(acc[a][b], qa[a].x, xa[b].x);
+                    dist_step<METRIC>(acc[a][b], qa[a].y, xa[b].y);
+                    dist_step<METRIC>(acc[a][b], qa[a].z, xa[b].z);
+                    dist_step<METRIC>(acc[a][b], qa[a].w, xa[b].w);
+                }
+        }
+        for (; kk < kmax; ++kk) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dist_step<METRIC>(acc[a][b], qs[(ty + 16 * a) * TLD + kk], xs[(tx + 16 * b) * TLD + kk]);
         }
         __syncthreads();
     }
@@ -92,7 +104,8 @@ __device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0
 // argmin with the reference's strict '<' from 100000 (lowest index on ties); warp-wide, result in every lane
 __device__ __forceinline__ void warp_argmin_row(const double* __restrict__ row, int64_t n, int lane, double& bv, int& bi) {
     bv = 100000.0; bi = -1;
-    for (int64_t j = lane; j < n; j += 32) {
+#pragma unroll 8
+    for (int64_t j = lane; j < n; j += 32) {                   // unrolled: eight loads in flight per lane, compared in index order
         const double v = row[j];
         if (v < bv) { bv = v; bi = (int)j; }
     }
@@ -121,6 +134,7 @@ __global__ void __launch_bounds__(128) twd_proposed_decide_kernel(double* __rest
     const int best_class = bi >= 0 ? labels[bi] : -1;
     int others = 0;
     const double inf = pos_inf();
+#pragma unroll 8
     for (int64_t j = lane; j < n; j += 32) {
         const double v = row[j];
         if (v == inf) continue;                                                              // instances_to_check[j] == 0

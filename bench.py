@@ -189,6 +189,7 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None      # pinned staging buffers next to the GPU's PCIe root
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -212,8 +213,12 @@ def run_gpu(args):
     dist_host = torch.empty((N_QUERY, k), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
-    gathered_d = gathered_i = None
+    gathered_d = gathered_i = q_stage_dev = None
     if world > 1:
+        q_stage_dev = torch.empty((N_QUERY, DIM), dtype=torch.float32, device=dev)
+        assert N_QUERY % world == 0
+        q_lo, q_hi = rank * N_QUERY // world, (rank + 1) * N_QUERY // world
+        q_slice_dev = torch.empty((q_hi - q_lo, DIM), dtype=torch.float32, device=dev)
         gathered_d = torch.empty((world * N_QUERY, k), dtype=torch.float32, device=dev)
         gathered_i = torch.empty((world * N_QUERY, k), dtype=torch.int32, device=dev)
 
@@ -227,18 +232,21 @@ def run_gpu(args):
 
     def step_host():
         # the call a user of the C-ABI makes: host buffers in, host buffers out (copies + sync inside)
-        q_stage = q_host.numpy()
-        idx, dd = gal.search(q_stage, k=k, path=fir_b200.PATH_AUTO)
         if world > 1:
-            di, ddv = torch.from_numpy(idx).to(dev, non_blocking=True), torch.from_numpy(dd).to(dev, non_blocking=True)
-            dist.all_gather_into_tensor(gathered_d, ddv)
-            dist.all_gather_into_tensor(gathered_i, di)
+            # sharded gallery: the rank's own top-k is an intermediate, so it stays on the device — pinned queries in,
+            # search (device pointers), all-gather + merge, merged result out to pinned host memory
+            q_slice_dev.copy_(q_host[q_lo:q_hi], non_blocking=True)          # 1/world of the batch over this rank's own PCIe link
+            dist.all_gather_into_tensor(q_stage_dev, q_slice_dev)            # the rest over NVLink
+            idx, dd = gal.search(q_stage_dev, k=k, path=fir_b200.PATH_AUTO)
+            dist.all_gather_into_tensor(gathered_d, dd)
+            dist.all_gather_into_tensor(gathered_i, idx)
             mi, md = fir_b200.merge_topk(gathered_d.view(world, N_QUERY, k), gathered_i.view(world, N_QUERY, k), stream=stream)
             idx_host.copy_(mi, non_blocking=True)
             dist_host.copy_(md, non_blocking=True)
             torch.cuda.synchronize()
             return idx_host.numpy(), dist_host.numpy()
-        return idx, dd
+        q_stage = q_host.numpy()
+        return gal.search(q_stage, k=k, path=fir_b200.PATH_AUTO)
 
     def barrier():
         if world > 1:
@@ -318,7 +326,10 @@ def run_gpu(args):
                                        "(BASELINE.json configs[1]); per GPU: one 100k-row shard, queries replicated" % k,
                            "gallery_per_gpu": N_GALLERY, "queries": N_QUERY, "dim": DIM, "k": k, "classes": N_CLASSES,
                            "parallelism": "gallery row-shards x%d + NCCL all-gather top-k merge" % world if world > 1 else "single GPU",
-                           "l2": "flushed before every timed step (256 MiB fill)", "timing": "per-step CUDA events on the launching stream"},
+                           "l2": "flushed before every timed step (256 MiB fill)", "timing": "per-step CUDA events on the launching stream",
+                           "e2e_path": ("pinned host queries: each rank uploads 1/N of the rows, NVLink all-gather assembles the batch; search; all-gather + merge of the top-k on the device; merged top-k -> pinned host"
+                                        if world > 1 else "fir_search_topk with host buffers (H2D of the queries, D2H of the top-k inside the call)"),
+                           "numa_node": numa},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
                         "h2d_bytes_per_step": N_QUERY * DIM * 4, "d2h_bytes_per_step": N_QUERY * k * 8},
                 "gpu_launches": launches_per_step * args.steps,
@@ -342,6 +353,28 @@ def run_gpu(args):
 
 def g_np_norm(g_dev):
     return g_dev.cpu().numpy()
+
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Multi-rank runs: run this process (and so allocate its pinned buffers) on the CPUs of the NUMA node the GPU hangs off.
+    Best effort — returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 def main():

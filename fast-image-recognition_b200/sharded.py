@@ -1,5 +1,6 @@
 """Gallery row-sharding across the GPUs of one box: one process per GPU (torchrun),
-rank r holds rows [lo_r, hi_r) of the class-major gallery with index_offset = lo_r, queries are replicated,
+rank r holds rows [lo_r, hi_r) of the class-major gallery with index_offset = lo_r, queries are replicated
+(a host batch is uploaded in 1/world slices and all-gathered over NVLink, `gather_queries`),
 each rank's exact (already reranked) top-k is all-gathered with torch.distributed and merged by (dist, idx).
 PNN class scores are summed (all-reduce); per-class minima are min-reduced on packed (dist, idx) keys.
 
@@ -62,6 +63,26 @@ class ShardedGallery:
         if g_d.is_cuda:
             return self._merge(g_d, g_i, k)
         return self._merge(g_d.numpy(), g_i.numpy(), k)
+
+    def gather_queries(self, q_host, device=None):
+        """Every rank holds the same query batch in HOST memory (replicated input).  Instead of eight identical H2D copies
+        competing for the host's PCIe roots, each rank uploads 1/world of the rows over its own link and the batch is
+        assembled on every GPU by an all-gather over NVLink.  Returns the full [nq, d] batch on this rank's device."""
+        import torch
+        t = q_host if torch.is_tensor(q_host) else torch.from_numpy(np.ascontiguousarray(q_host))
+        device = device if device is not None else self.device
+        if self.world == 1:
+            return t.to(device, non_blocking=True) if device is not None else t
+        nq, d = t.shape
+        per = -(-nq // self.world)                                    # equal slices (the last one padded)
+        rank = self.dist.get_rank()
+        lo, hi = min(nq, rank * per), min(nq, (rank + 1) * per)
+        part = torch.zeros((per, d), dtype=t.dtype, device=device)
+        if hi > lo:
+            part[: hi - lo].copy_(t[lo:hi], non_blocking=True)
+        full = torch.empty((self.world * per, d), dtype=t.dtype, device=device)
+        self.dist.all_gather_into_tensor(full, part)
+        return full[:nq]
 
     def pnn_scores(self, queries, var):
         sc, _ = self.local.pnn_scores(queries, var, n_total=self.n_total)

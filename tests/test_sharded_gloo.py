@@ -57,6 +57,8 @@ def _worker(rank, world, port_no, out):
     sc, lab = sg.pnn_scores(q, 2e-4)
     osc, olab = port.pnn_div("l2", g, gl, 6, q, 2e-4)
     ok = ok and np.allclose(sc, osc, rtol=1e-9) and np.array_equal(lab, olab)
+    full = sg.gather_queries(q)                         # 23 rows over 2 ranks: slices of 12 + 11 (padded), assembled everywhere
+    ok = ok and tuple(full.shape) == q.shape and np.array_equal(full.numpy().view(np.uint32), q.view(np.uint32))
     if rank == 0:
         with open(out, "w") as f:
             f.write("ok" if ok else "mismatch")

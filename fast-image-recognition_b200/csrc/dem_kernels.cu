@@ -147,7 +147,7 @@ __global__ void dem_pivot_phase_kernel(const float* __restrict__ pd, int64_t nq,
 template <int QPT>
 __global__ void __launch_bounds__(256) dem_likelihood_kernel(const float* __restrict__ pd, const int32_t* __restrict__ qlist, int nqc, int S,
                                                              const float* __restrict__ P, int64_t n, const unsigned char* __restrict__ in_tail,
-                                                             float* __restrict__ lik) {
+                                                             float* __restrict__ lik, float* __restrict__ gmin, int64_t ng) {
     __shared__ float dq[QPT][32];
     const int q0 = blockIdx.y * QPT;
     for (int t = threadIdx.x; t < QPT * 32; t += 256) {
@@ -156,24 +156,106 @@ __global__ void __launch_bounds__(256) dem_likelihood_kernel(const float* __rest
     }
     __syncthreads();
     const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (v >= n) return;
+    const bool valid = v < n;
     float acc[QPT];
 #pragma unroll
     for (int qq = 0; qq < QPT; ++qq) acc[qq] = 0.f;
-    for (int i = 0; i < S; ++i) {
-        const float m = P[(int64_t)i * n + v];
-        if (m >= 0.f) {                                                         // :456
+    if (valid) {
+        for (int i = 0; i < S; ++i) {
+            const float m = P[(int64_t)i * n + v];
+            if (m >= 0.f) {                                                     // :456
 #pragma unroll
-            for (int qq = 0; qq < QPT; ++qq) {
-                const float t = __fsub_rn(dq[qq][i], m);                        // :457
-                acc[qq] = __fadd_rn(acc[qq], __fmul_rn(t, t));                  // :458
+                for (int qq = 0; qq < QPT; ++qq) {
+                    const float t = __fsub_rn(dq[qq][i], m);                    // :457
+                    acc[qq] = __fadd_rn(acc[qq], __fmul_rn(t, t));              // :458
+                }
             }
         }
     }
-    const bool tail = in_tail[v] != 0;
+    const bool tail = valid && in_tail[v] != 0;
+    const float inf = __int_as_float(0x7f800000);
 #pragma unroll
-    for (int qq = 0; qq < QPT; ++qq)
-        if (q0 + qq < nqc) lik[(int64_t)(q0 + qq) * n + v] = tail ? acc[qq] : __int_as_float(0x7f800000);
+    for (int qq = 0; qq < QPT; ++qq) {
+        const float lv = tail ? acc[qq] : inf;
+        if (valid && q0 + qq < nqc) lik[(int64_t)(q0 + qq) * n + v] = lv;
+        if (gmin) {
+            // minimum of the 32 rows of this warp: a bound for the first round's select (dem_fast_* below)
+            float m = lv;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((threadIdx.x & 31) == 0 && q0 + qq < nqc && (v >> 5) < ng) gmin[(int64_t)(q0 + qq) * ng + (v >> 5)] = m;
+        }
+    }
+}
+
+// ---- fast first round ------------------------------------------------------------------------------
+// The round wants the `want` smallest (likelihood, row) pairs.  The want-th smallest of the per-warp minima (found by the
+// same radix select over an array 32x smaller) is an upper bound T for the want-th smallest likelihood: at least `want`
+// rows are <= T, and rows <= T only live in warps whose minimum is <= T, so there are at most 32 x (want + ties) of them.
+// One pass collects them, a shared-memory sort puts them in (likelihood, row) order and the first `want` ARE the round —
+// one read of the likelihood rows instead of four.  Anything unusual (ties overflowing the buffer, fewer rows than wanted)
+// leaves the query to the general path below.
+constexpr int FAST_CAP = 8192 + 1024;
+
+__global__ void __launch_bounds__(256) dem_fast_collect_kernel(const float* __restrict__ lik, const int32_t* __restrict__ qlist, int nqc, int64_t n,
+                                                               const QState* __restrict__ st, const int32_t* __restrict__ t_all,
+                                                               const uint32_t* __restrict__ t_key, uint32_t* __restrict__ fkey,
+                                                               int32_t* __restrict__ frow, int32_t* __restrict__ fcnt) {
+    const int qc = blockIdx.y;
+    if (st[qlist[qc]].done || t_all[qc]) return;
+    const float* lr = lik + (int64_t)qc * n;
+    const uint32_t T = t_key[qc];
+    for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < n; v += (int64_t)gridDim.x * 256) {
+        const uint32_t key = __float_as_uint(lr[v]);
+        if (key >= 0x7f800000u || key > T) continue;
+        const int pos = atomicAdd(&fcnt[qc], 1);
+        if (pos < FAST_CAP) { fkey[(int64_t)qc * FAST_CAP + pos] = key; frow[(int64_t)qc * FAST_CAP + pos] = (int32_t)v; }
+    }
+}
+
+// one block per query: sort the collected (key, row) pairs, emit the first `want` as the round's candidates
+__global__ void __launch_bounds__(256) dem_fast_finalize_kernel(const int32_t* __restrict__ qlist, int nqc, const QState* __restrict__ st,
+                                                                const int32_t* __restrict__ t_all, const int32_t* __restrict__ want,
+                                                                const uint32_t* __restrict__ fkey, const int32_t* __restrict__ frow,
+                                                                const int32_t* __restrict__ fcnt, int cap, int32_t* __restrict__ cand,
+                                                                uint32_t* __restrict__ cand_key, int32_t* __restrict__ round_n,
+                                                                uint32_t* __restrict__ key_sel, int32_t* __restrict__ last_tie,
+                                                                int32_t* __restrict__ take_all, int32_t* __restrict__ fast_ok) {
+    extern __shared__ unsigned long long fsort[];
+    const int qc = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int c = fcnt[qc], w = want[qc];
+    if (st[qlist[qc]].done || t_all[qc] || c > FAST_CAP || c < w || w <= 0 || w > cap) { if (tid == 0) fast_ok[qc] = 0; return; }
+    int P2 = 1;
+    while (P2 < c) P2 <<= 1;
+    for (int i = tid; i < P2; i += 256)
+        fsort[i] = i < c ? (((unsigned long long)fkey[(int64_t)qc * FAST_CAP + i] << 32) | (uint32_t)frow[(int64_t)qc * FAST_CAP + i]) : ~0ull;
+    __syncthreads();
+    for (int k2 = 2; k2 <= P2; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P2; i += 256) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = fsort[i], b = fsort[l];
+                    const bool up = (i & k2) == 0;
+                    if ((a > b) == up) { fsort[i] = b; fsort[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    int32_t* out = cand + (int64_t)qc * cap;
+    uint32_t* outk = cand_key + (int64_t)qc * cap;
+    for (int i = tid; i < cap; i += 256) {
+        if (i < w) { out[i] = (int32_t)(uint32_t)fsort[i]; outk[i] = (uint32_t)(fsort[i] >> 32); }
+        else out[i] = -1;
+    }
+    if (tid == 0) {
+        round_n[qc] = w;
+        key_sel[qc] = (uint32_t)(fsort[w - 1] >> 32);       // where the round ends in (key, row) order
+        last_tie[qc] = (int32_t)(uint32_t)fsort[w - 1];
+        take_all[qc] = 0;
+        fast_ok[qc] = 1;
+    }
 }
 
 __device__ __forceinline__ bool after_last(uint32_t key, int32_t idx, const QState& s) {
@@ -192,9 +274,10 @@ __device__ __forceinline__ uint32_t radix_digit(uint32_t key, int pass) {
 
 __global__ void __launch_bounds__(256) dem_hist_kernel(const float* __restrict__ lik, const int32_t* __restrict__ qlist, int nqc, int64_t n,
                                                        const QState* __restrict__ st, int pass, const uint32_t* __restrict__ prefix,
-                                                       const int32_t* __restrict__ take_all, uint32_t* __restrict__ hist) {
+                                                       const int32_t* __restrict__ take_all, uint32_t* __restrict__ hist, const int32_t* __restrict__ skip) {
     __shared__ uint32_t sh[2048];
     const int qc = blockIdx.y;
+    if (skip && skip[qc]) return;
     const QState s = st[qlist[qc]];
     if (s.done || (pass > 0 && take_all[qc])) return;
     for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0;
@@ -217,9 +300,10 @@ __global__ void __launch_bounds__(256) dem_hist_kernel(const float* __restrict__
 __global__ void __launch_bounds__(32) dem_pick_kernel(const uint32_t* __restrict__ hist, const int32_t* __restrict__ qlist, int nqc,
                                                       const QState* __restrict__ st, int pass, const int32_t* __restrict__ want_in,
                                                       uint32_t* __restrict__ prefix, int32_t* __restrict__ want_rem, int32_t* __restrict__ take_all,
-                                                      uint32_t* __restrict__ key_sel, int32_t* __restrict__ tie_take, int32_t* __restrict__ round_n) {
+                                                      uint32_t* __restrict__ key_sel, int32_t* __restrict__ tie_take, int32_t* __restrict__ round_n,
+                                                      const int32_t* __restrict__ skip) {
     const int qc = blockIdx.x;
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x != 0 || (skip && skip[qc])) return;
     const QState s = st[qlist[qc]];
     if (s.done) { round_n[qc] = 0; take_all[qc] = 0; key_sel[qc] = 0; tie_take[qc] = 0; return; }
     if (pass > 0 && take_all[qc]) return;
@@ -252,8 +336,9 @@ __global__ void __launch_bounds__(256) dem_collect_fast_kernel(const float* __re
                                                                const QState* __restrict__ st, const int32_t* __restrict__ take_all,
                                                                const uint32_t* __restrict__ key_sel, int cap, int32_t* __restrict__ cand,
                                                                uint32_t* __restrict__ cand_key, int32_t* __restrict__ cnt,
-                                                               int32_t* __restrict__ tie_buf, int32_t* __restrict__ tie_cnt) {
+                                                               int32_t* __restrict__ tie_buf, int32_t* __restrict__ tie_cnt, const int32_t* __restrict__ skip) {
     const int qc = blockIdx.y;
+    if (skip && skip[qc]) return;
     const QState s = st[qlist[qc]];
     if (s.done) return;
     const float* lr = lik + (int64_t)qc * n;
@@ -279,11 +364,11 @@ __global__ void dem_collect_fixup_kernel(const int32_t* __restrict__ qlist, int 
                                          const uint32_t* __restrict__ key_sel, const int32_t* __restrict__ tie_take, int cap,
                                          int32_t* __restrict__ cand, uint32_t* __restrict__ cand_key, int32_t* __restrict__ cnt,
                                          int32_t* __restrict__ tie_buf, const int32_t* __restrict__ tie_cnt, int32_t* __restrict__ last_tie_idx,
-                                         int32_t* __restrict__ overflow) {
+                                         int32_t* __restrict__ overflow, const int32_t* __restrict__ skip) {
     const int qc = blockIdx.x * blockDim.x + threadIdx.x;
     if (qc >= nqc) return;
     overflow[qc] = 0;
-    if (st[qlist[qc]].done) return;
+    if (st[qlist[qc]].done || (skip && skip[qc])) return;
     int32_t* out = cand + (int64_t)qc * cap;
     uint32_t* outk = cand_key + (int64_t)qc * cap;
     int c = min(cnt[qc], cap);
@@ -644,6 +729,10 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
     size_t need = al(4 * (size_t)nq * g->dp) + 2 * al(4 * (size_t)nq * S) + al(sizeof(QState) * (size_t)nq) + al(4 * (size_t)nq) +
                   al(4 * (size_t)QC * n) + al(4 * (size_t)QC * 2048) + 3 * al(4 * (size_t)QC * cap_max) + 14 * al(4 * (size_t)QC) + al(4 * (size_t)QC * TIE_CAP) +
                   al((size_t)nq * 9) + al(4 * (size_t)nq) * 2 + 65536;
+    static const int fast_on = [] { const char* e = getenv("FIR_DEM_FAST"); return e ? atoi(e) : 1; }();
+    const int64_t ng = ceil_div(n, 32);
+    const bool fast = fast_on != 0 && ng >= 1024;            // first-round select through per-warp minima (dem_fast_*)
+    if (fast) need += al(4 * (size_t)QC * ng) + 2 * al(4 * (size_t)QC * FAST_CAP) + 4 * al(4 * (size_t)QC);
     FIR_TRY(g->ws.reserve(need));
     // queries → zero-padded device rows
     const float* dq = nullptr;
@@ -679,6 +768,19 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
     int32_t* round_n = (int32_t*)g->ws.take(4 * (size_t)QC);
     int32_t* last_tie = (int32_t*)g->ws.take(4 * (size_t)QC);
     int32_t* counters = (int32_t*)g->ws.take(64);
+    float* gmin = nullptr; uint32_t* fkey = nullptr; int32_t* frow = nullptr; int32_t* fcnt = nullptr; int32_t* fast_ok = nullptr;
+    uint32_t* t_key = nullptr; int32_t* t_all = nullptr;
+    if (fast) {
+        gmin = (float*)g->ws.take(4 * (size_t)QC * ng);
+        fkey = (uint32_t*)g->ws.take(4 * (size_t)QC * FAST_CAP);
+        frow = (int32_t*)g->ws.take(4 * (size_t)QC * FAST_CAP);
+        fcnt = (int32_t*)g->ws.take(4 * (size_t)QC);
+        fast_ok = (int32_t*)g->ws.take(4 * (size_t)QC);
+        t_key = (uint32_t*)g->ws.take(4 * (size_t)QC);
+        t_all = (int32_t*)g->ws.take(4 * (size_t)QC);
+        if (!gmin || !fkey || !frow || !fcnt || !fast_ok || !t_key || !t_all) return fail(FIR_ERR_INTERNAL, "workspace underestimated (dem fast round)");
+        FIR_CUDA_TRY(cudaFuncSetAttribute(dem_fast_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    }
     int32_t* o_idx = out_idx; float* o_dist = out_dist; uint8_t* o_below = out_below; int32_t* o_evals = out_evals;
     if (memspace == FIR_HOST) {
         o_idx = (int32_t*)g->ws.take(4 * (size_t)nq);
@@ -704,25 +806,44 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
         const int nqc = std::min(QC, n_act - lo);
         const int32_t* ql = active + lo;
         { auto* ev = g->prof_begin(FIR_KERNEL_DEM_LIKELIHOOD);
-          if (nqc >= 24) dem_likelihood_kernel<32><<<dim3((unsigned)ceil_div(n, 256), (unsigned)ceil_div(nqc, 32)), 256, 0, s>>>(pd, ql, nqc, S, dm->P_search, n, dm->in_tail, lik);
-          else dem_likelihood_kernel<8><<<dim3((unsigned)ceil_div(n, 256), (unsigned)ceil_div(nqc, 8)), 256, 0, s>>>(pd, ql, nqc, S, dm->P_search, n, dm->in_tail, lik);
+          if (nqc >= 24) dem_likelihood_kernel<32><<<dim3((unsigned)ceil_div(n, 256), (unsigned)ceil_div(nqc, 32)), 256, 0, s>>>(pd, ql, nqc, S, dm->P_search, n, dm->in_tail, lik, gmin, ng);
+          else dem_likelihood_kernel<8><<<dim3((unsigned)ceil_div(n, 256), (unsigned)ceil_div(nqc, 8)), 256, 0, s>>>(pd, ql, nqc, S, dm->P_search, n, dm->in_tail, lik, gmin, ng);
           g->prof_end(ev); }
         int round_size = 256;
         int remaining = nqc;
+        bool first_round = true;
         while (remaining > 0) {
             const int cap = (int)std::min<int64_t>(round_size, cap_max);
             dem_want_kernel<<<(unsigned)ceil_div(nqc, 128), 128, 0, s>>>(st, ql, nqc, cap, M, want);
             const unsigned hb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 16), 64));
+            const int32_t* skip = nullptr;
+            if (fast && first_round) {
+                // bound from the per-warp minima (the same radix select over an array 32x smaller), one collecting pass, sort
+                const unsigned hg = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ng, 256 * 16), 64));
+                for (int pass = 0; pass < 3; ++pass) {
+                    FIR_CUDA_TRY(cudaMemsetAsync(hist, 0, 4 * (size_t)nqc * 2048, s));
+                    dem_hist_kernel<<<dim3(hg, (unsigned)nqc), 256, 0, s>>>(gmin, ql, nqc, ng, st, pass, prefix, take_all, hist, nullptr);
+                    dem_pick_kernel<<<(unsigned)nqc, 32, 0, s>>>(hist, ql, nqc, st, pass, want, prefix, want_rem, take_all, key_sel, tie_take, round_n, nullptr);
+                }
+                FIR_CUDA_TRY(cudaMemcpyAsync(t_key, key_sel, 4 * (size_t)nqc, cudaMemcpyDeviceToDevice, s));
+                FIR_CUDA_TRY(cudaMemcpyAsync(t_all, take_all, 4 * (size_t)nqc, cudaMemcpyDeviceToDevice, s));
+                FIR_CUDA_TRY(cudaMemsetAsync(fcnt, 0, 4 * (size_t)nqc, s));
+                dem_fast_collect_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, t_all, t_key, fkey, frow, fcnt);
+                dem_fast_finalize_kernel<<<(unsigned)nqc, 256, 16384 * 8, s>>>(ql, nqc, st, t_all, want, fkey, frow, fcnt, cap, cand, cand_key, round_n, key_sel, last_tie,
+                                                                              take_all, fast_ok);
+                skip = fast_ok;
+            }
+            first_round = false;
             for (int pass = 0; pass < 3; ++pass) {
                 FIR_CUDA_TRY(cudaMemsetAsync(hist, 0, 4 * (size_t)nqc * 2048, s));
-                dem_hist_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, pass, prefix, take_all, hist);
-                dem_pick_kernel<<<(unsigned)nqc, 32, 0, s>>>(hist, ql, nqc, st, pass, want, prefix, want_rem, take_all, key_sel, tie_take, round_n);
+                dem_hist_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, pass, prefix, take_all, hist, skip);
+                dem_pick_kernel<<<(unsigned)nqc, 32, 0, s>>>(hist, ql, nqc, st, pass, want, prefix, want_rem, take_all, key_sel, tie_take, round_n, skip);
             }
             FIR_CUDA_TRY(cudaMemsetAsync(cnt, 0, 4 * (size_t)nqc, s));
             FIR_CUDA_TRY(cudaMemsetAsync(tie_cnt, 0, 4 * (size_t)nqc, s));
-            dem_collect_fast_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, take_all, key_sel, cap, cand, cand_key, cnt, tie_buf, tie_cnt);
+            dem_collect_fast_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, take_all, key_sel, cap, cand, cand_key, cnt, tie_buf, tie_cnt, skip);
             dem_collect_fixup_kernel<<<(unsigned)ceil_div(nqc, 128), 128, 0, s>>>(ql, nqc, st, take_all, key_sel, tie_take, cap, cand, cand_key, cnt, tie_buf, tie_cnt,
-                                                                               last_tie, overflow);
+                                                                               last_tie, overflow, skip);
             dem_collect_kernel<<<(unsigned)ceil_div(nqc, 4), 128, 0, s>>>(lik, ql, nqc, n, st, overflow, key_sel, tie_take, cap, cand, cand_key, last_tie);
             // exact distances of the round's candidates: queries are addressed through the active list
             FIR_TRY(launch_pair_distances(g->metric, dq, nqc, g->dp, g->rows, g->dp, n, g->d, cand, cap, 0, cdist, s, nullptr, ql));

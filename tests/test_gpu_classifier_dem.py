@@ -131,3 +131,29 @@ def test_dem_index_walk_quirk(fir, port, ref_l2):
     rdem.close()
     dem.close()
     gal.close()
+
+
+def test_dem_search_large_gallery_fast_first_round(fir, port):
+    """40k rows: the first round of the candidate walk goes through the per-warp-minima bound (dem_fast_*), later rounds
+    through the general radix path starting from where the fast round ended.  Both a realistic threshold (early exits) and
+    a threshold far below the data (long ordered walks over several rounds) against the port."""
+    g, gl, q, ql = make_data(port, "l2", 40000, 96, 32, 400, seed=6, sigma=1.5)
+    g[20000:20040] = g[100:140]                                  # exact duplicates: ties at equal likelihood, resolved by row
+    gal = fir.Gallery(g, gl, "l2")
+    dem = fir.Dem(gal, pivot0=123, max_chain=40)
+    piv, P, thr = dem.pivots, dem.P, float(dem.threshold)
+    for M in (0, 200, 300, 3000):
+        got = dem.search(q, M)
+        want = port.dem_search("l2", g, piv, P, thr, M, q)
+        for name, a, b in zip(("idx", "dist", "below", "evals"), got, want):
+            assert np.array_equal(a, b), (M, name)
+    low = fir.Dem(gal, state=(piv, P, thr * 0.05))               # nothing is ever under the threshold: full budget is walked
+    for M in (100, 256, 257, 700, 2600):
+        got = low.search(q, M)
+        want = port.dem_search("l2", g, piv, P, thr * 0.05, M, q)
+        for name, a, b in zip(("idx", "dist", "below", "evals"), got, want):
+            assert np.array_equal(a, b), (M, name)
+        assert int(got[3].max()) == M
+    low.close()
+    dem.close()
+    gal.close()

@@ -289,8 +289,8 @@ static int range_pass(fir_gallery* g, const float* dq, const int32_t* qlist, con
 static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 size_t twd_workspace_bytes(const fir_gallery* g, int64_t nq, int64_t* mq_out) {
-    // the running-distance matrix is the big item: keep it near 2 GiB and walk the queries in chunks
-    int64_t mq = std::max<int64_t>(TT, ((int64_t)2 << 30) / (8 * std::max<int64_t>(g->n, 1)) / TT * TT);
+    // the running-distance matrix is the big item: keep it near 8 GiB and walk the queries in chunks
+    int64_t mq = std::max<int64_t>(TT, ((int64_t)8 << 30) / (8 * std::max<int64_t>(g->n, 1)) / TT * TT);
     mq = std::min<int64_t>(mq, (nq + TT - 1) / TT * TT);
     mq = std::min<int64_t>(mq, (int64_t)65535 * TT);                                         // grid.y of the range kernel
     *mq_out = mq;

@@ -213,12 +213,13 @@ def run_gpu(args):
     dist_host = torch.empty((N_QUERY, k), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
-    gathered_d = gathered_i = q_stage_dev = None
+    gathered_d = gathered_i = q_stage_dev = q_gather_dev = q_slice_dev = None
     if world > 1:
-        q_stage_dev = torch.empty((N_QUERY, DIM), dtype=torch.float32, device=dev)
-        assert N_QUERY % world == 0
-        q_lo, q_hi = rank * N_QUERY // world, (rank + 1) * N_QUERY // world
-        q_slice_dev = torch.empty((q_hi - q_lo, DIM), dtype=torch.float32, device=dev)
+        per = -(-N_QUERY // world)                                           # equal slices, the last one padded
+        q_lo, q_hi = min(N_QUERY, rank * per), min(N_QUERY, (rank + 1) * per)
+        q_gather_dev = torch.zeros((world * per, DIM), dtype=torch.float32, device=dev)
+        q_stage_dev = q_gather_dev[:N_QUERY]
+        q_slice_dev = torch.zeros((per, DIM), dtype=torch.float32, device=dev)
         gathered_d = torch.empty((world * N_QUERY, k), dtype=torch.float32, device=dev)
         gathered_i = torch.empty((world * N_QUERY, k), dtype=torch.int32, device=dev)
 
@@ -235,8 +236,8 @@ def run_gpu(args):
         if world > 1:
             # sharded gallery: the rank's own top-k is an intermediate, so it stays on the device — pinned queries in,
             # search (device pointers), all-gather + merge, merged result out to pinned host memory
-            q_slice_dev.copy_(q_host[q_lo:q_hi], non_blocking=True)          # 1/world of the batch over this rank's own PCIe link
-            dist.all_gather_into_tensor(q_stage_dev, q_slice_dev)            # the rest over NVLink
+            q_slice_dev[: q_hi - q_lo].copy_(q_host[q_lo:q_hi], non_blocking=True)   # 1/world of the batch over this rank's own PCIe link
+            dist.all_gather_into_tensor(q_gather_dev, q_slice_dev)                   # the rest over NVLink
             idx, dd = gal.search(q_stage_dev, k=k, path=fir_b200.PATH_AUTO)
             dist.all_gather_into_tensor(gathered_d, dd)
             dist.all_gather_into_tensor(gathered_i, idx)

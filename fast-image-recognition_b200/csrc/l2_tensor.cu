@@ -2,18 +2,21 @@
 //
 //   d²(q,x) = ‖q‖² + ‖x‖² − 2·q·xᵀ
 //
-// Stage 1 (this file, `l2_candidates_kernel`): q·xᵀ on tcgen05 tensor cores — fp16 operands staged by
-// TMA into 128B-swizzled shared memory, fp32 accumulators in TMEM (two 128x256 buffers), one elected
-// thread issuing `tcgen05.mma`.  The epilogue never materialises the Q x N matrix: each of the 128
-// epilogue threads owns one query row of the accumulator (TMEM lane = row), reads it with `tcgen05.ld`
-// and keeps that query's R best approximate distances in registers.
-// Stage 2 (exact_kernels.cu: pair_distance_kernel): the reference's own fp32 arithmetic
-// (feature_distance, qt_cpp/db_features.cpp:22-42) on the R·slots survivors.
+// Stage 0 (seed pass): the candidate kernel over a 2 % sample of the gallery in a branch-free minima mode gives every
+// query a starting threshold for its lists (see SeedPlan below).
+// Stage 1 (this file, `l2_candidates_kernel_2cta` / `l2_candidates_kernel`): q·xᵀ on tcgen05 tensor cores — fp16
+// operands staged by TMA into 128B-swizzled shared memory, fp32 accumulators in TMEM (two 256-column buffers), one
+// elected thread issuing `tcgen05.mma` (cta_group::2: one instruction drives both SMs of a CTA pair).  The epilogue never
+// materialises the Q x N matrix: each epilogue thread owns one query row of the accumulator (TMEM lane = row) and one
+// column half, reads it with `tcgen05.ld` and keeps that query's R best approximate distances in registers.
+// Stage 2 (`tensor_prune_kernel` + exact_kernels.cu: pair_list_kernel): candidates that provably cannot matter are
+// dropped; the reference's own fp32 arithmetic (feature_distance, qt_cpp/db_features.cpp:22-42) on the survivors.
 // Stage 3 (`tensor_select_kernel`): top-k by (exact distance, index) and a CERTIFICATE that no
 // non-candidate can beat the k-th exact distance, from a rigorous bound on |approx − true|
 // (Cauchy–Schwarz on the fp16 rounding residuals, which are measured per vector at pack time).
-// Queries whose certificate fails are re-run through the exact CUDA-core kernel on the GPU, so the
-// returned indices/distances are always bit-identical to BruteForce::recognize (qt_cpp/ann.cpp:113-126).
+// Queries whose certificate fails take a second, individually seeded tensor pass, and what even that cannot certify is
+// re-run through the exact CUDA-core kernel on the GPU, so the returned indices/distances are always bit-identical to
+// BruteForce::recognize (qt_cpp/ann.cpp:113-126).
 #include "fir_common.cuh"
 #include "handles.hpp"
 #include <cmath>

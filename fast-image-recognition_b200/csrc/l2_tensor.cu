@@ -934,15 +934,17 @@ __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ c
                                                            const ErrModel em, const int32_t* __restrict__ n_active,
                                                            uint32_t* __restrict__ pair_cells, int32_t* __restrict__ pair_count) {
     extern __shared__ __align__(16) unsigned char prune_smem[];
+    __shared__ int s_cnt[4];
+    __shared__ int s_off;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t q = (int64_t)blockIdx.x * 4 + warp;
-    if (q >= nq) return;
+    int base = 0;                                                              // survivors of this warp's query
+    if (q < nq && n_active && q >= *n_active) {                                // second pass: rows past the flagged count are padding
+        int32_t* ci = cand_idx + q * rt;
+        for (int c = lane; c < rt; c += 32) ci[c] = -1;
+    } else if (q < nq) {
     float* cv = cand_val + q * rt;
     int32_t* ci = cand_idx + q * rt;
-    if (n_active && q >= *n_active) {                                          // second pass: rows past the flagged count are padding
-        for (int c = lane; c < rt; c += 32) ci[c] = -1;
-        return;
-    }
     // Stage the VALID candidates compacted into shared memory first: one round trip to global memory instead of one per
     // selection round (a warp serves one query, so nothing else hides that latency when only a few queries are active).
     // (Seeded lists are mostly empty, so the capacity is counted in valid entries; a row with more takes the global path.)
@@ -986,7 +988,6 @@ __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ c
     const double cut = taken < k ? __longlong_as_double(0x7ff0000000000000LL) : ((double)kth + E) * (1.0 + rho) / (1.0 - rho) + E;
     // compact the survivors to the front of the query's row (order is irrelevant downstream; tensor_select_kernel and the
     // rerank rely on the survivors being a prefix)
-    int base = 0;
     for (int c0 = 0; c0 < nv; c0 += 32) {
         const int c = c0 + lane;
         int32_t idx = -1; float v = 0.f;
@@ -999,11 +1000,19 @@ __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ c
     }
     __syncwarp();
     for (int c = base + lane; c < rt; c += 32) ci[c] = -1;
-    if (pair_cells && base > 0) {
-        // the survivors of all queries go on one list so that the rerank's warps are full: cell = q * rt + position
-        int off = 0;
-        if (lane == 0) off = atomicAdd(pair_count, base);
-        off = __shfl_sync(0xffffffffu, off, 0);
+    }
+    // the survivors of all queries go on one list so that the rerank's warps are full: cell = q * rt + position.  One
+    // atomic per block, not per query: ten thousand same-address atomics serialise in L2 for longer than the kernel's work.
+    if (pair_cells) {                                                         // (uniform: every warp of the block gets here)
+        if (lane == 0) s_cnt[warp] = base;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int total = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+            s_off = total > 0 ? atomicAdd(pair_count, total) : 0;
+        }
+        __syncthreads();
+        int off = s_off;
+        for (int w = 0; w < warp; ++w) off += s_cnt[w];
         for (int c = lane; c < base; c += 32) pair_cells[off + c] = (uint32_t)(q * rt + c);
     }
 }
@@ -1066,7 +1075,9 @@ __global__ void __launch_bounds__(128) tensor_select_kernel(const float* __restr
         if (seed_out) seed_out[pos] = found >= k ? __double2float_ru((double)kth * em.dist_scale * (1.0 + rho) / (1.0 - rho) + 2.0 * E)
                                                  : __int_as_float(0x7f800000);
     }
-    atomicMax(reinterpret_cast<unsigned int*>(max_bound), __float_as_uint((float)E));
+    // (same-address atomics from every query serialise; the bound only ever grows, so most warps can see they have nothing to add)
+    if (__float_as_uint((float)E) > __ldcg(reinterpret_cast<const unsigned int*>(max_bound)))
+        atomicMax(reinterpret_cast<unsigned int*>(max_bound), __float_as_uint((float)E));
 }
 
 int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s, const int32_t* n_active,

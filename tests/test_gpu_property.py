@@ -1,0 +1,68 @@
+"""GPU: randomised parity of the CUDA path against the C restatement on ragged shapes (rows not a multiple of any tile, odd
+dimensions, duplicates, k above the gallery size, every metric), through the C-ABI with host buffers."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from util import bits
+
+pytestmark = pytest.mark.gpu
+SET = settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+
+
+def _rows(seed, n, d, metric, dup=0):
+    r = np.random.default_rng(seed)
+    x = r.normal(size=(n, d)).astype(np.float32)
+    if metric != "l2":
+        x = np.maximum(x, 0) + np.float32(0.01) * (r.random(size=(n, d)) < 0.7)
+    if dup:
+        x[n - dup:] = x[:dup]
+    return x
+
+
+@SET
+@given(seed=st.integers(0, 10**6), n=st.integers(1, 700), nq=st.integers(1, 70), d=st.integers(1, 150), k=st.integers(1, 12),
+       dup=st.integers(0, 20), metric=st.sampled_from(["l2", "chi2", "kl"]))
+def test_topk_any_shape(fir, port, seed, n, nq, d, k, dup, metric):
+    g = port.normalize_rows(metric, _rows(seed, n, d, metric, min(dup, n // 2)))
+    q = port.normalize_rows(metric, _rows(seed + 1, nq, d, metric))
+    g, q = np.nan_to_num(g), np.nan_to_num(q)             # an all-zero row normalises to NaN in the reference; keep the data finite
+    gal = fir.Gallery(g, None, metric)
+    idx, dist = gal.search(q, k=k)
+    pi, pd = port.topk(metric, g, q, k)
+    assert np.array_equal(idx, pi) and np.array_equal(bits(dist), bits(pd))
+    gal.close()
+
+
+@SET
+@given(seed=st.integers(0, 10**6), n=st.integers(4100, 9000), nq=st.integers(1, 8), d=st.integers(8, 96), k=st.integers(1, 10),
+       metric=st.sampled_from(["l2", "chi2", "kl"]))
+def test_latency_mode_any_shape(fir, port, seed, n, nq, d, k, metric):
+    g = np.nan_to_num(port.normalize_rows(metric, _rows(seed, n, d, metric, 7)))
+    q = np.nan_to_num(port.normalize_rows(metric, _rows(seed + 1, nq, d, metric)))
+    gal = fir.Gallery(g, None, metric)
+    idx, dist = gal.search(q, k=k)
+    pi, pd = port.topk(metric, g, q, k)
+    assert np.array_equal(idx, pi) and np.array_equal(bits(dist), bits(pd))
+    gal.close()
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+@given(seed=st.integers(0, 10**6), n=st.integers(6, 400), nq=st.integers(1, 90), fc=st.integers(1, 255), c=st.integers(5, 9),
+       th=st.sampled_from([0.5, 0.7, 0.9, 1.3]), kind=st.sampled_from(["posteriors", "diff", "ratio"]))
+def test_twd_any_shape(fir, port, seed, n, nq, fc, c, th, kind):
+    d = max(256, ((256 + fc - 1) // fc) * fc)
+    g = port.normalize_rows("l2", _rows(seed, n, d, "l2"))
+    q = port.normalize_rows("l2", _rows(seed + 7, nq, d, "l2") * 0.3 + g[np.arange(nq) % n])
+    gl = (np.arange(n) % c).astype(np.int32)
+    gal = fir.Gallery(g, gl, "l2")
+    got = gal.twd_proposed(q, fc, th)
+    want = port.twd_proposed("l2", g, gl, q, fc, th)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    cth = th * 0.01 if kind == "diff" else th * 0.5
+    got = gal.twd_conventional(q, kind, cth, fc)
+    want = port.twd_conventional("l2", g, gl, c, q, kind, cth, fc)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    gal.close()

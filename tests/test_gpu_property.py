@@ -66,3 +66,20 @@ def test_twd_any_shape(fir, port, seed, n, nq, fc, c, th, kind):
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
     gal.close()
+
+
+@settings(max_examples=14, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+@given(seed=st.integers(0, 10**6), n=st.integers(1, 6000), nq=st.integers(1, 300), d=st.integers(16, 520), k=st.integers(1, 28),
+       dup=st.integers(0, 40), scale=st.sampled_from([1.0, 1e-3, 37.0]))
+def test_tensor_path_any_shape(fir, port, seed, n, nq, d, k, dup, scale):
+    """The tcgen05 path forced on shapes it would not normally be chosen for: partial tiles, one-row galleries, k above the
+    gallery size, unnormalised magnitudes, duplicate rows (ties) — always the exact answer."""
+    g = _rows(seed, n, d, "l2", min(dup, n // 2)) * np.float32(scale)
+    q = _rows(seed + 1, nq, d, "l2") * np.float32(scale)
+    if nq > 3 and n > 3:
+        q[:3] = g[:3]                                              # exact hits: distance 0 against duplicates
+    gal = fir.Gallery(g, None, "l2")
+    idx, dist = gal.search(q, k=k, path=fir.PATH_TENSOR)
+    pi, pd = port.topk("l2", g, q, k)
+    assert np.array_equal(idx, pi) and np.array_equal(bits(dist), bits(pd))
+    gal.close()

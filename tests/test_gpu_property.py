@@ -83,3 +83,78 @@ def test_tensor_path_any_shape(fir, port, seed, n, nq, d, k, dup, scale):
     pi, pd = port.topk("l2", g, q, k)
     assert np.array_equal(idx, pi) and np.array_equal(bits(dist), bits(pd))
     gal.close()
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+@given(seed=st.integers(0, 10**6), n=st.integers(400, 3500), nq=st.integers(1, 60), d=st.integers(4, 72), c=st.integers(2, 40),
+       metric=st.sampled_from(["l2", "chi2"]), thr_scale=st.sampled_from([1.0, 1.0, 0.3, 0.02]), m_frac=st.sampled_from([0.0, 0.01, 0.1, 0.5, 1.0]))
+def test_dem_build_and_search_any_shape(fir, port, seed, n, nq, d, c, metric, thr_scale, m_frac):
+    """Directed enumeration: the farthest-point chain, the pivot matrix, the FAR-quantile threshold and the ordered candidate
+    walk (early exits, budget exhaustion, several rounds) against the restatement on random ragged problems."""
+    r = np.random.default_rng(seed)
+    labels = np.sort(r.integers(0, c, size=n)).astype(np.int32)          # class-major, ragged class sizes (some may be empty)
+    cen = r.normal(size=(c, d)).astype(np.float32)
+    x = cen[labels] + r.normal(scale=0.7, size=(n, d)).astype(np.float32)
+    qx = cen[r.integers(0, c, size=nq)] + r.normal(scale=0.7, size=(nq, d)).astype(np.float32)
+    if metric != "l2":
+        x, qx = np.abs(x), np.abs(qx)
+    g, q = port.normalize_rows(metric, x), port.normalize_rows(metric, qx)
+    pivot0 = int(r.integers(0, n))
+    gal = fir.Gallery(g, labels, metric)
+    dem = fir.Dem(gal, pivot0=pivot0)
+    pb = port.dem_build(metric, g, labels, pivot0)
+    assert dem.n_pivots == pb["n_pivots"]
+    assert np.array_equal(dem.pivots, pb["pivots"][: dem.n_pivots])
+    assert np.array_equal(bits(dem.P), bits(pb["P"]))
+    assert bits(np.float32(dem.threshold)) == bits(pb["threshold"])
+    thr = float(dem.threshold) * thr_scale
+    walker = dem if thr_scale == 1.0 else fir.Dem(gal, state=(dem.pivots, dem.P, thr))
+    M = int(m_frac * n)
+    got = walker.search(q, M)
+    want = port.dem_search(metric, g, dem.pivots, dem.P, thr, M, q)
+    for name, a, b in zip(("idx", "dist", "below", "evals"), got, want):
+        assert np.array_equal(a, b), name
+    if walker is not dem:
+        walker.close()
+    dem.close()
+    gal.close()
+
+
+@settings(max_examples=10, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+@given(seed=st.integers(0, 10**6), d=st.integers(3, 130), c=st.integers(5, 12), per=st.integers(2, 40), nq=st.integers(1, 80),
+       K=st.integers(1, 9), clusters=st.integers(1, 6))
+def test_fp64_classifiers_any_shape(fir, port, seed, d, c, per, nq, K, clusters):
+    """kNN / PNN / sequential PNN / FPNN / k-medoids + reduced PNN against the restatement, ragged class sizes."""
+    r = np.random.default_rng(seed)
+    sizes = r.integers(max(1, per // 2), per + 1, size=c)
+    labels = np.repeat(np.arange(c), sizes).astype(np.int32)
+    cen = r.normal(size=(c, d))
+    rows = cen[labels] + r.normal(scale=0.9, size=(len(labels), d))
+    rows /= np.linalg.norm(rows, axis=1, keepdims=True)
+    te = cen[r.integers(0, c, size=nq)] + r.normal(scale=0.9, size=(nq, d))
+    te /= np.linalg.norm(te, axis=1, keepdims=True)
+    avg = np.array([sum(rows[:, f].tolist()) for f in range(d)]) / len(rows)
+    sd = rows.std(axis=0, ddof=1) if len(rows) > 1 else np.ones(d)
+    clf = fir.Classifier(rows, labels, c, avg)
+    assert np.array_equal(clf.knn(te, K), port.knn(rows, labels, c, avg, te, K))
+    lab, sc = clf.pnn(te)
+    psc, plab = port.pnn(rows, labels, c, avg, te)
+    assert np.array_equal(lab, plab)
+    np.testing.assert_allclose(sc, psc, rtol=1e-5, atol=0)
+    assert np.array_equal(clf.pnn_sequential(te), port.pnn_seq(rows, labels, c, avg, te))
+    clf.close()
+    f = fir.Fpnn(rows, labels, c, avg, sd, 1.0)
+    pa, pJ = port.fpnn_train(rows, labels, c, avg, sd, 1.0)
+    assert f.J == pJ
+    np.testing.assert_allclose(f.coefficients, pa, rtol=0, atol=1e-12)
+    # labels: CUDA's cos/sin differ from glibc's in the last bits, so only near-ties may differ — none on this data
+    assert np.array_equal(f.predict(te), port.fpnn_predict(pa, pJ, c, avg, sd, te, 1.0))
+    assert np.array_equal(f.predict(te, sequential=True, output_ratio=0.95), port.fpnn_predict(pa, pJ, c, avg, sd, te, 1.0, sequential=True, output_ratio=0.95))
+    f.close()
+    try:
+        want = port.kmedoids(rows, labels, c, clusters)
+    except ValueError:                                                   # a cluster ran empty: undefined behaviour in the reference
+        with pytest.raises(fir.FirError):
+            fir.kmedoids_select(rows, labels, c, clusters)
+        return
+    assert np.array_equal(fir.kmedoids_select(rows, labels, c, clusters), want)

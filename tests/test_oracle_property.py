@@ -76,3 +76,32 @@ def test_sequential_pnn_and_fpnn(port, ref_l2, seed, d, c, per):
     pa, pJ = port.fpnn_train(rows[tr], trl, c, avg, sd, 1.0)
     assert pJ == J and np.array_equal(pa.view(np.int64), a.view(np.int64))
     assert np.array_equal(port.fpnn_predict(pa, pJ, c, avg, sd, rows[te], 1.0, sequential=True, output_ratio=0.95), lab)
+
+
+@settings(max_examples=10, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+@given(seed=st.integers(0, 10**6), n=st.integers(340, 1500), nq=st.integers(1, 25), d=st.integers(4, 48), c=st.integers(2, 25),
+       metric=st.sampled_from(["l2", "chi2", "kl"]), m_frac=st.sampled_from([0.0, 0.02, 0.2, 1.0]), thr_scale=st.sampled_from([1.0, 0.3, 0.02]))
+def test_directed_enumeration(port, request, seed, n, nq, d, c, metric, m_frac, thr_scale):
+    """DirectedEnumeration: verbatim constructor + recognize against the restatement — pivot chain, pivot-distance rows,
+    threshold, then the candidate walk with the state injected at a scaled threshold (early exits ... full budgets)."""
+    ref = request.getfixturevalue("ref_" + metric)
+    r = np.random.default_rng(seed)
+    labels = np.sort(r.integers(0, c, size=n)).astype(np.int32)
+    cen = r.normal(size=(c, d)).astype(np.float32)
+    x = cen[labels] + r.normal(scale=0.7, size=(n, d)).astype(np.float32)
+    qx = cen[r.integers(0, c, size=nq)] + r.normal(scale=0.7, size=(nq, d)).astype(np.float32)
+    if metric != "l2":
+        x, qx = np.abs(x) + np.float32(1e-3), np.abs(qx) + np.float32(1e-3)
+    g, q = port.normalize_rows(metric, x), port.normalize_rows(metric, qx)
+    rd = ref.dem_create(g, labels, seed=seed % 977 + 1)
+    pb = port.dem_build(metric, g, labels, int(rd.pivots[0]))
+    assert pb["n_pivots"] == rd.n_pivots and np.array_equal(pb["pivots"][: rd.n_pivots], rd.pivots)
+    assert np.array_equal(bits(pb["P"]), bits(rd.P())) and bits(pb["threshold"]) == bits(np.float32(rd.threshold))
+    M = int(m_frac * n)
+    thr = float(rd.threshold) * thr_scale
+    inj = rd if thr_scale == 1.0 else ref.dem_create_injected(g, labels, rd.pivots, rd.P(), thr)
+    for a, b in zip(inj.search(q, M), port.dem_search(metric, g, rd.pivots, rd.P(), thr, M, q)):
+        assert np.array_equal(a, b)
+    if inj is not rd:
+        inj.close()
+    rd.close()

@@ -87,7 +87,7 @@ def test_tensor_path_any_shape(fir, port, seed, n, nq, d, k, dup, scale):
 
 @settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
 @given(seed=st.integers(0, 10**6), n=st.integers(400, 3500), nq=st.integers(1, 60), d=st.integers(4, 72), c=st.integers(2, 40),
-       metric=st.sampled_from(["l2", "chi2"]), thr_scale=st.sampled_from([1.0, 1.0, 0.3, 0.02]), m_frac=st.sampled_from([0.0, 0.01, 0.1, 0.5, 1.0]))
+       metric=st.sampled_from(["l2", "chi2", "kl"]), thr_scale=st.sampled_from([1.0, 1.0, 0.3, 0.02]), m_frac=st.sampled_from([0.0, 0.01, 0.1, 0.5, 1.0]))
 def test_dem_build_and_search_any_shape(fir, port, seed, n, nq, d, c, metric, thr_scale, m_frac):
     """Directed enumeration: the farthest-point chain, the pivot matrix, the FAR-quantile threshold and the ordered candidate
     walk (early exits, budget exhaustion, several rounds) against the restatement on random ragged problems."""

@@ -148,11 +148,11 @@ template <int QPT>
 __global__ void __launch_bounds__(256) dem_likelihood_kernel(const float* __restrict__ pd, const int32_t* __restrict__ qlist, int nqc, int S,
                                                              const float* __restrict__ P, int64_t n, const unsigned char* __restrict__ in_tail,
                                                              float* __restrict__ lik, float* __restrict__ gmin, int64_t ng) {
-    __shared__ float dq[QPT][32];
+    __shared__ __align__(16) float dq[32][QPT];                // [pivot][query]: four queries per broadcast LDS.128
     const int q0 = blockIdx.y * QPT;
     for (int t = threadIdx.x; t < QPT * 32; t += 256) {
         const int qq = t >> 5, i = t & 31;
-        dq[qq][i] = (q0 + qq < nqc && i < S) ? pd[(int64_t)qlist[q0 + qq] * S + i] : 0.f;
+        dq[i][qq] = (q0 + qq < nqc && i < S) ? pd[(int64_t)qlist[q0 + qq] * S + i] : 0.f;
     }
     __syncthreads();
     const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -165,9 +165,13 @@ __global__ void __launch_bounds__(256) dem_likelihood_kernel(const float* __rest
             const float m = P[(int64_t)i * n + v];
             if (m >= 0.f) {                                                     // :456
 #pragma unroll
-                for (int qq = 0; qq < QPT; ++qq) {
-                    const float t = __fsub_rn(dq[qq][i], m);                    // :457
-                    acc[qq] = __fadd_rn(acc[qq], __fmul_rn(t, t));              // :458
+                for (int qq = 0; qq < QPT; qq += 4) {
+                    const float4 dv = *reinterpret_cast<const float4*>(&dq[i][qq]);
+                    float t;
+                    t = __fsub_rn(dv.x, m); acc[qq + 0] = __fadd_rn(acc[qq + 0], __fmul_rn(t, t));   // :457-458
+                    t = __fsub_rn(dv.y, m); acc[qq + 1] = __fadd_rn(acc[qq + 1], __fmul_rn(t, t));
+                    t = __fsub_rn(dv.z, m); acc[qq + 2] = __fadd_rn(acc[qq + 2], __fmul_rn(t, t));
+                    t = __fsub_rn(dv.w, m); acc[qq + 3] = __fadd_rn(acc[qq + 3], __fmul_rn(t, t));
                 }
             }
         }

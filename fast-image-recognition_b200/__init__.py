@@ -36,7 +36,11 @@ EXPORTS = [
     "fir_twd_conventional", "fir_twd_proposed", "fir_kmedoids_select", "fir_classifier_set_total",
     "fir_fpnn_create", "fir_fpnn_destroy", "fir_fpnn_info", "fir_fpnn_get_coefficients", "fir_fpnn_predict",
     "fir_dem_build", "fir_dem_from_state", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
-    "fir_dem_get_min_other", "fir_dem_search", "fir_index_save", "fir_index_load",
+    "fir_dem_get_min_other", "fir_dem_search", "fir_index_save", "fir_index_load", "fir_synth_rows",
+    "fir_comm_unique_id", "fir_comm_init_rank", "fir_comm_destroy", "fir_comm_info",
+    "fir_shard_search_topk", "fir_shard_class_min", "fir_shard_pnn_scores",
+    "fir_sharded_create", "fir_sharded_destroy", "fir_sharded_info", "fir_sharded_shard",
+    "fir_sharded_search_topk", "fir_sharded_class_min", "fir_sharded_pnn_scores",
 ]
 
 
@@ -109,6 +113,21 @@ def lib():
     L.fir_dem_get_pivot_matrix.argtypes = [vp, vp]
     L.fir_dem_get_min_other.argtypes = [vp, vp]
     L.fir_dem_search.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp]
+    L.fir_synth_rows.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, C.c_uint32, C.c_float, i32, vp]
+    L.fir_comm_unique_id.argtypes = [vp]
+    L.fir_comm_init_rank.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.fir_comm_destroy.argtypes = [vp]
+    L.fir_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.fir_shard_search_topk.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp]
+    L.fir_shard_class_min.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    L.fir_shard_pnn_scores.argtypes = [vp, vp, vp, i64, f64, i64, i32, vp, vp]
+    L.fir_sharded_create.argtypes = [vp, vp, i64, i32, i32, i32, C.POINTER(vp)]
+    L.fir_sharded_destroy.argtypes = [vp]
+    L.fir_sharded_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
+    L.fir_sharded_shard.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
+    L.fir_sharded_search_topk.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+    L.fir_sharded_class_min.argtypes = [vp, vp, i64, vp, vp]
+    L.fir_sharded_pnn_scores.argtypes = [vp, vp, i64, f64, vp, vp]
     _lib = L
     return L
 
@@ -498,3 +517,126 @@ class Dem:
         evals = _out((nq,), np.int32, "int32", space == DEVICE, dev)
         _check(lib().fir_dem_search(self._h, _ptr(q), nq, int(count_to_check), space, _ptr(idx), _ptr(dist), _ptr(below), _ptr(evals)))
         return idx, dist, below, evals
+
+
+COMM_ID_BYTES = 128
+
+
+class Comm:
+    """One rank of the library's NCCL communicator (fir_comm): one per process / GPU."""
+
+    def __init__(self, rank=0, world=1, comm_id=None):
+        h = C.c_void_p(None)
+        buf = (C.c_char * COMM_ID_BYTES).from_buffer_copy(comm_id) if comm_id is not None else None
+        _check(lib().fir_comm_init_rank(buf, int(rank), int(world), C.byref(h)))
+        self._h, self.rank, self.world = h, int(rank), int(world)
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * COMM_ID_BYTES)()
+        _check(lib().fir_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch_distributed(cls, dist):
+        """The launcher's process group only carries the 128-byte id from rank 0 to the others."""
+        if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+            return cls(0, 1)
+        box = [cls.unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(dist.get_rank(), dist.get_world_size(), box[0])
+
+    @property
+    def nccl_version(self):
+        v = C.c_int32(0)
+        _check(lib().fir_comm_info(self._h, None, None, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fir_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RankShard:
+    """This rank's row shard of a gallery + the communicator: collective search / class reductions (fir_shard_*)."""
+
+    def __init__(self, gallery, comm, n_total):
+        self.gallery, self.comm, self.n_total = gallery, comm, int(n_total)
+
+    def search(self, queries, k=1, path=PATH_AUTO, out=None):
+        q, space = _prep(queries, np.float32, "float32")
+        nq = int(q.shape[0])
+        if out is not None:
+            idx, dist = out
+        else:
+            idx = _out((nq, k), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
+            dist = _out((nq, k), np.float32, "float32", space == DEVICE, getattr(q, "device", None))
+        _check(lib().fir_shard_search_topk(self.gallery._h, self.comm._h, _ptr(q), nq, k, path, space, _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def class_min(self, queries):
+        q, space = _prep(queries, np.float32, "float32")
+        nq, nc = int(q.shape[0]), self.gallery.n_classes
+        mn = _out((nq, nc), np.float32, "float32", space == DEVICE, getattr(q, "device", None))
+        arg = _out((nq, nc), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
+        _check(lib().fir_shard_class_min(self.gallery._h, self.comm._h, _ptr(q), nq, space, _ptr(mn), _ptr(arg)))
+        return mn, arg
+
+    def pnn_scores(self, queries, var):
+        q, space = _prep(queries, np.float32, "float32")
+        nq, nc = int(q.shape[0]), self.gallery.n_classes
+        sc = _out((nq, nc), np.float64, "float64", space == DEVICE, getattr(q, "device", None))
+        lab = _out((nq,), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
+        _check(lib().fir_shard_pnn_scores(self.gallery._h, self.comm._h, _ptr(q), nq, float(var), self.n_total, space, _ptr(sc), _ptr(lab)))
+        return sc, lab
+
+
+class Sharded:
+    """The whole class-major gallery (host arrays) row-sharded over the GPUs of the box by ONE process (fir_sharded_*)."""
+
+    def __init__(self, rows, labels=None, metric="l2", n_gpus=0):
+        m = METRICS[metric] if isinstance(metric, str) else metric
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        lab = np.ascontiguousarray(labels, dtype=np.int32) if labels is not None else None
+        h = C.c_void_p(None)
+        _check(lib().fir_sharded_create(_ptr(rows), _ptr(lab), rows.shape[0], rows.shape[1], m, int(n_gpus), C.byref(h)))
+        self._h = h
+        g, n, d, nc = C.c_int32(0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        _check(lib().fir_sharded_info(self._h, C.byref(g), C.byref(n), C.byref(d), C.byref(nc)))
+        self.n_gpus, self.n, self.d, self.n_classes = g.value, n.value, d.value, nc.value
+
+    def search(self, queries, k=1, path=PATH_AUTO):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        idx, dist = np.empty((q.shape[0], k), np.int32), np.empty((q.shape[0], k), np.float32)
+        _check(lib().fir_sharded_search_topk(self._h, _ptr(q), q.shape[0], k, path, _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def class_min(self, queries):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        mn, arg = np.empty((q.shape[0], self.n_classes), np.float32), np.empty((q.shape[0], self.n_classes), np.int32)
+        _check(lib().fir_sharded_class_min(self._h, _ptr(q), q.shape[0], _ptr(mn), _ptr(arg)))
+        return mn, arg
+
+    def pnn_scores(self, queries, var):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        sc, lab = np.empty((q.shape[0], self.n_classes), np.float64), np.empty(q.shape[0], np.int32)
+        _check(lib().fir_sharded_pnn_scores(self._h, _ptr(q), q.shape[0], float(var), _ptr(sc), _ptr(lab)))
+        return sc, lab
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fir_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

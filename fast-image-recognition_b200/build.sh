@@ -18,5 +18,7 @@ for src in "$HERE"/csrc/*.cu; do
   fi
 done
 for p in "${pids[@]}"; do wait "$p"; done
-$NVCC -shared -cudart static -gencode arch=compute_100a,code=sm_100a -o "$OUT" "$OBJ"/*.o
+$NVCC -shared -cudart static -gencode arch=compute_100a,code=sm_100a -o "$OUT" "$OBJ"/*.o -ldl
+# host twin of the synthetic-workload generator (plain C, no CUDA): used by the CPU reference arm and the CPU tests
+gcc -O2 -ffp-contract=off -fPIC -shared -pthread -o "$HERE/libfir_synth_host.so" "$HERE/csrc/synth_host.c"
 echo "built $OUT"

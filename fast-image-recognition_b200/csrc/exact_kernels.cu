@@ -249,31 +249,54 @@ int launch_exact_tiles(int metric, const ExactParams& p, cudaStream_t s) {
 // Lexicographic (dist, idx) merge of n_parts sorted lists per query.  idx < 0 marks an empty slot.
 // Used for the gallery splits of one GPU and for the all-gathered per-GPU lists (fir_merge_topk).
 // ---------------------------------------------------------------------------------------------------
-__global__ void merge_parts_kernel(const float* __restrict__ pd, const int32_t* __restrict__ pi, int n_parts,
+// One warp per query.  Every part's current head is kept as a packed 64-bit key (ordered distance bits << 32 | index;
+// ~0 = exhausted) in shared memory, lane l looking after parts l, l+32, ...; a round is a lane-local scan of those keys, a
+// five-step shuffle tournament, and one global load by the lane whose part won.  The key order is exactly the
+// lexicographic (dist, idx) order of the reference's strict '<' scan in index order.
+constexpr int MERGE_WARPS = 4;
+__device__ __forceinline__ unsigned long long merge_key(const float* __restrict__ pd, const int32_t* __restrict__ pi, int64_t o) {
+    const int32_t ci = pi[o];
+    return ci < 0 ? ~0ull : (((unsigned long long)ordered_bits(pd[o]) << 32) | (uint32_t)ci);
+}
+__global__ void __launch_bounds__(MERGE_WARPS * 32) merge_parts_kernel(const float* __restrict__ pd, const int32_t* __restrict__ pi, int n_parts,
                                    int64_t part_stride, int64_t q_stride, int64_t nq, int k, int64_t index_offset,
                                    const int32_t* qmap, const int32_t* n_active, float* od, int32_t* oi, int64_t active_offset,
                                    int64_t active_cap) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(16) unsigned char merge_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int np32 = (n_parts + 31) & ~31;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(merge_smem) + (size_t)warp * np32;
+    unsigned short* head = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned long long*>(merge_smem) + (size_t)MERGE_WARPS * np32) + (size_t)warp * np32;
+    const int64_t i = (int64_t)blockIdx.x * MERGE_WARPS + warp;
     int64_t na = n_active ? (int64_t)*n_active : nq;
     if (n_active) { na = max((int64_t)0, na - active_offset); if (active_cap > 0) na = min(na, active_cap); }
     if (i >= na) return;
-    int64_t q = qmap ? (int64_t)qmap[active_offset + i] : i;
-    constexpr int MAXP = 1024;
-    unsigned short head[MAXP];
-    for (int s = 0; s < n_parts; ++s) head[s] = 0;
+    const int64_t q = qmap ? (int64_t)qmap[active_offset + i] : i;
+    for (int s = lane; s < np32; s += 32) {                     // parts are indexed by active position, outputs by query
+        keys[s] = s < n_parts ? merge_key(pd, pi, (int64_t)s * part_stride + i * q_stride) : ~0ull;
+        head[s] = 0;
+    }
+    __syncwarp();
     for (int r = 0; r < k; ++r) {
-        float bd = 0.f; int32_t bi = -1; int bs = -1;
-        for (int s = 0; s < n_parts; ++s) {
-            int h = head[s];
-            if (h >= k) continue;
-            int64_t o = (int64_t)s * part_stride + i * q_stride + h;   // parts are indexed by active position, outputs by query
-            int32_t ci = pi[o];
-            if (ci < 0) continue;
-            float cd = pd[o];
-            if (bs < 0 || cd < bd || (cd == bd && ci < bi)) { bd = cd; bi = ci; bs = s; }
+        unsigned long long best = ~0ull; int bs = -1;
+        for (int s = lane; s < np32; s += 32) { const unsigned long long v = keys[s]; if (v < best) { best = v; bs = s; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (ov < best) { best = ov; bs = os; }              // keys of live entries are distinct (an index appears once)
         }
-        if (bs >= 0) { head[bs]++; od[q * k + r] = bd; oi[q * k + r] = (int32_t)(bi + index_offset); }
-        else { od[q * k + r] = 0.f; oi[q * k + r] = -1; }
+        if (best == ~0ull) {                                    // every part exhausted: pad the rest
+            for (int t = r + lane; t < k; t += 32) { od[q * k + t] = 0.f; oi[q * k + t] = -1; }
+            break;
+        }
+        if ((bs & 31) == lane) {
+            od[q * k + r] = from_ordered_bits((uint32_t)(best >> 32));
+            oi[q * k + r] = (int32_t)((int64_t)(int32_t)(uint32_t)best + index_offset);
+            const int h = ++head[bs];
+            keys[bs] = h < k ? merge_key(pd, pi, (int64_t)bs * part_stride + i * q_stride + h) : ~0ull;
+        }
+        __syncwarp();
     }
 }
 
@@ -282,7 +305,8 @@ int launch_merge_parts(const float* pd, const int32_t* pi, int n_parts, int64_t 
                        float* od, int32_t* oi, cudaStream_t s, int64_t active_offset, int64_t active_cap) {
     if (nq <= 0) return FIR_OK;
     if (n_parts > 1024) return fail(FIR_ERR_UNSUPPORTED, "more than 1024 parts to merge");
-    merge_parts_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(pd, pi, n_parts, part_stride, q_stride, nq, k, index_offset,
+    const size_t smem = (size_t)MERGE_WARPS * ((n_parts + 31) & ~31) * (8 + 2);
+    merge_parts_kernel<<<(unsigned)ceil_div(nq, MERGE_WARPS), MERGE_WARPS * 32, smem, s>>>(pd, pi, n_parts, part_stride, q_stride, nq, k, index_offset,
                                                                    qmap, n_active, od, oi, active_offset, active_cap);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;

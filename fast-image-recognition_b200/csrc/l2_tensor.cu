@@ -372,7 +372,10 @@ struct CandParams {
     int32_t* cand_idx;
     float* slot_bound;
     const int32_t* skip_if_zero; // optional device counter: nothing to do when it reads 0 (second pass without flagged queries)
-    int debug_nolist;           // measurement aid (FIR_TENSOR_DEBUG_NOLIST=1): thresholds at -inf, nothing is ever listed — WRONG results
+#ifdef FIR_MEASURE
+    int debug_nolist;           // measurement builds only (-DFIR_MEASURE, FIR_TENSOR_DEBUG_NOLIST=1): thresholds at -inf, nothing is ever
+                                // listed — WRONG results; compiled out of the shipped library
+#endif
     int mins_only;              // seed pass (R = 4): the four slots are plain minima over the four 32-column groups, no lists
     const float* seed_thr;      // optional [nq]: approximate squared distance above which a row cannot matter (see seed pass)
 };
@@ -618,7 +621,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
                 mx = __int_as_float(0x7f800000);
                 cur_qb = qb;
                 { const int64_t qr = qb * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f));
-                  tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx; if (p.debug_nolist) tau = -mx; thr = tau; }
+                  tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx;
+#ifdef FIR_MEASURE
+                  if (p.debug_nolist) tau = -mx;
+#endif
+                  thr = tau; }
             }
             mbar_wait(smem_u32(&nx_full[as]), aphase);
             mbar_wait(smem_u32(&tmem_full[as]), aphase);
@@ -834,7 +841,11 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
                 mx = __int_as_float(0x7f800000);
                 cur_qb = qb;
                 { const int64_t qr = qb * (2 * BM) + rank * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f));
-                  tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx; if (p.debug_nolist) tau = -mx; thr = tau; }
+                  tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx;
+#ifdef FIR_MEASURE
+                  if (p.debug_nolist) tau = -mx;
+#endif
+                  thr = tau; }
             }
             mbar_wait(smem_u32(&nx_full[as]), aphase);
             mbar_wait_cluster(smem_u32(&tmem_full[as]), aphase);
@@ -882,7 +893,9 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     p.gal_norm2 = a.gal->norm2; p.qry_norm2 = a.qry->norm2;
     p.gal_meta = a.gal->meta; p.qry_row_scale = a.qry->row_scale;
     p.cand_val = a.cand_val; p.cand_idx = a.cand_idx; p.slot_bound = a.slot_bound; p.seed_thr = a.seed_thr; p.skip_if_zero = a.skip_if_zero; p.mins_only = a.mins_only;
+#ifdef FIR_MEASURE
     { static const int nolist = [] { const char* e = getenv("FIR_TENSOR_DEBUG_NOLIST"); return e ? atoi(e) : 0; }(); p.debug_nolist = nolist; }
+#endif
     const bool a_res = p.nkb <= MAX_RES_KB;
     const size_t smem = a.ctas == 2 ? cand_smem_bytes_2cta(a_res) : cand_smem_bytes(a_res);
     auto go = [&](auto kern) -> int {

@@ -38,7 +38,8 @@ typedef enum fir_status {
     FIR_ERR_CUDA = 2,
     FIR_ERR_OOM = 3,
     FIR_ERR_UNSUPPORTED = 4,
-    FIR_ERR_INTERNAL = 5
+    FIR_ERR_INTERNAL = 5,
+    FIR_ERR_NCCL = 6
 } fir_status;
 
 /* compile-time switch of the reference: USE_L2_DISTANCE (qt_cpp/db_features.h:12) and the
@@ -247,6 +248,52 @@ int fir_fpnn_predict(fir_fpnn* f, const double* queries, int64_t nq, int32_t seq
  * or out_dem itself is NULL. */
 int fir_index_save(const fir_gallery* g, const fir_dem* dem /* or NULL */, const char* path);
 int fir_index_load(const char* path, fir_gallery** out_gallery, fir_dem** out_dem /* or NULL */);
+
+/* ---- multi-GPU: gallery row shards + NCCL ----------------------------------------
+ * The reference is single-device; its callers (testANN qt_cpp/ann.cpp:52-69, testSetRecognition :94-109) walk ONE
+ * std::vector<ImageInfo>.  Here that vector is cut into contiguous row shards, one per GPU (global indices through
+ * index_offset), queries are replicated, every GPU runs the complete single-GPU pipeline on its shard and ONE exchange
+ * follows: top-k lists packed into 64-bit (ordered dist, idx) keys → ncclAllGather → k-way merge;
+ * per-class minima → ncclAllReduce(min) on the same keys; PNN partial sums → ncclAllReduce(sum, fp64).
+ * The answers equal the single-gallery ones bit for bit (ties are broken by GLOBAL index); fp64 PNN sums within 1e-5
+ * relative (the summation order across shards differs).  NCCL is dlopen'ed on first use.
+ *
+ * (1) one process per GPU: every rank creates its own shard handle (fir_gallery_create with index_offset = first row)
+ *     and joins a communicator; rank 0 obtains the id and the launcher distributes the 128 bytes. */
+typedef struct fir_comm fir_comm;
+#define FIR_COMM_ID_BYTES 128
+int fir_comm_unique_id(void* id_out /* FIR_COMM_ID_BYTES */);
+int fir_comm_init_rank(const void* id, int32_t rank, int32_t world, fir_comm** out); /* on the current device; world = 1 needs no id */
+int fir_comm_destroy(fir_comm* c);
+int fir_comm_info(const fir_comm* c, int32_t* rank, int32_t* world, int32_t* nccl_version);
+/* Collective: every rank calls with the same queries (FIR_DEVICE: replicated device batch, asynchronous on the shard's
+ * stream; FIR_HOST: the same host batch on every rank — each rank uploads 1/world of the rows over its own PCIe link,
+ * an NVLink all-gather assembles the batch, the call synchronises) and every rank receives the merged result. */
+int fir_shard_search_topk(fir_gallery* shard, fir_comm* c, const float* queries, int64_t nq, int32_t k, int32_t path, int32_t memspace,
+                          int32_t* out_idx, float* out_dist);
+int fir_shard_class_min(fir_gallery* shard, fir_comm* c, const float* queries, int64_t nq, int32_t memspace, float* out_min, int32_t* out_arg);
+int fir_shard_pnn_scores(fir_gallery* shard, fir_comm* c, const float* queries, int64_t nq, double var, int64_t n_total, int32_t memspace,
+                         double* out_scores, int32_t* out_label);
+/* (2) ONE process driving n_gpus devices (<= 0: all visible): rows/labels are the whole class-major gallery in host
+ *     memory; shard r = rows [n*r/G, n*(r+1)/G) on device r; ncclCommInitAll.  Host buffers in and out. */
+typedef struct fir_sharded fir_sharded;
+int fir_sharded_create(const float* rows, const int32_t* labels, int64_t n, int32_t d, int32_t metric, int32_t n_gpus, fir_sharded** out);
+int fir_sharded_destroy(fir_sharded* s);
+int fir_sharded_info(const fir_sharded* s, int32_t* n_gpus, int64_t* n, int32_t* d, int32_t* n_classes);
+int fir_sharded_shard(fir_sharded* s, int32_t rank, fir_gallery** shard, fir_comm** comm); /* borrowed handles of shard `rank` */
+int fir_sharded_search_topk(fir_sharded* s, const float* queries, int64_t nq, int32_t k, int32_t path, int32_t* out_idx, float* out_dist);
+int fir_sharded_class_min(fir_sharded* s, const float* queries, int64_t nq, float* out_min, int32_t* out_arg);
+int fir_sharded_pnn_scores(fir_sharded* s, const float* queries, int64_t nq, double var, double* out_scores, int32_t* out_label);
+
+/* ---- synthetic workloads (bench / tests; no reference counterpart) ----------------------------------
+ * Rows [row_lo, row_lo + n_rows) of the gallery (role 0) or query (role 1) matrix of a BASELINE.json config, generated on
+ * the device by a counter-based Philox4x32-10 keyed by (seed, row, column) — csrc/synth_common.h — so that every rank of a
+ * sharded run materialises its own rows of the SAME gallery and the host can regenerate identical bits
+ * (libfir_synth_host.so: fir_synth_rows_host, same arguments + a thread count).  Values are class centroid + sigma * noise,
+ * optionally ReLU'd; the caller applies fir_normalize_rows afterwards.  Gallery labels are class-major equal blocks
+ * ((row * n_classes) / n_total), query labels pseudo-random.  Device pointers; out_labels may be NULL. */
+int fir_synth_rows(float* out_rows, int32_t* out_labels, int64_t row_lo, int64_t n_rows, int64_t n_total, int32_t d,
+                   int32_t n_classes, int32_t role, uint32_t seed, float sigma, int32_t relu, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,10 @@ class _OracleLocal:
         i, d = self.port.topk(self.metric, self.rows, q, k)
         return np.where(i < 0, -1, i + self.lo).astype(np.int32), d
 
+    def class_min(self, q):
+        mn, arg = self.port.class_min(self.metric, self.rows, self.labels, 6, q)
+        return mn, np.where(arg < 0, -1, arg + self.lo).astype(np.int32)
+
     def pnn_scores(self, q, var, n_total=0):
         sc, lab = self.port.pnn_div(self.metric, self.rows, self.labels, 6, q, var)
         return sc * (self.rows.shape[0] / float(n_total)), lab
@@ -54,6 +58,9 @@ def _worker(rank, world, port_no, out):
     idx, dd = sg.search(q, k=7)
     oi, od = port.topk("l2", g, q, 7)
     ok = np.array_equal(idx, oi) and np.array_equal(dd.view(np.uint32), od.view(np.uint32))
+    mn, arg = sg.class_min(q)                           # all-reduce(min) of packed (dist, idx) keys
+    omn, oarg = port.class_min("l2", g, gl, 6, q)
+    ok = ok and np.array_equal(arg, oarg) and np.array_equal(mn.view(np.uint32), omn.view(np.uint32))
     sc, lab = sg.pnn_scores(q, 2e-4)
     osc, olab = port.pnn_div("l2", g, gl, 6, q, 2e-4)
     ok = ok and np.allclose(sc, osc, rtol=1e-9) and np.array_equal(lab, olab)
@@ -80,6 +87,23 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_key_format_roundtrip_and_order():
+    sharded = importlib.import_module("fast-image-recognition_b200.sharded")
+    rng = np.random.default_rng(0)
+    d = rng.standard_normal(4096).astype(np.float32)
+    d[:8] = [0.0, 1e-38, 3.4e38, -1.0, 0.5, 0.5, 100000.0, 1e-45]
+    i = rng.integers(0, 2**31 - 1, 4096).astype(np.int32)
+    i[100:110] = -1
+    keys = sharded.pack_keys(d, i)
+    dd, ii = sharded.unpack_keys(keys)
+    live = i >= 0
+    assert np.array_equal(ii, i) and np.array_equal(dd[live].view(np.uint32), d[live].view(np.uint32))
+    order = np.argsort(keys[live], kind="stable")
+    want = np.lexsort((i[live], d[live]))
+    assert np.array_equal(order, want)                  # key order = lexicographic (dist, idx); empties sort last
+    assert (keys[~live] == sharded.EMPTY_KEY).all() and keys[live].max() < sharded.EMPTY_KEY
 
 
 def test_merge_host_ties_and_empties():

@@ -58,6 +58,24 @@ def make_split_device(n_gallery, n_query, d, n_classes, metric="l2", sigma=0.5, 
     return g, gl, q, ql
 
 
+def caltech_sizes():
+    """Class sizes of a Caltech-101-shaped collection (qt_cpp/db.h:11,35,86): 101 classes, 8677 images, four classes above the
+    loader's 400-image cap (db_features.cpp:119,147-149), the rest between 31 and 239 — the real list is not in the reference
+    tree, so the tail is a fixed synthetic sequence with the same total."""
+    big = [800, 798, 435, 435]
+    rest = [31 + (i * 37) % 60 + (i % 7) * 5 for i in range(97)]
+    rest[0] = 239
+    fix = 8677 - sum(big) - sum(rest)
+    i = 1
+    while fix != 0:
+        step = 1 if fix > 0 else -1
+        if 31 <= rest[i] + step <= 239:
+            rest[i] += step
+            fix -= step
+        i = 1 + i % 96
+    return big + rest
+
+
 def write_features_file(path, rows, class_names, file_names=None):
     """The reference's text format: 3 lines per image — file name, class name, D floats printed as
     '{:f} ' (qt_cpp/dnn_feature_extractor.py:58-64; parsed by qt_cpp/db_features.cpp:52-57)."""

@@ -38,6 +38,9 @@ inline int& features_count() { static int d = 1536; return d; }          // qt_c
 inline int& metric() { static int m = FIR_L2; return m; }                // qt_cpp/db_features.h:12 default
 inline double& fraction() { static double f = 0.03; return f; }          // qt_cpp/db.h:72 (USE_CALTECH)
 inline bool& caltech_mode() { static bool c = true; return c; }          // qt_cpp/db.h:11
+// GPUs the matchers built from now on spread their gallery over (row shards + NCCL, fir_sharded_*): 1 = one GPU (default),
+// 0 = every visible device.  The reference is single-device; this is the one additive knob of the multi-GPU build.
+inline int& n_gpus() { static int g = 1; return g; }
 inline void check(int status, const char* what) {
     if (status != FIR_OK) throw std::runtime_error(std::string(what) + ": " + fir_last_error_string());
 }
@@ -66,8 +69,8 @@ namespace detail {
 struct PackedGallery {
     fir_gallery* g;
     int d;
-    PackedGallery(const std::vector<ImageInfo>& db, int metric) : g(0), d(db.empty() ? 0 : (int)db[0].features.size()) {
-        if (db.empty()) return;                                          // the reference answers -1 for every query
+    PackedGallery(const std::vector<ImageInfo>& db, int metric, bool build = true) : g(0), d(db.empty() ? 0 : (int)db[0].features.size()) {
+        if (db.empty() || !build) return;                                // empty: the reference answers -1 for every query
         std::vector<float> rows((size_t)db.size() * d);
         std::vector<int32_t> labels(db.size());
         for (size_t j = 0; j < db.size(); ++j) {
@@ -81,6 +84,25 @@ private:
     PackedGallery(const PackedGallery&);
     PackedGallery& operator=(const PackedGallery&);
 };
+// the same gallery cut into row shards over fir::n_gpus() devices (one process driving them all, csrc/sharded.cu)
+struct ShardedPackedGallery {
+    fir_sharded* s;
+    int d;
+    ShardedPackedGallery(const std::vector<ImageInfo>& db, int metric, int n_gpus) : s(0), d(db.empty() ? 0 : (int)db[0].features.size()) {
+        if (db.empty() || n_gpus == 1) return;
+        std::vector<float> rows((size_t)db.size() * d);
+        std::vector<int32_t> labels(db.size());
+        for (size_t j = 0; j < db.size(); ++j) {
+            std::copy(db[j].features.begin(), db[j].features.begin() + d, rows.begin() + j * (size_t)d);
+            labels[j] = db[j].classNo;
+        }
+        fir::check(fir_sharded_create(rows.data(), labels.data(), (int64_t)db.size(), d, metric, n_gpus, &s), "fir_sharded_create");
+    }
+    ~ShardedPackedGallery() { fir_sharded_destroy(s); }
+private:
+    ShardedPackedGallery(const ShardedPackedGallery&);
+    ShardedPackedGallery& operator=(const ShardedPackedGallery&);
+};
 inline std::vector<float> pack_queries(const std::vector<ImageInfo>& q, int d) {
     std::vector<float> rows((size_t)q.size() * d);
     for (size_t i = 0; i < q.size(); ++i) std::copy(q[i].features.begin(), q[i].features.begin() + d, rows.begin() + i * (size_t)d);
@@ -88,16 +110,17 @@ inline std::vector<float> pack_queries(const std::vector<ImageInfo>& q, int d) {
 }
 }  // namespace detail
 
-// feature_distance (db_features.cpp:22-42): a one-row gallery and a one-row query through fir_pair_distances.
-// start_pos must be 0 (every caller on the path passes 0); end_pos < 0 means all dimensions.
+// feature_distance (db_features.cpp:22-42): a one-row gallery and a one-row query through fir_pair_distances over the
+// window [start_pos, end_pos) — the sum starts at start_pos and the mean divides by end_pos - start_pos (:40);
+// end_pos < 0 means all dimensions (the reference's default is the FEATURES_COUNT macro).
 inline float feature_distance(const FeaturesVector& lhs, const FeaturesVector& rhs, int start_pos, int end_pos) {
     const int d = (int)std::min(lhs.size(), rhs.size());
     if (end_pos < 0 || end_pos > d) end_pos = d;
-    if (start_pos != 0) throw std::invalid_argument("feature_distance: start_pos != 0 is not on the accelerated path");
+    if (start_pos < 0 || start_pos >= end_pos) throw std::invalid_argument("feature_distance: empty window");
     fir_gallery* g = 0;
-    fir::check(fir_gallery_create(rhs.data(), 0, 1, end_pos, fir::metric(), FIR_HOST, 0, &g), "fir_gallery_create");
+    fir::check(fir_gallery_create(rhs.data() + start_pos, 0, 1, end_pos - start_pos, fir::metric(), FIR_HOST, 0, &g), "fir_gallery_create");
     int32_t idx = 0; float out = 0.f;
-    int st = fir_pair_distances(g, lhs.data(), 1, &idx, 1, 0, FIR_HOST, &out);
+    int st = fir_pair_distances(g, lhs.data() + start_pos, 1, &idx, 1, 0, FIR_HOST, &out);
     fir_gallery_destroy(g);
     fir::check(st, "fir_pair_distances");
     return out;
@@ -232,32 +255,49 @@ protected:
 
 class BruteForce : public ClassificationMethod {                         // ann.h:42-47, ann.cpp:113-126
 public:
-    BruteForce(std::vector<ImageInfo>& db) : ClassificationMethod("BF", db), pg(db, fir::metric()) {}
+    // fir::n_gpus() == 1: one device gallery; otherwise row shards over the GPUs of the box + NCCL candidate merge
+    BruteForce(std::vector<ImageInfo>& db) : ClassificationMethod("BF", db), sg(db, fir::metric(), fir::n_gpus()),
+                                             pg(db, fir::metric(), sg.s == 0) {}
     int recognize(ImageInfo& testImage) {
         std::vector<ImageInfo> one(1, testImage);
         return recognize_batch(one)[0];
     }
     std::vector<int> recognize_batch(std::vector<ImageInfo>& testImages) {
         std::vector<int> out(testImages.size(), -1);
-        if (!pg.g || testImages.empty()) return out;
-        std::vector<float> q = detail::pack_queries(testImages, pg.d);
+        if ((!pg.g && !sg.s) || testImages.empty()) return out;
+        std::vector<float> q = detail::pack_queries(testImages, sg.s ? sg.d : pg.d);
         std::vector<int32_t> idx(testImages.size());
-        fir::check(fir_search_topk(pg.g, q.data(), (int64_t)testImages.size(), 1, 0, FIR_PATH_AUTO, FIR_HOST, idx.data(), 0), "fir_search_topk");
+        if (sg.s) fir::check(fir_sharded_search_topk(sg.s, q.data(), (int64_t)testImages.size(), 1, FIR_PATH_AUTO, idx.data(), 0), "fir_sharded_search_topk");
+        else fir::check(fir_search_topk(pg.g, q.data(), (int64_t)testImages.size(), 1, 0, FIR_PATH_AUTO, FIR_HOST, idx.data(), 0), "fir_search_topk");
         distanceCalcCount = (int)dbImages.size();
         for (size_t i = 0; i < out.size(); ++i) out[i] = idx[i];
         return out;
     }
 private:
+    detail::ShardedPackedGallery sg;
     detail::PackedGallery pg;
 };
 
 class DirectedEnumeration : public ClassificationMethod {                // ann.h:61-100, ann.cpp:270-507
 public:
-    // pivot0 < 0: the first pivot comes from `seed` (the reference takes the head of an unseeded random_shuffle)
+    // The reference's first pivot is the head of std::random_shuffle over 0..N-1 (ann.cpp:366-369; the rest of that
+    // shuffle is overwritten by the farthest-point chain, :328-330).  With the reference's four arguments the same shuffle
+    // is drawn here — same rand() consumption, so under the same srand() the pivot chain is the reference's (libstdc++).
+    // pivot0 >= 0 fixes the first pivot instead; pivot0 < 0 with seed != 0 derives it from `seed` without touching rand().
     DirectedEnumeration(std::vector<ImageInfo>& faceImages, float falseAcceptRate = 0.01f, float threshold = 0, int imageCountToCheck = 0,
                         int pivot0 = -1, unsigned seed = 0)
         : ClassificationMethod("dem", faceImages), isFoundLessThreshold(false), bestDistance(0), pg(faceImages, fir::metric()), dem(0) {
         setImageCountToCheck(imageCountToCheck);
+        if (pivot0 < 0 && seed == 0 && !faceImages.empty()) {
+            std::vector<int> indices(faceImages.size());
+            for (size_t i = 0; i < indices.size(); ++i) indices[i] = (int)i;
+#if __cplusplus < 201703L
+            std::random_shuffle(indices.begin(), indices.end());
+#else
+            for (size_t i = indices.size() - 1; i > 0; --i) std::swap(indices[i], indices[std::rand() % (i + 1)]);
+#endif
+            pivot0 = indices[0];
+        }
         fir_dem_params p;
         p.pivot0 = pivot0; p.seed = seed; p.false_accept_rate = falseAcceptRate; p.threshold = threshold; p.max_chain = 0; p.max_pivots = 0;
         std::chrono::high_resolution_clock::time_point t1 = std::chrono::high_resolution_clock::now();

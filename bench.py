@@ -431,6 +431,7 @@ def run_gpu(args):
     gal.profile(True)
     t_dev = env.timed(step_device, steps)
     prof = {kk: gal.profile_read(kk) for kk in (0, 1, 2, 5)}
+    dem_stats = dem.search_stats() if dem is not None else None
     gal.profile(False)
     st = gal.stats() if cfg["kind"] == "bf" else None
     t_e2e = env.timed(step_host, steps, host_clock=True)
@@ -485,8 +486,24 @@ def run_gpu(args):
                     "traffic": traffic_from_profiles(args.config if world == 1 else "", "exact_tile_kernel")}
         res_host = (sc_host.numpy(), lab_host.numpy())
     else:
-        k_ms, k_n = prof[2]
-        launches = None
+        launches = dem_stats["gpu_launches"] * steps
+        k_ms, k_n = dem_stats["candidates_kernel_ms"], dem_stats["candidates_kernel_launches"]
+        if dem_stats["tensor_round"] and k_n:
+            t_k = k_ms / k_n * 1e-3
+            flops = 2.0 * 32 * nq * n
+            ach = flops / t_k / 1e12
+            peak = peaks["tensor_tflops_burst"]
+            roof = {"bound": "tensor", "kernel": "l2_candidates_kernel_2cta over the pivot-space gallery P^T [N][32] (first round of the candidate walk: "
+                                                 "likelihood = squared Euclidean distance between pivot-distance vectors)",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "kernel_ms": 1e3 * t_k, "kernel_share_of_step": (k_ms / 1e3) / t_dev,
+                    "algorithmic": "2*32 flop per (query, gallery row) likelihood", "flops_per_launch": flops,
+                    "binding": "the TMEM->register epilogue (one accumulator element per (query, row), ~3 instructions each): a K = 32 contraction cannot "
+                               "load the tensor pipe; the CUDA-core form of the same pass costs 96 rounded FP32 instructions per element",
+                    "epilogue_elements_per_s": float(nq) * n / t_k,
+                    "peak_source": "%s burst fp16/bf16 dense" % peaks["source"], "traffic": traffic_from_profiles(args.config, "l2_candidates_kernel_2cta")}
+        elif prof[2][1]:
+            roof = {"bound": "hbm", "kernel": "dem_likelihood_kernel (CUDA cores)", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
+                    "kernel_ms": prof[2][0] / prof[2][1], "traffic": None}
         res_host = tuple(o.numpy() for o in out_h)
 
     if rank == 0:
@@ -558,7 +575,10 @@ def parity_and_cpu(env, synth, cfg, args, q_host, res_host, gal, k, dem):
     elif cfg["kind"] == "pnn":
         sc, lab = res_host
         C = cfg["classes"]
-        psc, plab = port.pnn_div(m, g, gl, C, qs, cfg["var"])
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=nthreads) as ex:                  # the port is single-threaded; ctypes releases the GIL: one query per task
+            parts = list(ex.map(lambda i: port.pnn_div(m, g, gl, C, qs[i:i + 1], cfg["var"]), range(len(qs))))
+        psc, plab = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
         rel = np.abs(sc[sample] - psc) / np.maximum(np.abs(psc), 1e-300)
         big = psc > psc.max(axis=1, keepdims=True) * 1e-30
         par["against"] = "oracle port fir_oracle_pnn_div (reference-exact distances, fp64 Parzen sums) on the full gallery"

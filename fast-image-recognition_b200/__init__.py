@@ -29,14 +29,14 @@ PATH_AUTO, PATH_EXACT, PATH_TENSOR, PATH_APPROX = 0, 1, 2, 3
 
 EXPORTS = [
     "fir_last_error_string", "fir_version", "fir_device_count", "fir_set_device",
-    "fir_gallery_create", "fir_gallery_destroy", "fir_gallery_set_stream", "fir_gallery_info", "fir_gallery_set_num_classes",
+    "fir_gallery_create", "fir_gallery_destroy", "fir_gallery_set_stream", "fir_gallery_info", "fir_gallery_index_offset", "fir_gallery_set_num_classes",
     "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
     "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates", "fir_profile_enable", "fir_profile_read",
     "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn", "fir_classifier_pnn_sequential",
     "fir_twd_conventional", "fir_twd_proposed", "fir_kmedoids_select", "fir_classifier_set_total",
     "fir_fpnn_create", "fir_fpnn_destroy", "fir_fpnn_info", "fir_fpnn_get_coefficients", "fir_fpnn_predict",
     "fir_dem_build", "fir_dem_from_state", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
-    "fir_dem_get_min_other", "fir_dem_search", "fir_index_save", "fir_index_load", "fir_synth_rows",
+    "fir_dem_get_min_other", "fir_dem_search", "fir_dem_search_stats", "fir_index_save", "fir_index_load", "fir_synth_rows",
     "fir_comm_unique_id", "fir_comm_init_rank", "fir_comm_destroy", "fir_comm_info",
     "fir_shard_search_topk", "fir_shard_class_min", "fir_shard_pnn_scores",
     "fir_sharded_create", "fir_sharded_destroy", "fir_sharded_info", "fir_sharded_shard",
@@ -78,6 +78,7 @@ def lib():
     L.fir_gallery_destroy.argtypes = [vp]
     L.fir_gallery_set_stream.argtypes = [vp, vp]
     L.fir_gallery_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.fir_gallery_index_offset.argtypes = [vp, C.POINTER(i64)]
     L.fir_gallery_set_num_classes.argtypes = [vp, i32]
     L.fir_normalize_rows.argtypes = [vp, i64, i32, i32, i32, vp]
     L.fir_search_topk.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, vp]
@@ -113,6 +114,7 @@ def lib():
     L.fir_dem_get_pivot_matrix.argtypes = [vp, vp]
     L.fir_dem_get_min_other.argtypes = [vp, vp]
     L.fir_dem_search.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp]
+    L.fir_dem_search_stats.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(f64), C.POINTER(i32)]
     L.fir_synth_rows.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, C.c_uint32, C.c_float, i32, vp]
     L.fir_comm_unique_id.argtypes = [vp]
     L.fir_comm_init_rank.argtypes = [vp, i32, i32, C.POINTER(vp)]
@@ -169,6 +171,17 @@ def _out(shape, dtype_np, dtype_name, like_device, device=None):
     return np.empty(shape, dtype=dtype_np)
 
 
+def _check_out(buf, shape, dtype_name, space, like):
+    """A caller-supplied result buffer goes to the C ABI as a raw pointer: wrong shape / dtype / memory space would corrupt memory."""
+    if _is_torch(buf):
+        ok = buf.is_cuda == (space == DEVICE) and tuple(buf.shape) == tuple(shape) and str(buf.dtype) == "torch." + dtype_name and buf.is_contiguous()
+        ok = ok and (space != DEVICE or buf.device == like.device)
+    else:
+        ok = space == HOST and isinstance(buf, np.ndarray) and buf.shape == tuple(shape) and buf.dtype == np.dtype(dtype_name) and buf.flags["C_CONTIGUOUS"]
+    if not ok:
+        raise ValueError("out buffer must be a contiguous %s array of shape %s in the same memory space as the queries" % (dtype_name, tuple(shape)))
+
+
 def device_count():
     n = C.c_int(0)
     _check(lib().fir_device_count(C.byref(n)))
@@ -197,7 +210,9 @@ class Gallery:
         _check(lib().fir_gallery_info(self._h, C.byref(n), C.byref(d), C.byref(m), C.byref(nc)))
         self.n, self.d, self.n_classes = n.value, d.value, nc.value
         self.metric_name = {v: k for k, v in METRICS.items()}[m.value]
-        self.index_offset = 0
+        off = C.c_int64(0)
+        _check(lib().fir_gallery_index_offset(self._h, C.byref(off)))
+        self.index_offset = off.value                       # a loaded index keeps the offset it was saved with
         self._device = None
         return self
 
@@ -246,6 +261,8 @@ class Gallery:
         nq = int(q.shape[0])
         if out is not None:
             idx, dist = out
+            _check_out(idx, (nq, k), "int32", space, q)
+            _check_out(dist, (nq, k), "float32", space, q)
         else:
             idx = _out((nq, k), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
             dist = _out((nq, k), np.float32, "float32", space == DEVICE, getattr(q, "device", None))
@@ -507,6 +524,12 @@ class Dem:
         _check(lib().fir_dem_get_min_other(self._h, _ptr(out)))
         return out
 
+    def search_stats(self):
+        """Counters of the last search: kernels launched, tensor first round on/off, its candidate kernel's (ms, launches) while profiling."""
+        a, b, ms, n = C.c_int32(0), C.c_int32(0), C.c_double(0), C.c_int32(0)
+        _check(lib().fir_dem_search_stats(self._h, C.byref(a), C.byref(b), C.byref(ms), C.byref(n)))
+        return {"gpu_launches": a.value, "tensor_round": bool(b.value), "candidates_kernel_ms": ms.value, "candidates_kernel_launches": n.value}
+
     def search(self, queries, count_to_check=0):
         q, space = _prep(queries, np.float32, "float32")
         nq = int(q.shape[0])
@@ -575,6 +598,8 @@ class RankShard:
         nq = int(q.shape[0])
         if out is not None:
             idx, dist = out
+            _check_out(idx, (nq, k), "int32", space, q)
+            _check_out(dist, (nq, k), "float32", space, q)
         else:
             idx = _out((nq, k), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
             dist = _out((nq, k), np.float32, "float32", space == DEVICE, getattr(q, "device", None))

@@ -17,6 +17,7 @@ int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
 
 int Workspace::reserve(size_t bytes) {
     off = 0;
+    ++generation;                        // whatever the previous call left in the workspace is no longer addressable
     if (bytes <= cap) return FIR_OK;
     if (base) {
         FIR_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -207,6 +208,12 @@ int fir_gallery_info(const fir_gallery* g, int64_t* n, int32_t* d, int32_t* metr
     return FIR_OK;
 }
 
+int fir_gallery_index_offset(const fir_gallery* g, int64_t* index_offset) {
+    if (!g || !index_offset) return fail(FIR_ERR_BAD_ARG, "null argument");
+    *index_offset = g->index_offset;
+    return FIR_OK;
+}
+
 int fir_gallery_set_num_classes(fir_gallery* g, int32_t n_classes) {
     if (!g) return fail(FIR_ERR_BAD_ARG, "gallery is null");
     int32_t mx = 0;
@@ -242,6 +249,7 @@ int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k,
     if (k < 1 || k > 1024) return fail(FIR_ERR_BAD_ARG, "k must be in [1,1024]");
     if (max_features < 0 || max_features > g->d) return fail(FIR_ERR_BAD_ARG, "max_features out of range");
     g->stats = fir_search_stats{};
+    g->dbg_cand_idx = nullptr; g->dbg_cand_val = nullptr; g->dbg_cand_exact = nullptr;      // diagnostics of an earlier tensor call are stale now
     if (nq == 0) return FIR_OK;
     FIR_CUDA_TRY(cudaSetDevice(g->device));
     const int d_end = max_features > 0 ? max_features : g->d;
@@ -252,8 +260,10 @@ int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k,
     if (use_tensor) return tensor_search_topk(g, queries, nq, k, memspace, out_idx, out_dist);
     const bool approx_ok = g->metric != FIR_L2 && max_features == 0 && k <= 28;
     if (path == FIR_PATH_APPROX && !approx_ok) return fail(FIR_ERR_UNSUPPORTED, "approximate path needs chi2/KL, all dimensions and k<=28");
-    if (path == FIR_PATH_APPROX || (path == FIR_PATH_AUTO && approx_ok && nq > kStreamMaxQueries && nq * g->n >= (int64_t)1 << 22))
-        return approx_search_topk(g, queries, nq, k, memspace, out_idx, out_dist);
+    if (path == FIR_PATH_APPROX || (path == FIR_PATH_AUTO && approx_ok && nq > kStreamMaxQueries && nq * g->n >= (int64_t)1 << 22)) {
+        const int st = approx_search_topk(g, queries, nq, k, memspace, out_idx, out_dist);
+        if (st != kApproxDeclined) return st;                  // KL over a mixed-sign gallery: fall through to the exact kernels
+    }
 
     if (nq <= kStreamMaxQueries && k <= kStreamMaxK && g->n >= 4096) {
         // latency mode: one pass over the gallery for all (<= 8) queries, then per-segment top-k + merge
@@ -407,7 +417,7 @@ static int class_reduce(fir_gallery* g, const float* queries, int64_t nq, int me
         FIR_TRY(launch_fill_u64(keys, (int64_t)cells, ~0ull, g->stream));
         p.cls_key = keys;
         if (stream) FIR_TRY(launch_stream_class(sdist, g->n, g->n, (int)nq, g->labels, C, MODE_CLASSMIN, 0.0, keys, nullptr, g->stream));
-        else FIR_TRY(launch_exact_tiles(g->metric, p, g->stream));
+        else { auto* ev = g->prof_begin(FIR_KERNEL_EXACT_TILES); const int st_ = launch_exact_tiles(g->metric, p, g->stream); g->prof_end(ev); FIR_TRY(st_); }
         FIR_TRY(launch_classmin_finalize(keys, (int64_t)cells, g->index_offset, dmin, darg, g->stream));
         if (memspace == FIR_HOST) {
             FIR_CUDA_TRY(cudaMemcpyAsync(out_min, dmin, cells * 4, cudaMemcpyDeviceToHost, g->stream));
@@ -423,7 +433,7 @@ static int class_reduce(fir_gallery* g, const float* queries, int64_t nq, int me
         FIR_CUDA_TRY(cudaMemsetAsync(sc, 0, cells * 8, g->stream));
         p.cls_score = sc; p.two_var = 2 * var;
         if (stream) FIR_TRY(launch_stream_class(sdist, g->n, g->n, (int)nq, g->labels, C, MODE_PNN, 2 * var, nullptr, sc, g->stream));
-        else FIR_TRY(launch_exact_tiles(g->metric, p, g->stream));
+        else { auto* ev = g->prof_begin(FIR_KERNEL_EXACT_TILES); const int st_ = launch_exact_tiles(g->metric, p, g->stream); g->prof_end(ev); FIR_TRY(st_); }
         FIR_TRY(launch_pnn_finalize(sc, nq, C, (double)(n_total > 0 ? n_total : g->n), lab, g->stream));
         if (memspace == FIR_HOST) {
             if (out_scores) FIR_CUDA_TRY(cudaMemcpyAsync(out_scores, sc, cells * 8, cudaMemcpyDeviceToHost, g->stream));

@@ -148,18 +148,26 @@ __global__ void __launch_bounds__(256) approx_tile_kernel(ApproxParams p) {
     }
 }
 
-// ‖row‖₁ per row (warp per row) and its maximum (float bits, non-negative ⇒ unsigned order)
-__global__ void row_l1_kernel(const float* __restrict__ rows, int64_t n, int d, int ld, float* __restrict__ out, unsigned int* __restrict__ max_bits) {
+// ‖row‖₁ per row (warp per row) and its maximum (float bits, non-negative ⇒ unsigned order).
+// The KL error model (E = abs_coef·(‖q‖₁ + max‖x‖₁)) rests on 2l/(l+r) ≤ 2, i.e. on NON-NEGATIVE features; the reference's
+// own guards (`l + r > 0`, `l > 0`, db_features.cpp:33-36) also admit mixed-sign rows (PCA'd / un-ReLU'd features), where
+// log(2l/(l+r)) is unbounded as l + r → 0⁺.  A row with a negative element therefore reports ‖row‖₁ = +inf (its query can
+// never be certified and is re-run exactly) and raises neg_flag (a gallery with negatives routes KL to the exact kernels).
+__global__ void row_l1_kernel(const float* __restrict__ rows, int64_t n, int d, int ld, float* __restrict__ out, unsigned int* __restrict__ max_bits,
+                              unsigned int* __restrict__ neg_flag) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n) return;
     double s = 0.0;
-    for (int c = lane; c < d; c += 32) s += fabs((double)rows[r * ld + c]);
+    bool neg = false;
+    for (int c = lane; c < d; c += 32) { const float v = rows[r * ld + c]; s += fabs((double)v); neg = neg || v < 0.f; }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    neg = __any_sync(0xffffffffu, neg);
     if (lane == 0) {
-        const float f = __double2float_ru(s);
+        const float f = neg ? __int_as_float(0x7f800000) : __double2float_ru(s);
         if (out) out[r] = f;
-        if (max_bits) atomicMax(max_bits, __float_as_uint(f));
+        if (max_bits && !neg) atomicMax(max_bits, __float_as_uint(f));
+        if (neg_flag && neg) atomicOr(neg_flag, 1u);
     }
 }
 
@@ -170,9 +178,15 @@ int approx_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     if (!g->d_l1max) {
         FIR_CUDA_TRY(cudaMalloc(&g->d_l1max, 256));
         FIR_CUDA_TRY(cudaMemsetAsync(g->d_l1max, 0, 256, s));
-        row_l1_kernel<<<(unsigned)ceil_div(g->n, 8), 256, 0, s>>>(g->rows, g->n, g->d, g->dp, nullptr, reinterpret_cast<unsigned int*>(g->d_l1max));
+        row_l1_kernel<<<(unsigned)ceil_div(g->n, 8), 256, 0, s>>>(g->rows, g->n, g->d, g->dp, nullptr, reinterpret_cast<unsigned int*>(g->d_l1max),
+                                                                  reinterpret_cast<unsigned int*>(g->d_l1max) + 1);
         FIR_CUDA_TRY(cudaGetLastError());
+        unsigned int neg = 0;                                   // once per gallery: does any gallery element carry a minus sign?
+        FIR_CUDA_TRY(cudaMemcpyAsync(&neg, reinterpret_cast<unsigned int*>(g->d_l1max) + 1, 4, cudaMemcpyDeviceToHost, s));
+        FIR_CUDA_TRY(cudaStreamSynchronize(s));
+        g->has_negative = neg != 0;
     }
+    if (metric == FIR_KL && g->has_negative) return kApproxDeclined;      // mixed-sign gallery: the KL bound does not hold — exact kernels
     const int R = k <= 4 ? 8 : (k <= 12 ? 16 : 32);
     const int64_t qblocks = ceil_div(nq, ATS), ntiles = ceil_div(g->n, ATS);
     const int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ceil_div((int64_t)g->n_sm * 4, qblocks), ntiles), 32));
@@ -211,7 +225,7 @@ int approx_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     int32_t* n_flagged = reinterpret_cast<int32_t*>(g->d_l1max + 4);
     float* max_bound = g->d_l1max + 5;
     FIR_CUDA_TRY(cudaMemsetAsync(g->d_l1max + 4, 0, 8, s));
-    row_l1_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, s>>>(dq, nq, g->d, g->dp, q_l1, nullptr);
+    row_l1_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, s>>>(dq, nq, g->d, g->dp, q_l1, nullptr, nullptr);   // +inf for a mixed-sign query ⇒ exact re-run
 
     ApproxParams p{};
     p.q = dq; p.nq = nq; p.ldq = g->dp; p.x = g->rows; p.n = g->n; p.ldx = g->dp; p.d = g->d; p.R = R; p.nsplit = nsplit;

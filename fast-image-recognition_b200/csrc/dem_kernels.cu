@@ -33,6 +33,15 @@ struct fir_dem {
     unsigned char* in_tail = nullptr;  // [n] 1 = ν is a candidate after the pivot phase
     int32_t* d_pivots = nullptr;       // [n_pivots]
     int64_t tail_size = 0;
+    // pivot-space gallery for the first round on tensor cores (see "round 0" below); absent for small galleries / S != 32
+    fir_gallery* pt = nullptr;         // rows ν = (P[0][ν] .. P[S-1][ν]), L2 — its exact rerank IS the reference's likelihood sum
+    float* center = nullptr;           // [32] per-pivot mean of P (shadow centring)
+    unsigned char* exclude = nullptr;  // [n] rows outside the tensor round: the special rows below
+    int n_special = 0;                 // rows touched by the reference's index walk (positions < S and the pivots themselves)
+    int32_t* sp_rows = nullptr;        // [n_special]
+    uint32_t* sp_mask = nullptr;       // [n_special] bit i = step i contributes to the row's likelihood
+    unsigned char* sp_tail = nullptr;  // [n_special] 1 = the row is a candidate
+    int32_t last_launches = 0;         // kernels launched by the last fir_dem_search
 };
 
 namespace fir {
@@ -455,8 +464,9 @@ __global__ void __launch_bounds__(128) dem_reduce_kernel(const float* __restrict
     const int lane = threadIdx.x & 31;
     const int qc = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (qc >= nqc) return;
-    QState s = st[qlist[qc]];
-    if (s.done) return;
+    const int qi = qlist ? qlist[qc] : qc;
+    QState s = st[qi];
+    if (s.done || round_n[qc] < 0) return;
     const int m = min(round_n[qc], cap);
     const int32_t* ci = cand + (int64_t)qc * cap;
     const uint32_t* ck = cand_key + (int64_t)qc * cap;
@@ -491,7 +501,7 @@ __global__ void __launch_bounds__(128) dem_reduce_kernel(const float* __restrict
         if (lane == 0) {
             s.best_dist = hd; s.best_idx = hi; s.below = 1; s.done = 1;
             s.count += rank + 1;
-            st[qlist[qc]] = s;
+            st[qi] = s;
         }
         return;
     }
@@ -507,7 +517,7 @@ __global__ void __launch_bounds__(128) dem_reduce_kernel(const float* __restrict
         }
         if (s.count >= M || (int64_t)(s.count - S) >= tail_size) s.done = 1;
         if (!s.done) atomicAdd(n_active, 1);
-        st[qlist[qc]] = s;
+        st[qi] = s;
     }
 }
 
@@ -535,6 +545,110 @@ __global__ void dem_active_list_kernel(const QState* __restrict__ st, int64_t nq
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     if (!st[q].done) { int p = atomicAdd(count, 1); list[p] = (int32_t)q; }
+}
+
+// ---- round 0 on tensor cores -----------------------------------------------------------------------
+// likelihood[ν] = Σ_i (d_i − P[i][ν])² is the squared Euclidean distance, in the 32-dimensional "pivot space", between the
+// query's pivot-distance vector (d_0..d_31) and column ν of P: the candidate order of recognize() (ann.cpp:453-476) is a
+// nearest-neighbour order.  So the first round is ONE call of the tensor-core brute force (l2_tensor.cu) over the derived
+// gallery Pᵀ [N][32]: tcgen05 candidates (q·xᵀ over K = 32), exact fp32 rerank — whose sequential sum fl(acc + fl(t·t)),
+// t = fl(d_i − P_iν), is bit for bit the reference's likelihood accumulation (:457-458; the mean's division by 32 is exact)
+// — certificate, top-k by (likelihood, row).  The [Q][N] likelihood matrix is never formed: per (query, row) the work is
+// one accumulator element of a K = 32 MMA instead of 96 rounded FP32 instructions.  The ≤ 64 rows whose likelihood the
+// reference's index walk truncates (pivots and positions < S) are excluded from the derived gallery and merged in exactly
+// from a side list.  Queries that need more than the first round continue in the general path below from the round's
+// closing (likelihood, row) key.
+constexpr int kRound0K = 24;            // candidates of the first round (the tensor path serves k <= 28)
+constexpr int64_t kDemTensorMinRows = 8192;
+
+__global__ void dem_center_kernel(const float* __restrict__ P, int64_t n, float* __restrict__ center) {
+    __shared__ double sh[256];
+    const float* row = P + (int64_t)blockIdx.x * n;
+    double a = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += 256) a += (double)row[j];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) center[blockIdx.x] = (float)(sh[0] / (double)n);
+}
+// PT[ν][i] = P[i][ν]; excluded rows get a far sentinel so that even the exact CUDA-core fallback never lists them (≥ 100000)
+__global__ void dem_transpose_kernel(const float* __restrict__ P, int64_t n, int S, const unsigned char* __restrict__ exclude, float* __restrict__ PT) {
+    __shared__ float tile[32][33];
+    const int64_t v0 = (int64_t)blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) { const int64_t v = v0 + threadIdx.x; tile[i][threadIdx.x] = (i < S && v < n) ? P[(int64_t)i * n + v] : 0.f; }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int64_t v = v0 + r;
+        if (v < n) PT[v * 32 + threadIdx.x] = exclude[v] ? (threadIdx.x < S ? 1e18f : 0.f) : tile[threadIdx.x][r];
+    }
+}
+
+// one warp per query: the round's candidates = the first `want` of (tensor top-k over the ordinary rows) ∪ (special rows with
+// their truncated likelihoods, computed here), in (likelihood, row) order
+__global__ void __launch_bounds__(128) dem_round0_merge_kernel(const int32_t* __restrict__ t_idx, const float* __restrict__ t_dist, int k0, int64_t nq,
+                                                               const float* __restrict__ pd, int S, const float* __restrict__ P, int64_t n,
+                                                               const int32_t* __restrict__ sp_rows, const uint32_t* __restrict__ sp_mask,
+                                                               const unsigned char* __restrict__ sp_tail, int n_special, int M,
+                                                               const QState* __restrict__ st, int32_t* __restrict__ cand, uint32_t* __restrict__ cand_key,
+                                                               int32_t* __restrict__ round_n, uint32_t* __restrict__ key_sel, int32_t* __restrict__ last_tie) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const QState s = st[q];
+    int32_t* out = cand + q * k0;
+    uint32_t* outk = cand_key + q * k0;
+    if (s.done) {
+        if (lane < k0) out[lane] = -1;
+        if (lane == 0) { round_n[q] = 0; key_sel[q] = 0; last_tie[q] = -1; }
+        return;
+    }
+    const int want = min(k0, M - s.count);
+    unsigned long long e0 = ~0ull, e1 = ~0ull, e2 = ~0ull;
+    bool tiny = false;
+    if (lane < k0) {
+        const int32_t idx = t_idx[q * k0 + lane];
+        if (idx >= 0) {
+            const float dd = t_dist[q * k0 + lane];
+            tiny = dd != 0.f && dd < 7.9e-31f;                   // fl(acc/32) may have lost bits below 2^-100: leave the query to the general path
+            e0 = ((unsigned long long)__float_as_uint(__fmul_rn(dd, 32.f)) << 32) | (uint32_t)idx;
+        }
+    }
+    for (int h = 0; h < 2; ++h) {
+        const int j = lane + 32 * h;
+        if (j < n_special && sp_tail[j]) {
+            const int32_t row = sp_rows[j];
+            const uint32_t mask = sp_mask[j];
+            float acc = 0.f;
+            for (int i = 0; i < S; ++i)
+                if ((mask >> i) & 1u) { const float t = __fsub_rn(pd[q * S + i], P[(int64_t)i * n + row]); acc = __fadd_rn(acc, __fmul_rn(t, t)); }
+            const unsigned long long key = ((unsigned long long)__float_as_uint(acc) << 32) | (uint32_t)row;
+            if (h == 0) e1 = key; else e2 = key;
+        }
+    }
+    if (__any_sync(0xffffffffu, tiny)) {
+        if (lane < k0) out[lane] = -1;
+        if (lane == 0) { round_n[q] = -1; key_sel[q] = 0; last_tie[q] = -1; }
+        return;
+    }
+    int taken = 0;
+    unsigned long long last = 0;
+    for (int r = 0; r < want; ++r) {
+        unsigned long long mine = e0 < e1 ? e0 : e1;
+        mine = mine < e2 ? mine : e2;
+        unsigned long long best = mine;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long ov = __shfl_xor_sync(0xffffffffu, best, o); best = ov < best ? ov : best; }
+        if (best == ~0ull) break;                                // fewer rows than wanted: the tail is exhausted
+        if (mine == best) { if (e0 == best) e0 = ~0ull; else if (e1 == best) e1 = ~0ull; else e2 = ~0ull; }   // keys are distinct (one row each)
+        if (lane == 0) { out[r] = (int32_t)(uint32_t)best; outk[r] = (uint32_t)(best >> 32); }
+        last = best; ++taken;
+    }
+    for (int r = taken + lane; r < k0; r += 32) out[r] = -1;
+    if (lane == 0) {
+        round_n[q] = taken;
+        key_sel[q] = taken < want ? 0xffffffffu : (uint32_t)(last >> 32);
+        last_tie[q] = taken > 0 ? (int32_t)(uint32_t)last : -1;
+    }
 }
 
 }  // namespace fir
@@ -579,6 +693,40 @@ static int finalize_search_state(fir_dem* dm) {
     dm->tail_size = n - S;                               // each step moves exactly one position into the prefix
     FIR_CUDA_TRY(cudaMemcpyAsync(dm->d_pivots, dm->pivots.data(), 4 * (size_t)S, cudaMemcpyHostToDevice, s));
     FIR_CUDA_TRY(cudaStreamSynchronize(s));
+    // round 0 on tensor cores: the pivot-space gallery (see dem_round0_merge_kernel)
+    static const int tensor_on = [] { const char* e = getenv("FIR_DEM_TENSOR"); return e ? atoi(e) : 1; }();
+    if (tensor_on && S == 32 && n >= kDemTensorMinRows && g->cc_major >= 10 && tensor_path_supported(32)) {
+        const int ns = (int)sp.size();
+        std::vector<int32_t> rows(ns);
+        std::vector<uint32_t> mask(ns, 0u);
+        std::vector<unsigned char> tail(ns, 0), excl((size_t)n, 0);
+        for (int k = 0; k < ns; ++k) {
+            rows[k] = (int32_t)sp[k];
+            for (int i = 0; i < S; ++i) if (member[i][k]) mask[k] |= 1u << i;
+            tail[k] = member[S - 1][k];
+            excl[(size_t)sp[k]] = 1;
+        }
+        dm->n_special = ns;
+        float* PT = nullptr;
+        auto drop = [&](int code) { cudaFree(PT); return code; };
+        if (cudaMalloc(&dm->sp_rows, 4 * (size_t)ns) != cudaSuccess || cudaMalloc(&dm->sp_mask, 4 * (size_t)ns) != cudaSuccess ||
+            cudaMalloc(&dm->sp_tail, (size_t)ns) != cudaSuccess || cudaMalloc(&dm->exclude, (size_t)n) != cudaSuccess ||
+            cudaMalloc(&dm->center, 4 * 32) != cudaSuccess || cudaMalloc(&PT, 4 * (size_t)n * 32) != cudaSuccess)
+            return drop(fail(FIR_ERR_OOM, "DEM pivot-space gallery allocation failed"));
+        FIR_CUDA_TRY(cudaMemcpyAsync(dm->sp_rows, rows.data(), 4 * (size_t)ns, cudaMemcpyHostToDevice, s));
+        FIR_CUDA_TRY(cudaMemcpyAsync(dm->sp_mask, mask.data(), 4 * (size_t)ns, cudaMemcpyHostToDevice, s));
+        FIR_CUDA_TRY(cudaMemcpyAsync(dm->sp_tail, tail.data(), (size_t)ns, cudaMemcpyHostToDevice, s));
+        FIR_CUDA_TRY(cudaMemcpyAsync(dm->exclude, excl.data(), (size_t)n, cudaMemcpyHostToDevice, s));
+        dem_center_kernel<<<32, 256, 0, s>>>(dm->P_raw, n, dm->center);
+        dem_transpose_kernel<<<(unsigned)ceil_div(n, 32), dim3(32, 8), 0, s>>>(dm->P_raw, n, S, dm->exclude, PT);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) return drop(fail(FIR_ERR_CUDA, "DEM pivot-space gallery kernels failed"));
+        const int st_ = fir_gallery_create(PT, nullptr, n, 32, FIR_L2, FIR_DEVICE, 0, &dm->pt);
+        cudaFree(PT); PT = nullptr;
+        if (st_ != FIR_OK) return st_;
+        fir_gallery_set_stream(dm->pt, s);
+        dm->pt->tensor_center = dm->center;
+        dm->pt->tensor_exclude = dm->exclude;
+    }
     return FIR_OK;
 }
 
@@ -687,6 +835,8 @@ int fir_dem_from_state(fir_gallery* g, const int32_t* pivots, int32_t n_pivots, 
 int fir_dem_destroy(fir_dem* dm) {
     if (!dm) return FIR_OK;
     cudaFree(dm->P_raw); cudaFree(dm->P_search); cudaFree(dm->in_tail); cudaFree(dm->d_pivots);
+    if (dm->pt) fir_gallery_destroy(dm->pt);
+    cudaFree(dm->center); cudaFree(dm->exclude); cudaFree(dm->sp_rows); cudaFree(dm->sp_mask); cudaFree(dm->sp_tail);
     delete dm;
     return FIR_OK;
 }
@@ -696,6 +846,15 @@ int fir_dem_info(const fir_dem* dm, int32_t* n_pivots, int32_t* chain_rows, floa
     if (n_pivots) *n_pivots = dm->n_pivots;
     if (chain_rows) *chain_rows = dm->chain_rows;
     if (threshold) *threshold = dm->threshold;
+    return FIR_OK;
+}
+int fir_dem_search_stats(fir_dem* dm, int32_t* gpu_launches, int32_t* tensor_round, double* candidates_kernel_ms, int32_t* candidates_kernel_launches) {
+    if (!dm) return fail(FIR_ERR_BAD_ARG, "dem is null");
+    if (gpu_launches) *gpu_launches = dm->last_launches;
+    if (tensor_round) *tensor_round = dm->pt ? 1 : 0;
+    if (candidates_kernel_ms) *candidates_kernel_ms = 0;
+    if (candidates_kernel_launches) *candidates_kernel_launches = 0;
+    if (dm->pt && dm->pt->profiling) return fir_profile_read(dm->pt, FIR_KERNEL_L2_CANDIDATES, candidates_kernel_ms, candidates_kernel_launches);
     return FIR_OK;
 }
 int fir_dem_get_pivots(const fir_dem* dm, int32_t* out_pivots) {
@@ -737,7 +896,11 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
     const int64_t ng = ceil_div(n, 32);
     const bool fast = fast_on != 0 && ng >= 1024;            // first-round select through per-warp minima (dem_fast_*)
     if (fast) need += al(4 * (size_t)QC * ng) + 2 * al(4 * (size_t)QC * FAST_CAP) + 4 * al(4 * (size_t)QC);
+    const bool tensor0 = dm->pt != nullptr && M > S;
+    const int k0 = tensor0 ? std::min(kRound0K, M - S) : 0;
+    if (tensor0) need += 5 * al(4 * (size_t)nq * k0) + 3 * al(4 * (size_t)nq);
     FIR_TRY(g->ws.reserve(need));
+    int launches = 0;
     // queries → zero-padded device rows
     const float* dq = nullptr;
     if (memspace == FIR_DEVICE && g->d == g->dp) dq = queries;
@@ -800,8 +963,32 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
     dem_fill_pivot_cand_kernel<<<(unsigned)ceil_div(nq * S, 256), 256, 0, s>>>(dm->d_pivots, S, nq, pcand);
     FIR_TRY(launch_pair_distances(g->metric, dq, nq, g->dp, g->rows, g->dp, n, g->d, pcand, S, 0, pd, s));
     dem_pivot_phase_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(pd, nq, S, dm->d_pivots, dm->threshold, M, st);
-    // 2. queries that go on to the candidate walk
+    launches += 3;
     FIR_CUDA_TRY(cudaMemsetAsync(counters, 0, 64, s));
+    // 1b. round 0: the first k0 candidates of every query through the tensor-core brute force in pivot space
+    if (tensor0) {
+        int32_t* t_idx = (int32_t*)g->ws.take(4 * (size_t)nq * k0);
+        float* t_dist = (float*)g->ws.take(4 * (size_t)nq * k0);
+        int32_t* c0 = (int32_t*)g->ws.take(4 * (size_t)nq * k0);
+        uint32_t* ck0 = (uint32_t*)g->ws.take(4 * (size_t)nq * k0);
+        float* cd0 = (float*)g->ws.take(4 * (size_t)nq * k0);
+        int32_t* rn0 = (int32_t*)g->ws.take(4 * (size_t)nq);
+        uint32_t* ks0 = (uint32_t*)g->ws.take(4 * (size_t)nq);
+        int32_t* lt0 = (int32_t*)g->ws.take(4 * (size_t)nq);
+        if (!t_idx || !t_dist || !c0 || !ck0 || !cd0 || !rn0 || !ks0 || !lt0) return fail(FIR_ERR_INTERNAL, "workspace underestimated (dem round 0)");
+        dm->pt->stream = s; dm->pt->ws.stream = s;
+        if (dm->pt->profiling != g->profiling) { dm->pt->profiling = g->profiling; dm->pt->ev_used = 0; }   // follows fir_profile_enable of the gallery
+        dm->pt->stats = fir_search_stats{};
+        FIR_TRY(tensor_search_topk(dm->pt, pd, nq, k0, FIR_DEVICE, t_idx, t_dist));
+        launches += dm->pt->stats.gpu_launches;
+        dem_round0_merge_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(t_idx, t_dist, k0, nq, pd, S, dm->P_raw, n, dm->sp_rows, dm->sp_mask, dm->sp_tail,
+                                                                         dm->n_special, M, st, c0, ck0, rn0, ks0, lt0);
+        FIR_TRY(launch_pair_distances(g->metric, dq, nq, g->dp, g->rows, g->dp, n, g->d, c0, k0, 0, cd0, s));
+        dem_reduce_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cd0, c0, ck0, nullptr, (int)nq, k0, rn0, ks0, lt0, dm->threshold, M, dm->tail_size, S, st, counters + 2);
+        FIR_CUDA_TRY(cudaGetLastError());
+        launches += 3;
+    }
+    // 2. queries that go on to the candidate walk
     dem_active_list_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(st, nq, active, counters);
     int32_t n_act = 0;
     FIR_CUDA_TRY(cudaMemcpyAsync(&n_act, counters, 4, cudaMemcpyDeviceToHost, s));
@@ -815,7 +1002,7 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
           g->prof_end(ev); }
         int round_size = 256;
         int remaining = nqc;
-        bool first_round = true;
+        bool first_round = !tensor0;                         // after round 0 the walk resumes behind its closing key: the general select
         while (remaining > 0) {
             const int cap = (int)std::min<int64_t>(round_size, cap_max);
             dem_want_kernel<<<(unsigned)ceil_div(nqc, 128), 128, 0, s>>>(st, ql, nqc, cap, M, want);
@@ -861,6 +1048,7 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
     }
     dem_output_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(st, nq, g->index_offset, o_idx, o_dist, o_below, o_evals);
     FIR_CUDA_TRY(cudaGetLastError());
+    dm->last_launches = launches + 2;
     if (memspace == FIR_HOST) {
         FIR_CUDA_TRY(cudaMemcpyAsync(out_idx, o_idx, 4 * (size_t)nq, cudaMemcpyDeviceToHost, s));
         if (out_dist) FIR_CUDA_TRY(cudaMemcpyAsync(out_dist, o_dist, 4 * (size_t)nq, cudaMemcpyDeviceToHost, s));

@@ -32,6 +32,7 @@ int fail(int code, const std::string& msg);
 struct Workspace {
     char* base = nullptr;
     size_t cap = 0, off = 0;
+    uint64_t generation = 0;     // bumped by every reserve(): pointers handed out before it are dead
     cudaStream_t stream = 0;
     int reserve(size_t bytes);   // make sure cap >= bytes (may sync + realloc); resets off
     void* take(size_t bytes);    // nullptr if it does not fit
@@ -100,7 +101,8 @@ struct TensorSide {              // fp16 shadow of a set of fp32 rows
 
 size_t tensor_side_bytes(int64_t rows, int d, int row_tile);
 int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out,
-                     float* d_stats /*[2]: max ||x||, max resid (device)*/, bool permute, bool per_row_scale, cudaStream_t s);
+                     float* d_stats /*[2]: max ||x||, max resid (device)*/, bool permute, bool per_row_scale, cudaStream_t s,
+                     const float* center = nullptr /*[d] device: shadow of x - center*/, const unsigned char* exclude = nullptr /*[n] device*/);
 struct TensorSearchArgs {
     const TensorSide* gal; const TensorSide* qry;
     const CUtensorMap* tmap_a; const CUtensorMap* tmap_b;

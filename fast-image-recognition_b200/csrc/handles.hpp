@@ -18,12 +18,15 @@ struct fir_gallery {
     fir::TensorSide tside;
     CUtensorMap tmap_b;           // box 64 x 256 rows (single-CTA kernel)
     CUtensorMap tmap_b_half;      // box 64 x 128 rows (each CTA of a pair loads half a tile)
+    const float* tensor_center = nullptr;          // optional [dp] (device, owned by the creator): the shadows are of x − center
+    const unsigned char* tensor_exclude = nullptr; // optional [n] (device): rows that never become tensor-path candidates
     float* d_stats = nullptr;     // [2] max ||x||, max ||x - fp16(x)||
     float* d_l1max = nullptr;     // chi2/KL approximate path: [0] max ||x||_1, [4] flagged count, [5] max bound
+    bool has_negative = false;    // set with d_l1max: some gallery element is < 0 (KL's approximate error model then does not apply)
     fir::Workspace ws;
     // diagnostics: where the last tensor-path call left its candidate lists (valid until the next call)
     const float* dbg_cand_val = nullptr; const float* dbg_cand_exact = nullptr; const int32_t* dbg_cand_idx = nullptr;
-    int64_t dbg_nq = 0; int dbg_slots = 0, dbg_R = 0;
+    int64_t dbg_nq = 0; int dbg_slots = 0, dbg_R = 0; uint64_t dbg_generation = 0;
     // optional per-kernel timing: CUDA event pairs recorded on the launching stream around the dominant kernel
     bool profiling = false;
     struct EvPair { cudaEvent_t a, b; int kind; };
@@ -42,6 +45,7 @@ int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_
                       const int32_t* n_active, float* part_d, int32_t* part_i, int nsplit, float* od, int32_t* oi,
                       int64_t active_offset = 0, int64_t active_cap = 0);
 int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
+constexpr int kApproxDeclined = -100;   // approx_search_topk: the error model does not cover this gallery — the caller takes the exact path
 int approx_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
 const fir_gallery* dem_gallery(const fir_dem* dem);      // the gallery a DEM handle was built over
 size_t twd_workspace_bytes(const fir_gallery* g, int64_t nq, int64_t* mq_out);

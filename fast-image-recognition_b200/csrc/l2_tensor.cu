@@ -128,13 +128,18 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t
 // fp16 shadow copies: h = fp16(x * scale) with |h| < 2^-14 flushed to zero (no reliance on fp16
 // subnormal handling), ‖x‖² in fp64 → fp32, and the residual norm ‖x − h/scale‖ that feeds the certificate.
 // ---------------------------------------------------------------------------------------------------
-__global__ void absmax_kernel(const float* __restrict__ rows, int64_t n, int ld, int d, unsigned int* out_bits) {
+// `center` (optional, [d]): the shadow is taken of x − center (a shift common to both sides leaves ‖q − x‖² unchanged and
+// shrinks the fp16 rounding residuals when the vectors share a large mean — the pivot-space vectors of directed enumeration);
+// `exclude` (optional, [n]): rows that must never become candidates (zero shadow, +inf norm, not counted in the statistics).
+__global__ void absmax_kernel(const float* __restrict__ rows, int64_t n, int ld, int d, unsigned int* out_bits, const float* __restrict__ center,
+                              const unsigned char* __restrict__ exclude) {
     int64_t total = n * d;
     float m = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i / d;
         int c = (int)(i - r * d);
-        m = fmaxf(m, fabsf(rows[r * ld + c]));
+        if (exclude && exclude[r]) continue;
+        m = fmaxf(m, center ? (float)fabs((double)rows[r * ld + c] - (double)center[c]) : fabsf(rows[r * ld + c]));
     }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
@@ -143,7 +148,8 @@ __global__ void absmax_kernel(const float* __restrict__ rows, int64_t n, int ld,
 // meta[0] = absmax bits (in), meta[1] = scale (out, float bits)
 __global__ void pack_rows_kernel(const float* __restrict__ rows, int64_t n, int64_t rows_padded, int ld, int d, int dph,
                                  __half* __restrict__ h, float* __restrict__ norm2, float* __restrict__ resid,
-                                 unsigned int* meta, unsigned int* stats_bits, int64_t perm_a, int64_t perm_b, float* __restrict__ row_scale) {
+                                 unsigned int* meta, unsigned int* stats_bits, int64_t perm_a, int64_t perm_b, float* __restrict__ row_scale,
+                                 const float* __restrict__ center, const unsigned char* __restrict__ exclude) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows_padded) return;
@@ -151,7 +157,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ rows, int64_t n, int6
     // its max|x|), or one per row for queries (row_scale != nullptr: no separate max pass, each epilogue thread owns a row)
     float amax = 0.f;
     if (row_scale) {
-        if (row < n) for (int c = lane; c < d; c += 32) amax = fmaxf(amax, fabsf(rows[row * ld + c]));
+        if (row < n) for (int c = lane; c < d; c += 32) amax = fmaxf(amax, center ? (float)fabs((double)rows[row * ld + c] - (double)center[c]) : fabsf(rows[row * ld + c]));
         for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     } else amax = __uint_as_float(meta[0]);
     float scale = 1.f;
@@ -163,23 +169,24 @@ __global__ void pack_rows_kernel(const float* __restrict__ rows, int64_t n, int6
     if (row_scale && lane == 0) row_scale[row] = scale;
     if (row == 0 && lane == 0) meta[1] = __float_as_uint(scale);
     __half* hr = h + row * dph;
-    if (row >= n) {
+    const int64_t src_row = row < n ? (row * perm_a + perm_b) % n : 0;
+    if (row >= n || (exclude && exclude[src_row])) {
         for (int c = lane; c < dph; c += 32) hr[c] = __float2half_rn(0.f);
         if (lane == 0) { norm2[row] = __int_as_float(0x7f800000); resid[row] = 0.f; }
         return;
     }
     const float inv = 1.f / scale;        // exact: power of two
-    const int64_t src_row = (row * perm_a + perm_b) % n;
     double n2 = 0.0, r2 = 0.0;
     for (int c = lane; c < dph; c += 32) {
-        float x = c < d ? rows[src_row * ld + c] : 0.f;
-        float xs = x * scale;
+        // the (optionally centred) value in double: its rounding to fp32 and then to fp16 both land in the measured residual
+        const double x = c < d ? (center ? (double)rows[src_row * ld + c] - (double)center[c] : (double)rows[src_row * ld + c]) : 0.0;
+        float xs = (float)x * scale;
         __half hv = __float2half_rn(xs);
         if (fabsf(__half2float(hv)) < 6.103515625e-05f) hv = __float2half_rn(0.f);
         hr[c] = hv;
         float back = __half2float(hv) * inv;
-        double df = (double)x - (double)back;
-        n2 += (double)x * (double)x;
+        double df = x - (double)back;
+        n2 += x * x;
         r2 += df * df;
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -209,7 +216,7 @@ size_t tensor_side_bytes(int64_t rows, int d, int row_tile) {
 static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
 int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out, float* d_stats,
-                     bool permute, bool per_row_scale, cudaStream_t s) {
+                     bool permute, bool per_row_scale, cudaStream_t s, const float* center, const unsigned char* exclude) {
     int64_t rp = ceil_div(n, row_tile) * row_tile;
     int dph = round_up(d, BK);
     char* p = (char*)(((uintptr_t)buf + 1023) & ~(uintptr_t)1023);     // TMA global address alignment (>=16B); keep 1 KiB
@@ -231,11 +238,12 @@ int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, 
     FIR_CUDA_TRY(cudaMemsetAsync(out->meta, 0, 16, s));
     if (!per_row_scale) {
         int blocks = (int)std::min<int64_t>(1184, ceil_div(n * d, 256 * 8));
-        absmax_kernel<<<std::max(blocks, 1), 256, 0, s>>>(rows, n, ld, d, out->meta);
+        absmax_kernel<<<std::max(blocks, 1), 256, 0, s>>>(rows, n, ld, d, out->meta, center, exclude);
         FIR_CUDA_TRY(cudaGetLastError());
     }
     pack_rows_kernel<<<(unsigned)ceil_div(rp, 8), 256, 0, s>>>(rows, n, rp, ld, d, dph, out->h, out->norm2, out->resid, out->meta,
-                                                              (unsigned int*)d_stats, out->perm_a, out->perm_b, per_row_scale ? out->row_scale : nullptr);
+                                                              (unsigned int*)d_stats, out->perm_a, out->perm_b, per_row_scale ? out->row_scale : nullptr,
+                                                              center, exclude);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
@@ -1116,10 +1124,11 @@ int launch_select(const float* cand_exact, const int32_t* cand_idx, const float*
 static int ensure_gallery_side(fir_gallery* g) {
     if (g->tensor_ready) return FIR_OK;
     size_t bytes = tensor_side_bytes(g->n, g->d, BN);
-    FIR_CUDA_TRY(cudaMalloc(&g->tensor_buf, bytes));
-    FIR_CUDA_TRY(cudaMalloc(&g->d_stats, 64));
+    // a failed earlier attempt may have left its buffers behind: allocate only what is missing, so nothing leaks on a retry
+    if (!g->tensor_buf) FIR_CUDA_TRY(cudaMalloc(&g->tensor_buf, bytes));
+    if (!g->d_stats) FIR_CUDA_TRY(cudaMalloc(&g->d_stats, 64));
     FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, 64, g->stream));
-    FIR_TRY(tensor_pack_side(g->rows, g->n, g->dp, g->d, BN, g->tensor_buf, &g->tside, g->d_stats, true, false, g->stream));
+    FIR_TRY(tensor_pack_side(g->rows, g->n, g->dp, g->d, BN, g->tensor_buf, &g->tside, g->d_stats, true, false, g->stream, g->tensor_center, g->tensor_exclude));
     FIR_TRY(tensor_encode_map(&g->tmap_b, g->tside.h, g->tside.rows_padded, g->tside.dph, BN));
     FIR_TRY(tensor_encode_map(&g->tmap_b_half, g->tside.h, g->tside.rows_padded, g->tside.dph, BN / 2));
     g->tensor_ready = true;
@@ -1170,7 +1179,10 @@ static size_t seed_plan(fir_gallery* g, int64_t nq, int k, int ctas, SeedPlan* s
     *sp = SeedPlan{};
     static const int div = [] { const char* e = getenv("FIR_TENSOR_SEED_DIV"); int v = e ? atoi(e) : 50; return v > 0 ? v : 50; }();
     static const int m_override = [] { const char* e = getenv("FIR_TENSOR_SEED_M"); return e ? atoi(e) : 0; }();
-    const int64_t S = g->n / div / BN * BN;               // 2 % of the gallery, whole tiles
+    // 2 % of the gallery in whole tiles, at most 64 tiles: about m·N/S rows of the whole gallery fall under the seeded threshold
+    // — a few thousand list insertions per query over tens of thousands of tiles at N = 10M, where a 2 % sample would cost
+    // 2 % of the whole search (16 ms of 850 at C5)
+    const int64_t S = std::min<int64_t>(g->n / div / BN * BN, 64 * BN);
     if (!seed_enabled() || S < 4 * BN || nq < 4 * BM) return 0;
     sp->S = S;
     // m >= k would make a too-small seed impossible, but every step down in m removes list replacements from the first
@@ -1248,7 +1260,7 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     TensorSide qs;
     const bool first = prof_kind == FIR_KERNEL_L2_CANDIDATES;
     auto* ev_pack = first ? g->prof_begin(FIR_PHASE_PACK_QUERIES) : nullptr;
-    FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, pb.qbuf, &qs, nullptr, false, true, g->stream));
+    FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, pb.qbuf, &qs, nullptr, false, true, g->stream, g->tensor_center, nullptr));
     CUtensorMap tmap_a;
     FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
     const int rt = pb.n_slots * pb.R;
@@ -1299,6 +1311,7 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
 }  // namespace
 
 int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist) {
+    g->dbg_cand_idx = nullptr; g->dbg_cand_val = nullptr; g->dbg_cand_exact = nullptr;      // the previous call's lists die with its workspace
     FIR_TRY(ensure_gallery_side(g));
     const int ctas = tensor_cta_mode();
     // Pass 1: each query gets (slots x 2 column halves) short lists over disjoint, pseudo-randomly interleaved parts of the
@@ -1398,7 +1411,7 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     g->stats.n_candidates = p1.n_slots * p1.R;
     g->stats.n_fallback = -1;     // resolved lazily by fir_search_last_stats
     g->dbg_cand_val = p1.cand_val; g->dbg_cand_exact = p1.cand_exact; g->dbg_cand_idx = p1.cand_idx;
-    g->dbg_nq = nq; g->dbg_slots = p1.n_slots; g->dbg_R = p1.R;
+    g->dbg_nq = nq; g->dbg_slots = p1.n_slots; g->dbg_R = p1.R; g->dbg_generation = g->ws.generation;
     if (memspace == FIR_HOST) {
         FIR_CUDA_TRY(cudaMemcpyAsync(out_idx, oi, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
         if (out_dist) FIR_CUDA_TRY(cudaMemcpyAsync(out_dist, od, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
@@ -1411,7 +1424,8 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
 
 extern "C" int fir_debug_tensor_candidates(fir_gallery* g, int32_t* n_slots, int32_t* R, int32_t* idx, float* approx, float* exact) {
     using namespace fir;
-    if (!g || !g->dbg_cand_idx) return fail(FIR_ERR_BAD_ARG, "no tensor-path call recorded on this gallery");
+    if (!g || !g->dbg_cand_idx || g->dbg_generation != g->ws.generation)      // any later call on the handle re-used (or re-allocated) the workspace
+        return fail(FIR_ERR_BAD_ARG, "no tensor-path call recorded on this gallery (the lists are valid until the next call on the handle)");
     if (n_slots) *n_slots = g->dbg_slots;
     if (R) *R = g->dbg_R;
     const size_t cells = (size_t)g->dbg_nq * g->dbg_slots * g->dbg_R;

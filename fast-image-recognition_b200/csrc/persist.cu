@@ -11,6 +11,7 @@
 #include "handles.hpp"
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <vector>
 
@@ -66,13 +67,14 @@ int fir_index_save(const fir_gallery* g, const fir_dem* dem, const char* path) {
     int32_t np = 0, chain = 0; float thr = 0.f;
     if (dem) FIR_TRY(fir_dem_info(dem, &np, &chain, &thr));
     h.n_pivots = (uint32_t)np; h.threshold = thr;
-    std::vector<int32_t> labels((size_t)g->n);
-    std::vector<float> rows((size_t)g->n * g->d);
+    std::vector<int32_t> labels, pivots;
+    std::vector<float> rows, P;
+    try {                                                          // no exception may cross the extern "C" boundary
+        labels.resize((size_t)g->n); rows.resize((size_t)g->n * g->d); pivots.resize((size_t)np); P.resize((size_t)np * g->n);
+    } catch (const std::exception&) { return fail(FIR_ERR_OOM, "fir_index_save: not enough host memory to stage the index"); }
     FIR_CUDA_TRY(cudaMemcpy(labels.data(), g->labels, sizeof(int32_t) * (size_t)g->n, cudaMemcpyDeviceToHost));
     FIR_CUDA_TRY(cudaMemcpy2D(rows.data(), sizeof(float) * g->d, g->rows, sizeof(float) * g->dp, sizeof(float) * g->d, (size_t)g->n,
                               cudaMemcpyDeviceToHost));
-    std::vector<int32_t> pivots((size_t)np);
-    std::vector<float> P((size_t)np * g->n);
     if (np > 0) {
         FIR_TRY(fir_dem_get_pivots(dem, pivots.data()));
         FIR_TRY(fir_dem_get_pivot_matrix(dem, P.data()));
@@ -103,7 +105,10 @@ int fir_index_load(const char* path, fir_gallery** out_gallery, fir_dem** out_de
     if (!get(in.f, sum, &h, sizeof(h))) return fail(FIR_ERR_BAD_ARG, "index file: truncated header");
     if (std::memcmp(h.magic, kMagic, 8) != 0) return fail(FIR_ERR_BAD_ARG, "index file: bad magic");
     if (h.version != 1) return fail(FIR_ERR_UNSUPPORTED, "index file: unknown version");
-    if (h.n == 0 || h.d == 0 || h.metric > (uint32_t)FIR_KL || h.n > 0x7fffffffull || h.n_pivots > h.n)
+    // every field is range-checked before any size is computed from it: n < 2^31, d <= 2^20, at most 32 search pivots
+    // (what fir_dem_from_state accepts) and a non-negative offset keep all the products below far inside 64 bits
+    if (h.n == 0 || h.d == 0 || h.metric > (uint32_t)FIR_KL || h.n > 0x7fffffffull || h.d > (1u << 20) || h.n_pivots > 32 || h.n_pivots > h.n ||
+        h.index_offset < 0 || (uint64_t)h.index_offset + h.n > 0x7fffffffull || h.n_classes == 0 || h.n_classes > 0x7fffffffu)
         return fail(FIR_ERR_BAD_ARG, "index file: inconsistent header");
     // the sizes must add up to the file before anything is allocated from them
     const uint64_t body = h.n * 4 + h.n * (uint64_t)h.d * 4 + (uint64_t)h.n_pivots * 4 + (uint64_t)h.n_pivots * h.n * 4;
@@ -111,10 +116,11 @@ int fir_index_load(const char* path, fir_gallery** out_gallery, fir_dem** out_de
     const long long size = std::ftell(in.f);
     if (size < 0 || (uint64_t)size != sizeof(Header) + body + 8) return fail(FIR_ERR_BAD_ARG, "index file: size does not match its header (truncated?)");
     if (std::fseek(in.f, (long)sizeof(Header), SEEK_SET) != 0) return fail(FIR_ERR_INTERNAL, "index file: seek failed");
-    std::vector<int32_t> labels((size_t)h.n);
-    std::vector<float> rows((size_t)h.n * h.d);
-    std::vector<int32_t> pivots((size_t)h.n_pivots);
-    std::vector<float> P((size_t)h.n_pivots * h.n);
+    std::vector<int32_t> labels, pivots;
+    std::vector<float> rows, P;
+    try {                                                          // no exception may cross the extern "C" boundary
+        labels.resize((size_t)h.n); rows.resize((size_t)h.n * h.d); pivots.resize((size_t)h.n_pivots); P.resize((size_t)h.n_pivots * h.n);
+    } catch (const std::exception&) { return fail(FIR_ERR_OOM, "index file: not enough host memory for its payload"); }
     uint64_t digest = 0;
     if (!get(in.f, sum, labels.data(), labels.size() * 4) || !get(in.f, sum, rows.data(), rows.size() * 4) ||
         !get(in.f, sum, pivots.data(), pivots.size() * 4) || !get(in.f, sum, P.data(), P.size() * 4) || std::fread(&digest, 1, 8, in.f) != 8)

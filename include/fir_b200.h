@@ -85,6 +85,7 @@ int fir_gallery_create(const float* rows, const int32_t* labels, int64_t n, int3
 int fir_gallery_destroy(fir_gallery* g);
 int fir_gallery_set_stream(fir_gallery* g, void* cuda_stream);
 int fir_gallery_info(const fir_gallery* g, int64_t* n, int32_t* d, int32_t* metric, int32_t* n_classes);
+int fir_gallery_index_offset(const fir_gallery* g, int64_t* index_offset); /* global index of local row 0 (a loaded index carries its own) */
 /* the class count defaults to max(label)+1 of THIS handle's rows; a row shard sets the global count so that per-class
  * outputs (fir_class_min, fir_pnn_scores) have the same width on every shard */
 int fir_gallery_set_num_classes(fir_gallery* g, int32_t n_classes);
@@ -211,6 +212,10 @@ int fir_dem_build(fir_gallery* g, const fir_dem_params* params, fir_dem** out);
 int fir_dem_from_state(fir_gallery* g, const int32_t* pivots, int32_t n_pivots, const float* P, float threshold, fir_dem** out);
 int fir_dem_destroy(fir_dem* dem);
 int fir_dem_info(const fir_dem* dem, int32_t* n_pivots, int32_t* chain_rows, float* threshold);
+/* counters of the last fir_dem_search: kernels launched; whether the first round runs as a tensor-core brute force in
+ * pivot space (galleries of >= 8192 rows with 32 pivots); and, while fir_profile_enable is on for the gallery, the summed
+ * duration / count of that round's tcgen05 candidate kernel since profiling was enabled. */
+int fir_dem_search_stats(fir_dem* dem, int32_t* gpu_launches, int32_t* tensor_round, double* candidates_kernel_ms, int32_t* candidates_kernel_launches);
 int fir_dem_get_pivots(const fir_dem* dem, int32_t* out_pivots /* n_pivots */);
 int fir_dem_get_pivot_matrix(const fir_dem* dem, float* out_P /* n_pivots x n, host */);
 int fir_dem_get_min_other(const fir_dem* dem, float* out /* chain_rows, host */);

@@ -51,7 +51,7 @@ def test_c1_shape_adapters_match_reference(ref_l2, tmp_path):
     bi, bd = ref_l2.bf(db, te, dbl, nthreads=os.cpu_count() or 1)
     assert np.array_equal(ints("BF"), bi)                                       # per-query neighbour indices
     err = 100.0 * float(np.mean((bi < 0) | (dbl[np.maximum(bi, 0)] != tel)))
-    assert abs(float(lines["BFERR"][0]) - err) < 1e-9                           # error % of testSetRecognition (ann.cpp:99-103)
+    assert abs(float(lines["BFERR"][0]) - err) < 1e-6                           # error % of testSetRecognition (ann.cpp:99-103)
     assert bits(np.float32(float(lines["WINDOW"][0]))) == bits(ref_l2.distance(te[0], db[1], 64, 320))
     assert bits(np.float32(float(lines["WINDOW"][1]))) == bits(ref_l2.distance(te[1], db[2], 100, 101))
     dem = ref_l2.dem_create(db, dbl, seed=DEM_SEED)                             # the verbatim constructor under the same srand
@@ -60,5 +60,5 @@ def test_c1_shape_adapters_match_reference(ref_l2, tmp_path):
         di = dem.search(te, int(ratio * len(db)), nthreads=os.cpu_count() or 1)[0]
         assert np.array_equal(ints("DEM%d" % r), di)
         derr = 100.0 * float(np.mean((di < 0) | (dbl[np.maximum(di, 0)] != tel)))
-        assert abs(float(lines["DEMERR%d" % r][0]) - derr) < 1e-9
+        assert abs(float(lines["DEMERR%d" % r][0]) - derr) < 1e-6
     dem.close()

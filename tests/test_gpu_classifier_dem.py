@@ -157,3 +157,36 @@ def test_dem_search_large_gallery_fast_first_round(fir, port):
     low.close()
     dem.close()
     gal.close()
+
+
+def test_dem_tensor_first_round_matches_verbatim_reference(fir, port, ref_l2):
+    """>= 8192 rows with 32 pivots: the first 24 candidates of every query come from the tensor-core brute force over the
+    pivot-space gallery (dem_round0_merge_kernel).  The pivot list carries the index-walk quirk (pivots whose gallery index is
+    below their ordinal, so some rows have truncated likelihoods and one stays in the tail), budgets end inside / exactly at /
+    just after the first round, and a threshold far below the data forces the walk to resume in the general path behind the
+    round's closing key.  Checked against the verbatim recognize(); a second gallery with duplicated rows (equal likelihoods —
+    where the reference's unstable partial_sort is implementation-defined) is checked against the port's (likelihood, row) order."""
+    g, gl, q, ql = make_data(port, "l2", 12000, 150, 64, 120, seed=9, sigma=1.2)
+    rng = np.random.default_rng(3)
+    piv = rng.choice(np.arange(40, 12000), 32, replace=False).astype(np.int32)
+    piv[5], piv[9], piv[20], piv[31] = 2, 7, 11, 30               # p_i < i: the reference's 'swap' duplicates / drops an index
+    for dup in (False, True):
+        if dup:
+            g = g.copy()
+            g[7000:7030] = g[300:330]                            # exact duplicates: ties at equal likelihood, resolved by row
+        gal = fir.Gallery(g, gl, "l2")
+        P = ref_l2.all_distances(g, g[piv], gallery_is_lhs=True)
+        other = np.array([P[i][gl != gl[piv[i]]].min() for i in range(32)])
+        for thr in (float(np.sort(other)[0]), 1e-9):
+            dem = fir.Dem(gal, state=(piv, P, thr))
+            rdem = None if dup else ref_l2.dem_create_injected(g, gl, piv, P, thr)
+            for M in (33, 35, 55, 56, 57, 80, 600, 0 if thr > 1e-6 else 1500):
+                got = dem.search(q, M)
+                assert dem.search_stats()["tensor_round"]
+                want = port.dem_search("l2", g, piv, P, thr, M, q) if dup else rdem.search(q, M)
+                for name, a, b in zip(("idx", "dist", "below", "evals"), got, want):
+                    assert np.array_equal(a, b), (dup, thr, M, name)
+            if rdem is not None:
+                rdem.close()
+            dem.close()
+        gal.close()

@@ -191,3 +191,31 @@ def test_approximate_pass_with_exact_rerank(fir, port, metric, n, nq, d, c):
         oi, od = port.topk(metric, g, q, k, nthreads=8)
         assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od)), (metric, k, gal.stats())
     gal.close()
+
+
+def test_kl_approx_path_with_mixed_sign_rows(fir, port):
+    """The KL error model of the approximate path assumes non-negative features; the reference's guards (`l + r > 0`, `l > 0`,
+    db_features.cpp:33-36) also accept mixed-sign rows (PCA'd features), where log(2l/(l+r)) is unbounded.  Mixed-sign queries
+    must be re-run exactly, and a mixed-sign gallery must not use the approximate kernels at all — answers stay the port's."""
+    g, gl, q, ql = make_data(port, "kl", 5000, 96, 96, 12, seed=31)
+    rng = np.random.default_rng(5)
+    q2 = q.copy()
+    rows = rng.choice(len(q2), 24, replace=False)
+    for r in rows:                                               # negative entries that nearly cancel a gallery value: l + r -> 0+
+        cols = rng.choice(96, 6, replace=False)
+        q2[r, cols] = -g[rng.integers(0, len(g)), cols] * np.float32(1 - 1e-6)
+    gal = fir.Gallery(g, gl, "kl")
+    idx, dist = gal.search(q2, k=5, path=fir.PATH_APPROX)
+    st = gal.stats()
+    assert st["path_used"] == fir.PATH_APPROX and st["n_fallback"] >= len(rows)      # every mixed-sign query went to the exact re-run
+    oi, od = port.topk("kl", g, q2, 5)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+    gal.close()
+    g2 = g.copy()
+    g2[rng.choice(len(g2), 200, replace=False), 3] *= -1         # mixed-sign gallery
+    gal = fir.Gallery(g2, gl, "kl")
+    idx, dist = gal.search(q, k=5, path=fir.PATH_APPROX)
+    assert gal.stats()["path_used"] == fir.PATH_EXACT
+    oi, od = port.topk("kl", g2, q, 5)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+    gal.close()

@@ -38,7 +38,7 @@ EXPORTS = [
     "fir_dem_build", "fir_dem_from_state", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
     "fir_dem_get_min_other", "fir_dem_search", "fir_dem_search_stats", "fir_index_save", "fir_index_load", "fir_synth_rows",
     "fir_comm_unique_id", "fir_comm_init_rank", "fir_comm_destroy", "fir_comm_info",
-    "fir_shard_search_topk", "fir_shard_class_min", "fir_shard_pnn_scores",
+    "fir_shard_search_topk", "fir_shard_class_min", "fir_shard_pnn_scores", "fir_shard_dem_build",
     "fir_sharded_create", "fir_sharded_destroy", "fir_sharded_info", "fir_sharded_shard",
     "fir_sharded_search_topk", "fir_sharded_class_min", "fir_sharded_pnn_scores",
 ]
@@ -123,6 +123,7 @@ def lib():
     L.fir_shard_search_topk.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp]
     L.fir_shard_class_min.argtypes = [vp, vp, vp, i64, i32, vp, vp]
     L.fir_shard_pnn_scores.argtypes = [vp, vp, vp, i64, f64, i64, i32, vp, vp]
+    L.fir_shard_dem_build.argtypes = [vp, vp, i64, C.POINTER(DemParams), C.POINTER(vp)]
     L.fir_sharded_create.argtypes = [vp, vp, i64, i32, i32, i32, C.POINTER(vp)]
     L.fir_sharded_destroy.argtypes = [vp]
     L.fir_sharded_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
@@ -605,6 +606,13 @@ class RankShard:
             dist = _out((nq, k), np.float32, "float32", space == DEVICE, getattr(q, "device", None))
         _check(lib().fir_shard_search_topk(self.gallery._h, self.comm._h, _ptr(q), nq, k, path, space, _ptr(idx), _ptr(dist)))
         return idx, dist
+
+    def dem(self, pivot0=-1, seed=0, false_accept_rate=0.01, threshold=0.0, max_chain=0, max_pivots=0):
+        """Collective: ONE DirectedEnumeration over the whole sharded gallery; .search() on the result is collective too."""
+        p = DemParams(int(pivot0), int(seed), float(false_accept_rate), float(threshold), int(max_chain), int(max_pivots))
+        h = C.c_void_p(None)
+        _check(lib().fir_shard_dem_build(self.gallery._h, self.comm._h, self.n_total, C.byref(p), C.byref(h)))
+        return Dem._adopt(self.gallery, h)
 
     def class_min(self, queries):
         q, space = _prep(queries, np.float32, "float32")

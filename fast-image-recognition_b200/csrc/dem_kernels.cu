@@ -16,6 +16,7 @@
 //         distanceCalcCount.
 #include "fir_common.cuh"
 #include "handles.hpp"
+#include "sharded.hpp"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -42,6 +43,12 @@ struct fir_dem {
     uint32_t* sp_mask = nullptr;       // [n_special] bit i = step i contributes to the row's likelihood
     unsigned char* sp_tail = nullptr;  // [n_special] 1 = the row is a candidate
     int32_t last_launches = 0;         // kernels launched by the last fir_dem_search
+    // row-sharded build (fir_shard_dem_build): this handle covers gallery rows [row_lo, row_lo + g->n) of n_total; pivots,
+    // QState indices and the candidate order are GLOBAL; the pivots' feature rows are replicated on every rank
+    bool sharded = false;
+    fir_comm* comm = nullptr;          // borrowed
+    int64_t row_lo = 0, n_total = 0, min_shard_rows = 0;
+    float* pivot_rows = nullptr;       // [n_pivots][dp]
 };
 
 namespace fir {
@@ -54,15 +61,17 @@ const fir_gallery* dem_gallery(const fir_dem* dem) { return dem ? dem->g : nullp
 constexpr int RB = 256;   // threads per block of the reduction kernels
 
 // far-sum update + block-level arg-max / min-other for one chain step
+// (row shards: *cur_pivot is a GLOBAL row, `lo` the global index of local row 0, and the pivot's class comes from the
+//  broadcast pivot record — the pivot itself may live on another rank)
 __global__ void __launch_bounds__(RB) dem_step_kernel(const float* __restrict__ row, int64_t n, const int32_t* __restrict__ labels,
                                                       const int32_t* __restrict__ cur_pivot, double* __restrict__ far_sum,
                                                       float* __restrict__ keep_row, double* __restrict__ blk_max, int32_t* __restrict__ blk_arg,
-                                                      float* __restrict__ blk_min) {
+                                                      float* __restrict__ blk_min, int64_t lo, const uint32_t* __restrict__ pivot_label) {
     __shared__ double s_max[RB];
     __shared__ int32_t s_arg[RB];
     __shared__ float s_min[RB];
-    const int pivot = *cur_pivot;
-    const int pl = labels[pivot];
+    const int64_t pivot = (int64_t)*cur_pivot - lo;
+    const int pl = pivot_label ? (int)*pivot_label : labels[pivot];
     double best = 0.0; int32_t arg = -1;                     // maxFarDist = 0, mostFarModel = -1  (ann.cpp:305-306)
     float mn = 3.402823466e+38f;                             // numeric_limits<float>::max()      (:307)
     for (int64_t j = (int64_t)blockIdx.x * RB + threadIdx.x; j < n; j += (int64_t)gridDim.x * RB) {
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(RB) dem_step_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(RB) dem_step_final_kernel(const double* __restrict__ blk_max, const int32_t* __restrict__ blk_arg,
                                                             const float* __restrict__ blk_min, int nblk, int step, int chain_rows,
                                                             int32_t* __restrict__ pivots, float* __restrict__ min_other,
-                                                            int32_t* __restrict__ cur_pivot) {
+                                                            int32_t* __restrict__ cur_pivot, int64_t lo, unsigned long long* __restrict__ trip) {
     __shared__ double s_max[RB];
     __shared__ int32_t s_arg[RB];
     __shared__ float s_min[RB];
@@ -112,9 +121,39 @@ __global__ void __launch_bounds__(RB) dem_step_final_kernel(const double* __rest
         __syncthreads();
     }
     if (threadIdx.x == 0) {
+        if (trip) {                                                             // row shard: this rank's (far-sum maximum, global row, minimum) goes to the exchange
+            trip[0] = (unsigned long long)__double_as_longlong(s_max[0]);
+            trip[1] = ((unsigned long long)(uint32_t)(s_arg[0] < 0 ? -1 : (int32_t)(s_arg[0] + lo)) << 32) | __float_as_uint(s_min[0]);
+            return;
+        }
         min_other[step] = s_min[0];                                             // ann.cpp:327
         if (step + 1 < chain_rows) { pivots[step + 1] = s_arg[0]; *cur_pivot = s_arg[0] < 0 ? 0 : s_arg[0]; }   // :328-330
     }
+}
+
+// ---- row-sharded build: the pivot's feature row + class travel as raw bits (non-owners contribute zeros, all-reduce(max)
+// over uint32 returns the owner's bits exactly), every rank's (maximum, row, minimum) triple is all-gathered and combined in
+// the reference's scan order (strict '>' over ascending global rows ⇒ lowest row on ties) --------------------------------
+__global__ void dem_pivot_record_kernel(const float* __restrict__ rows, int ld, const int32_t* __restrict__ labels, int64_t lo, int64_t n,
+                                        const int32_t* __restrict__ cur_pivot, uint32_t* __restrict__ rec /* [ld + 1] */) {
+    const int64_t p = (int64_t)*cur_pivot - lo;
+    const bool mine = p >= 0 && p < n;
+    for (int c = threadIdx.x; c <= ld; c += blockDim.x)
+        rec[c] = !mine ? 0u : (c < ld ? __float_as_uint(rows[p * ld + c]) : (uint32_t)labels[p]);
+}
+__global__ void dem_pick_global_kernel(const unsigned long long* __restrict__ trips, int world, int step, int chain_rows, int32_t* __restrict__ pivots,
+                                       float* __restrict__ min_other, int32_t* __restrict__ cur_pivot) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double best = 0.0; int32_t arg = -1; float mn = 3.402823466e+38f;
+    for (int r = 0; r < world; ++r) {                                           // ranks hold ascending row ranges
+        const double v = __longlong_as_double((long long)trips[2 * r]);
+        const int32_t a = (int32_t)(uint32_t)(trips[2 * r + 1] >> 32);
+        const float m = __uint_as_float((uint32_t)trips[2 * r + 1]);
+        if (a >= 0 && (arg < 0 || v > best)) { best = v; arg = a; }
+        mn = fminf(mn, m);
+    }
+    min_other[step] = mn;
+    if (step + 1 < chain_rows) { pivots[step + 1] = arg; *cur_pivot = arg < 0 ? 0 : arg; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -287,7 +326,8 @@ __device__ __forceinline__ uint32_t radix_digit(uint32_t key, int pass) {
 
 __global__ void __launch_bounds__(256) dem_hist_kernel(const float* __restrict__ lik, const int32_t* __restrict__ qlist, int nqc, int64_t n,
                                                        const QState* __restrict__ st, int pass, const uint32_t* __restrict__ prefix,
-                                                       const int32_t* __restrict__ take_all, uint32_t* __restrict__ hist, const int32_t* __restrict__ skip) {
+                                                       const int32_t* __restrict__ take_all, uint32_t* __restrict__ hist, const int32_t* __restrict__ skip,
+                                                       int32_t ioff = 0 /* row shards: QState rows are global, v is local */) {
     __shared__ uint32_t sh[2048];
     const int qc = blockIdx.y;
     if (skip && skip[qc]) return;
@@ -300,7 +340,7 @@ __global__ void __launch_bounds__(256) dem_hist_kernel(const float* __restrict__
     for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < n; v += (int64_t)gridDim.x * 256) {
         const uint32_t key = __float_as_uint(lr[v]);
         if (key >= 0x7f800000u) continue;                    // +inf: not in the tail
-        if (!after_last(key, (int32_t)v, s)) continue;
+        if (!after_last(key, (int32_t)v + ioff, s)) continue;
         if (radix_match(key, pass, pre)) atomicAdd(&sh[radix_digit(key, pass)], 1u);
     }
     __syncthreads();
@@ -349,7 +389,8 @@ __global__ void __launch_bounds__(256) dem_collect_fast_kernel(const float* __re
                                                                const QState* __restrict__ st, const int32_t* __restrict__ take_all,
                                                                const uint32_t* __restrict__ key_sel, int cap, int32_t* __restrict__ cand,
                                                                uint32_t* __restrict__ cand_key, int32_t* __restrict__ cnt,
-                                                               int32_t* __restrict__ tie_buf, int32_t* __restrict__ tie_cnt, const int32_t* __restrict__ skip) {
+                                                               int32_t* __restrict__ tie_buf, int32_t* __restrict__ tie_cnt, const int32_t* __restrict__ skip,
+                                                               int32_t ioff = 0) {
     const int qc = blockIdx.y;
     if (skip && skip[qc]) return;
     const QState s = st[qlist[qc]];
@@ -361,7 +402,7 @@ __global__ void __launch_bounds__(256) dem_collect_fast_kernel(const float* __re
     uint32_t* outk = cand_key + (int64_t)qc * cap;
     for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < n; v += (int64_t)gridDim.x * 256) {
         const uint32_t key = __float_as_uint(lr[v]);
-        if (key >= 0x7f800000u || !after_last(key, (int32_t)v, s)) continue;
+        if (key >= 0x7f800000u || !after_last(key, (int32_t)v + ioff, s)) continue;
         if (all || key < ksel) {
             const int pos = atomicAdd(&cnt[qc], 1);
             if (pos < cap) { out[pos] = (int32_t)v; outk[pos] = key; }
@@ -407,7 +448,7 @@ __global__ void __launch_bounds__(128) dem_collect_kernel(const float* __restric
                                                           const QState* __restrict__ st, const int32_t* __restrict__ overflow,
                                                           const uint32_t* __restrict__ key_sel, const int32_t* __restrict__ tie_take,
                                                           int cap, int32_t* __restrict__ cand, uint32_t* __restrict__ cand_key,
-                                                          int32_t* __restrict__ last_tie_idx) {
+                                                          int32_t* __restrict__ last_tie_idx, int32_t ioff = 0) {
     const int lane = threadIdx.x & 31;
     const int qc = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (qc >= nqc) return;
@@ -426,7 +467,7 @@ __global__ void __launch_bounds__(128) dem_collect_kernel(const float* __restric
         uint32_t key = 0;
         if (v < n) {
             key = __float_as_uint(lr[v]);
-            if (key < 0x7f800000u && after_last(key, (int32_t)v, s)) {
+            if (key < 0x7f800000u && after_last(key, (int32_t)v + ioff, s)) {
                 if (take_all || key < ksel) ok = true;
                 else if (key == ksel) tie = true;
             }
@@ -519,6 +560,98 @@ __global__ void __launch_bounds__(128) dem_reduce_kernel(const float* __restrict
         if (!s.done) atomicAdd(n_active, 1);
         st[qi] = s;
     }
+}
+
+// ---- row shards: the round's exchange ---------------------------------------------------------------
+// Every rank walks ITS rows: the local next-`want` candidates after the query's (last_key, last_idx) in (likelihood, row)
+// order, with their exact distances, packed as records {likelihood bits, GLOBAL row, distance bits}.  The records of all
+// ranks are all-gathered; the global first `want` of the union are the first `want` of the whole gallery's walk (each rank
+// supplied its own first `want`), so sorting the union and folding it in order reproduces recognize() (ann.cpp:472-476) —
+// identically on every rank, which keeps the replicated query states in step.
+__global__ void dem_pack_records_kernel(const int32_t* __restrict__ cand, const uint32_t* __restrict__ cand_key, const float* __restrict__ cdist,
+                                        const int32_t* __restrict__ round_n, int nqc, int cap, int32_t ioff, uint32_t* __restrict__ rec) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nqc * cap) return;
+    const int qc = (int)(t / cap), j = (int)(t - (int64_t)qc * cap);
+    const int32_t v = cand[t];
+    const bool live = v >= 0 && j < max(round_n[qc], 0);
+    rec[3 * t + 0] = live ? cand_key[t] : 0xffffffffu;
+    rec[3 * t + 1] = live ? (uint32_t)(v + ioff) : 0xffffffffu;
+    rec[3 * t + 2] = live ? __float_as_uint(cdist[t]) : 0u;
+}
+
+// one block per query: bitonic sort of the union by (likelihood, global row), then the in-order fold
+__global__ void __launch_bounds__(256) dem_global_reduce_kernel(const uint32_t* __restrict__ rec /* [world][nqc][cap][3] */, int world, int nqc, int cap,
+                                                                const int32_t* __restrict__ qlist, int round_size, float threshold, int M,
+                                                                int64_t tail_size, int S, QState* __restrict__ st, int32_t* __restrict__ n_active) {
+    extern __shared__ unsigned long long gsort[];          // [P2] keys, then [P2] uint32 distance bits
+    __shared__ int s_hit_pos;
+    __shared__ unsigned long long s_best;                  // (ordered distance bits << 32) | position: first minimum in order
+    const int qc = blockIdx.x, tid = threadIdx.x;
+    const int q = qlist ? qlist[qc] : qc;
+    QState s = st[q];
+    if (s.done) return;
+    const int total = world * cap;
+    int P2 = 1;
+    while (P2 < total) P2 <<= 1;
+    uint32_t* gdist = reinterpret_cast<uint32_t*>(gsort + P2);
+    // sort key = (likelihood bits << 32 | global row); the distance rides along through an index sort: keys are unique per
+    // live record (a row appears once), so the payload is looked up again by binary position after sorting pairs together
+    for (int i = tid; i < P2; i += 256) {
+        unsigned long long k = ~0ull; uint32_t d = 0u;
+        if (i < total) {
+            const int r = i / cap, j = i - r * cap;
+            const uint32_t* e = rec + 3 * (((int64_t)r * nqc + qc) * cap + j);
+            if (e[1] != 0xffffffffu) { k = ((unsigned long long)e[0] << 32) | e[1]; d = e[2]; }
+        }
+        gsort[i] = k; gdist[i] = d;
+    }
+    if (tid == 0) { s_hit_pos = 0x7fffffff; s_best = ~0ull; }
+    __syncthreads();
+    for (int k2 = 2; k2 <= P2; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P2; i += 256) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = gsort[i], b = gsort[l];
+                    const bool up = (i & k2) == 0;
+                    if ((a > b) == up) { gsort[i] = b; gsort[l] = a; const uint32_t t = gdist[i]; gdist[i] = gdist[l]; gdist[l] = t; }
+                }
+            }
+            __syncthreads();
+        }
+    const int want = max(0, min(round_size, M - s.count));
+    // live records are a prefix after sorting; count them (binary search by thread 0 is enough: P2 <= 16384)
+    int valid;
+    { int lo = 0, hi = total; while (lo < hi) { const int mid = (lo + hi) >> 1; if (gsort[mid] != ~0ull) lo = mid + 1; else hi = mid; } valid = lo; }
+    const int m = min(want, valid);
+    for (int i = tid; i < m; i += 256) {
+        const float d = __uint_as_float(gdist[i]);
+        if (d < threshold) atomicMin(&s_hit_pos, i);
+        atomicMin(&s_best, ((unsigned long long)ordered_bits(d) << 32) | (uint32_t)i);
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    if (s_hit_pos != 0x7fffffff) {                          // CHECK_FOR_BEST_DIST (ann.cpp:390-400): the first candidate under the threshold ends the walk
+        const int p = s_hit_pos;
+        s.best_dist = __uint_as_float(gdist[p]); s.best_idx = (int32_t)(uint32_t)gsort[p]; s.below = 1; s.done = 1;
+        s.count += p + 1;
+        st[q] = s;
+        return;
+    }
+    if (m > 0) {
+        const int p = (int)(uint32_t)s_best;
+        const float bd = __uint_as_float(gdist[p]);
+        if (bd < s.best_dist) { s.best_dist = bd; s.best_idx = (int32_t)(uint32_t)gsort[p]; }
+        s.count += m;
+        s.started = 1;
+        s.last_key = (uint32_t)(gsort[m - 1] >> 32);
+        s.last_idx = (int32_t)(uint32_t)gsort[m - 1];
+    }
+    if (valid < want) s.done = 1;                           // every rank handed over all it had left: the tail is exhausted
+    if (s.count >= M || (int64_t)(s.count - S) >= tail_size) s.done = 1;
+    if (!s.done) atomicAdd(n_active, 1);
+    st[q] = s;
 }
 
 __global__ void dem_fill_pivot_cand_kernel(const int32_t* __restrict__ pivots, int S, int64_t nq, int32_t* __restrict__ cand) {
@@ -682,6 +815,18 @@ static int finalize_search_state(fir_dem* dm) {
             member[i][k] = (unsigned char)mult;
         }
     }
+    // (row shards: the walk above is over GLOBAL rows; this handle applies it to the special rows it holds and drops the rest)
+    if (dm->sharded) {
+        std::vector<int64_t> sp_local;
+        std::vector<std::vector<unsigned char> > member_local(S);
+        for (size_t k = 0; k < sp.size(); ++k)
+            if (sp[k] >= dm->row_lo && sp[k] < dm->row_lo + n) {
+                sp_local.push_back(sp[k] - dm->row_lo);
+                for (int i = 0; i < S; ++i) member_local[i].push_back(member[i][k]);
+            }
+        sp.swap(sp_local);
+        member.swap(member_local);
+    }
     FIR_CUDA_TRY(cudaMemcpyAsync(dm->P_search, dm->P_raw, 4 * (size_t)S * n, cudaMemcpyDeviceToDevice, s));
     FIR_CUDA_TRY(cudaMemsetAsync(dm->in_tail, 1, (size_t)n, s));
     const float neg = -1.f; const unsigned char zero = 0;
@@ -690,12 +835,13 @@ static int finalize_search_state(fir_dem* dm) {
             if (!member[i][k]) FIR_CUDA_TRY(cudaMemcpyAsync(dm->P_search + (size_t)i * n + sp[k], &neg, 4, cudaMemcpyHostToDevice, s));
         if (!member[S - 1][k]) FIR_CUDA_TRY(cudaMemcpyAsync(dm->in_tail + sp[k], &zero, 1, cudaMemcpyHostToDevice, s));
     }
-    dm->tail_size = n - S;                               // each step moves exactly one position into the prefix
+    dm->tail_size = (dm->sharded ? dm->n_total : n) - S; // each step moves exactly one position into the prefix
     FIR_CUDA_TRY(cudaMemcpyAsync(dm->d_pivots, dm->pivots.data(), 4 * (size_t)S, cudaMemcpyHostToDevice, s));
     FIR_CUDA_TRY(cudaStreamSynchronize(s));
     // round 0 on tensor cores: the pivot-space gallery (see dem_round0_merge_kernel)
     static const int tensor_on = [] { const char* e = getenv("FIR_DEM_TENSOR"); return e ? atoi(e) : 1; }();
-    if (tensor_on && S == 32 && n >= kDemTensorMinRows && g->cc_major >= 10 && tensor_path_supported(32)) {
+    // (row shards: every rank must take the same decision — the rounds are collective — so it rests on the smallest shard)
+    if (tensor_on && S == 32 && (dm->sharded ? dm->min_shard_rows : n) >= kDemTensorMinRows && g->cc_major >= 10 && tensor_path_supported(32)) {
         const int ns = (int)sp.size();
         std::vector<int32_t> rows(ns);
         std::vector<uint32_t> mask(ns, 0u);
@@ -781,8 +927,8 @@ int fir_dem_build(fir_gallery* g, const fir_dem_params* params, fir_dem** out) {
         // P[ii][j] = feature_distance(db[j], db[pivot])  (lhs = gallery row j, rhs = pivot, ann.cpp:309)
         int st_ = launch_pair_distances(g->metric, nullptr, 1, g->dp, g->rows, g->dp, n, g->d, nullptr, (int)n, 1, row, s, cur);
         if (st_ != FIR_OK) return cleanup(st_);
-        dem_step_kernel<<<nblk, RB, 0, s>>>(row, n, g->labels, cur, far_sum, ii < keep ? dm->P_raw + (size_t)ii * n : nullptr, blk_max, blk_arg, blk_min);
-        dem_step_final_kernel<<<1, RB, 0, s>>>(blk_max, blk_arg, blk_min, nblk, ii, np, d_chain, d_min_other, cur);
+        dem_step_kernel<<<nblk, RB, 0, s>>>(row, n, g->labels, cur, far_sum, ii < keep ? dm->P_raw + (size_t)ii * n : nullptr, blk_max, blk_arg, blk_min, 0, nullptr);
+        dem_step_final_kernel<<<1, RB, 0, s>>>(blk_max, blk_arg, blk_min, nblk, ii, np, d_chain, d_min_other, cur, 0, nullptr);
     }
     if (cudaGetLastError() != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, "DEM build kernel launch failed"));
     dm->pivots.resize(np);
@@ -794,6 +940,109 @@ int fir_dem_build(fir_gallery* g, const fir_dem_params* params, fir_dem** out) {
     for (int i = 0; i < np; ++i)
         if (dm->pivots[i] < 0) return cleanup(fail(FIR_ERR_UNSUPPORTED, "degenerate gallery: the farthest-point chain found no next pivot (the reference indexes dbImages[-1] here)"));
     // threshold: getThreshold(otherClassesDists, FAR) = element (int)(size*FAR) of the sorted list (ann.cpp:84-93), unless overridden (:277-279,340)
+    if (params->threshold > 0) dm->threshold = params->threshold;
+    else {
+        std::vector<float> o(dm->min_other);
+        int ind = (int)((float)o.size() * params->false_accept_rate);
+        ind = std::max(0, std::min(ind, (int)o.size() - 1));
+        std::nth_element(o.begin(), o.begin() + ind, o.end());
+        dm->threshold = o[ind];
+    }
+    { int st2 = finalize_search_state(dm); if (st2 != FIR_OK) return cleanup(st2); }
+    *out = dm;
+    return cleanup(FIR_OK);
+}
+
+// Row-sharded build (collective: every rank of `c` calls it with its own shard handle).  The farthest-point chain is global:
+// per step the current pivot's row + class are exchanged as raw bits (all-reduce(max) with zeros from the non-owners), every
+// rank computes P[ii][j] for ITS rows j and its far-sum maximum / minimum other-class distance, the (maximum, row, minimum)
+// triples are all-gathered and combined in the reference's scan order.  The next pivot never leaves the device: two small
+// collectives per step, no host synchronisation inside the chain.  Pivots, threshold and the candidate order are those of
+// ONE DirectedEnumeration over the whole gallery (ann.cpp:270-348).
+int fir_shard_dem_build(fir_gallery* g, fir_comm* c, int64_t n_total, const fir_dem_params* params, fir_dem** out) {
+    if (!out) return fail(FIR_ERR_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (!g || !c || !params) return fail(FIR_ERR_BAD_ARG, "null argument");
+    if (c->world > 1 && !nccl_api()) return fail(FIR_ERR_NCCL, "NCCL unavailable");
+    FIR_CUDA_TRY(cudaSetDevice(g->device));
+    const int64_t n = g->n, lo = g->index_offset, N = n_total;
+    if (N < 2 || lo < 0 || lo + n > N) return fail(FIR_ERR_BAD_ARG, "shard rows [index_offset, index_offset + n) must lie inside n_total");
+    int np = (int)((double)N * 0.015);                              // ann.cpp:373
+    if (np < 5) np = 5;
+    if (params->max_chain > 0 && params->max_chain < np) np = params->max_chain;
+    if (np > N) np = (int)N;
+    int keep = params->max_pivots > 0 ? std::min(params->max_pivots, 32) : 32;
+    keep = std::min(keep, np);
+    int pivot0 = params->pivot0;
+    if (pivot0 < 0) {
+        uint64_t z = (uint64_t)params->seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+        z ^= z >> 31; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 29;
+        pivot0 = (int)(z % (uint64_t)N);
+    }
+    if (pivot0 >= N) return fail(FIR_ERR_BAD_ARG, "pivot0 out of range");
+    fir_dem* dm = new fir_dem();
+    dm->g = g; dm->chain_rows = np; dm->n_pivots = keep;
+    dm->sharded = true; dm->comm = c; dm->row_lo = lo; dm->n_total = N;
+    cudaStream_t s = g->stream;
+    const int dp = g->dp, W = c->world;
+    const int nblk = (int)std::min<int64_t>(ceil_div(n, RB), 1184);
+    float* row = nullptr; double* far_sum = nullptr; double* blk_max = nullptr; int32_t* blk_arg = nullptr; float* blk_min = nullptr;
+    int32_t* d_chain = nullptr; float* d_min_other = nullptr; int32_t* cur = nullptr; uint32_t* rec = nullptr; unsigned long long* trips = nullptr;
+    auto cleanup = [&](int code) {
+        cudaFree(row); cudaFree(far_sum); cudaFree(blk_max); cudaFree(blk_arg); cudaFree(blk_min); cudaFree(d_chain); cudaFree(d_min_other); cudaFree(cur);
+        cudaFree(rec); cudaFree(trips);
+        if (code != FIR_OK) fir_dem_destroy(dm);
+        return code;
+    };
+    if (cudaMalloc(&row, 4 * (size_t)n) != cudaSuccess || cudaMalloc(&far_sum, 8 * (size_t)n) != cudaSuccess ||
+        cudaMalloc(&blk_max, 8 * (size_t)nblk) != cudaSuccess || cudaMalloc(&blk_arg, 4 * (size_t)nblk) != cudaSuccess ||
+        cudaMalloc(&blk_min, 4 * (size_t)nblk) != cudaSuccess || cudaMalloc(&d_chain, 4 * (size_t)np) != cudaSuccess ||
+        cudaMalloc(&d_min_other, 4 * (size_t)np) != cudaSuccess || cudaMalloc(&cur, 4) != cudaSuccess ||
+        cudaMalloc(&rec, 4 * (size_t)(dp + 1)) != cudaSuccess || cudaMalloc(&trips, 16 * (size_t)(W + 1)) != cudaSuccess ||
+        cudaMalloc(&dm->P_raw, 4 * (size_t)keep * n) != cudaSuccess || cudaMalloc(&dm->P_search, 4 * (size_t)keep * n) != cudaSuccess ||
+        cudaMalloc(&dm->in_tail, (size_t)n) != cudaSuccess || cudaMalloc(&dm->d_pivots, 4 * (size_t)keep) != cudaSuccess ||
+        cudaMalloc(&dm->pivot_rows, 4 * (size_t)keep * dp) != cudaSuccess)
+        return cleanup(fail(FIR_ERR_OOM, "sharded DEM build allocation failed"));
+    cudaMemsetAsync(far_sum, 0, 8 * (size_t)n, s);
+    cudaMemsetAsync(d_chain, 0xFF, 4 * (size_t)np, s);
+    cudaMemcpyAsync(d_chain, &pivot0, 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(cur, &pivot0, 4, cudaMemcpyHostToDevice, s);
+    NcclApi* NC = W > 1 ? nccl_api() : nullptr;
+    unsigned long long* my_trip = trips + 2 * (size_t)W;            // this rank's triple; trips[0 .. 2W) receives everyone's
+    {   // smallest shard of the communicator (decides, identically everywhere, whether the first round runs on tensor cores)
+        unsigned long long v = (unsigned long long)n;
+        cudaMemcpyAsync(my_trip, &v, 8, cudaMemcpyHostToDevice, s);
+        if (NC) { ncclResult_t e = NC->AllReduce(my_trip, my_trip, 1, ncclUint64, ncclMin, c->comm, s);
+                  if (e != ncclSuccess) return cleanup(fail(FIR_ERR_NCCL, std::string("ncclAllReduce (shard rows): ") + NC->GetErrorString(e))); }
+        cudaMemcpyAsync(&v, my_trip, 8, cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, "sharded DEM build: stream error"));
+        dm->min_shard_rows = (int64_t)v;
+    }
+    for (int ii = 0; ii < np; ++ii) {
+        dem_pivot_record_kernel<<<1, 256, 0, s>>>(g->rows, dp, g->labels, lo, n, cur, rec);
+        if (NC) { ncclResult_t e = NC->AllReduce(rec, rec, (size_t)dp + 1, ncclUint32, ncclMax, c->comm, s);
+                  if (e != ncclSuccess) return cleanup(fail(FIR_ERR_NCCL, std::string("ncclAllReduce (pivot record): ") + NC->GetErrorString(e))); }
+        if (ii < keep) cudaMemcpyAsync(dm->pivot_rows + (size_t)ii * dp, rec, 4 * (size_t)dp, cudaMemcpyDeviceToDevice, s);
+        // P[ii][j] = feature_distance(db[j], pivot)  (lhs = gallery row j, rhs = the pivot, ann.cpp:309)
+        int st_ = launch_pair_distances(g->metric, reinterpret_cast<const float*>(rec), 1, dp, g->rows, dp, n, g->d, nullptr, (int)n, 1, row, s);
+        if (st_ != FIR_OK) return cleanup(st_);
+        dem_step_kernel<<<nblk, RB, 0, s>>>(row, n, g->labels, cur, far_sum, ii < keep ? dm->P_raw + (size_t)ii * n : nullptr, blk_max, blk_arg, blk_min, lo,
+                                            rec + dp);
+        dem_step_final_kernel<<<1, RB, 0, s>>>(blk_max, blk_arg, blk_min, nblk, ii, np, d_chain, d_min_other, cur, lo, my_trip);
+        if (NC) { ncclResult_t e = NC->AllGather(my_trip, trips, 2, ncclUint64, c->comm, s);
+                  if (e != ncclSuccess) return cleanup(fail(FIR_ERR_NCCL, std::string("ncclAllGather (chain step): ") + NC->GetErrorString(e))); }
+        else cudaMemcpyAsync(trips, my_trip, 16, cudaMemcpyDeviceToDevice, s);
+        dem_pick_global_kernel<<<1, 32, 0, s>>>(trips, W, ii, np, d_chain, d_min_other, cur);
+    }
+    if (cudaGetLastError() != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, "sharded DEM build kernel launch failed"));
+    dm->pivots.resize(np);
+    dm->min_other.resize(np);
+    cudaError_t e = cudaMemcpyAsync(dm->pivots.data(), d_chain, 4 * (size_t)np, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dm->min_other.data(), d_min_other, 4 * (size_t)np, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cleanup(fail(FIR_ERR_CUDA, std::string("sharded DEM build: ") + cudaGetErrorString(e)));
+    for (int i = 0; i < np; ++i)
+        if (dm->pivots[i] < 0) return cleanup(fail(FIR_ERR_UNSUPPORTED, "degenerate gallery: the farthest-point chain found no next pivot"));
     if (params->threshold > 0) dm->threshold = params->threshold;
     else {
         std::vector<float> o(dm->min_other);
@@ -837,6 +1086,7 @@ int fir_dem_destroy(fir_dem* dm) {
     cudaFree(dm->P_raw); cudaFree(dm->P_search); cudaFree(dm->in_tail); cudaFree(dm->d_pivots);
     if (dm->pt) fir_gallery_destroy(dm->pt);
     cudaFree(dm->center); cudaFree(dm->exclude); cudaFree(dm->sp_rows); cudaFree(dm->sp_mask); cudaFree(dm->sp_tail);
+    cudaFree(dm->pivot_rows);
     delete dm;
     return FIR_OK;
 }
@@ -883,18 +1133,24 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
     cudaStream_t s = g->stream;
     const int64_t n = g->n;
     const int S = dm->n_pivots;
-    const int M = (count_to_check > 0 && count_to_check < n) ? count_to_check : (int)n;     // ann.h:20-22
+    const bool sharded = dm->sharded && dm->comm && dm->comm->world > 1;
+    const int64_t n_all = dm->sharded ? dm->n_total : n;                                     // rows of the WHOLE gallery
+    const int32_t ioff = dm->sharded ? (int32_t)dm->row_lo : 0;                               // row shards: QState rows are global
+    const int M = (count_to_check > 0 && count_to_check < n_all) ? count_to_check : (int)n_all;   // ann.h:20-22
     // (the reference has undefined behaviour for M < S — partial_sort with middle < first, ann.cpp:469; here the
     //  candidate phase simply does not run, which is also what its while-loop at :472 does.)
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const int QC = (int)std::max<int64_t>(8, std::min<int64_t>(std::min<int64_t>(nq, 2048), ((int64_t)4 << 30) / (4 * n)));   // lik chunk ≤ 4 GiB
-    const int cap_max = (int)std::min<int64_t>(n, std::max<int64_t>(256, ((int64_t)256 << 20) / ((int64_t)QC * 12)));
+    // (row shards: chunking must be identical on every rank — the rounds are collective — so it is sized from the largest shard)
+    const int64_t n_sz = sharded ? ceil_div(n_all, dm->comm->world) : n;
+    const int QC = (int)std::max<int64_t>(8, std::min<int64_t>(std::min<int64_t>(nq, 2048), ((int64_t)4 << 30) / (4 * n_sz)));   // lik chunk ≤ 4 GiB
+    int cap_max = (int)std::min<int64_t>(n_sz, std::max<int64_t>(256, ((int64_t)256 << 20) / ((int64_t)QC * 12)));
+    if (sharded) cap_max = std::min(cap_max, 1024);          // the exchange sorts world x cap records per query in shared memory
     size_t need = al(4 * (size_t)nq * g->dp) + 2 * al(4 * (size_t)nq * S) + al(sizeof(QState) * (size_t)nq) + al(4 * (size_t)nq) +
                   al(4 * (size_t)QC * n) + al(4 * (size_t)QC * 2048) + 3 * al(4 * (size_t)QC * cap_max) + 14 * al(4 * (size_t)QC) + al(4 * (size_t)QC * TIE_CAP) +
                   al((size_t)nq * 9) + al(4 * (size_t)nq) * 2 + 65536;
     static const int fast_on = [] { const char* e = getenv("FIR_DEM_FAST"); return e ? atoi(e) : 1; }();
     const int64_t ng = ceil_div(n, 32);
-    const bool fast = fast_on != 0 && ng >= 1024;            // first-round select through per-warp minima (dem_fast_*)
+    const bool fast = fast_on != 0 && ng >= 1024 && !sharded;   // first-round select through per-warp minima (dem_fast_*)
     if (fast) need += al(4 * (size_t)QC * ng) + 2 * al(4 * (size_t)QC * FAST_CAP) + 4 * al(4 * (size_t)QC);
     const bool tensor0 = dm->pt != nullptr && M > S;
     const int k0 = tensor0 ? std::min(kRound0K, M - S) : 0;
@@ -960,11 +1216,34 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
         return fail(FIR_ERR_INTERNAL, "workspace underestimated (dem search)");
 
     // 1. pivot distances + pivot phase
-    dem_fill_pivot_cand_kernel<<<(unsigned)ceil_div(nq * S, 256), 256, 0, s>>>(dm->d_pivots, S, nq, pcand);
-    FIR_TRY(launch_pair_distances(g->metric, dq, nq, g->dp, g->rows, g->dp, n, g->d, pcand, S, 0, pd, s));
+    if (dm->sharded) {                                      // the pivots' rows are replicated on every rank: an S-row gallery, identity candidates
+        FIR_TRY(launch_pair_distances(g->metric, dq, nq, g->dp, dm->pivot_rows, g->dp, S, g->d, nullptr, S, 0, pd, s));
+    } else {
+        dem_fill_pivot_cand_kernel<<<(unsigned)ceil_div(nq * S, 256), 256, 0, s>>>(dm->d_pivots, S, nq, pcand);
+        FIR_TRY(launch_pair_distances(g->metric, dq, nq, g->dp, g->rows, g->dp, n, g->d, pcand, S, 0, pd, s));
+    }
     dem_pivot_phase_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(pd, nq, S, dm->d_pivots, dm->threshold, M, st);
     launches += 3;
     FIR_CUDA_TRY(cudaMemsetAsync(counters, 0, 64, s));
+    // row shards: pack this rank's round → all-gather → the same in-order fold on every rank (dem_global_reduce_kernel)
+    auto exchange_reduce = [&](const int32_t* c_, const uint32_t* ck_, const float* cd_, const int32_t* rn_, const int32_t* ql_, int nqc_, int cap_,
+                               int round_size_, int32_t* n_active_) -> int {
+        fir_comm* c = dm->comm;
+        const size_t cells = (size_t)nqc_ * cap_;
+        uint32_t* rec = nullptr; uint32_t* rec_all = nullptr;
+        FIR_TRY(comm_take(c, 10, 12 * cells, s, (void**)&rec));
+        FIR_TRY(comm_take(c, 11, 12 * cells * c->world, s, (void**)&rec_all));
+        dem_pack_records_kernel<<<(unsigned)ceil_div((int64_t)cells, 256), 256, 0, s>>>(c_, ck_, cd_, rn_, nqc_, cap_, ioff, rec);
+        FIR_NCCL_TRY(nccl_api()->AllGather(rec, rec_all, 3 * cells, ncclUint32, c->comm, s));
+        int P2 = 1;
+        while (P2 < c->world * cap_) P2 <<= 1;
+        const size_t smem = (size_t)P2 * 12;
+        FIR_CUDA_TRY(cudaFuncSetAttribute(dem_global_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 49152)));
+        dem_global_reduce_kernel<<<(unsigned)nqc_, 256, smem, s>>>(rec_all, c->world, nqc_, cap_, ql_, round_size_, dm->threshold, M, dm->tail_size, S, st, n_active_);
+        FIR_CUDA_TRY(cudaGetLastError());
+        launches += 2;
+        return FIR_OK;
+    };
     // 1b. round 0: the first k0 candidates of every query through the tensor-core brute force in pivot space
     if (tensor0) {
         int32_t* t_idx = (int32_t*)g->ws.take(4 * (size_t)nq * k0);
@@ -984,7 +1263,8 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
         dem_round0_merge_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(t_idx, t_dist, k0, nq, pd, S, dm->P_raw, n, dm->sp_rows, dm->sp_mask, dm->sp_tail,
                                                                          dm->n_special, M, st, c0, ck0, rn0, ks0, lt0);
         FIR_TRY(launch_pair_distances(g->metric, dq, nq, g->dp, g->rows, g->dp, n, g->d, c0, k0, 0, cd0, s));
-        dem_reduce_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cd0, c0, ck0, nullptr, (int)nq, k0, rn0, ks0, lt0, dm->threshold, M, dm->tail_size, S, st, counters + 2);
+        if (sharded) FIR_TRY(exchange_reduce(c0, ck0, cd0, rn0, nullptr, (int)nq, k0, k0, counters + 2));
+        else dem_reduce_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cd0, c0, ck0, nullptr, (int)nq, k0, rn0, ks0, lt0, dm->threshold, M, dm->tail_size, S, st, counters + 2);
         FIR_CUDA_TRY(cudaGetLastError());
         launches += 3;
     }
@@ -1027,26 +1307,27 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
             first_round = false;
             for (int pass = 0; pass < 3; ++pass) {
                 FIR_CUDA_TRY(cudaMemsetAsync(hist, 0, 4 * (size_t)nqc * 2048, s));
-                dem_hist_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, pass, prefix, take_all, hist, skip);
+                dem_hist_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, pass, prefix, take_all, hist, skip, ioff);
                 dem_pick_kernel<<<(unsigned)nqc, 32, 0, s>>>(hist, ql, nqc, st, pass, want, prefix, want_rem, take_all, key_sel, tie_take, round_n, skip);
             }
             FIR_CUDA_TRY(cudaMemsetAsync(cnt, 0, 4 * (size_t)nqc, s));
             FIR_CUDA_TRY(cudaMemsetAsync(tie_cnt, 0, 4 * (size_t)nqc, s));
-            dem_collect_fast_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, take_all, key_sel, cap, cand, cand_key, cnt, tie_buf, tie_cnt, skip);
+            dem_collect_fast_kernel<<<dim3(hb, (unsigned)nqc), 256, 0, s>>>(lik, ql, nqc, n, st, take_all, key_sel, cap, cand, cand_key, cnt, tie_buf, tie_cnt, skip, ioff);
             dem_collect_fixup_kernel<<<(unsigned)ceil_div(nqc, 128), 128, 0, s>>>(ql, nqc, st, take_all, key_sel, tie_take, cap, cand, cand_key, cnt, tie_buf, tie_cnt,
                                                                                last_tie, overflow, skip);
-            dem_collect_kernel<<<(unsigned)ceil_div(nqc, 4), 128, 0, s>>>(lik, ql, nqc, n, st, overflow, key_sel, tie_take, cap, cand, cand_key, last_tie);
+            dem_collect_kernel<<<(unsigned)ceil_div(nqc, 4), 128, 0, s>>>(lik, ql, nqc, n, st, overflow, key_sel, tie_take, cap, cand, cand_key, last_tie, ioff);
             // exact distances of the round's candidates: queries are addressed through the active list
             FIR_TRY(launch_pair_distances(g->metric, dq, nqc, g->dp, g->rows, g->dp, n, g->d, cand, cap, 0, cdist, s, nullptr, ql));
             FIR_CUDA_TRY(cudaMemsetAsync(counters + 1, 0, 4, s));
-            dem_reduce_kernel<<<(unsigned)ceil_div(nqc, 4), 128, 0, s>>>(cdist, cand, cand_key, ql, nqc, cap, round_n, key_sel, last_tie, dm->threshold, M,
+            if (sharded) FIR_TRY(exchange_reduce(cand, cand_key, cdist, round_n, ql, nqc, cap, cap, counters + 1));
+            else dem_reduce_kernel<<<(unsigned)ceil_div(nqc, 4), 128, 0, s>>>(cdist, cand, cand_key, ql, nqc, cap, round_n, key_sel, last_tie, dm->threshold, M,
                                                                        dm->tail_size, S, st, counters + 1);
             FIR_CUDA_TRY(cudaMemcpyAsync(&remaining, counters + 1, 4, cudaMemcpyDeviceToHost, s));
             FIR_CUDA_TRY(cudaStreamSynchronize(s));
             if (round_size < cap_max) round_size = (int)std::min<int64_t>((int64_t)round_size * 8, cap_max);
         }
     }
-    dem_output_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(st, nq, g->index_offset, o_idx, o_dist, o_below, o_evals);
+    dem_output_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(st, nq, dm->sharded ? 0 : g->index_offset, o_idx, o_dist, o_below, o_evals);
     FIR_CUDA_TRY(cudaGetLastError());
     dm->last_launches = launches + 2;
     if (memspace == FIR_HOST) {

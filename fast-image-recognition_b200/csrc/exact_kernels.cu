@@ -123,9 +123,9 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
             const float* qb = qs + st * TS * LDT;
             const float* xb = xs + st * TS * LDT;
             const int kmax = min(CH, p.d_end - c * CH);
-            if (kmax == CH) {
-                // L2's 3-instruction step unrolls fully (24 KB of code); the division / logf steps are ~16-60 instructions
-                // each, so their k-loop stays rolled to fit the instruction cache (ncu: 28 % stall_no_inst when unrolled)
+            if (kmax == CH && METRIC != FIR_KL) {
+                // L2's 3-instruction step unrolls fully (24 KB of code); the division step is ~16 instructions, so its k-loop
+                // stays rolled to fit the instruction cache (ncu: 28 % stall_no_inst when unrolled)
 #pragma unroll (METRIC == FIR_L2 ? CH / 4 : kDivUnroll)
                 for (int k4 = 0; k4 < CH / 4; ++k4) {
                     float4 qa[4], xa[4];
@@ -147,6 +147,9 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
                     }
                 }
             } else {
+                // KL always comes here: one dimension per trip keeps 32 inlined logf bodies (57 KB of code) instead of 128
+                // (229 KB — ncu: 36 % of the warp stalls were instruction-cache misses, profiles/r2_ncu_exact_kl.txt)
+#pragma unroll 1
                 for (int kk = 0; kk < kmax; ++kk) {
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {

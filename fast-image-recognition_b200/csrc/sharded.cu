@@ -18,31 +18,15 @@
 // never load it.
 #include "fir_common.cuh"
 #include "handles.hpp"
+#include "sharded.hpp"
 #include <dlfcn.h>
-#include <nccl.h>      // types and enums only; every call goes through the table below
 #include <algorithm>
 #include <cstring>
 #include <mutex>
 
 namespace fir {
 
-struct NcclApi {
-    void* handle = nullptr;
-    ncclResult_t (*GetVersion)(int*) = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    std::string error;
-};
-
-static NcclApi* nccl_api() {
+NcclApi* nccl_api() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
@@ -67,28 +51,11 @@ static NcclApi* nccl_api() {
     return api.handle ? &api : nullptr;
 }
 
-#define FIR_NCCL_TRY(expr)                                                                                       \
-    do {                                                                                                         \
-        ncclResult_t _r = (expr);                                                                                \
-        if (_r != ncclSuccess) return ::fir::fail(FIR_ERR_NCCL, std::string(#expr) + ": " + nccl_api()->GetErrorString(_r)); \
-    } while (0)
-
 }  // namespace fir
-
-// one rank of the communicator + its grow-only staging buffers (kept apart from the gallery's bump workspace, which every
-// search call resets)
-struct fir_comm {
-    ncclComm_t comm = nullptr;
-    int rank = 0, world = 1, device = 0;
-    bool owns_comm = true;
-    enum { SLOTS = 10 };
-    void* buf[SLOTS] = {};
-    size_t cap[SLOTS] = {};
-};
 
 namespace fir {
 
-static int comm_take(fir_comm* c, int slot, size_t bytes, cudaStream_t s, void** out) {
+int comm_take(fir_comm* c, int slot, size_t bytes, cudaStream_t s, void** out) {
     if (bytes > c->cap[slot]) {
         if (c->buf[slot]) { FIR_CUDA_TRY(cudaStreamSynchronize(s)); FIR_CUDA_TRY(cudaFree(c->buf[slot])); c->buf[slot] = nullptr; c->cap[slot] = 0; }
         const size_t want = bytes + bytes / 8 + 4096;

@@ -279,6 +279,14 @@ int fir_shard_search_topk(fir_gallery* shard, fir_comm* c, const float* queries,
 int fir_shard_class_min(fir_gallery* shard, fir_comm* c, const float* queries, int64_t nq, int32_t memspace, float* out_min, int32_t* out_arg);
 int fir_shard_pnn_scores(fir_gallery* shard, fir_comm* c, const float* queries, int64_t nq, double var, int64_t n_total, int32_t memspace,
                          double* out_scores, int32_t* out_label);
+/* Directed enumeration over row shards (collective): ONE DirectedEnumeration over the whole gallery — the same pivots,
+ * threshold and candidate order as a single-gallery build (qt_cpp/ann.cpp:270-507).  Rank r holds the pivot-distance columns
+ * of its own rows; per chain step the pivot's row travels by all-reduce and the (far-sum maximum, row, minimum other-class
+ * distance) triples by all-gather; in the search every rank walks its rows and each round's candidates (likelihood, global
+ * row, exact distance) are all-gathered and folded in likelihood order identically on every rank.  fir_dem_search /
+ * fir_dem_info / fir_dem_get_* on the returned handle are collective calls too; fir_dem_get_pivot_matrix returns the local
+ * columns (n_pivots x shard rows); indices are global. */
+int fir_shard_dem_build(fir_gallery* shard, fir_comm* c, int64_t n_total, const fir_dem_params* params, fir_dem** out);
 /* (2) ONE process driving n_gpus devices (<= 0: all visible): rows/labels are the whole class-major gallery in host
  *     memory; shard r = rows [n*r/G, n*(r+1)/G) on device r; ncclCommInitAll.  Host buffers in and out. */
 typedef struct fir_sharded fir_sharded;

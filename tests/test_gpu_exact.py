@@ -207,7 +207,9 @@ def test_kl_approx_path_with_mixed_sign_rows(fir, port):
     gal = fir.Gallery(g, gl, "kl")
     idx, dist = gal.search(q2, k=5, path=fir.PATH_APPROX)
     st = gal.stats()
-    assert st["path_used"] == fir.PATH_APPROX and st["n_fallback"] >= len(rows)      # every mixed-sign query went to the exact re-run
+    n_mixed = int((q2 < 0).any(axis=1).sum())                    # (a ReLU zero times -1 is -0.0: not a negative value)
+    assert n_mixed >= 10
+    assert st["path_used"] == fir.PATH_APPROX and st["n_fallback"] >= n_mixed        # every mixed-sign query went to the exact re-run
     oi, od = port.topk("kl", g, q2, 5)
     assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
     gal.close()

@@ -99,6 +99,41 @@ def _worker(rank, world, port_no, out):
     torch.cuda.synchronize()
     oi, od = port.topk("l2", g, q, 10, nthreads=4)
     ok = ok and np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dd.cpu().numpy().view(np.uint32), od.view(np.uint32))
+    # ---- directed enumeration over the shards: ONE index over the whole gallery (pivots, threshold, candidate order) ----
+    def dem_case(n, d, classes, seed, max_chain, budgets):
+        from util import make_data
+        good = True
+        gg, ggl, qq, _ = make_data(port, "l2", n, 120, d, classes, seed=seed, sigma=1.2)
+        a, b = sharded.shard_bounds(n, world, rank)
+        shard = fir_b200.Gallery(torch.from_numpy(gg[a:b]).to(dev), torch.from_numpy(ggl[a:b]).to(dev), "l2", index_offset=a)
+        shard.set_num_classes(classes)
+        rsh = fir_b200.RankShard(shard, comm, n)
+        dem = rsh.dem(pivot0=77, max_chain=max_chain)
+        single = fir_b200.Gallery(torch.from_numpy(gg).to(dev), torch.from_numpy(ggl).to(dev), "l2")      # the same build on ONE gallery
+        sdem = fir_b200.Dem(single, pivot0=77, max_chain=max_chain)
+        good = good and np.array_equal(dem.pivots, sdem.pivots) and np.float32(dem.threshold).view(np.uint32) == np.float32(sdem.threshold).view(np.uint32)
+        good = good and np.array_equal(dem.P.view(np.uint32), sdem.P[:, a:b].view(np.uint32))
+        piv, P, thr = sdem.pivots, sdem.P, float(sdem.threshold)
+        for t, low in ((thr, False), (thr * 0.05, True)):
+            d1 = dem if not low else None
+            if low:                                              # nothing is ever under the threshold: the walk runs its whole budget
+                p_ = fir_b200.DemParams(77, 0, 0.01, t, max_chain, 0)
+                h = fir_b200.C.c_void_p(None)
+                fir_b200._check(fir_b200.lib().fir_shard_dem_build(shard._h, comm._h, n, fir_b200.C.byref(p_), fir_b200.C.byref(h)))
+                d1 = fir_b200.Dem._adopt(shard, h)
+            for M in budgets:
+                got = d1.search(qq, M)
+                want = port.dem_search("l2", gg, piv, P, t, M, qq)
+                for name, x, y in zip(("idx", "dist", "below", "evals"), got, want):
+                    if not np.array_equal(x, y):
+                        good = False
+                        print("DEM mismatch rank", rank, n, low, M, name, int((x != y).sum()), flush=True)
+            if low:
+                d1.close()
+        dem.close(); sdem.close(); single.close(); shard.close()
+        return good
+    ok = ok and dem_case(5000, 48, 40, 7, 40, (0, 33, 60, 300, 900))             # small shards: CUDA-core rounds only
+    ok = ok and dem_case(20000, 64, 150, 8, 40, (0, 40, 56, 57, 200, 1500))      # >= 8192 rows per shard: tensor first round + exchange
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)                                                     # every rank must have received the merged answer
     if rank == 0:
@@ -117,3 +152,21 @@ def test_rank_shards_over_nccl_match_single_gallery_oracle(tmp_path, port):
     out = str(tmp_path / "result.txt")
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert open(out).read().startswith("ok")
+
+
+def test_shard_dem_world_one_matches_plain_build(fir, port):
+    """fir_shard_dem_build with a one-rank communicator (no NCCL needed) walks the same code as the multi-rank build — the
+    pivot record, the triple exchange, global row indices — and must equal the plain single-gallery DEM."""
+    from util import make_data
+    g, gl, q, ql = make_data(port, "l2", 9000, 90, 48, 60, seed=12, sigma=1.2)
+    gal = fir.Gallery(g, gl, "l2")
+    comm = fir.Comm(0, 1)
+    rs = fir.RankShard(gal, comm, len(g))
+    dem = rs.dem(pivot0=5, max_chain=40)
+    plain = fir.Dem(gal, pivot0=5, max_chain=40)
+    assert np.array_equal(dem.pivots, plain.pivots) and np.array_equal(dem.P.view(np.uint32), plain.P.view(np.uint32))
+    assert np.float32(dem.threshold).view(np.uint32) == np.float32(plain.threshold).view(np.uint32)
+    for M in (0, 40, 56, 500):
+        for a, b in zip(dem.search(q, M), plain.search(q, M)):
+            assert np.array_equal(a, b), M
+    dem.close(); plain.close(); comm.close(); gal.close()

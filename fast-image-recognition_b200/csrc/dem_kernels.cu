@@ -674,10 +674,29 @@ __global__ void dem_output_kernel(const QState* __restrict__ st, int64_t nq, int
     if (below) below[q] = (uint8_t)s.below;
     if (evals) evals[q] = s.count;
 }
-__global__ void dem_active_list_kernel(const QState* __restrict__ st, int64_t nq, int32_t* list, int32_t* count) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    if (!st[q].done) { int p = atomicAdd(count, 1); list[p] = (int32_t)q; }
+// The unfinished queries in ASCENDING order (one block walks the queries 1024 at a time; ballot + prefix counts keep the order).
+// The order matters for row shards: position qc of the list names the same query on every rank, so the records exchanged
+// for qc belong together (an atomic-append list would be permuted differently on each GPU).
+__global__ void __launch_bounds__(1024) dem_active_list_kernel(const QState* __restrict__ st, int64_t nq, int32_t* list, int32_t* count) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int64_t q0 = 0; q0 < nq; q0 += 1024) {
+        const int64_t q = q0 + threadIdx.x;
+        const bool act = q < nq && !st[q].done;
+        const uint32_t m = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (act) list[s_base + before + __popc(m & ((1u << lane) - 1))] = (int32_t)q;
+        __syncthreads();
+        if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 32; ++w) tot += s_warp[w]; s_base += tot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = s_base;
 }
 
 // ---- round 0 on tensor cores -----------------------------------------------------------------------
@@ -1269,7 +1288,7 @@ int fir_dem_search(fir_dem* dm, const float* queries, int64_t nq, int32_t count_
         launches += 3;
     }
     // 2. queries that go on to the candidate walk
-    dem_active_list_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, s>>>(st, nq, active, counters);
+    dem_active_list_kernel<<<1, 1024, 0, s>>>(st, nq, active, counters);
     int32_t n_act = 0;
     FIR_CUDA_TRY(cudaMemcpyAsync(&n_act, counters, 4, cudaMemcpyDeviceToHost, s));
     FIR_CUDA_TRY(cudaStreamSynchronize(s));

@@ -9,6 +9,7 @@
   c2            100k x 512 gallery, 10k queries (configs[1])          c1   Caltech-101-shaped split, D = 1536 (configs[0])
   c3-chi2/-kl   1M x 1280 gallery, chi-square / KL distances + PNN class scores (configs[2])
   c4            directed-enumeration ANN on a 1M x 512 gallery with the reference's full pivot chain (configs[3])
+  cls           the fp64 kNN / PNN classifiers of classification.cpp at the Caltech split shape
 
 A "step" is one pass of the hot path over one query batch.  Every line carries
   value      the metric with inputs resident in HBM, CUDA-event timed on the launching stream, max over ranks;
@@ -48,6 +49,9 @@ CONFIGS = {
     "c3-kl": dict(kind="pnn", metric="kl", n=1_000_000, nq=256, d=1280, classes=1000, parity_q=8, var=2e-5,
                   name="C3 KL: synthetic 1280-d EfficientNet-style (ReLU, L1-normalised) features, 1M gallery x 256 queries, "
                        "PNN class scores + labels (BASELINE.json configs[2])"),
+    "cls": dict(kind="cls", metric="l2", n=3030, nq=5647, d=1536, classes=101, parity_q=256, K=3,
+                name="fp64 classifiers of classification.cpp at the Caltech-101 split shape (3030 training rows, 5647 queries, D = 1536, 101 classes): "
+                     "PNNClassifier::predict_bf (Parzen scores + labels), kNN (K = 3) reported beside it (BASELINE.json configs[0] data, SURVEY 8(a) a8/a9)"),
     "c4": dict(kind="dem", metric="l2", n=1_000_000, nq=10_000, d=512, classes=10_000, parity_q=64, ratio=0.05,
                name="C4: directed-enumeration ANN (32 pivots, FAR 0.01, the reference's full 0.015 N pivot chain) on a 1M x 512 gallery, "
                     "10k queries, imageCountToCheck = 0.05 N (BASELINE.json configs[3])"),
@@ -366,6 +370,10 @@ def run_gpu(args):
         env.close()
         return
     steps, warmup = max(1, args.steps), max(3, args.warmup)
+    if cfg["kind"] == "cls":
+        run_cls(env, synth, cfg, args, peaks, steps, warmup)
+        env.close()
+        return
 
     # ---- this rank's shard of the SAME gallery (strong sharding), queries replicated -----------------------------------
     lo, hi = (n * rank) // world, (n * (rank + 1)) // world
@@ -535,6 +543,76 @@ def run_gpu(args):
         dem.close()
     gal.close()
     env.close()
+
+
+def run_cls(env, synth, cfg, args, peaks, steps, warmup):
+    """fp64 PNN / kNN (classification.cpp:116-226) — single GPU; with --gpus N every rank runs a replica (the path does not shard)."""
+    import numpy as np
+    from oracle import oracle_py
+    torch, fir = env.torch, env.fir
+    n, nq, d, C, K = cfg["n"], cfg["nq"], cfg["d"], cfg["classes"], cfg["K"]
+    g, gl = device_rows(env, synth, synth.ROLE_GALLERY, 0, n, n, cfg)
+    q, _ = device_rows(env, synth, synth.ROLE_QUERY, 0, nq, nq, cfg)
+    tr = g.cpu().numpy().astype(np.float64)
+    tl = gl.cpu().numpy()
+    avg = np.array([sum(tr[:, f].tolist()) for f in range(d)]) / n             # sequential column sums (split_train_test, classification.cpp:969-976)
+    clf = fir.Classifier(tr, tl, C, avg)
+    clf.set_stream(env.stream)
+    q_dev = q.double()
+    q_host = torch.empty((nq, d), dtype=torch.float64).pin_memory()
+    q_host.copy_(q_dev)
+    torch.cuda.synchronize()
+    step_device = lambda: clf.pnn(q_dev)
+    step_host = lambda: clf.pnn(q_host.numpy())
+    for _ in range(warmup):
+        step_device()
+    lab_h, sc_h = step_host()
+    env.barrier()
+    sampler = ClockSampler(env.local_rank) if env.rank == 0 else None
+    if sampler:
+        sampler.start()
+    clf.profile(True)
+    t_dev = env.timed(step_device, steps)
+    k_ms, k_n = clf.profile(False)
+    t_e2e = env.timed(step_host, steps, host_clock=True)
+    knn_lab = clf.knn(q_dev, K)
+    t_knn = env.timed(lambda: clf.knn(q_dev, K), max(1, steps // 2))
+    clocks = sampler.stop() if sampler else None
+    if env.rank != 0:
+        return
+    work = float(nq) * n
+    pipes = peaks.get("pipes", {})
+    t_k = k_ms / max(k_n, 1) * 1e-3
+    ops = 3.0 * work * d                                                        # DSUB, DMUL, DADD per element, separately rounded
+    peak = (pipes.get("dadd", 0) * 2 + pipes.get("dfma", 0)) / 3.0 if pipes else None
+    sample = np.unique(np.linspace(0, nq - 1, cfg["parity_q"]).astype(np.int64))
+    port = oracle_py.Port()
+    t0 = time.perf_counter()
+    psc, plab = port.pnn(tr, tl, C, avg, q_host.numpy()[sample])
+    t_cpu = time.perf_counter() - t0
+    pk = port.knn(tr, tl, C, avg, q_host.numpy()[sample], K)
+    rel = np.abs(sc_h[sample] - psc) / np.maximum(np.abs(psc), 1e-300)
+    big = psc > psc.max(axis=1, keepdims=True) * 1e-30
+    line = {"metric": "distance_evals_per_s", "value": work * steps / t_dev, "unit": "evals/s", "n_gpus": env.world, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "queries_per_s": nq * steps / t_dev,
+            "config": {"workload": cfg["name"], "gallery": n, "queries": nq, "dim": d, "classes": C, "parallelism": "single GPU (replicas only: the classifier does not shard)",
+                       "l2": "256 MiB fill before every timed step", "timing": "per-step CUDA events on the launching stream"},
+            "e2e": {"value": work * steps / t_e2e, "unit": "evals/s", "ms_per_step": 1e3 * t_e2e / steps, "h2d_bytes_per_step": nq * d * 8, "d2h_bytes_per_step": nq * C * 8 + nq * 4},
+            "gpu_launches": 5 * steps,
+            "knn": {"K": K, "value": work * max(1, steps // 2) / t_knn, "unit": "evals/s", "ms": 1e3 * t_knn / max(1, steps // 2)},
+            "roofline": {"bound": "fp64", "kernel": "cls_dist_kernel<FUSE_PNN> (fp64 tiles, fused Parzen class sums)", "achieved": ops / t_k / 1e12 if k_n else None,
+                         "peak": peak / 1e12 if peak else None, "unit": "Tlane-op/s", "frac": (ops / t_k / peak) if (k_n and peak) else None,
+                         "algorithmic": "3 separately rounded fp64 operations per (query, row, dimension)", "kernel_ms": 1e3 * t_k,
+                         "kernel_share_of_step": (k_ms / 1e3) / t_dev, "peak_source": "profiles/r2_peak_pipes.json (2 x DADD-rate + DFMA-rate) / 3", "traffic": None},
+            "clocks": clocks,
+            "parity": {"sample_queries": int(len(sample)), "against": "oracle port fir_oracle_pnn / fir_oracle_knn (pinned to classification.cpp in oracle/_ref)",
+                       "pnn_labels_equal": bool(np.array_equal(plab, lab_h[sample])), "pnn_scores_max_rel_err": float(rel[big].max()),
+                       "pnn_scores_within_1e-5": bool(rel[big].max() <= 1e-5), "knn_labels_equal": bool(np.array_equal(pk, knn_lab.cpu().numpy()[sample]))},
+            "cpu_baseline": {"value": len(sample) * float(n) / t_cpu, "unit": "evals/s", "cores": 1, "kind": "port",
+                             "sample": "%d of %d queries, PNNClassifier::predict_bf restated in C (oracle/fir_oracle.c), 1 thread" % (len(sample), nq)}}
+    print(json.dumps(line))
+    clf.close()
 
 
 def parity_and_cpu(env, synth, cfg, args, q_host, res_host, gal, k, dem):

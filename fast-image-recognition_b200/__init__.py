@@ -32,7 +32,7 @@ EXPORTS = [
     "fir_gallery_create", "fir_gallery_destroy", "fir_gallery_set_stream", "fir_gallery_info", "fir_gallery_index_offset", "fir_gallery_set_num_classes",
     "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
     "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates", "fir_profile_enable", "fir_profile_read",
-    "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn", "fir_classifier_pnn_sequential",
+    "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn", "fir_classifier_pnn_sequential", "fir_classifier_knn_ex", "fir_classifier_pnn_ex", "fir_classifier_set_stream", "fir_classifier_profile",
     "fir_twd_conventional", "fir_twd_proposed", "fir_kmedoids_select", "fir_classifier_set_total",
     "fir_fpnn_create", "fir_fpnn_destroy", "fir_fpnn_info", "fir_fpnn_get_coefficients", "fir_fpnn_predict",
     "fir_dem_build", "fir_dem_from_state", "fir_dem_destroy", "fir_dem_info", "fir_dem_get_pivots", "fir_dem_get_pivot_matrix",
@@ -95,6 +95,10 @@ def lib():
     L.fir_classifier_knn.argtypes = [vp, vp, i64, i32, vp]
     L.fir_classifier_pnn.argtypes = [vp, vp, i64, vp, vp]
     L.fir_classifier_pnn_sequential.argtypes = [vp, vp, i64, vp]
+    L.fir_classifier_knn_ex.argtypes = [vp, vp, i64, i32, i32, vp]
+    L.fir_classifier_pnn_ex.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.fir_classifier_set_stream.argtypes = [vp, vp]
+    L.fir_classifier_profile.argtypes = [vp, i32, C.POINTER(f64), C.POINTER(i32)]
     L.fir_kmedoids_select.argtypes = [vp, vp, i64, i32, i32, i32, vp, C.POINTER(i64)]
     L.fir_classifier_set_total.argtypes = [vp, i64]
     L.fir_fpnn_create.argtypes = [vp, vp, i64, i32, i32, vp, vp, f64, C.POINTER(vp)]
@@ -396,10 +400,19 @@ class Classifier:
             pass
 
     def knn(self, queries, K):
-        q = np.ascontiguousarray(queries, dtype=np.float64)
-        lab = np.empty(q.shape[0], np.int32)
-        _check(lib().fir_classifier_knn(self._h, _ptr(q), q.shape[0], int(K), _ptr(lab)))
+        q, space = _prep(queries, np.float64, "float64")
+        lab = _out((q.shape[0],), np.int32, "int32", space == DEVICE, getattr(q, "device", None))
+        _check(lib().fir_classifier_knn_ex(self._h, _ptr(q), q.shape[0], int(K), space, _ptr(lab)))
         return lab
+
+    def set_stream(self, stream):
+        _check(lib().fir_classifier_set_stream(self._h, C.c_void_p(int(stream))))
+
+    def profile(self, on=True):
+        """Switch the distance-kernel timing on/off; returns (ms, launches) accumulated since it was last switched on."""
+        ms, n = C.c_double(0), C.c_int32(0)
+        _check(lib().fir_classifier_profile(self._h, int(on), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def set_total(self, n_total):
         """PNN denominator when the rows are a reduced (clustered) training set."""
@@ -413,10 +426,11 @@ class Classifier:
         return lab
 
     def pnn(self, queries, scores=True):
-        q = np.ascontiguousarray(queries, dtype=np.float64)
-        lab = np.empty(q.shape[0], np.int32)
-        sc = np.empty((q.shape[0], self.n_classes), np.float64) if scores else None
-        _check(lib().fir_classifier_pnn(self._h, _ptr(q), q.shape[0], _ptr(sc), _ptr(lab)))
+        q, space = _prep(queries, np.float64, "float64")
+        dev = getattr(q, "device", None)
+        lab = _out((q.shape[0],), np.int32, "int32", space == DEVICE, dev)
+        sc = _out((q.shape[0], self.n_classes), np.float64, "float64", space == DEVICE, dev) if scores else None
+        _check(lib().fir_classifier_pnn_ex(self._h, _ptr(q), q.shape[0], space, _ptr(sc), _ptr(lab)))
         return lab, sc
 
 

@@ -189,6 +189,14 @@ int fir_classifier_destroy(fir_classifier* c);
 int fir_classifier_knn(fir_classifier* c, const double* queries, int64_t nq, int32_t K, int32_t* out_label);
 int fir_classifier_pnn(fir_classifier* c, const double* queries, int64_t nq, double* out_scores /* nq x C or NULL */,
                        int32_t* out_label);
+/* The same two with an explicit memory space for the queries and outputs (FIR_DEVICE: asynchronous on the classifier's
+ * stream).  The Parzen sums are fused into the epilogue of the fp64 distance tiles — the Q x N distance matrix is only
+ * materialised for the kNN walk.  fir_classifier_profile(c, on, &ms, &launches) returns the summed CUDA-event duration of the
+ * distance kernel since profiling was last switched on (NULL outputs: just switch). */
+int fir_classifier_knn_ex(fir_classifier* c, const double* queries, int64_t nq, int32_t K, int32_t memspace, int32_t* out_label);
+int fir_classifier_pnn_ex(fir_classifier* c, const double* queries, int64_t nq, int32_t memspace, double* out_scores, int32_t* out_label);
+int fir_classifier_set_stream(fir_classifier* c, void* cuda_stream);
+int fir_classifier_profile(fir_classifier* c, int32_t on, double* total_ms, int32_t* launches);
 /* replaces: PNNClassifier::predict_sequentional (qt_cpp/classification.cpp:228-295; PNNClassifier(bf=false)): 32-dimension
  * chunks, classes scoring below max/1e9 are dropped, stop when one class is left.   */
 int fir_classifier_pnn_sequential(fir_classifier* c, const double* queries, int64_t nq, int32_t* out_label);

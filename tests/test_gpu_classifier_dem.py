@@ -42,6 +42,30 @@ def test_knn_pnn_match_port_ragged(fir, port):
     clf.close()
 
 
+def test_classifier_device_memspace_and_unsorted_rows(fir, port):
+    """Queries and outputs in device memory (asynchronous on the classifier's stream), more queries than one 64-row tile,
+    a training set that is NOT class-major (the fused Parzen epilogue folds runs of equal labels, whatever the order)."""
+    import torch
+    rows, labels = _cls_problem(port, 700, 70, 9, seed=4)
+    perm = np.random.default_rng(1).permutation(500)
+    tr, te = perm, np.arange(500, 700)
+    avg = rows[tr].mean(axis=0)
+    clf = fir.Classifier(rows[tr], labels[tr], 9, avg)
+    qd = torch.from_numpy(rows[te]).cuda()
+    lab, sc = clf.pnn(qd)
+    knn = clf.knn(qd, 3)
+    torch.cuda.synchronize()
+    psc, plab = port.pnn(rows[tr], labels[tr], 9, avg, rows[te])
+    assert np.array_equal(lab.cpu().numpy(), plab)
+    np.testing.assert_allclose(sc.cpu().numpy(), psc, rtol=1e-5, atol=0)
+    assert np.array_equal(knn.cpu().numpy(), port.knn(rows[tr], labels[tr], 9, avg, rows[te], 3))
+    clf.profile(True)
+    clf.pnn(qd)
+    ms, n = clf.profile(False)
+    assert n == 1 and ms > 0
+    clf.close()
+
+
 def _misleading_head(rows, seed, sigma):
     """Replace the first 32 dimensions with class-independent noise so the sequential PNN prunes on a misleading chunk."""
     r = np.random.default_rng(seed)

@@ -62,3 +62,9 @@ def test_c1_shape_adapters_match_reference(ref_l2, tmp_path):
         derr = 100.0 * float(np.mean((di < 0) | (dbl[np.maximum(di, 0)] != tel)))
         assert abs(float(lines["DEMERR%d" % r][0]) - derr) < 1e-6
     dem.close()
+    # the same program with fir::n_gpus() = all devices: BruteForce over row shards + NCCL merge inside ONE process
+    import torch
+    if torch.cuda.device_count() >= 2:
+        out2 = subprocess.run([exe, txt, str(D), str(SPLIT_SEED), str(DEM_SEED), "0"], check=True, capture_output=True, text=True).stdout
+        lines2 = {l.split()[0]: l.split()[1:] for l in out2.splitlines() if l and l.split()[0].isupper()}
+        assert lines2["BF"] == lines["BF"] and lines2["BFERR"] == lines["BFERR"]

@@ -41,6 +41,7 @@ EXPORTS = [
     "fir_shard_search_topk", "fir_shard_class_min", "fir_shard_pnn_scores", "fir_shard_dem_build",
     "fir_sharded_create", "fir_sharded_destroy", "fir_sharded_info", "fir_sharded_shard",
     "fir_sharded_search_topk", "fir_sharded_class_min", "fir_sharded_pnn_scores",
+    "fir_sharded_dem_build", "fir_sharded_dem_destroy", "fir_sharded_dem_info", "fir_sharded_dem_get_pivots", "fir_sharded_dem_search",
 ]
 
 
@@ -135,6 +136,11 @@ def lib():
     L.fir_sharded_search_topk.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.fir_sharded_class_min.argtypes = [vp, vp, i64, vp, vp]
     L.fir_sharded_pnn_scores.argtypes = [vp, vp, i64, f64, vp, vp]
+    L.fir_sharded_dem_build.argtypes = [vp, C.POINTER(DemParams), C.POINTER(vp)]
+    L.fir_sharded_dem_destroy.argtypes = [vp]
+    L.fir_sharded_dem_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float)]
+    L.fir_sharded_dem_get_pivots.argtypes = [vp, vp]
+    L.fir_sharded_dem_search.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -677,9 +683,51 @@ class Sharded:
         _check(lib().fir_sharded_pnn_scores(self._h, _ptr(q), q.shape[0], float(var), _ptr(sc), _ptr(lab)))
         return sc, lab
 
+    def dem(self, pivot0=-1, seed=0, false_accept_rate=0.01, threshold=0.0, max_chain=0, max_pivots=0):
+        """ONE DirectedEnumeration over the whole sharded gallery → ShardedDem."""
+        return ShardedDem(self, DemParams(int(pivot0), int(seed), float(false_accept_rate), float(threshold), int(max_chain), int(max_pivots)))
+
     def close(self):
         if getattr(self, "_h", None):
             lib().fir_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardedDem:
+    """DirectedEnumeration over a Sharded gallery (fir_sharded_dem_*); keeps the gallery alive."""
+
+    def __init__(self, sharded, params):
+        self.sharded = sharded
+        h = C.c_void_p(None)
+        _check(lib().fir_sharded_dem_build(sharded._h, C.byref(params), C.byref(h)))
+        self._h = h
+        a, b, t = C.c_int32(0), C.c_int32(0), C.c_float(0)
+        _check(lib().fir_sharded_dem_info(self._h, C.byref(a), C.byref(b), C.byref(t)))
+        self.n_pivots, self.chain_rows, self.threshold = a.value, b.value, np.float32(t.value)
+
+    @property
+    def pivots(self):
+        out = np.empty(self.n_pivots, np.int32)
+        _check(lib().fir_sharded_dem_get_pivots(self._h, _ptr(out)))
+        return out
+
+    def search(self, queries, count_to_check=0):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        idx, dist = np.empty(nq, np.int32), np.empty(nq, np.float32)
+        below, evals = np.empty(nq, np.uint8), np.empty(nq, np.int32)
+        _check(lib().fir_sharded_dem_search(self._h, _ptr(q), nq, int(count_to_check), _ptr(idx), _ptr(dist), _ptr(below), _ptr(evals)))
+        return idx, dist, below, evals
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fir_sharded_dem_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -186,6 +186,7 @@ int fir_gallery_destroy(fir_gallery* g) {
     if (g->tensor_buf) cudaFree(g->tensor_buf);
     if (g->d_stats) cudaFree(g->d_stats);
     if (g->d_l1max) cudaFree(g->d_l1max);
+    if (g->kl_ent) cudaFree(g->kl_ent);
     for (auto& e : g->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     g->ws.release();
     delete g;

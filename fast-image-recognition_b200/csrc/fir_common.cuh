@@ -126,12 +126,14 @@ bool tensor_path_supported(int d);
 // How far an approximate candidate value can be from the reference's own result, per query:
 //   |approx − dist_scale·reference| ≤ E + rel·(dist_scale·reference)
 struct ErrModel {
-    int kind;                 // 0: fp16 tensor-core L2 (Cauchy–Schwarz on measured residuals); 1: relative only; 2: E from L1 norms
+    int kind;                 // 0: fp16 tensor-core L2 (Cauchy–Schwarz on measured residuals); 1: relative only; 2: E from L1 norms;
+                              // 3: KL entropy form: E = (‖q‖₁ + max‖x‖₁)·(abs_coef + lam_coef·Λ), Λ from the smallest positive elements
     int d, nkb;
     const float* q_norm2; const float* q_resid; const float* gal_stats;     // kind 0
     double rel;               // relative part (kind 0: the reference's sequential-sum error (D+4)·2⁻²⁴)
     double abs_coef;          // kind 2: E = abs_coef · (‖q‖₁ + max‖x‖₁)
-    const float* q_l1; const float* x_l1_max;                               // kind 2 (device)
+    const float* q_l1; const float* x_l1_max;                               // kind 2, 3 (device)
+    double lam_coef; const float* q_minpos; const float* x_minpos;          // kind 3 (device)
     double dist_scale;        // approx units per reference-distance unit: D on the tensor path (squared distance), 1 otherwise
 };
 int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s, const int32_t* n_active = nullptr,

@@ -22,6 +22,7 @@ struct fir_gallery {
     const unsigned char* tensor_exclude = nullptr; // optional [n] (device): rows that never become tensor-path candidates
     float* d_stats = nullptr;     // [2] max ||x||, max ||x - fp16(x)||
     float* d_l1max = nullptr;     // chi2/KL approximate path: [0] max ||x||_1, [4] flagged count, [5] max bound
+    double* kl_ent = nullptr;     // KL entropy form: Σ x·ln x + ln2·Σ x per gallery row (set with d_l1max)
     bool has_negative = false;    // set with d_l1max: some gallery element is < 0 (KL's approximate error model then does not apply)
     fir::Workspace ws;
     // diagnostics: where the last tensor-path call left its candidate lists (valid until the next call)

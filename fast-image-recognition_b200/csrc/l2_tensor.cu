@@ -941,6 +941,11 @@ __device__ __forceinline__ void err_bounds(const ErrModel& m, int64_t q, double&
     rho = m.rel;
     if (m.kind == 0) E = approx_error_bound((double)m.q_norm2[q], (double)m.q_resid[q], (double)m.gal_stats[0], (double)m.gal_stats[1], m.nkb);
     else if (m.kind == 2) E = m.abs_coef * ((double)m.q_l1[q] + (double)*m.x_l1_max);
+    else if (m.kind == 3) {
+        const double mp = fmin((double)m.q_minpos[q], (double)*m.x_minpos);      // +inf when a side has no positive element
+        const double lam = fmax(1.0, -log2(fmin(mp, 1.0)));
+        E = ((double)m.q_l1[q] + (double)*m.x_l1_max) * (m.abs_coef + m.lam_coef * lam);
+    }
     else E = 0.0;
 }
 __device__ __forceinline__ double approx_error_bound(double nq2, double rq, double NX, double RX, int nkb) {

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 namespace fir {
 
@@ -284,6 +285,30 @@ static int run_all(fir_sharded* s, std::vector<ShardCall>& calls) {
     return FIR_OK;
 }
 
+// ---- directed enumeration over the shards of ONE process: one host thread per GPU runs the rank-level collective calls
+// (fir_shard_dem_build / fir_dem_search on the shard's handle); the communicators of ncclCommInitAll are used one per thread.
+struct fir_sharded_dem {
+    fir_sharded* s = nullptr;
+    std::vector<fir_dem*> dems;
+};
+
+template <class F>
+static int on_every_shard(fir_sharded* s, F f) {
+    std::vector<int> st((size_t)s->n_gpus, FIR_OK);
+    std::vector<std::string> msg((size_t)s->n_gpus);
+    std::vector<std::thread> th;
+    for (int r = 0; r < s->n_gpus; ++r)
+        th.emplace_back([&, r] {
+            if (cudaSetDevice(s->devices[r]) != cudaSuccess) { st[r] = FIR_ERR_CUDA; msg[r] = "cudaSetDevice failed"; return; }
+            st[r] = f(r);
+            if (st[r] != FIR_OK) msg[r] = fir_last_error_string();          // the message is thread-local: carry it to the caller's thread
+        });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < s->n_gpus; ++r)
+        if (st[r] != FIR_OK) return fail(st[r], "shard " + std::to_string(r) + ": " + msg[r]);
+    return FIR_OK;
+}
+
 extern "C" {
 
 int fir_comm_unique_id(void* id_out) {
@@ -470,6 +495,57 @@ int fir_sharded_pnn_scores(fir_sharded* s, const float* queries, int64_t nq, dou
     if (!(var > 0)) return fail(FIR_ERR_BAD_ARG, "var must be > 0");
     ShardCall a; a.op = OP_PNN; a.q_in = queries; a.memspace = FIR_HOST; a.nq = nq; a.var = var; a.n_total = s ? s->n : 0; a.out_a = out_scores; a.out_b = out_label;
     return sharded_run(s, a);
+}
+
+int fir_sharded_dem_destroy(fir_sharded_dem* d) {
+    if (!d) return FIR_OK;
+    for (size_t r = 0; r < d->dems.size(); ++r) { cudaSetDevice(d->s->devices[r]); fir_dem_destroy(d->dems[r]); }
+    delete d;
+    return FIR_OK;
+}
+
+int fir_sharded_dem_build(fir_sharded* s, const fir_dem_params* params, fir_sharded_dem** out) {
+    if (!out) return fail(FIR_ERR_BAD_ARG, "out is null");
+    *out = nullptr;
+    if (!s || !params) return fail(FIR_ERR_BAD_ARG, "null argument");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    fir_sharded_dem* d = new fir_sharded_dem();
+    d->s = s;
+    d->dems.assign((size_t)s->n_gpus, nullptr);
+    const int st = on_every_shard(s, [&](int r) { return fir_shard_dem_build(s->shards[r], s->comms[r], s->n, params, &d->dems[r]); });
+    cudaSetDevice(prev);
+    if (st != FIR_OK) { fir_sharded_dem_destroy(d); return st; }
+    *out = d;
+    return FIR_OK;
+}
+
+int fir_sharded_dem_info(const fir_sharded_dem* d, int32_t* n_pivots, int32_t* chain_rows, float* threshold) {
+    if (!d || d->dems.empty()) return fail(FIR_ERR_BAD_ARG, "sharded dem is null");
+    return fir_dem_info(d->dems[0], n_pivots, chain_rows, threshold);
+}
+
+int fir_sharded_dem_get_pivots(const fir_sharded_dem* d, int32_t* out_pivots) {
+    if (!d || d->dems.empty()) return fail(FIR_ERR_BAD_ARG, "sharded dem is null");
+    return fir_dem_get_pivots(d->dems[0], out_pivots);
+}
+
+int fir_sharded_dem_search(fir_sharded_dem* d, const float* queries, int64_t nq, int32_t count_to_check, int32_t* out_idx, float* out_dist,
+                           uint8_t* out_below, int32_t* out_evals) {
+    if (!d) return fail(FIR_ERR_BAD_ARG, "sharded dem is null");
+    if (nq < 0 || (nq > 0 && (!queries || !out_idx))) return fail(FIR_ERR_BAD_ARG, "bad arguments");
+    if (nq == 0) return FIR_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    fir_sharded* s = d->s;
+    std::vector<std::vector<int32_t> > scratch((size_t)s->n_gpus);           // every rank receives the answer; rank 0 writes the caller's buffers
+    const int st = on_every_shard(s, [&](int r) {
+        if (r == 0) return fir_dem_search(d->dems[0], queries, nq, count_to_check, FIR_HOST, out_idx, out_dist, out_below, out_evals);
+        scratch[r].resize((size_t)nq);
+        return fir_dem_search(d->dems[r], queries, nq, count_to_check, FIR_HOST, scratch[r].data(), nullptr, nullptr, nullptr);
+    });
+    cudaSetDevice(prev);
+    return st;
 }
 
 }  // extern "C"

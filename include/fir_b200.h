@@ -305,6 +305,15 @@ int fir_sharded_shard(fir_sharded* s, int32_t rank, fir_gallery** shard, fir_com
 int fir_sharded_search_topk(fir_sharded* s, const float* queries, int64_t nq, int32_t k, int32_t path, int32_t* out_idx, float* out_dist);
 int fir_sharded_class_min(fir_sharded* s, const float* queries, int64_t nq, float* out_min, int32_t* out_arg);
 int fir_sharded_pnn_scores(fir_sharded* s, const float* queries, int64_t nq, double var, double* out_scores, int32_t* out_label);
+/* DirectedEnumeration over the shards of a fir_sharded gallery (one host thread per GPU runs the collective rank-level calls):
+ * same pivots, threshold and answers as ONE index over the whole gallery; global indices. */
+typedef struct fir_sharded_dem fir_sharded_dem;
+int fir_sharded_dem_build(fir_sharded* s, const fir_dem_params* params, fir_sharded_dem** out);
+int fir_sharded_dem_destroy(fir_sharded_dem* d);
+int fir_sharded_dem_info(const fir_sharded_dem* d, int32_t* n_pivots, int32_t* chain_rows, float* threshold);
+int fir_sharded_dem_get_pivots(const fir_sharded_dem* d, int32_t* out_pivots /* n_pivots */);
+int fir_sharded_dem_search(fir_sharded_dem* d, const float* queries, int64_t nq, int32_t count_to_check, int32_t* out_idx, float* out_dist,
+                           uint8_t* out_below, int32_t* out_evals);
 
 /* ---- synthetic workloads (bench / tests; no reference counterpart) ----------------------------------
  * Rows [row_lo, row_lo + n_rows) of the gallery (role 0) or query (role 1) matrix of a BASELINE.json config, generated on

@@ -286,7 +286,8 @@ public:
     // pivot0 >= 0 fixes the first pivot instead; pivot0 < 0 with seed != 0 derives it from `seed` without touching rand().
     DirectedEnumeration(std::vector<ImageInfo>& faceImages, float falseAcceptRate = 0.01f, float threshold = 0, int imageCountToCheck = 0,
                         int pivot0 = -1, unsigned seed = 0)
-        : ClassificationMethod("dem", faceImages), isFoundLessThreshold(false), bestDistance(0), pg(faceImages, fir::metric()), dem(0) {
+        : ClassificationMethod("dem", faceImages), isFoundLessThreshold(false), bestDistance(0), sg(faceImages, fir::metric(), fir::n_gpus()),
+          pg(faceImages, fir::metric(), sg.s == 0), dem(0), sdem(0) {
         setImageCountToCheck(imageCountToCheck);
         if (pivot0 < 0 && seed == 0 && !faceImages.empty()) {
             std::vector<int> indices(faceImages.size());
@@ -301,11 +302,12 @@ public:
         fir_dem_params p;
         p.pivot0 = pivot0; p.seed = seed; p.false_accept_rate = falseAcceptRate; p.threshold = threshold; p.max_chain = 0; p.max_pivots = 0;
         std::chrono::high_resolution_clock::time_point t1 = std::chrono::high_resolution_clock::now();
-        fir::check(fir_dem_build(pg.g, &p, &dem), "fir_dem_build");
+        if (sg.s) fir::check(fir_sharded_dem_build(sg.s, &p, &sdem), "fir_sharded_dem_build");      // fir::n_gpus() != 1: ONE index over the row shards
+        else fir::check(fir_dem_build(pg.g, &p, &dem), "fir_dem_build");
         std::cout << "init took " << std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::high_resolution_clock::now() - t1).count()
                   << " milliseconds" << std::endl;
     }
-    ~DirectedEnumeration() { fir_dem_destroy(dem); }
+    ~DirectedEnumeration() { fir_dem_destroy(dem); fir_sharded_dem_destroy(sdem); }
     int recognize(ImageInfo& testImage) {
         std::vector<ImageInfo> one(1, testImage);
         return recognize_batch(one)[0];
@@ -314,11 +316,12 @@ public:
         const size_t nq = testImages.size();
         std::vector<int> out(nq, -1);
         if (nq == 0) return out;
-        std::vector<float> q = detail::pack_queries(testImages, pg.d);
+        std::vector<float> q = detail::pack_queries(testImages, sg.s ? sg.d : pg.d);
         std::vector<int32_t> idx(nq), evals(nq);
         std::vector<float> dist(nq);
         std::vector<uint8_t> below(nq);
-        fir::check(fir_dem_search(dem, q.data(), (int64_t)nq, imageCountToCheck, FIR_HOST, idx.data(), dist.data(), below.data(), evals.data()), "fir_dem_search");
+        if (sdem) fir::check(fir_sharded_dem_search(sdem, q.data(), (int64_t)nq, imageCountToCheck, idx.data(), dist.data(), below.data(), evals.data()), "fir_sharded_dem_search");
+        else fir::check(fir_dem_search(dem, q.data(), (int64_t)nq, imageCountToCheck, FIR_HOST, idx.data(), dist.data(), below.data(), evals.data()), "fir_dem_search");
         for (size_t i = 0; i < nq; ++i) {
             out[i] = idx[i];
             avgCheckedPercent += (float)(100. * evals[i] / dbImages.size());        // ann.cpp:505
@@ -326,12 +329,14 @@ public:
         isFoundLessThreshold = below[nq - 1] != 0; bestDistance = dist[nq - 1]; distanceCalcCount = evals[nq - 1];
         return out;
     }
-    float threshold() const { float t = 0; fir_dem_info(dem, 0, 0, &t); return t; }
+    float threshold() const { float t = 0; if (sdem) fir_sharded_dem_info(sdem, 0, 0, &t); else fir_dem_info(dem, 0, 0, &t); return t; }
     bool isFoundLessThreshold;
     float bestDistance;
 private:
+    detail::ShardedPackedGallery sg;
     detail::PackedGallery pg;
     fir_dem* dem;
+    fir_sharded_dem* sdem;
 };
 
 // ---- classification.cpp ------------------------------------------------------------------------------

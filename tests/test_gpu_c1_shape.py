@@ -68,3 +68,4 @@ def test_c1_shape_adapters_match_reference(ref_l2, tmp_path):
         out2 = subprocess.run([exe, txt, str(D), str(SPLIT_SEED), str(DEM_SEED), "0"], check=True, capture_output=True, text=True).stdout
         lines2 = {l.split()[0]: l.split()[1:] for l in out2.splitlines() if l and l.split()[0].isupper()}
         assert lines2["BF"] == lines["BF"] and lines2["BFERR"] == lines["BFERR"]
+        assert lines2["THRESHOLD"] == lines["THRESHOLD"] and lines2["DEM0"] == lines["DEM0"] and lines2["DEM1"] == lines["DEM1"]   # DEM over the shards

@@ -59,6 +59,24 @@ def test_single_process_sharded_matches_oracle(fir, port):
         sh.close()
 
 
+def test_single_process_sharded_dem(fir, port):
+    """fir_sharded_dem_*: one host thread per GPU runs the collective build / search; equals ONE index over the whole gallery."""
+    import torch
+    from util import make_data
+    g, gl, q, ql = make_data(port, "l2", 18000, 100, 48, 120, seed=14, sigma=1.2)
+    single = fir.Gallery(g, gl, "l2")
+    sdem = fir.Dem(single, pivot0=9, max_chain=40)
+    for n_gpus in sorted({1, torch.cuda.device_count()}):
+        sh = fir.Sharded(g, gl, "l2", n_gpus=n_gpus)
+        dem = sh.dem(pivot0=9, max_chain=40)
+        assert np.array_equal(dem.pivots, sdem.pivots) and np.float32(dem.threshold).view(np.uint32) == np.float32(sdem.threshold).view(np.uint32)
+        for M in (0, 40, 56, 300):
+            for a, b in zip(dem.search(q, M), sdem.search(q, M)):
+                assert np.array_equal(a, b), (n_gpus, M)
+        dem.close(); sh.close()
+    sdem.close(); single.close()
+
+
 def test_sharded_rejects_bad_arguments(fir):
     import torch
     with pytest.raises(fir.FirError):

@@ -5,6 +5,7 @@
 #include "handles.hpp"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -184,6 +185,8 @@ int fir_gallery_destroy(fir_gallery* g) {
     if (g->rows) cudaFree(g->rows);
     if (g->labels) cudaFree(g->labels);
     if (g->tensor_buf) cudaFree(g->tensor_buf);
+    if (g->tensor_buf_nat) cudaFree(g->tensor_buf_nat);
+    if (g->d_cls_begin) cudaFree(g->d_cls_begin);
     if (g->d_stats) cudaFree(g->d_stats);
     if (g->d_l1max) cudaFree(g->d_l1max);
     if (g->kl_ent) cudaFree(g->kl_ent);
@@ -395,6 +398,13 @@ static int class_reduce(fir_gallery* g, const float* queries, int64_t nq, int me
     const int C = g->n_classes;
     const size_t cells = (size_t)nq * C;
     const bool stream = nq <= kStreamMaxQueries && g->n >= 4096;
+    // Euclidean per-class nearest neighbour of a large batch: tcgen05 candidate passes + exact rerank (l2_tensor.cu)
+    static const int cls_tensor_on = [] { const char* e = getenv("FIR_CLASSMIN_TENSOR"); return e ? atoi(e) : 1; }();
+    if (mode == MODE_CLASSMIN && cls_tensor_on && g->metric == FIR_L2 && !stream && tensor_path_supported(g->d) && g->cc_major >= 10 && tensor_cta_mode() == 2 &&
+        out_min && out_arg && nq * g->n >= (int64_t)1 << 24 && (int64_t)C * 4 <= 1 << 20) {
+        const int st = tensor_class_min(g, queries, nq, memspace, out_min, out_arg);
+        if (st != kApproxDeclined) return st;
+    }
     size_t need = al(sizeof(float) * (size_t)nq * g->dp) + al(cells * 8) + al(cells * 4) * 2 + al((size_t)nq * 4) + 4096;
     if (stream) need += al(sizeof(float) * (size_t)kStreamMaxQueries * g->dp) + al(sizeof(float) * (size_t)nq * g->n);
     FIR_TRY(g->ws.reserve(need));

@@ -20,6 +20,12 @@ struct fir_gallery {
     CUtensorMap tmap_b_half;      // box 64 x 128 rows (each CTA of a pair loads half a tile)
     const float* tensor_center = nullptr;          // optional [dp] (device, owned by the creator): the shadows are of x − center
     const unsigned char* tensor_exclude = nullptr; // optional [n] (device): rows that never become tensor-path candidates
+    // natural-order (class-major) shadow for the per-class reductions on tensor cores (built lazily by tensor_class_min)
+    bool nat_ready = false; int nat_classes = 0;
+    void* tensor_buf_nat = nullptr;
+    fir::TensorSide tside_nat;
+    CUtensorMap tmap_nat_half;
+    int32_t* d_cls_begin = nullptr;   // [nat_classes + 1]
     float* d_stats = nullptr;     // [2] max ||x||, max ||x - fp16(x)||
     float* d_l1max = nullptr;     // chi2/KL approximate path: [0] max ||x||_1, [4] flagged count, [5] max bound
     double* kl_ent = nullptr;     // KL entropy form: Σ x·ln x + ln2·Σ x per gallery row (set with d_l1max)
@@ -48,6 +54,8 @@ int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_
 int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
 constexpr int kApproxDeclined = -100;   // approx_search_topk: the error model does not cover this gallery — the caller takes the exact path
 int approx_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
+// per-class nearest neighbour (L2) through the tensor-core candidate kernel; kApproxDeclined when the gallery is not class-major
+int tensor_class_min(fir_gallery* g, const float* queries, int64_t nq, int memspace, float* out_min, int32_t* out_arg);
 const fir_gallery* dem_gallery(const fir_dem* dem);      // the gallery a DEM handle was built over
 size_t twd_workspace_bytes(const fir_gallery* g, int64_t nq, int64_t* mq_out);
 int twd_run(fir_gallery* g, const float* dq, int64_t nq, int64_t mq, int kind, int type, double threshold, int feat_count, int last_feature,

@@ -386,7 +386,16 @@ struct CandParams {
 #endif
     int mins_only;              // seed pass (R = 4): the four slots are plain minima over the four 32-column groups, no lists
     const float* seed_thr;      // optional [nq]: approximate squared distance above which a row cannot matter (see seed pass)
+    // per-class nearest neighbour (CLS = 1, 2): NATURAL-order shadow (class-major rows), see tensor_class_min
+    const int32_t* cls_begin;   // [n_classes + 1] row range of every class
+    int n_classes;
+    unsigned long long* cls_keys;   // [nq][n_classes] packed (ordered v bits, row): pass 1 writes, pass 2 reads
+    int32_t* cls_cnt;           // [nq][n_classes] rows within the margin of the class minimum (pass 2)
+    int32_t* cls_cand;          // [nq][n_classes][kClsSlots]
+    const float* cls_E;         // [nq] approximation error bound of the query
+    double cls_rho;             // relative error of the reference's sequential sum
 };
+constexpr int kClsSlots = 4;
 
 // Running top-R of one query row, UNSORTED, in registers: mx is the current maximum (+inf until the list is full) and
 // thr = min(mx, tau) is what a new value has to beat; tau is the query's seed threshold (+inf when there is none).
@@ -662,6 +671,109 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
 }
 
 
+// ---- per-class nearest neighbour in the tensor epilogue -------------------------------------------------
+// The gallery is class-major, so a thread that walks a query row's accumulator columns in row order sees every class as ONE
+// run.  PASS 1 keeps the running minimum of v = ‖x‖² − 2·q̂·x̂ of the current class and, at the class change, folds it into
+// cls_keys[q][class] with a 64-bit atomicMin (packed (ordered v, row)).  PASS 2 re-scans with the per-(query, class)
+// threshold "approximate class minimum + margin" — every row whose REFERENCE distance could be the class minimum lies under
+// it (the prune rule of the top-k path with kth := the class minimum) — and lists those rows in cls_cand[q][class][0..3];
+// their exact fp32 distances decide.  A chunk of 32 columns that lies inside the current class takes a branch-free
+// minimum; only the chunks that contain a class boundary (warp-uniform test) walk their columns one by one.
+struct ClsState { int cls, end; float bv; int bi; float thr; };
+
+__device__ __forceinline__ void cls_flush_min(const CandParams& p, int64_t qrow, ClsState& st) {
+    if (st.bi >= 0 && qrow < p.nq)
+        atomicMin(&p.cls_keys[qrow * p.n_classes + st.cls], ((unsigned long long)ordered_bits(st.bv) << 32) | (uint32_t)st.bi);
+    st.bv = __int_as_float(0x7f800000); st.bi = -1;
+}
+__device__ __forceinline__ void cls_advance(const CandParams& p, ClsState& st, int row) {      // row >= st.end: the class that holds `row`
+    int c = st.cls;
+    do { ++c; } while (p.cls_begin[c + 1] <= row);                                              // classes without rows are skipped
+    st.cls = c; st.end = p.cls_begin[c + 1];
+}
+__device__ __forceinline__ float cls_threshold(const CandParams& p, int64_t qrow, int cls) {
+    if (qrow >= p.nq) return -__int_as_float(0x7f800000);
+    const unsigned long long key = p.cls_keys[qrow * p.n_classes + cls];
+    if (key == ~0ull) return -__int_as_float(0x7f800000);
+    const double nqv = (double)p.qry_norm2[qrow], E = (double)p.cls_E[qrow];
+    const double m = (double)from_ordered_bits((uint32_t)(key >> 32)) + nqv;                    // approximate squared distance of the class minimum
+    return __double2float_ru((m + E) * (1.0 + p.cls_rho) / (1.0 - p.cls_rho) + E - nqv);
+}
+__device__ __forceinline__ void cls_emit(const CandParams& p, int64_t qrow, int cls, int row) {
+    if (qrow >= p.nq) return;
+    const int64_t cell = qrow * p.n_classes + cls;
+    const int slot = atomicAdd(&p.cls_cnt[cell], 1);
+    if (slot < kClsSlots) p.cls_cand[cell * kClsSlots + slot] = row;
+}
+
+template <int PASS>
+__device__ __forceinline__ void epilogue_scan_tile_cls(uint32_t taddr, const float* __restrict__ nxs, int jbase, float negc, const CandParams& p,
+                                                       int64_t qrow, ClsState& st) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
+        uint32_t rr[32];
+        tc_ld32(taddr + c0, rr);
+        tc_wait_ld();
+        const int j0 = jbase + c0;
+        float gm[8];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
+            const float v0 = fmaf(negc, __uint_as_float(rr[i + 0]), nx4.x), v1 = fmaf(negc, __uint_as_float(rr[i + 1]), nx4.y);
+            const float v2 = fmaf(negc, __uint_as_float(rr[i + 2]), nx4.z), v3 = fmaf(negc, __uint_as_float(rr[i + 3]), nx4.w);
+            rr[i + 0] = __float_as_uint(v0); rr[i + 1] = __float_as_uint(v1); rr[i + 2] = __float_as_uint(v2); rr[i + 3] = __float_as_uint(v3);
+            gm[i >> 2] = fminf(fminf(v0, v1), fminf(v2, v3));
+        }
+        const float vmin = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+        if (j0 + 32 <= st.end) {                                   // warp-uniform: the whole chunk lies inside the current class
+            if (PASS == 1) {
+                if (vmin < st.bv) {
+                    int at = 31;
+#pragma unroll
+                    for (int i = 30; i >= 0; --i) at = (__uint_as_float(rr[i]) == vmin) ? i : at;
+                    st.bv = vmin; st.bi = j0 + at;
+                }
+            } else {
+                // a lane whose chunk minimum is under its threshold lists that column, blanks it and looks again — almost
+                // always once (about 1.1 rows per (query, class) lie inside the margin), so the warp pays one select chain
+                // instead of 32 predicated emit bodies
+                float cur = vmin;
+#pragma unroll 1
+                while (__any_sync(0xffffffffu, cur <= st.thr)) {
+                    if (cur <= st.thr) {
+                        int at = -1;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const bool hit = at < 0 && __uint_as_float(rr[i]) == cur;
+                            at = hit ? i : at;
+                            rr[i] = hit ? 0x7f800000u : rr[i];
+                        }
+                        cls_emit(p, qrow, st.cls, j0 + at);
+                        float m = __uint_as_float(rr[0]);
+#pragma unroll
+                        for (int i = 1; i < 32; ++i) m = fminf(m, __uint_as_float(rr[i]));
+                        cur = m;
+                    }
+                }
+            }
+        } else {                                                   // a class boundary (or the end of the gallery) inside the chunk
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int row = j0 + i;
+                if (row >= p.n) break;                             // padding rows of the last tile
+                if (row >= st.end) {                               // warp-uniform
+                    if (PASS == 1) cls_flush_min(p, qrow, st);
+                    cls_advance(p, st, row);
+                    if (PASS == 2) st.thr = cls_threshold(p, qrow, st.cls);
+                }
+                const float v = __uint_as_float(rr[i]);
+                if (PASS == 1) { if (v < st.bv) { st.bv = v; st.bi = row; } }
+                else if (v <= st.thr) cls_emit(p, qrow, st.cls, row);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2).  Two CTAs of a cluster (the two SMs of a TPC) share every gallery tile:
 // each loads HALF of the 256-row B tile (128 rows x 64 k, 16 KiB per k-block) and keeps its own 128 query rows
@@ -709,7 +821,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256
 constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;   // 16 KiB
 
-template <int R, bool A_RES>
+template <int R, bool A_RES, int CLS = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const CandParams p) {
     constexpr int STAGES = 6;
@@ -838,11 +950,16 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         const float sg = __uint_as_float(p.gal_meta[1]);
         float negc = 0.f;                              // −2 / (gallery scale · this row's query scale), set per query block
         float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000), mx = thr, tau = thr;
+        ClsState cst; cst.cls = -1; cst.end = 0; cst.bv = thr; cst.bi = -1; cst.thr = -thr;
         int64_t cur_qb = -1;
         int as = 0; uint32_t aphase = 0;
         for (WorkIter wi = work0; !wi.done(); wi.advance()) {
             const int64_t qb = wi.qb; const int64_t tile = wi.tile;
             if (qb != cur_qb) {
+                if constexpr (CLS != 0) {
+                    if (CLS == 1 && cur_qb >= 0) cls_flush_min(p, cur_qb * (2 * BM) + rank * BM + row, cst);
+                    cst.cls = -1; cst.end = 0; cst.bv = __int_as_float(0x7f800000); cst.bi = -1; cst.thr = -__int_as_float(0x7f800000);
+                } else
                 if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
 #pragma unroll
                 for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = p.mins_only ? 0 : -1; }
@@ -859,7 +976,10 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
             mbar_wait_cluster(smem_u32(&tmem_full[as]), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + half * EPI_COLS);
-            if constexpr (R == 4) {
+            if constexpr (CLS != 0) {
+                epilogue_scan_tile_cls<CLS>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, p,
+                                            cur_qb * (2 * BM) + rank * BM + row, cst);
+            } else if constexpr (R == 4) {
                 if (p.mins_only) epilogue_scan_tile_mins(taddr, nx_s + as * BN + half * EPI_COLS, negc, lv);
                 else epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, mx, thr, tau);
             } else {
@@ -870,7 +990,8 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
             if (lane == 0) { mbar_arrive(smem_u32(&nx_empty[as])); if (leader) mbar_arrive(smem_u32(&tmem_empty[as])); else mbar_arrive_leader(smem_u32(&tmem_empty[as])); }
             as ^= 1; if (as == 0) aphase ^= 1;
         }
-        if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
+        if constexpr (CLS != 0) { if (CLS == 1 && cur_qb >= 0) cls_flush_min(p, cur_qb * (2 * BM) + rank * BM + row, cst); }
+        else if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
     }
 
     tc_fence_before();
@@ -1421,6 +1542,202 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
         FIR_CUDA_TRY(cudaMemcpyAsync(out_idx, oi, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
         if (out_dist) FIR_CUDA_TRY(cudaMemcpyAsync(out_dist, od, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, g->stream));
         FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    }
+    return FIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-class nearest neighbour (fir_class_min, Euclidean) on the tensor path — see epilogue_scan_tile_cls.
+// ---------------------------------------------------------------------------------------------------
+static int ensure_gallery_nat(fir_gallery* g) {
+    if (g->nat_ready && g->nat_classes == g->n_classes) return FIR_OK;
+    for (size_t i = 1; i < g->h_labels.size(); ++i)
+        if (g->h_labels[i] < g->h_labels[i - 1]) return kApproxDeclined;       // not class-major: the exact kernels fold arbitrary label runs
+    const int C = g->n_classes;
+    std::vector<int32_t> begin((size_t)C + 1, 0);
+    for (int32_t l : g->h_labels) begin[(size_t)l + 1]++;
+    for (int c = 0; c < C; ++c) begin[(size_t)c + 1] += begin[(size_t)c];
+    if (!g->d_stats) { FIR_CUDA_TRY(cudaMalloc(&g->d_stats, 64)); FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, 64, g->stream)); }
+    if (!g->tensor_buf_nat) {
+        FIR_CUDA_TRY(cudaMalloc(&g->tensor_buf_nat, tensor_side_bytes(g->n, g->d, BN)));
+        FIR_TRY(tensor_pack_side(g->rows, g->n, g->dp, g->d, BN, g->tensor_buf_nat, &g->tside_nat, g->d_stats, /*permute=*/false, false, g->stream));
+        FIR_TRY(tensor_encode_map(&g->tmap_nat_half, g->tside_nat.h, g->tside_nat.rows_padded, g->tside_nat.dph, BN / 2));
+    }
+    if (g->d_cls_begin) { FIR_CUDA_TRY(cudaStreamSynchronize(g->stream)); FIR_CUDA_TRY(cudaFree(g->d_cls_begin)); g->d_cls_begin = nullptr; }
+    FIR_CUDA_TRY(cudaMalloc(&g->d_cls_begin, 4 * ((size_t)C + 1)));
+    FIR_CUDA_TRY(cudaMemcpyAsync(g->d_cls_begin, begin.data(), 4 * ((size_t)C + 1), cudaMemcpyHostToDevice, g->stream));
+    FIR_CUDA_TRY(cudaStreamSynchronize(g->stream));                            // `begin` is a local
+    g->nat_classes = C;
+    g->nat_ready = true;
+    return FIR_OK;
+}
+
+__global__ void cls_margin_kernel(const float* __restrict__ q_norm2, const float* __restrict__ q_resid, const float* __restrict__ gal_stats, int nkb,
+                                  int64_t nq, float* __restrict__ E) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) E[q] = __double2float_ru(approx_error_bound((double)q_norm2[q], (double)q_resid[q], (double)gal_stats[0], (double)gal_stats[1], nkb));
+}
+
+// the listed (cell, slot) entries of all queries on one dense list for the exact rerank (pair_list_kernel): one atomic per block
+__global__ void __launch_bounds__(256) cls_compact_kernel(const int32_t* __restrict__ cand, int64_t entries, uint32_t* __restrict__ pair_cells,
+                                                          int32_t* __restrict__ pair_count) {
+    __shared__ int s_warp[8];
+    __shared__ int s_off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool live = e < entries && cand[e] >= 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_off = tot > 0 ? atomicAdd(pair_count, tot) : 0;
+    }
+    __syncthreads();
+    if (live) pair_cells[s_off + s_warp[warp] + __popc(m & ((1u << lane) - 1))] = (uint32_t)e;
+}
+
+// one thread per (query, class): the exact minimum over the listed rows, strict '<' on (distance, row); a class with more rows
+// inside the margin than the list holds goes on the overflow list — its rows are then all evaluated exactly (cls_cell_exact_kernel)
+__global__ void cls_pick_kernel(const int32_t* __restrict__ cand, const int32_t* __restrict__ cnt, const float* __restrict__ exact, int64_t cells,
+                                int64_t index_offset, float* __restrict__ out_min, int32_t* __restrict__ out_arg,
+                                uint32_t* __restrict__ over_list, int32_t* __restrict__ over_count) {
+    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= cells) return;
+    const int c = cnt[cell];
+    if (c > kClsSlots) { over_list[atomicAdd(over_count, 1)] = (uint32_t)cell; return; }
+    float bd = 100000.0f; int32_t bi = -1;                                    // ann.cpp:116: nothing >= 100000 is ever accepted
+    for (int s = 0; s < c; ++s) {
+        const int32_t r = cand[cell * kClsSlots + s];
+        const float d = exact[cell * kClsSlots + s];
+        if (r >= 0 && (d < bd || (d == bd && bi >= 0 && r < bi))) { bd = d; bi = r; }
+    }
+    out_min[cell] = bd;
+    out_arg[cell] = bi < 0 ? -1 : (int32_t)(bi + index_offset);
+}
+
+// one warp per overflowed (query, class) cell: the reference's own arithmetic over every row of the class (lane l takes rows
+// b + l, b + l + 32, ...; each distance is the sequential fp32 sum), then the (distance, row) minimum of the warp
+__global__ void __launch_bounds__(128) cls_cell_exact_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ x, int ldx, int d,
+                                                             const int32_t* __restrict__ cls_begin, int n_classes, const uint32_t* __restrict__ over_list,
+                                                             const int32_t* __restrict__ over_count, int64_t index_offset,
+                                                             float* __restrict__ out_min, int32_t* __restrict__ out_arg) {
+    const int lane = threadIdx.x & 31;
+    const int total = *over_count;
+    for (int w = blockIdx.x * 4 + (threadIdx.x >> 5); w < total; w += gridDim.x * 4) {
+        const uint32_t cell = over_list[w];
+        const int64_t qi = cell / (uint32_t)n_classes;
+        const int c = (int)(cell - (uint32_t)qi * (uint32_t)n_classes);
+        const float* qr = q + qi * ldq;
+        float bd = 100000.0f; int32_t bi = -1;
+        for (int r = cls_begin[c] + lane; r < cls_begin[c + 1]; r += 32) {
+            const float* xr = x + (int64_t)r * ldx;
+            float acc = 0.f;
+            for (int k = 0; k < d; k += 4) {                                   // rows are zero padded to a multiple of 32 floats
+                const float4 a = *reinterpret_cast<const float4*>(qr + k), b = *reinterpret_cast<const float4*>(xr + k);
+                dist_step<FIR_L2>(acc, a.x, b.x);
+                if (k + 1 < d) dist_step<FIR_L2>(acc, a.y, b.y);
+                if (k + 2 < d) dist_step<FIR_L2>(acc, a.z, b.z);
+                if (k + 3 < d) dist_step<FIR_L2>(acc, a.w, b.w);
+            }
+            const float dd = __fdiv_rn(acc, (float)d);
+            if (dd < bd) { bd = dd; bi = r; }                                  // ascending rows within a lane: strict '<' keeps the lowest
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o); const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; }
+        }
+        if (lane == 0) { out_min[cell] = bd; out_arg[cell] = bi < 0 ? -1 : (int32_t)(bi + index_offset); }
+    }
+}
+
+int tensor_class_min(fir_gallery* g, const float* queries, int64_t nq, int memspace, float* out_min, int32_t* out_arg) {
+    { const int st = ensure_gallery_nat(g); if (st != FIR_OK) return st; }
+    const int C = g->n_classes, d = g->d, dp = g->dp;
+    const size_t cells = (size_t)nq * C;
+    cudaStream_t s = g->stream;
+    const size_t qside = tensor_side_bytes(nq, d, BM);
+    if (cells >= 0xffffffffull) return kApproxDeclined;           // cells are addressed with 32 bits
+    size_t need = al256(sizeof(float) * (size_t)nq * dp) + qside + al256(4 * (size_t)nq) * 2 + al256(8 * cells) + 2 * al256(4 * cells) + 3 * al256(4 * cells * kClsSlots) +
+                  2 * al256(4 * cells) + 65536;
+    FIR_TRY(g->ws.reserve(need));
+    const float* dq = nullptr;
+    if (memspace == FIR_DEVICE && d == dp) dq = queries;
+    else {
+        float* buf = (float*)g->ws.take(sizeof(float) * (size_t)nq * dp);
+        if (!buf) return fail(FIR_ERR_INTERNAL, "workspace underestimated (class-min queries)");
+        if (memspace == FIR_HOST) {
+            if (d != dp) FIR_CUDA_TRY(cudaMemsetAsync(buf, 0, sizeof(float) * (size_t)nq * dp, s));
+            FIR_CUDA_TRY(cudaMemcpy2DAsync(buf, sizeof(float) * dp, queries, sizeof(float) * d, sizeof(float) * d, (size_t)nq, cudaMemcpyHostToDevice, s));
+        } else FIR_TRY(launch_pad_rows(queries, nq, d, buf, dp, s));
+        dq = buf;
+    }
+    void* qbuf = g->ws.take(qside);
+    float* E = (float*)g->ws.take(4 * (size_t)nq);
+    uint32_t* over_list = (uint32_t*)g->ws.take(4 * cells);
+    uint32_t* pair_cells = (uint32_t*)g->ws.take(4 * cells * kClsSlots);
+    int32_t* fcount = (int32_t*)g->ws.take(256);              // [0] overflowed cells, [1] live (cell, slot) entries
+    unsigned long long* keys = (unsigned long long*)g->ws.take(8 * cells);
+    int32_t* cnt = (int32_t*)g->ws.take(4 * cells);
+    int32_t* cand = (int32_t*)g->ws.take(4 * cells * kClsSlots);
+    float* exact = (float*)g->ws.take(4 * cells * kClsSlots);
+    float* dmin = out_min; int32_t* darg = out_arg;
+    if (memspace == FIR_HOST) { dmin = (float*)g->ws.take(4 * cells); darg = (int32_t*)g->ws.take(4 * cells); }
+    if (!qbuf || !E || !over_list || !pair_cells || !fcount || !keys || !cnt || !cand || !exact || !dmin || !darg)
+        return fail(FIR_ERR_INTERNAL, "workspace underestimated (class-min tensor path)");
+    TensorSide qs;
+    FIR_TRY(tensor_pack_side(dq, nq, dp, d, BM, qbuf, &qs, nullptr, false, true, s));
+    CUtensorMap tmap_a;
+    FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
+    CandParams p{};
+    p.part = make_partition(nq, g->n, g->n_sm, 2);
+    p.nq = nq; p.n = g->n; p.perm_a = 1; p.perm_b = 0;
+    p.nkb = g->tside_nat.dph / BK; p.n_slots = 1;
+    p.gal_norm2 = g->tside_nat.norm2; p.qry_norm2 = qs.norm2; p.gal_meta = g->tside_nat.meta; p.qry_row_scale = qs.row_scale;
+    p.cls_begin = g->d_cls_begin; p.n_classes = C; p.cls_keys = keys; p.cls_cnt = cnt; p.cls_cand = cand; p.cls_E = E;
+    p.cls_rho = (double)(d + 4) * 5.9604644775390625e-08;
+    const bool a_res = p.nkb <= MAX_RES_KB;
+    const size_t smem = cand_smem_bytes_2cta(a_res);
+    auto go = [&](auto kern) -> int {
+        FIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<p.part.grid * 2, NUM_THREADS, smem, s>>>(tmap_a, g->tmap_nat_half, p);
+        FIR_CUDA_TRY(cudaGetLastError());
+        return FIR_OK;
+    };
+    FIR_CUDA_TRY(cudaMemsetAsync(keys, 0xFF, 8 * cells, s));
+    FIR_CUDA_TRY(cudaMemsetAsync(cnt, 0, 4 * cells, s));
+    FIR_CUDA_TRY(cudaMemsetAsync(cand, 0xFF, 4 * cells * kClsSlots, s));
+    FIR_CUDA_TRY(cudaMemsetAsync(fcount, 0, 8, s));
+    cls_margin_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, s>>>(qs.norm2, qs.resid, g->d_stats, p.nkb, nq, E);
+    { auto* ev = g->prof_begin(FIR_KERNEL_L2_CANDIDATES);
+      const int st = a_res ? go(l2_candidates_kernel_2cta<4, true, 1>) : go(l2_candidates_kernel_2cta<4, false, 1>);
+      g->prof_end(ev); FIR_TRY(st); }
+    { auto* ev = g->prof_begin(FIR_KERNEL_L2_CANDIDATES_PASS2);
+      const int st = a_res ? go(l2_candidates_kernel_2cta<4, true, 2>) : go(l2_candidates_kernel_2cta<4, false, 2>);
+      g->prof_end(ev); FIR_TRY(st); }
+    // the reference's own fp32 arithmetic on the listed rows, then the per-class pick
+    { auto* ev = g->prof_begin(FIR_PHASE_RERANK);
+      const int64_t entries = (int64_t)cells * kClsSlots;
+      int st = FIR_OK;
+      if ((uint64_t)entries < 0xffffffffull) {                 // dense list of the live entries, one lane per (query, row) pair
+          cls_compact_kernel<<<(unsigned)ceil_div(entries, 256), 256, 0, s>>>(cand, entries, pair_cells, fcount + 1);
+          st = launch_pair_list(FIR_L2, dq, dp, g->rows, dp, d, pair_cells, fcount + 1, entries, C * kClsSlots, cand, exact, s);
+      } else st = launch_pair_distances(FIR_L2, dq, nq, dp, g->rows, dp, g->n, d, cand, C * kClsSlots, 0, exact, s);
+      g->prof_end(ev); FIR_TRY(st); }
+    cls_pick_kernel<<<(unsigned)ceil_div((int64_t)cells, 256), 256, 0, s>>>(cand, cnt, exact, (int64_t)cells, g->index_offset, dmin, darg, over_list, fcount);
+    // classes with more rows inside the margin than the list holds (about 1e-4 of the cells on clustered data): every row of the
+    // class through the reference's arithmetic, one warp per cell, device-side count
+    cls_cell_exact_kernel<<<g->n_sm * 8, 128, 0, s>>>(dq, dp, g->rows, dp, d, g->d_cls_begin, C, over_list, fcount, g->index_offset, dmin, darg);
+    FIR_CUDA_TRY(cudaGetLastError());
+    g->stats.path_used = FIR_PATH_TENSOR;
+    g->stats.gpu_launches += 8;
+    g->stats.n_fallback = -3;                                 // resolved lazily: fcount lives in the workspace, copied below
+    FIR_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<int32_t*>(g->d_stats + 4), fcount, 4, cudaMemcpyDeviceToDevice, s));
+    if (memspace == FIR_HOST) {
+        FIR_CUDA_TRY(cudaMemcpyAsync(out_min, dmin, 4 * cells, cudaMemcpyDeviceToHost, s));
+        FIR_CUDA_TRY(cudaMemcpyAsync(out_arg, darg, 4 * cells, cudaMemcpyDeviceToHost, s));
+        FIR_CUDA_TRY(cudaStreamSynchronize(s));
     }
     return FIR_OK;
 }

@@ -52,3 +52,43 @@ def test_missing_library_fails_loudly(fir, monkeypatch, tmp_path):
     monkeypatch.setattr(fir, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(fir.FirError):
         fir.lib()
+
+
+def test_new_entry_points_reject_null_arguments(fir):
+    """The multi-GPU / DEM / classifier additions validate their arguments before touching a device (status codes, never a crash)."""
+    L, C = fir.lib(), ctypes
+    BAD = 1
+    null = C.c_void_p(None)
+    out = C.c_void_p(None)
+    assert L.fir_comm_unique_id(null) == BAD
+    assert L.fir_comm_init_rank(null, 0, 0, C.byref(out)) == BAD            # world < 1
+    assert L.fir_comm_init_rank(null, 3, 2, C.byref(out)) == BAD            # rank outside the world
+    assert L.fir_comm_info(null, None, None, None) == BAD
+    assert L.fir_comm_destroy(null) == 0                                     # destroying nothing is fine, like free(NULL)
+    assert L.fir_shard_search_topk(null, null, null, 1, 1, 0, 0, null, null) == BAD
+    assert L.fir_shard_class_min(null, null, null, 1, 0, null, null) == BAD
+    assert L.fir_shard_pnn_scores(null, null, null, 1, 1e-3, 10, 0, null, null) == BAD
+    assert L.fir_shard_dem_build(null, null, 10, None, C.byref(out)) == BAD
+    assert L.fir_sharded_create(null, null, 0, 8, 0, 1, C.byref(out)) == BAD
+    assert L.fir_sharded_info(null, None, None, None, None) == BAD
+    assert L.fir_sharded_search_topk(null, null, 1, 1, 0, null, null) == BAD
+    assert L.fir_sharded_dem_build(null, None, C.byref(out)) == BAD
+    assert L.fir_sharded_dem_search(null, null, 1, 0, null, null, null, null) == BAD
+    assert L.fir_sharded_destroy(null) == 0 and L.fir_sharded_dem_destroy(null) == 0
+    assert L.fir_dem_search_stats(null, None, None, None, None) == BAD
+    assert L.fir_classifier_knn_ex(null, null, 1, 3, 0, null) == BAD
+    assert L.fir_classifier_pnn_ex(null, null, 1, 0, null, null) == BAD
+    assert L.fir_classifier_profile(null, 1, None, None) == BAD
+    assert L.fir_gallery_index_offset(null, None) == BAD
+    assert L.fir_synth_rows(null, null, 0, 1, 1, 8, 2, 0, 1, 0.5, 0, null) == BAD
+    assert b"" != L.fir_last_error_string()
+
+
+def test_sharded_host_model_matches_c_key_format():
+    """sharded.py's key format is the one csrc/sharded.cu packs: ordered distance bits << 32 | global index, ~0 = empty."""
+    import importlib
+    sh = importlib.import_module("fast-image-recognition_b200.sharded")
+    k = sh.pack_keys(np.array([0.0, 1.5, -2.0], np.float32), np.array([7, 2**31 - 1, -1]))
+    assert k[0] == (0x80000000 << 32) | 7 and k[1] == ((0x3FC00000 | 0x80000000) << 32) | (2**31 - 1) and k[2] == sh.EMPTY_KEY
+    d, i = sh.unpack_keys(k)
+    assert i.tolist() == [7, 2**31 - 1, -1] and d[:2].tolist() == [0.0, 1.5]

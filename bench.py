@@ -686,6 +686,21 @@ def parity_and_cpu(env, synth, cfg, args, q_host, res_host, gal, k, dem):
             par["evals_equal"] = bool(np.array_equal(np.asarray(re_).astype(np.int32), evals[sample]))
             cpu = {"value": len(sample) / t, "unit": "queries/s", "cores": nthreads, "kind": "reference",
                    "sample": "%d of %d queries, DirectedEnumeration::recognize (ann.cpp:416-507) over the full %d-row gallery, %d threads" % (len(sample), nq, n, nthreads)}
+            # the other check budgets (ratio of the gallery a query may examine, ann.h:26): agreement with the verbatim recognize(), checked-%, q/s
+            sweep = []
+            qd = env.torch.from_numpy(q_host).to(env.dev)
+            for ratio in (0.025, 0.1, 0.25, 0.5):
+                Mr = int(ratio * n)
+                dem.search(qd, Mr)
+                a, b = env.torch.cuda.Event(enable_timing=True), env.torch.cuda.Event(enable_timing=True)
+                a.record(); gi, gd, gb, ge = dem.search(qd, Mr); b.record(); env.torch.cuda.synchronize()
+                gi, gd, gb, ge = (x.cpu().numpy() for x in (gi, gd, gb, ge))
+                ri, rd, rb, re_, _ = rdem.search(qs, Mr, nthreads=nthreads, timing=True)
+                sweep.append({"ratio": ratio, "queries_per_s": nq / (a.elapsed_time(b) * 1e-3), "checked_percent": float(100.0 * ge.mean() / n),
+                              "below_threshold_frac": float(gb.mean()),
+                              "equal_to_reference": bool(np.array_equal(ri, gi[sample]) and np.array_equal(np.asarray(rd, np.float32).view(np.uint32), gd[sample].view(np.uint32))
+                                                         and np.array_equal(np.asarray(rb).astype(np.uint8), gb[sample]) and np.array_equal(np.asarray(re_).astype(np.int32), ge[sample]))})
+            par["ratio_sweep"] = sweep
             rdem.close()
         bi, _ = gal.search(env.torch.from_numpy(q_host).to(env.dev), k=1)
         par["recall_at_1_vs_bf"] = float((bi.cpu().numpy()[:, 0] == idx).mean())

@@ -31,7 +31,7 @@ EXPORTS = [
     "fir_last_error_string", "fir_version", "fir_device_count", "fir_set_device",
     "fir_gallery_create", "fir_gallery_destroy", "fir_gallery_set_stream", "fir_gallery_info", "fir_gallery_index_offset", "fir_gallery_set_num_classes",
     "fir_normalize_rows", "fir_search_topk", "fir_search_last_stats", "fir_pair_distances",
-    "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates", "fir_profile_enable", "fir_profile_read",
+    "fir_class_min", "fir_pnn_scores", "fir_merge_topk", "fir_debug_tensor_candidates", "fir_debug_partition_check", "fir_profile_enable", "fir_profile_read",
     "fir_classifier_create", "fir_classifier_destroy", "fir_classifier_knn", "fir_classifier_pnn", "fir_classifier_pnn_sequential", "fir_classifier_knn_ex", "fir_classifier_pnn_ex", "fir_classifier_set_stream", "fir_classifier_profile",
     "fir_twd_conventional", "fir_twd_proposed", "fir_kmedoids_select", "fir_classifier_set_total",
     "fir_fpnn_create", "fir_fpnn_destroy", "fir_fpnn_info", "fir_fpnn_get_coefficients", "fir_fpnn_predict",
@@ -85,6 +85,7 @@ def lib():
     L.fir_search_topk.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, vp]
     L.fir_search_last_stats.argtypes = [vp, C.POINTER(SearchStats)]
     L.fir_debug_tensor_candidates.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp]
+    L.fir_debug_partition_check.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64, C.POINTER(i32), C.POINTER(i32)]
     L.fir_profile_enable.argtypes = [vp, i32]
     L.fir_profile_read.argtypes = [vp, i32, C.POINTER(f64), C.POINTER(i32)]
     L.fir_pair_distances.argtypes = [vp, vp, i64, vp, i32, i32, i32, vp]

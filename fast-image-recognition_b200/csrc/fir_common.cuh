@@ -115,8 +115,9 @@ struct TensorSearchArgs {
     int mins_only;                        // seed pass: per-slot column-group minima instead of top-R lists (R must be 4)
     int grid; int n_sm;
     int ctas;                     // 1: cta_group::1 kernel, 2: CTA-pair kernel (grid counts pairs)
+    unsigned int* sync_ctr;       // optional zeroed device word: lets the pairs of a full round re-align (galleries larger than L2)
 };
-int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots, int* min_slots = nullptr);
+int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots, int* min_slots = nullptr, int64_t row_bytes = 0);
 int tensor_cta_mode();
 int tensor_encode_map(CUtensorMap* map, const __half* base, int64_t rows_padded, int dph, int box_rows);
 int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s);

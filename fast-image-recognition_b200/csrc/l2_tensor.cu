@@ -281,34 +281,96 @@ int tensor_encode_map(CUtensorMap* map, const __half* base, int64_t rows_padded,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Work partition: items are (query block, gallery tile) pairs in query-block-major order, cut into
-// `grid` contiguous, equally sized ranges — one per CTA.  A query block is therefore covered by at
-// most n_slots consecutive CTAs, each of which writes its own candidate slot.
-// ---------------------------------------------------------------------------------------------------
-// Work partition.  Units are CTAs (or CTA pairs); a query block is BM (or 2·BM) queries; an item is (query block, tile).
+// Work partition.  Units are CTAs (or CTA pairs); a query block is BM (or 2·BM) queries; an item is (query block, tile);
+// a unit's work is a short list of SEGMENTS (query block, tile range).
 //  * FULL ROUNDS: while at least `grid` query blocks remain, unit u takes query block r·grid + u and sweeps ALL gallery tiles
 //    from tile 0.  Every unit walks the gallery in the same order at the same pace, so a B tile is fetched from HBM once per
 //    round and served to the other units from L2 — this is what keeps a 10 GB gallery from being re-streamed per query block.
-//  * REMAINDER: the last nqb mod grid query blocks are cut, in query-block-major item order, into `grid` contiguous, equally
-//    sized ranges (perfect balance); a remainder query block is then covered by several consecutive units, one slot each.
-struct Partition { int64_t ntiles, nqb, full_rounds, rem_total; int grid; };
+//  * REMAINDER (the last nqb mod grid query blocks), BALANCED form: cut, in query-block-major item order, into `grid`
+//    contiguous, equally sized ranges (perfect balance); a remainder query block is then covered by several consecutive units,
+//    one slot each.  Every unit is at a different place of the gallery, which is fine while the shadow fits L2.
+//  * REMAINDER, PHASED form (galleries larger than L2, after at least one full round): up to four phases; in a phase each of
+//    its query blocks is cut into g equal tile ranges and unit u = j·g + s sweeps range s for the phase's j-th block — the
+//    units of a range walk it together, so the gallery is again read from HBM once per phase instead of once per remainder
+//    query block (C5: 214 GB of 268 GB per launch were remainder reads).  The phases (g per phase) minimise the total sweep
+//    length Σ 1/g over the ways to seat the remaining blocks: 21 blocks on 74 units → 18 blocks × 4 ranges, then
+//    3 blocks × 24 ranges = 0.292 sweeps against 0.284 for the perfectly balanced cut.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxPhases = 4;
+constexpr int kMaxRanges = 32;          // ranges per query block in a phase = candidate slots of its queries
+struct PartPhase { int qb0, nqb, g; };  // query blocks [qb0, qb0 + nqb) of the remainder, each cut into g tile ranges
+struct Partition { int64_t ntiles, nqb, full_rounds, rem_total; int grid; int n_phases; PartPhase ph[kMaxPhases]; };
 __host__ __device__ inline int64_t part_rem_lo(const Partition& P, int64_t u) { return u * P.rem_total / P.grid; }
-__host__ __device__ inline int64_t part_count(const Partition& P, int64_t u) {
-    return P.full_rounds * P.ntiles + (part_rem_lo(P, u + 1) - part_rem_lo(P, u));
+__host__ __device__ inline PartPhase part_phase(const Partition& P, int j) {      // (no dynamic indexing of a kernel parameter)
+    PartPhase ph = P.ph[0];
+    if (j == 1) ph = P.ph[1];
+    if (j == 2) ph = P.ph[2];
+    if (j == 3) ph = P.ph[3];
+    return ph;
 }
-__host__ __device__ inline void part_locate(const Partition& P, int64_t u, int64_t li, int64_t& qb, int64_t& tile) {
-    const int64_t full_items = P.full_rounds * P.ntiles;
-    if (li < full_items) { const int64_t r = li / P.ntiles; qb = r * P.grid + u; tile = li - r * P.ntiles; }
-    else { const int64_t it = part_rem_lo(P, u) + (li - full_items); const int64_t q = it / P.ntiles; qb = P.full_rounds * P.grid + q; tile = it - q * P.ntiles; }
+// segment i of unit u → true while there is one (lo == hi: this unit sits the segment out)
+__host__ __device__ inline bool part_segment(const Partition& P, int64_t u, int64_t i, int64_t& qb, int& lo, int& hi) {
+    if (i < P.full_rounds) { qb = i * P.grid + u; lo = 0; hi = (int)P.ntiles; return true; }
+    const int64_t j = i - P.full_rounds, base = P.full_rounds * P.grid;
+    if (P.n_phases > 0) {
+        if (j >= P.n_phases) return false;
+        const PartPhase ph = part_phase(P, (int)j);
+        qb = -1; lo = hi = 0;
+        if (u < (int64_t)ph.nqb * ph.g) {
+            const int64_t jq = u / ph.g, r = u - jq * ph.g;
+            qb = base + ph.qb0 + jq; lo = (int)(r * P.ntiles / ph.g); hi = (int)((r + 1) * P.ntiles / ph.g);
+        }
+        return true;
+    }
+    const int64_t a = part_rem_lo(P, u), b = part_rem_lo(P, u + 1);
+    if (a >= b) return false;
+    const int64_t q = a / P.ntiles + j;
+    const int64_t s0 = a > q * P.ntiles ? a : q * P.ntiles, e0 = b < (q + 1) * P.ntiles ? b : (q + 1) * P.ntiles;
+    if (s0 >= e0) return false;
+    qb = base + q; lo = (int)(s0 - q * P.ntiles); hi = (int)(e0 - q * P.ntiles);
+    return true;
 }
+// candidate slot unit u writes for query block qb
 __host__ __device__ inline int part_slot(const Partition& P, int64_t u, int64_t qb) {
     const int64_t rq = qb - P.full_rounds * P.grid;
     if (rq < 0) return 0;
+    if (P.n_phases > 0) {
+        for (int j = 0; j < kMaxPhases; ++j) {
+            const PartPhase ph = part_phase(P, j);
+            if (j < P.n_phases && rq >= ph.qb0 && rq < ph.qb0 + ph.nqb) return (int)(u % ph.g);
+        }
+        return 0;
+    }
     const int64_t first = ((rq * P.ntiles + 1) * P.grid - 1) / P.rem_total;     // first unit whose range reaches this query block
     return (int)(u - first);
 }
-inline Partition make_partition(int64_t nq, int64_t n, int n_sm, int ctas) {
-    Partition P;
+// the remainder goes through phases when the shadow is larger than this (bytes); smaller ones stay in L2 whatever the order
+static int64_t phased_min_bytes() {
+    static const int64_t v = [] { const char* e = getenv("FIR_TENSOR_PHASED_MIN_BYTES"); return e ? (int64_t)atoll(e) : ((int64_t)48 << 20); }();
+    return v;
+}
+// seats r query blocks on G units: cost[r][depth] = least Σ 1/g over at most `depth` phases
+static double phase_plan(int r, int G, int depth, PartPhase* out, int* n_out) {
+    if (r == 0) { *n_out = 0; return 0.0; }
+    if (depth == 0) { *n_out = 0; return 1e30; }
+    double best = 1e30;
+    const int g_lo = std::max(1, std::min(kMaxRanges, G / r));
+    for (int g = g_lo; g <= std::min(G, kMaxRanges); ++g) {
+        const int seats = std::min(r, G / g);
+        if (seats <= 0) break;
+        PartPhase sub[kMaxPhases]; int n_sub = 0;
+        const double c = 1.0 / g + phase_plan(r - seats, G, depth - 1, sub, &n_sub);
+        if (c < best - 1e-12) {
+            best = c;
+            out[0] = PartPhase{0, seats, g};
+            for (int t = 0; t < n_sub; ++t) { out[t + 1] = sub[t]; out[t + 1].qb0 += seats; }
+            *n_out = n_sub + 1;
+        }
+    }
+    return best;
+}
+inline Partition make_partition(int64_t nq, int64_t n, int n_sm, int ctas, int64_t row_bytes = 0) {
+    Partition P{};
     P.ntiles = ceil_div(n, BN);
     P.nqb = ceil_div(nq, BM * ctas);
     const int64_t units = std::max<int64_t>(1, n_sm / ctas);
@@ -316,54 +378,87 @@ inline Partition make_partition(int64_t nq, int64_t n, int n_sm, int ctas) {
     const int64_t rem_qb = P.nqb - P.full_rounds * units;
     P.rem_total = rem_qb * P.ntiles;
     P.grid = (int)(P.full_rounds > 0 ? units : std::min<int64_t>(units, std::max<int64_t>(1, P.rem_total)));
+    if (P.full_rounds > 0 && rem_qb > 0 && P.ntiles * BN * row_bytes > phased_min_bytes() && P.ntiles >= 4 * kMaxRanges) {
+        int np = 0;
+        const double c = phase_plan((int)rem_qb, P.grid, kMaxPhases, P.ph, &np);
+        P.n_phases = c < 1e29 ? np : 0;
+    }
     return P;
 }
 
 // Walks a unit's items in order with adds and compares only: the MMA issuer is ONE thread, and a 64-bit division per
-// item (what part_locate costs) is hundreds of serial instructions — enough to starve the tensor pipe between tiles.
+// item is hundreds of serial instructions — enough to starve the tensor pipe between tiles.  Divisions happen once per
+// segment (part_segment).
 struct WorkIter {
-    int64_t qb, left, in_full, rem_qb0;
-    int tile, ntiles, grid, rem_tile0;
-    __device__ __forceinline__ void init(const Partition& P, int64_t u) {
-        ntiles = (int)P.ntiles; grid = P.grid;
-        in_full = P.full_rounds * P.ntiles;
-        const int64_t lo = part_rem_lo(P, u), cnt = part_rem_lo(P, u + 1) - lo;
-        const int64_t q = P.ntiles ? lo / P.ntiles : 0;
-        rem_qb0 = P.full_rounds * P.grid + q; rem_tile0 = (int)(lo - q * P.ntiles);
-        left = in_full + cnt;
-        if (in_full > 0) { qb = u; tile = 0; } else { qb = rem_qb0; tile = rem_tile0; }
+    const Partition* P;
+    int64_t u, qb, seg;
+    int tile, lo, hi;
+    __device__ __forceinline__ void load_next() {
+        bool ok;
+        do { ++seg; ok = part_segment(*P, u, seg, qb, lo, hi); } while (ok && lo >= hi);
+        if (!ok) qb = -1;
+        tile = lo;
     }
-    __device__ __forceinline__ bool done() const { return left <= 0; }
+    __device__ __forceinline__ void init(const Partition& part, int64_t unit) { P = &part; u = unit; seg = -1; qb = -1; lo = hi = 0; load_next(); }
+    __device__ __forceinline__ bool done() const { return qb < 0; }
+    __device__ __forceinline__ bool in_full() const { return seg < P->full_rounds; }
     __device__ __forceinline__ int64_t next_qb() const {          // query block of the following item, -1 if none
-        if (left <= 1) return -1;
-        if (in_full > 0) return in_full == 1 ? rem_qb0 : (tile + 1 == ntiles ? qb + grid : qb);
-        return tile + 1 == ntiles ? qb + 1 : qb;
+        if (tile + 1 < hi) return qb;
+        int64_t s = seg, q; int a, b; bool ok;
+        do { ++s; ok = part_segment(*P, u, s, q, a, b); } while (ok && a >= b);
+        return ok ? q : -1;
     }
-    __device__ __forceinline__ void advance() {
-        --left;
-        if (in_full > 0) {
-            --in_full;
-            if (in_full == 0) { qb = rem_qb0; tile = rem_tile0; }
-            else if (++tile == ntiles) { tile = 0; qb += grid; }
-        } else if (++tile == ntiles) { tile = 0; ++qb; }
-    }
+    __device__ __forceinline__ void advance() { if (++tile >= hi) load_next(); }
 };
 
-int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots, int* min_slots) {
-    const Partition P = make_partition(nq, n, n_sm, ctas);
+int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots, int* min_slots, int64_t row_bytes) {
+    const Partition P = make_partition(nq, n, n_sm, ctas, row_bytes);
     int slots = 1, least = P.full_rounds > 0 ? 1 : (1 << 30);
     const int64_t rem_qb = P.nqb - P.full_rounds * P.grid;
-    for (int64_t rq = 0; rq < rem_qb; ++rq) {
-        const int64_t qb = P.full_rounds * P.grid + rq;
-        const int64_t last_item = (rq + 1) * P.ntiles - 1;
-        const int64_t last_unit = ((last_item + 1) * P.grid - 1) / P.rem_total;
-        slots = std::max<int>(slots, part_slot(P, last_unit, qb) + 1);
-        least = std::min<int>(least, part_slot(P, last_unit, qb) + 1);
+    if (P.n_phases > 0) {
+        for (int j = 0; j < P.n_phases; ++j) slots = std::max(slots, P.ph[j].g);
+    } else {
+        for (int64_t rq = 0; rq < rem_qb; ++rq) {
+            const int64_t qb = P.full_rounds * P.grid + rq;
+            const int64_t last_item = (rq + 1) * P.ntiles - 1;
+            const int64_t last_unit = ((last_item + 1) * P.grid - 1) / P.rem_total;
+            slots = std::max<int>(slots, part_slot(P, last_unit, qb) + 1);
+            least = std::min<int>(least, part_slot(P, last_unit, qb) + 1);
+        }
     }
     *grid = P.grid;
     *n_slots = slots;
     if (min_slots) *min_slots = least == (1 << 30) ? 1 : least;
     return FIR_OK;
+}
+
+// Host-side self check of the partition (no GPU): every (query block, tile) item is covered exactly once, slots are distinct
+// per query block and below n_slots.  0 = consistent; used by tests/test_cabi.py over many shapes.
+extern "C" int fir_debug_partition_check(int64_t nq, int64_t n, int n_sm, int ctas, int64_t row_bytes, int* n_phases_out, int* n_slots_out) {
+    const Partition P = make_partition(nq, n, n_sm, ctas, row_bytes);
+    int grid = 0, n_slots = 0, least = 0;
+    tensor_plan(nq, n, n_sm, ctas, &grid, &n_slots, &least, row_bytes);
+    if (n_phases_out) *n_phases_out = P.n_phases;
+    if (n_slots_out) *n_slots_out = n_slots;
+    if (P.nqb * P.ntiles > ((int64_t)1 << 26)) return -1;                       // the check keeps a byte per item
+    std::vector<unsigned char> seen((size_t)(P.nqb * P.ntiles), 0);
+    std::vector<uint64_t> slot_mask((size_t)P.nqb * 4, 0);                     // 256 slot bits per query block
+    for (int64_t u = 0; u < P.grid; ++u) {
+        int64_t qb; int lo, hi;
+        for (int64_t i = 0; part_segment(P, u, i, qb, lo, hi); ++i) {
+            if (lo >= hi) continue;
+            if (qb < 0 || qb >= P.nqb || lo < 0 || hi > P.ntiles) return 1;
+            for (int t = lo; t < hi; ++t) { unsigned char& c = seen[(size_t)(qb * P.ntiles + t)]; if (c) return 2; c = 1; }
+            const int sl = part_slot(P, u, qb);
+            if (sl < 0 || sl >= n_slots || sl >= 256) return 3;
+            uint64_t& word = slot_mask[(size_t)qb * 4 + (size_t)(sl >> 6)];
+            if (word >> (sl & 63) & 1) return 4;                                // two segments of one query block on the same slot
+            word |= (uint64_t)1 << (sl & 63);
+            if (i > P.full_rounds + kMaxPhases + 2) return 5;
+        }
+    }
+    for (unsigned char c : seen) if (!c) return 6;
+    return 0;
 }
 
 struct CandParams {
@@ -394,7 +489,13 @@ struct CandParams {
     int32_t* cls_cand;          // [nq][n_classes][kClsSlots]
     const float* cls_E;         // [nq] approximation error bound of the query
     double cls_rho;             // relative error of the reference's sequential sum
+    // full rounds of a gallery larger than L2: the pairs re-align every kSyncTiles tiles (see the TMA producer)
+    int sync_tiles;             // tiles between two re-alignments (a power of two, > kSyncLag)
+    unsigned int* sync_ctr;     // [1 + kMaxPhases * kMaxRanges] zeroed before the launch ([0]: full rounds, then one per (phase, range)); nullptr = off
 };
+constexpr int kSyncTiles = 512;         // default CandParams::sync_tiles: 128 MiB of 512-d shadow between two re-alignments
+constexpr int kSyncLag = 4;             // tiles between a pair's arrival and its wait: the counter's round trip hides behind them
+constexpr unsigned kSyncTimeoutNs = 400000;   // a pair that is not answered (grid not co-resident) moves on: the barrier can only cost time
 constexpr int kClsSlots = 4;
 
 // Running top-R of one query row, UNSORTED, in registers: mx is the current maximum (+inf until the list is full) and
@@ -530,7 +631,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) l2_candidates_kernel(const __g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Partition P = p.part;
     const int64_t unit = blockIdx.x;
-    WorkIter work0; work0.init(P, unit);
+    WorkIter work0; work0.init(p.part, unit);
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();     // SWIZZLE_128B tiles need 1 KiB alignment
@@ -849,7 +950,7 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
     const int pair = blockIdx.x >> 1;
     const Partition P = p.part;
     const int64_t unit = pair;
-    WorkIter work0; work0.init(P, unit);
+    WorkIter work0; work0.init(p.part, unit);
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -876,10 +977,46 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         int stage = 0; uint32_t phase = 0; uint32_t a_loads = 0;
+        unsigned sync_epoch = 0, sync_members = 0; unsigned int* sync_at = nullptr; int64_t sync_seg = -2;
         int64_t cur_qb = -1;
         for (WorkIter wi = work0; !wi.done(); wi.advance()) {
             const int64_t qb = wi.qb; const int64_t tile = wi.tile;
             const int arow = (int)(qb * (2 * BM) + rank * BM);
+            // Re-alignment of the pairs that sweep the same tiles in the same order (all pairs in a full round; the pairs of
+            // one tile range in a phase of the remainder).  Pairs
+            // that drift apart by more than what L2 holds each stream the gallery from HBM on their own (C5 before this:
+            // 806 GB per launch against 51 GB for five shared sweeps).  Every kSyncTiles tiles the leader's producer adds
+            // one to a global counter and, kSyncLag tiles later, waits until all pairs of that epoch have arrived — the
+            // fastest pairs idle for the few microseconds they were ahead.  The wait is bounded, so a grid that is not
+            // co-resident loses time, never progress.
+            if (p.sync_ctr != nullptr && leader) {
+                if (wi.seg != sync_seg) {                          // a new segment: which counter, how many pairs share it
+                    sync_seg = wi.seg;
+                    if (wi.in_full()) { sync_at = p.sync_ctr; sync_members = (unsigned)P.grid; }             // one monotone counter over all full rounds
+                    else {
+                        const int j = (int)(wi.seg - P.full_rounds);
+                        const PartPhase ph = part_phase(P, j);
+                        const bool on = P.n_phases > 0 && (wi.hi - wi.lo) > 2 * p.sync_tiles;
+                        sync_at = on ? p.sync_ctr + 1 + j * kMaxRanges + (int)(unit % ph.g) : nullptr;
+                        sync_members = (unsigned)ph.nqb; sync_epoch = 0;
+                    }
+                }
+                const int ph = (wi.tile - wi.lo) & (p.sync_tiles - 1);
+                if (sync_at != nullptr && ph == 0) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(sync_at) : "memory"); ++sync_epoch; }
+                else if (sync_at != nullptr && ph == kSyncLag) {
+                    const unsigned target = sync_epoch * sync_members;
+                    unsigned seen, t0 = 0, t1;
+                    bool timed = false;
+                    while (true) {
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync_at) : "memory");
+                        if ((int)(seen - target) >= 0) break;
+                        asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t1));
+                        if (!timed) { t0 = t1; timed = true; }
+                        else if (t1 - t0 > kSyncTimeoutNs) break;
+                        __nanosleep(100);
+                    }
+                }
+            }
             if (A_RES && qb != cur_qb) {
                 mbar_wait(smem_u32(a_empty), (a_loads & 1) ^ 1);
                 if (leader) mbar_expect_tx(smem_u32(a_full), 2u * (uint32_t)p.nkb * A_KB_BYTES);
@@ -1014,7 +1151,7 @@ static size_t cand_smem_bytes(bool a_res) {
 
 int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     CandParams p{};
-    p.part = make_partition(a.qry->rows, a.gal->rows, a.n_sm, a.ctas);
+    p.part = make_partition(a.qry->rows, a.gal->rows, a.n_sm, a.ctas, (int64_t)a.gal->dph * 2);
     p.nq = a.qry->rows; p.n = a.gal->rows;
     p.perm_a = a.gal->perm_a; p.perm_b = a.gal->perm_b;
     p.nkb = a.gal->dph / BK;
@@ -1022,6 +1159,15 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     p.gal_norm2 = a.gal->norm2; p.qry_norm2 = a.qry->norm2;
     p.gal_meta = a.gal->meta; p.qry_row_scale = a.qry->row_scale;
     p.cand_val = a.cand_val; p.cand_idx = a.cand_idx; p.slot_bound = a.slot_bound; p.seed_thr = a.seed_thr; p.skip_if_zero = a.skip_if_zero; p.mins_only = a.mins_only;
+    {   // re-alignment of the pairs: only where it pays (the shadow does not fit L2 and there are full rounds) and cannot hurt (whole grid resident)
+        static const int sync_on = [] { const char* e = getenv("FIR_TENSOR_SYNC"); return e ? atoi(e) : 1; }();
+        static const int sync_tiles = [] { const char* e = getenv("FIR_TENSOR_SYNC_TILES"); const int v = e ? atoi(e) : kSyncTiles;
+                                           return (v >= 2 * kSyncLag && (v & (v - 1)) == 0) ? v : kSyncTiles; }();     // (tests shrink it to reach the path at small sizes)
+        const int64_t shadow_bytes = (int64_t)a.gal->rows_padded * a.gal->dph * 2;
+        p.sync_tiles = sync_tiles;
+        p.sync_ctr = (sync_on && a.ctas == 2 && a.sync_ctr && p.part.full_rounds >= 1 && shadow_bytes > phased_min_bytes() && p.part.grid * 2 <= a.n_sm &&
+                      p.part.ntiles > 2 * sync_tiles) ? a.sync_ctr : nullptr;
+    }
 #ifdef FIR_MEASURE
     { static const int nolist = [] { const char* e = getenv("FIR_TENSOR_DEBUG_NOLIST"); return e ? atoi(e) : 0; }(); p.debug_nolist = nolist; }
 #endif
@@ -1317,7 +1463,7 @@ static size_t seed_plan(fir_gallery* g, int64_t nq, int k, int ctas, SeedPlan* s
     sp->m = m_override > 0 ? m_override : std::max(2, (3 * k + 9) / 10);
     sp->R = 4;                                            // four column-group minima per (slot, half): see epilogue_scan_tile_mins
     int least = 1;
-    tensor_plan(nq, S, g->n_sm, ctas, &sp->grid, &sp->n_slots, &least);
+    tensor_plan(nq, S, g->n_sm, ctas, &sp->grid, &sp->n_slots, &least, (int64_t)g->tside.dph * 2);
     sp->n_slots *= EPI_WARPS / 4;
     return 2 * al256((size_t)nq * sp->n_slots * sp->R * 4) + al256((size_t)nq * sp->n_slots * 4) + al256((size_t)nq * 4) + 1024;
 }
@@ -1362,7 +1508,7 @@ struct PassBuffers { void* qbuf; float* cand_val; int32_t* cand_idx; float* cand
 
 size_t pass_bytes(fir_gallery* g, int64_t nq, int R, int ctas, PassBuffers* pb) {
     int grid = 0, n_slots = 1, least = 1;
-    tensor_plan(nq, g->n, g->n_sm, ctas, &grid, &n_slots, &least);
+    tensor_plan(nq, g->n, g->n_sm, ctas, &grid, &n_slots, &least, (int64_t)g->tside.dph * 2);
     n_slots *= EPI_WARPS / 4;                           // one list per (CTA slot, column half)
     pb->n_slots = n_slots; pb->min_lists = least * (EPI_WARPS / 4); pb->grid = grid; pb->R = R;
     pb->qside = tensor_side_bytes(nq, g->d, BM);
@@ -1376,7 +1522,7 @@ bool pass_take(fir_gallery* g, int64_t nq, PassBuffers* pb) {
     pb->cand_exact = (float*)g->ws.take(cells * 4);
     pb->slot_bound = (float*)g->ws.take((size_t)nq * pb->n_slots * 4);
     pb->pair_cells = (uint32_t*)g->ws.take(cells * 4);
-    pb->pair_count = (int32_t*)g->ws.take(256);
+    pb->pair_count = (int32_t*)g->ws.take(1024);      // [0] listed pairs; words 32.. : re-alignment counters of the candidate kernel
     return pb->qbuf && pb->cand_val && pb->cand_idx && pb->cand_exact && pb->slot_bound && pb->pair_cells && pb->pair_count;
 }
 // pack → tcgen05 candidates → exact rerank → select + certificate, for nq device-resident fp32 queries
@@ -1413,6 +1559,10 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
         g->prof_end(evs);
         g->stats.gpu_launches += 2;
         a.seed_thr = sp->seed;
+    }
+    if (first) {                                                          // re-alignment counters of the pairs (words 32.. of the count block)
+        FIR_CUDA_TRY(cudaMemsetAsync(pb.pair_count + 32, 0, 4 * (1 + kMaxPhases * kMaxRanges), g->stream));
+        a.sync_ctr = reinterpret_cast<unsigned int*>(pb.pair_count + 32);
     }
     { auto* ev = g->prof_begin(prof_kind); int st_ = launch_tensor_candidates(a, g->stream); g->prof_end(ev); FIR_TRY(st_); }
     ErrModel em{};
@@ -1451,7 +1601,8 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     // list length from the number of lists L a query is spread over: room for twice its fair share k / L of the k best, plus slack
     auto pick_R = [&](int lists, int extra) { int want = (2 * k + lists - 1) / lists + 2 + extra; return want <= 4 ? 4 : (want <= 8 ? 8 : (want <= 16 ? 16 : 32)); };
     // (sized for the queries spread over the FEWEST lists: a full-round query block has one slot, i.e. two lists)
-    const int R1 = pick_R(p1.min_lists, 0);
+    static const int r1_override = [] { const char* e = getenv("FIR_TENSOR_R1"); const int v = e ? atoi(e) : 0; return (v == 4 || v == 8 || v == 16 || v == 32) ? v : 0; }();
+    const int R1 = r1_override ? std::max(r1_override, pick_R(p1.min_lists, 0)) : pick_R(p1.min_lists, 0);   // tuning knob: any R >= the rule's is valid
     // the second pass starts every list from the query's own bound (k-th best found in pass 1 plus the error margins, see
     // tensor_select_kernel), so its lists only ever hold rows that can matter: k plus the rows within the error margin of the
     // k-th best, spread over all the lists of the query — 8 per list overflows only on mass ties (-> exact re-run)
@@ -1691,7 +1842,7 @@ int tensor_class_min(fir_gallery* g, const float* queries, int64_t nq, int memsp
     CUtensorMap tmap_a;
     FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
     CandParams p{};
-    p.part = make_partition(nq, g->n, g->n_sm, 2);
+    p.part = make_partition(nq, g->n, g->n_sm, 2, (int64_t)g->tside_nat.dph * 2);
     p.nq = nq; p.n = g->n; p.perm_a = 1; p.perm_b = 0;
     p.nkb = g->tside_nat.dph / BK; p.n_slots = 1;
     p.gal_norm2 = g->tside_nat.norm2; p.qry_norm2 = qs.norm2; p.gal_meta = g->tside_nat.meta; p.qry_row_scale = qs.row_scale;

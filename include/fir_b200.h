@@ -135,6 +135,10 @@ int fir_profile_read(fir_gallery* g, int32_t kernel, double* total_ms, int32_t* 
  * next call): nq x n_slots x R local indices (-1 = empty), their tensor-core approximate squared distances
  * and their exact fp32 feature_distance values.  Pass NULL arrays to query n_slots/R first. */
 int fir_debug_tensor_candidates(fir_gallery* g, int32_t* n_slots, int32_t* R, int32_t* idx, float* approx, float* exact);
+/* Host-side self check of the tensor path's work partition (no device needed): 0 when every (query block, gallery tile) item of
+ * an nq x n search over n_sm SMs (ctas per work unit = 1 or 2; row_bytes = bytes of one shadow row, decides the phased form of the
+ * remainder for galleries larger than L2) is covered exactly once and the candidate slots of a query block are distinct. */
+int fir_debug_partition_check(int64_t nq, int64_t n, int n_sm, int ctas, int64_t row_bytes, int* n_phases, int* n_slots);
 
 /* replaces: ImageInfo::distance / feature_distance (qt_cpp/db_features.h:24-26, db_features.cpp:22-42)
  * for explicit (query, gallery index) pairs: cand_idx is nq x r LOCAL row indices (-1 = skip),

@@ -9,10 +9,15 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
 nq = int(sys.argv[3]) if len(sys.argv) > 3 else 10_000
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 dev = torch.device("cuda", 0)
-g, gl, q, ql = synth.make_split(n, nq, 512, 1000, "l2")
-g_dev, q_dev = torch.from_numpy(g).to(dev), torch.from_numpy(q).to(dev)
+if n > 2_000_000:      # the bench's generator (counter-based, on the device): a 10M-row gallery takes minutes to build on the host
+    g_dev, gl_dev = synth.synth_rows_device(synth.ROLE_GALLERY, 0, n, n, 512, 1000, 0x5EED0000, device=dev)
+    q_dev, _ = synth.synth_rows_device(synth.ROLE_QUERY, 0, nq, nq, 512, 1000, 0x5EED0000, device=dev)
+else:
+    g, gl, q, ql = synth.make_split(n, nq, 512, 1000, "l2")
+    g_dev, q_dev, gl_dev = torch.from_numpy(g).to(dev), torch.from_numpy(q).to(dev), torch.from_numpy(gl).to(dev)
 fir_b200.normalize_rows(g_dev, "l2"); fir_b200.normalize_rows(q_dev, "l2")
-gal = fir_b200.Gallery(g_dev, torch.from_numpy(gl).to(dev), "l2", stream=torch.cuda.current_stream().cuda_stream)
+gal = fir_b200.Gallery(g_dev, gl_dev, "l2", stream=torch.cuda.current_stream().cuda_stream)
+del g_dev
 for _ in range(3): gal.search(q_dev, k=k)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 # unprofiled step time first

@@ -94,12 +94,16 @@ def test_tensor_device_pointers(fir, port):
     gal.close()
 
 
-@pytest.mark.parametrize("env", [{"FIR_TENSOR_SEED": "0"}, {"FIR_TENSOR_SEED_M": "1"}, {"FIR_TENSOR_CTAS": "1"}])
+@pytest.mark.parametrize("env", [{"FIR_TENSOR_SEED": "0"}, {"FIR_TENSOR_SEED_M": "1"}, {"FIR_TENSOR_CTAS": "1"},
+                                 {"FIR_TENSOR_PHASED_MIN_BYTES": "0", "FIR_TENSOR_SYNC_TILES": "8", "FIR_TEST_NQ": "24220"},
+                                 {"FIR_TENSOR_PHASED_MIN_BYTES": "0", "FIR_TENSOR_SYNC_TILES": "8", "FIR_TEST_NQ": "19000", "FIR_TENSOR_R1": "8"}])
 def test_tensor_path_variants_stay_exact(env):
     """The list seeds are an optimisation, never a correctness input: with the sample pass switched off, with a seed rank that
     is deliberately too small (most queries then fail the first certificate and take the second pass / the exact re-run), and
-    with the single-CTA kernel, the tensor path still returns the exact kernel's answer bit for bit.  (The switches are read
-    once per process, hence the subprocess.)"""
+    with the single-CTA kernel, the tensor path still returns the exact kernel's answer bit for bit.  The last two run what a
+    gallery larger than L2 gets — full rounds with the pairs re-aligned every few tiles, the remainder's query blocks in phases
+    of shared tile ranges (21 and 1 remainder blocks on 74 pairs) — at a size the exact kernel can check in full.  (The switches
+    are read once per process, hence the subprocess.)"""
     import subprocess
     import sys
     code = r'''
@@ -107,7 +111,8 @@ import importlib, sys, numpy as np, torch
 sys.path.insert(0, %r)
 import fir_b200
 synth = importlib.import_module("fast-image-recognition_b200.synth")
-g, gl, q, ql = synth.make_split(60000, 1536, 512, 300, "l2", seed=4)
+import os
+g, gl, q, ql = synth.make_split(60000, int(os.environ.get("FIR_TEST_NQ", "1536")), 512, 300, "l2", seed=4)
 dev = torch.device("cuda", 0)
 gd, qd = torch.from_numpy(g).to(dev), torch.from_numpy(q).to(dev)
 fir_b200.normalize_rows(gd, "l2"); fir_b200.normalize_rows(qd, "l2")

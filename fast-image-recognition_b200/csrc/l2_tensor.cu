@@ -1602,7 +1602,12 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     auto pick_R = [&](int lists, int extra) { int want = (2 * k + lists - 1) / lists + 2 + extra; return want <= 4 ? 4 : (want <= 8 ? 8 : (want <= 16 ? 16 : 32)); };
     // (sized for the queries spread over the FEWEST lists: a full-round query block has one slot, i.e. two lists)
     static const int r1_override = [] { const char* e = getenv("FIR_TENSOR_R1"); const int v = e ? atoi(e) : 0; return (v == 4 || v == 8 || v == 16 || v == 32) ? v : 0; }();
-    const int R1 = r1_override ? std::max(r1_override, pick_R(p1.min_lists, 0)) : pick_R(p1.min_lists, 0);   // tuning knob: any R >= the rule's is valid
+    // A second pass is one more sweep of the whole gallery for a single query block: where a sweep is long (at least one full
+    // round) the lists get 8 entries even for k = 1 — at N = 10M four-entry lists leave 69 of 100k queries uncertified (the
+    // 4th best of half the gallery sits within the error margin of the best), whose second pass costs 17 ms of an 800 ms search.
+    const bool long_sweeps = ceil_div(nq, (int64_t)BM * ctas) >= std::max(1, g->n_sm / ctas);
+    int R1 = std::max(pick_R(p1.min_lists, 0), long_sweeps ? 8 : 4);
+    if (r1_override) R1 = std::max(R1, r1_override);                         // tuning knob: any R >= the rule's is valid
     // the second pass starts every list from the query's own bound (k-th best found in pass 1 plus the error margins, see
     // tensor_select_kernel), so its lists only ever hold rows that can matter: k plus the rows within the error margin of the
     // k-th best, spread over all the lists of the query — 8 per list overflows only on mass ties (-> exact re-run)

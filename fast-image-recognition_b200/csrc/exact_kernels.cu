@@ -44,6 +44,21 @@ static size_t exact_smem_bytes(int k, int mode) {
 // THIN: the launch serves a device-side list of queries that is usually nearly empty (the certificate fallback of the
 // tensor / approximate paths).  A warp owns query rows {2w, 2w+1} + 16a of the tile; with THIN it skips the arithmetic of
 // the rows past the active count, so one stray query costs a pass over the gallery, not 64 queries' worth of FLOPs.
+// One KL step for the two pairs of a lane whose query element l is the same in every lane of the warp (db_features.cpp:33-36).
+// l == 0 (either sign): l + r is r exactly, the l-term is skipped by the reference's `l > 0` guard and the r-term is
+// r·logf(2r / r) = r·logf(2) whenever r > 0 (2r / r is exactly 2 as long as 2r does not overflow — `light_ok` is false for the
+// whole warp otherwise) — no division, no logf, and the branch is uniform.  Any other l takes the general step.
+__device__ __forceinline__ void kl_step_uniform(float& acc0, float& acc1, float l, float r0, float r1, float log2c, bool light_ok) {
+    if (l == 0.f && light_ok) {
+        const float a0 = __fadd_rn(acc0, __fmul_rn(r0, log2c)), a1 = __fadd_rn(acc1, __fmul_rn(r1, log2c));
+        acc0 = r0 > 0.f ? a0 : acc0;
+        acc1 = r1 > 0.f ? a1 : acc1;
+    } else {
+        dist_step<FIR_KL>(acc0, l, r0);
+        dist_step<FIR_KL>(acc1, l, r1);
+    }
+}
+
 template <int METRIC, bool THIN>
 __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -55,18 +70,27 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
     int* tki = reinterpret_cast<int*>(tkd + TS * p.k);
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    // Pair ownership.  L2 / chi-square: thread (ty, tx) owns the 4 x 4 pairs {ty + 16a} x {tx + 16b}.  KL: warp w owns query rows
+    // {w + 8a}, lane l gallery rows {l + 32b} — 8 x 2 pairs — so that the query element of a step is WARP-UNIFORM: for a zero query
+    // element (half of ReLU-style features) the step is r·logf(2) for the lanes with r > 0, decided by a uniform branch instead of
+    // two masked logf bodies (see kl_step_uniform).
+    constexpr bool KLMAP = METRIC == FIR_KL;
+    constexpr int NA = KLMAP ? 8 : 4, NB = KLMAP ? 2 : 4;
+    const int qr0 = KLMAP ? (tid >> 5) : ty, qstep = KLMAP ? 8 : 16;       // query row of pair (a, .) = qr0 + qstep * a
+    const int xr0 = KLMAP ? (tid & 31) : tx, xstep = KLMAP ? 32 : 16;      // gallery row of pair (., b) = xr0 + xstep * b
     int64_t n_active = p.n_active ? (int64_t)*p.n_active : p.nq;
     const int32_t* qmap_ = p.qmap ? p.qmap + p.active_offset : nullptr;          // chunked fallback: window of the active list
     if (p.n_active) { n_active = max((int64_t)0, n_active - p.active_offset); if (p.active_cap > 0) n_active = min(n_active, p.active_cap); }
     const int64_t q0 = (int64_t)blockIdx.x * TS;
     if (q0 >= n_active) return;
     const int rows_live = (int)min((int64_t)TS, n_active - q0);      // query rows of this tile that exist
-    const int wrow = (tid >> 5) * 2;                                  // first query row of this warp (a = 0)
+    const int wrow = KLMAP ? (tid >> 5) : (tid >> 5) * 2;             // first query row of this warp (a = 0)
     const int64_t ntiles = (p.n + TS - 1) / TS;
     const int64_t t_lo = (int64_t)blockIdx.y * p.tiles_per_split;
     const int64_t t_hi = min(ntiles, t_lo + p.tiles_per_split);
     const int nchunks = (p.d_end + CH - 1) / CH;
     const float inv_den = (float)p.d_end;
+    const float log2c = KLMAP ? glibc_logf(2.0f) : 0.f;              // the reference's own logf(2) (0x3f317218), computed by the same code
 
     // this thread's two (row, 16B column) slots of each 64x32 stage tile
     const int lr0 = tid >> 3, lc = (tid & 7) * 4;     // rows lr0 and lr0+32
@@ -92,11 +116,11 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
 
     for (int64_t t = t_lo; t < t_hi; ++t) {
         const int64_t x0 = t * TS;
-        float acc[4][4];
+        float acc[NA][NB];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < NA; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+            for (int b = 0; b < NB; ++b) acc[a][b] = 0.f;
 
         auto load_chunk = [&](int c, int st) {
             const int kk = c * CH + lc;
@@ -123,7 +147,8 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
             const float* qb = qs + st * TS * LDT;
             const float* xb = xs + st * TS * LDT;
             const int kmax = min(CH, p.d_end - c * CH);
-            if (kmax == CH && METRIC != FIR_KL) {
+            if constexpr (!KLMAP) {
+            if (kmax == CH) {
                 // L2's 3-instruction step unrolls fully (24 KB of code); the division step is ~16 instructions, so its k-loop
                 // stays rolled to fit the instruction cache (ncu: 28 % stall_no_inst when unrolled)
 #pragma unroll (METRIC == FIR_L2 ? CH / 4 : kDivUnroll)
@@ -147,8 +172,6 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
                     }
                 }
             } else {
-                // KL always comes here: one dimension per trip keeps 32 inlined logf bodies (57 KB of code) instead of 128
-                // (229 KB — ncu: 36 % of the warp stalls were instruction-cache misses, profiles/r2_ncu_exact_kl.txt)
 #pragma unroll 1
                 for (int kk = 0; kk < kmax; ++kk) {
 #pragma unroll
@@ -160,13 +183,28 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
                     }
                 }
             }
+            } else {
+                // KL: one dimension per trip keeps 16 inlined logf-pair bodies (the fully unrolled form was 229 KB of code — ncu: 36 %
+                // of the warp stalls were instruction-cache misses, profiles/r2_ncu_exact_kl.txt)
+#pragma unroll 1
+                for (int kk = 0; kk < kmax; ++kk) {
+                    const float r0 = xb[xr0 * LDT + kk], r1 = xb[(xr0 + 32) * LDT + kk];
+                    const bool light_ok = !__any_sync(0xffffffffu, r0 > 1.7014118e38f || r1 > 1.7014118e38f);   // 2r finite in every lane
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) {
+                        if (THIN && wrow + 8 * a >= rows_live) continue;           // warp-uniform
+                        const float l = qb[(qr0 + 8 * a) * LDT + kk];              // one address per warp: a broadcast
+                        kl_step_uniform(acc[a][0], acc[a][1], l, r0, r1, log2c, light_ok);
+                    }
+                }
+            }
             __syncthreads();
         }
 
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < NA; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) ds[(ty + 16 * a) * LDD + tx + 16 * b] = __fdiv_rn(acc[a][b], inv_den);   // db_features.cpp:40
+            for (int b = 0; b < NB; ++b) ds[(qr0 + qstep * a) * LDD + xr0 + xstep * b] = __fdiv_rn(acc[a][b], inv_den);   // db_features.cpp:40
         __syncthreads();
 
         if (my_q_out >= 0) {

@@ -349,25 +349,30 @@ static int64_t phased_min_bytes() {
     static const int64_t v = [] { const char* e = getenv("FIR_TENSOR_PHASED_MIN_BYTES"); return e ? (int64_t)atoll(e) : ((int64_t)48 << 20); }();
     return v;
 }
-// seats r query blocks on G units: cost[r][depth] = least Σ 1/g over at most `depth` phases
-static double phase_plan(int r, int G, int depth, PartPhase* out, int* n_out) {
-    if (r == 0) { *n_out = 0; return 0.0; }
-    if (depth == 0) { *n_out = 0; return 1e30; }
-    double best = 1e30;
-    const int g_lo = std::max(1, std::min(kMaxRanges, G / r));
-    for (int g = g_lo; g <= std::min(G, kMaxRanges); ++g) {
-        const int seats = std::min(r, G / g);
-        if (seats <= 0) break;
-        PartPhase sub[kMaxPhases]; int n_sub = 0;
-        const double c = 1.0 / g + phase_plan(r - seats, G, depth - 1, sub, &n_sub);
-        if (c < best - 1e-12) {
-            best = c;
-            out[0] = PartPhase{0, seats, g};
-            for (int t = 0; t < n_sub; ++t) { out[t + 1] = sub[t]; out[t + 1].qb0 += seats; }
-            *n_out = n_sub + 1;
-        }
+// seats r query blocks on G units in at most kMaxPhases phases with the least total sweep length Σ 1/g
+// (dynamic programme over (blocks left, phases left): a phase with g ranges per block seats min(r, G / g) blocks)
+static int phase_plan(int r, int G, PartPhase* out) {
+    if (r <= 0 || r > 1024) return 0;
+    std::vector<double> cost((size_t)(r + 1) * (kMaxPhases + 1), 1e30);
+    std::vector<int> pick((size_t)(r + 1) * (kMaxPhases + 1), 0);
+    auto at = [&](int left, int depth) -> size_t { return (size_t)left * (kMaxPhases + 1) + depth; };
+    for (int depth = 0; depth <= kMaxPhases; ++depth) cost[at(0, depth)] = 0.0;
+    for (int depth = 1; depth <= kMaxPhases; ++depth)
+        for (int left = 1; left <= r; ++left)
+            for (int g = std::max(1, std::min(kMaxRanges, G / left)); g <= std::min(G, kMaxRanges); ++g) {
+                const int seats = std::min(left, G / g);
+                if (seats <= 0) break;
+                const double c = 1.0 / g + cost[at(left - seats, depth - 1)];
+                if (c < cost[at(left, depth)] - 1e-12) { cost[at(left, depth)] = c; pick[at(left, depth)] = g; }
+            }
+    if (cost[at(r, kMaxPhases)] > 1e29) return 0;
+    int n = 0, left = r, depth = kMaxPhases;
+    while (left > 0) {
+        const int g = pick[at(left, depth)], seats = std::min(left, G / g);
+        out[n++] = PartPhase{r - left, seats, g};
+        left -= seats; --depth;
     }
-    return best;
+    return n;
 }
 inline Partition make_partition(int64_t nq, int64_t n, int n_sm, int ctas, int64_t row_bytes = 0) {
     Partition P{};
@@ -379,9 +384,7 @@ inline Partition make_partition(int64_t nq, int64_t n, int n_sm, int ctas, int64
     P.rem_total = rem_qb * P.ntiles;
     P.grid = (int)(P.full_rounds > 0 ? units : std::min<int64_t>(units, std::max<int64_t>(1, P.rem_total)));
     if (P.full_rounds > 0 && rem_qb > 0 && P.ntiles * BN * row_bytes > phased_min_bytes() && P.ntiles >= 4 * kMaxRanges) {
-        int np = 0;
-        const double c = phase_plan((int)rem_qb, P.grid, kMaxPhases, P.ph, &np);
-        P.n_phases = c < 1e29 ? np : 0;
+        P.n_phases = phase_plan((int)rem_qb, P.grid, P.ph);
     }
     return P;
 }

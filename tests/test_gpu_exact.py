@@ -79,6 +79,34 @@ def test_zero_vectors_chi2_kl(fir, port):
         gal.close()
 
 
+def test_kl_tile_special_values(fir, port):
+    """The KL tile kernel decides per warp whether a step's query element is zero (then the step is r*logf(2), no division, no
+    logf) — the shortcut must be invisible: signed zeros, negative and mixed-sign elements, denormals, values whose double
+    overflows (2r = inf), infinities and NaNs on either side all give the port's bits, through top-k, class minima and PNN sums."""
+    rng = np.random.default_rng(17)
+    n, nq, d = 300, 70, 96
+    g = np.maximum(rng.standard_normal((n, d)), 0).astype(np.float32)
+    q = np.maximum(rng.standard_normal((nq, d)), 0).astype(np.float32)
+    g[:, 5] = 0; q[:, 7] = 0                                        # a zero column on each side
+    q[3, :] = 0; g[11, :] = 0                                       # all-zero rows
+    q[4, ::2] = -0.0; g[12, 1::2] = -0.0                            # negative zeros
+    q[5, :6] = [-0.25, -1e-30, 1e-41, 3e38, 2e38, 1.7014118e38]     # negative, tiny, denormal, 2l overflows
+    g[13, :6] = [1e-41, -0.5, 3e38, 1e-45, 1.7014120e38, 2.5e38]    # 2r overflows against zero and non-zero l
+    g[14, 20] = np.inf; g[15, 21] = np.nan; q[6, 22] = np.inf; q[8, 23] = np.nan
+    q[9, :] = 0; q[9, 2] = 1.0                                      # one non-zero element: every other step is the shortcut
+    gl = np.sort(rng.integers(0, 9, n)).astype(np.int32)
+    gal = fir.Gallery(g, gl, "kl")
+    idx, dist = gal.search(q, k=4, path=fir.PATH_EXACT)
+    oi, od = port.topk("kl", g, q, 4)
+    fin = ~np.isnan(od)                                             # rows with NaN distances: the reference never accepts them; compare the rest bit for bit
+    assert np.array_equal(np.isnan(dist), np.isnan(od))
+    assert np.array_equal(idx[fin], oi[fin]) and np.array_equal(bits(dist)[fin], bits(od)[fin])
+    mn, arg = gal.class_min(q)
+    omn, oarg = port.class_min("kl", g, gl, gal.n_classes, q)
+    assert np.array_equal(arg, oarg) and np.array_equal(bits(mn), bits(omn))
+    gal.close()
+
+
 def test_pair_distances_both_operand_orders(fir, port):
     rng = np.random.default_rng(7)
     for metric in ("l2", "chi2", "kl"):

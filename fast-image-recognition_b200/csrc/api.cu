@@ -61,11 +61,14 @@ static int stage_queries(fir_gallery* g, const float* queries, int64_t nq, int m
     return FIR_OK;
 }
 
-static int pick_nsplit(int64_t nq, int64_t n, int n_sm) {
+// gallery splits of the exact tile kernel: enough blocks for four per SM.  The top-k mode merges one partial list per split
+// (cap 64); the class modes fold through atomics, so a small batch may be cut much finer (256 queries x 1M rows: 592 blocks
+// instead of 256 — the kernel is latency-bound below ~4 blocks per SM)
+static int pick_nsplit(int64_t nq, int64_t n, int n_sm, int64_t cap = 64) {
     int64_t qblocks = ceil_div(nq, kExactTile);
     int64_t ntiles = ceil_div(n, kExactTile);
     int64_t want = ceil_div((int64_t)n_sm * 4, qblocks);
-    want = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, ntiles), 64));
+    want = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, ntiles), cap));
     return (int)want;
 }
 
@@ -416,7 +419,7 @@ static int class_reduce(fir_gallery* g, const float* queries, int64_t nq, int me
     p.q = dq; p.nq = nq; p.ldq = g->dp;
     p.x = g->rows; p.n = g->n; p.ldx = g->dp;
     p.labels = g->labels; p.d_end = g->d; p.k = 0; p.mode = mode;
-    p.nsplit = pick_nsplit(nq, g->n, g->n_sm);
+    p.nsplit = pick_nsplit(nq, g->n, g->n_sm, 1024);
     p.tiles_per_split = ceil_div(ceil_div(g->n, kExactTile), p.nsplit);
     p.n_classes = C;
     if (mode == MODE_CLASSMIN) {

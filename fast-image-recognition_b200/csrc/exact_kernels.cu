@@ -116,11 +116,17 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
 
     for (int64_t t = t_lo; t < t_hi; ++t) {
         const int64_t x0 = t * TS;
-        float acc[NA][NB];
+        float acc[KLMAP ? 1 : NA][KLMAP ? 1 : NB];
+        if constexpr (KLMAP) {
+            // (the previous tile's fold has finished reading ds: every thread passed the __syncthreads that ends the tile loop body)
 #pragma unroll
-        for (int a = 0; a < NA; ++a)
+            for (int a = 0; a < NA; ++a) { ds[(qr0 + 8 * a) * LDD + xr0] = 0.f; ds[(qr0 + 8 * a) * LDD + xr0 + 32] = 0.f; }
+        } else {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) acc[a][b] = 0.f;
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) acc[a][b] = 0.f;
+        }
 
         auto load_chunk = [&](int c, int st) {
             const int kk = c * CH + lc;
@@ -184,27 +190,43 @@ __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
                 }
             }
             } else {
-                // KL: one dimension per trip keeps 16 inlined logf-pair bodies (the fully unrolled form was 229 KB of code — ncu: 36 %
-                // of the warp stalls were instruction-cache misses, profiles/r2_ncu_exact_kl.txt)
+                // KL: the running sums live in the output tile `ds` between chunks, so the loops over the warp's query rows and over
+                // the dimensions both stay ROLLED around two inlined steps (4 logf bodies, ~6 KB of code).  Fully unrolled the loop
+                // body was 229 KB, with only the dimension loop rolled 57 KB — ncu: 36 % of the warp stalls were instruction-cache
+                // misses (profiles/r2_ncu_exact_kl.txt); latency is hidden by the other warps, not by unrolling.
 #pragma unroll 1
-                for (int kk = 0; kk < kmax; ++kk) {
-                    const float r0 = xb[xr0 * LDT + kk], r1 = xb[(xr0 + 32) * LDT + kk];
-                    const bool light_ok = !__any_sync(0xffffffffu, r0 > 1.7014118e38f || r1 > 1.7014118e38f);   // 2r finite in every lane
-#pragma unroll
-                    for (int a = 0; a < NA; ++a) {
-                        if (THIN && wrow + 8 * a >= rows_live) continue;           // warp-uniform
-                        const float l = qb[(qr0 + 8 * a) * LDT + kk];              // one address per warp: a broadcast
-                        kl_step_uniform(acc[a][0], acc[a][1], l, r0, r1, log2c, light_ok);
+                for (int a = 0; a < NA; a += 2) {
+                    if (THIN && wrow + 8 * a >= rows_live) break;                  // warp-uniform (rows ascend with a)
+                    float* d0 = &ds[(qr0 + 8 * a) * LDD + xr0];
+                    float* d1 = d0 + 8 * LDD;
+                    float a00 = d0[0], a01 = d0[32], a10 = d1[0], a11 = d1[32];
+                    const float* ql0 = &qb[(qr0 + 8 * a) * LDT];
+                    const float* ql1 = ql0 + 8 * LDT;
+                    const float* xr = &xb[xr0 * LDT];
+#pragma unroll 1
+                    for (int kk = 0; kk < kmax; ++kk) {
+                        const float r0 = xr[kk], r1 = xr[32 * LDT + kk];
+                        const bool light_ok = !__any_sync(0xffffffffu, r0 > 1.7014118e38f || r1 > 1.7014118e38f);   // 2r finite in every lane
+                        kl_step_uniform(a00, a01, ql0[kk], r0, r1, log2c, light_ok);   // query elements: one address per warp, a broadcast
+                        kl_step_uniform(a10, a11, ql1[kk], r0, r1, log2c, light_ok);
                     }
+                    d0[0] = a00; d0[32] = a01; d1[0] = a10; d1[32] = a11;
                 }
             }
             __syncthreads();
         }
 
+        if constexpr (KLMAP) {
 #pragma unroll
-        for (int a = 0; a < NA; ++a)
+            for (int a = 0; a < NA; ++a)
 #pragma unroll
-            for (int b = 0; b < NB; ++b) ds[(qr0 + qstep * a) * LDD + xr0 + xstep * b] = __fdiv_rn(acc[a][b], inv_den);   // db_features.cpp:40
+                for (int b = 0; b < NB; ++b) { float* o = &ds[(qr0 + 8 * a) * LDD + xr0 + 32 * b]; *o = __fdiv_rn(*o, inv_den); }   // this thread's own cells
+        } else {
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) ds[(qr0 + qstep * a) * LDD + xr0 + xstep * b] = __fdiv_rn(acc[a][b], inv_den);   // db_features.cpp:40
+        }
         __syncthreads();
 
         if (my_q_out >= 0) {

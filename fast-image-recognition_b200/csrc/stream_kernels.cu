@@ -24,7 +24,7 @@ constexpr int SLD = SCH + 4;   // row stride in floats (36): LDS.128 conflict-fr
 
 template <int METRIC, int NQ>
 __global__ void __launch_bounds__(SW * 32) stream_distance_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ x, int ldx, int64_t n,
-                                                                  int d_end, float* __restrict__ out, int64_t out_stride) {
+                                                                  int d_end, float* __restrict__ out, int64_t out_stride, int nq_live) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int dq_pad = (d_end + SCH - 1) / SCH * SCH;
     float* qs = reinterpret_cast<float*>(smem_raw);                                  // [NQ][dq_pad]
@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(SW * 32) stream_distance_kernel(const float* _
         if (myrow < n) {
             const float den = (float)d_end;
 #pragma unroll
-            for (int qi = 0; qi < NQ; ++qi) out[(int64_t)qi * out_stride + myrow] = __fdiv_rn(acc[qi], den);
+            for (int qi = 0; qi < NQ; ++qi)
+                if (qi < nq_live) out[(int64_t)qi * out_stride + myrow] = __fdiv_rn(acc[qi], den);    // `out` holds nq_live rows, not NQ
         }
     }
 }
@@ -99,7 +100,7 @@ static int launch_stream_metric(int nq, const float* q, int ldq, const float* x,
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ceil_div(n, 32), SW), (int64_t)n_sm * 6));
     auto go = [&](auto kern) -> int {
         FIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, SW * 32, smem, s>>>(q, ldq, x, ldx, n, d_end, out, out_stride);
+        kern<<<grid, SW * 32, smem, s>>>(q, ldq, x, ldx, n, d_end, out, out_stride, nq);
         FIR_CUDA_TRY(cudaGetLastError());
         return FIR_OK;
     };
@@ -111,7 +112,7 @@ static int launch_stream_metric(int nq, const float* q, int ldq, const float* x,
     }
 }
 
-// q must hold 8 (NQ rounded up) rows; rows beyond nq may be anything (their outputs are ignored)
+// q must hold 8 (NQ rounded up) rows; rows beyond nq may be anything (they are computed and dropped: `out` has nq rows)
 int launch_stream_distances(int metric, int nq, const float* q, int ldq, const float* x, int ldx, int64_t n, int d_end, float* out,
                             int64_t out_stride, int n_sm, cudaStream_t s) {
     switch (metric) {

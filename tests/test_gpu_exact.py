@@ -188,7 +188,7 @@ def test_small_batch_streaming_path(fir, port, metric):
     g, gl, q, ql = make_data(port, metric, 5000, 8, 200, 12, seed=13)
     g[4000:4100] = g[10:110]                              # ties across segments
     gal = fir.Gallery(g, gl, metric)
-    for nq in (1, 3, 8):
+    for nq in (1, 3, 5, 6, 7, 8):                        # (3, 5, 6, 7: the kernel runs 4 / 8 query slots and must drop the spare ones)
         for k in (1, 7, 16):
             idx, dist = gal.search(q[:nq], k=k, path=fir.PATH_EXACT)
             oi, od = port.topk(metric, g, q[:nq], k)

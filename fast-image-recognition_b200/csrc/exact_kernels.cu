@@ -44,21 +44,6 @@ static size_t exact_smem_bytes(int k, int mode) {
 // THIN: the launch serves a device-side list of queries that is usually nearly empty (the certificate fallback of the
 // tensor / approximate paths).  A warp owns query rows {2w, 2w+1} + 16a of the tile; with THIN it skips the arithmetic of
 // the rows past the active count, so one stray query costs a pass over the gallery, not 64 queries' worth of FLOPs.
-// One KL step for the two pairs of a lane whose query element l is the same in every lane of the warp (db_features.cpp:33-36).
-// l == 0 (either sign): l + r is r exactly, the l-term is skipped by the reference's `l > 0` guard and the r-term is
-// r·logf(2r / r) = r·logf(2) whenever r > 0 (2r / r is exactly 2 as long as 2r does not overflow — `light_ok` is false for the
-// whole warp otherwise) — no division, no logf, and the branch is uniform.  Any other l takes the general step.
-__device__ __forceinline__ void kl_step_uniform(float& acc0, float& acc1, float l, float r0, float r1, float log2c, bool light_ok) {
-    if (l == 0.f && light_ok) {
-        const float a0 = __fadd_rn(acc0, __fmul_rn(r0, log2c)), a1 = __fadd_rn(acc1, __fmul_rn(r1, log2c));
-        acc0 = r0 > 0.f ? a0 : acc0;
-        acc1 = r1 > 0.f ? a1 : acc1;
-    } else {
-        dist_step<FIR_KL>(acc0, l, r0);
-        dist_step<FIR_KL>(acc1, l, r1);
-    }
-}
-
 template <int METRIC, bool THIN>
 __global__ void __launch_bounds__(256) exact_tile_kernel(ExactParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

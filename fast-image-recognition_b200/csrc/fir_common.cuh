@@ -230,5 +230,27 @@ __device__ __forceinline__ void dist_step(float& acc, float l, float r) {
     }
 }
 
+// One KL step for pairs whose query element l is the same in every lane of the warp (db_features.cpp:33-36).
+// l == 0 (either sign): l + r is r exactly, the l-term is skipped by the reference's `l > 0` guard and the r-term is
+// r·logf(2r / r) = r·logf(2) whenever r > 0 (2r / r is exactly 2 as long as 2r does not overflow — `light_ok` is false for the
+// whole warp otherwise) — no division, no logf, and the branch is uniform.  Any other l takes the general step.
+// log2c = glibc_logf(2.0f), the reference's own value, computed by the caller with the same code.
+__device__ __forceinline__ void kl_step_uniform1(float& acc, float l, float r, float log2c, bool light_ok) {
+    if (l == 0.f && light_ok) {
+        const float a = __fadd_rn(acc, __fmul_rn(r, log2c));
+        acc = r > 0.f ? a : acc;
+    } else dist_step<FIR_KL>(acc, l, r);
+}
+__device__ __forceinline__ void kl_step_uniform(float& acc0, float& acc1, float l, float r0, float r1, float log2c, bool light_ok) {
+    if (l == 0.f && light_ok) {
+        const float a0 = __fadd_rn(acc0, __fmul_rn(r0, log2c)), a1 = __fadd_rn(acc1, __fmul_rn(r1, log2c));
+        acc0 = r0 > 0.f ? a0 : acc0;
+        acc1 = r1 > 0.f ? a1 : acc1;
+    } else {
+        dist_step<FIR_KL>(acc0, l, r0);
+        dist_step<FIR_KL>(acc1, l, r1);
+    }
+}
+
 }  // namespace fir
 #endif

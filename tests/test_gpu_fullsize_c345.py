@@ -44,7 +44,7 @@ def to_host(t, step=1 << 20):
     return out
 
 
-@pytest.mark.parametrize("metric,nq_sample", [("chi2", 12), ("kl", 3)])
+@pytest.mark.parametrize("metric,nq_sample", [("chi2", 12), ("kl", 2)])
 def test_c3_full_size_scores_and_neighbours(fir, port, metric, nq_sample):
     """C3: 1M x 1280 ReLU'd, L1-normalised features, 1000 classes.  PNN class scores (<= 1e-5 relative, the bar north_star
     states), predicted labels, per-class minima and the nearest neighbour (bit-exact) against the port over the full gallery;

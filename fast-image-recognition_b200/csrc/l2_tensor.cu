@@ -351,7 +351,7 @@ static int64_t phased_min_bytes() {
 }
 // seats r query blocks on G units in at most kMaxPhases phases with the least total sweep length Σ 1/g
 // (dynamic programme over (blocks left, phases left): a phase with g ranges per block seats min(r, G / g) blocks)
-static int phase_plan(int r, int G, PartPhase* out) {
+static int phase_plan(int r, int G, int max_ranges, PartPhase* out) {
     if (r <= 0 || r > 1024) return 0;
     std::vector<double> cost((size_t)(r + 1) * (kMaxPhases + 1), 1e30);
     std::vector<int> pick((size_t)(r + 1) * (kMaxPhases + 1), 0);
@@ -359,7 +359,7 @@ static int phase_plan(int r, int G, PartPhase* out) {
     for (int depth = 0; depth <= kMaxPhases; ++depth) cost[at(0, depth)] = 0.0;
     for (int depth = 1; depth <= kMaxPhases; ++depth)
         for (int left = 1; left <= r; ++left)
-            for (int g = std::max(1, std::min(kMaxRanges, G / left)); g <= std::min(G, kMaxRanges); ++g) {
+            for (int g = std::max(1, std::min(max_ranges, G / left)); g <= std::min(G, max_ranges); ++g) {
                 const int seats = std::min(left, G / g);
                 if (seats <= 0) break;
                 const double c = 1.0 / g + cost[at(left - seats, depth - 1)];
@@ -384,7 +384,11 @@ inline Partition make_partition(int64_t nq, int64_t n, int n_sm, int ctas, int64
     P.rem_total = rem_qb * P.ntiles;
     P.grid = (int)(P.full_rounds > 0 ? units : std::min<int64_t>(units, std::max<int64_t>(1, P.rem_total)));
     if (P.full_rounds > 0 && rem_qb > 0 && P.ntiles * BN * row_bytes > phased_min_bytes() && P.ntiles >= 4 * kMaxRanges) {
-        P.n_phases = phase_plan((int)rem_qb, P.grid, P.ph);
+        // every query's candidate arrays are sized for the largest range count (one slot per range): keep them under ~8 GiB
+        // (2 lists per slot, 16 entries of 16 bytes each) — with very many queries the remainder is a negligible part of the work
+        const int64_t fit = ((int64_t)8 << 30) / (std::max<int64_t>(nq, 1) * 512);
+        const int max_ranges = (int)std::max<int64_t>(4, std::min<int64_t>(kMaxRanges, fit));
+        P.n_phases = phase_plan((int)rem_qb, P.grid, max_ranges, P.ph);
     }
     return P;
 }

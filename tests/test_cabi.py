@@ -104,6 +104,7 @@ def test_tensor_work_partition_covers_every_item_once(fir):
     assert chk(100_000, 2_000_000, 148, 2, 1024) == 0 and ph.value == 2 and sl.value == 24     # C5's query side (gallery cut to keep the check small)
     assert chk(10_000, 100_000, 148, 2, 1024) == 0 and ph.value == 0                              # C2: no full round → balanced cut
     assert chk(100_000, 40_000, 148, 2, 1024) == 0 and ph.value == 0                              # shadow fits L2 → balanced cut
+    assert chk(3_000_000 + 300, 40_000, 148, 2, 10**6) == 0 and ph.value >= 1 and sl.value <= 5   # very many queries: few ranges, small candidate arrays
     rng = np.random.default_rng(5)
     seen_phased = 0
     for _ in range(300):

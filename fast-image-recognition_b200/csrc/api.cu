@@ -189,6 +189,7 @@ int fir_gallery_destroy(fir_gallery* g) {
     if (g->labels) cudaFree(g->labels);
     if (g->tensor_buf) cudaFree(g->tensor_buf);
     if (g->tensor_buf_nat) cudaFree(g->tensor_buf_nat);
+    if (g->prefix_norm2) cudaFree(g->prefix_norm2);
     if (g->d_cls_begin) cudaFree(g->d_cls_begin);
     if (g->d_stats) cudaFree(g->d_stats);
     if (g->d_l1max) cudaFree(g->d_l1max);
@@ -260,11 +261,11 @@ int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k,
     if (nq == 0) return FIR_OK;
     FIR_CUDA_TRY(cudaSetDevice(g->device));
     const int d_end = max_features > 0 ? max_features : g->d;
-    bool tensor_ok = g->metric == FIR_L2 && max_features == 0 && tensor_path_supported(g->d) && g->cc_major >= 10 && k <= 28;
+    bool tensor_ok = g->metric == FIR_L2 && tensor_path_supported(g->d) && g->cc_major >= 10 && k <= 28 && !(max_features > 0 && g->tensor_center);
     if (path == FIR_PATH_TENSOR && !tensor_ok)
-        return fail(FIR_ERR_UNSUPPORTED, "tensor path needs L2, all dimensions, k<=28 and an sm_100 device");
+        return fail(FIR_ERR_UNSUPPORTED, "tensor path needs L2, k<=28 and an sm_100 device");
     bool use_tensor = (path == FIR_PATH_TENSOR) || (path == FIR_PATH_AUTO && tensor_ok && nq * g->n >= (int64_t)1 << 22);
-    if (use_tensor) return tensor_search_topk(g, queries, nq, k, memspace, out_idx, out_dist);
+    if (use_tensor) return tensor_search_topk(g, queries, nq, k, memspace, out_idx, out_dist, d_end);
     const bool approx_ok = g->metric != FIR_L2 && max_features == 0 && k <= 28;
     if (path == FIR_PATH_APPROX && !approx_ok) return fail(FIR_ERR_UNSUPPORTED, "approximate path needs chi2/KL, all dimensions and k<=28");
     if (path == FIR_PATH_APPROX || (path == FIR_PATH_AUTO && approx_ok && nq > kStreamMaxQueries && nq * g->n >= (int64_t)1 << 22)) {

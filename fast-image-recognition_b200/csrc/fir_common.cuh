@@ -115,6 +115,8 @@ struct TensorSearchArgs {
     int mins_only;                        // seed pass: per-slot column-group minima instead of top-R lists (R must be 4)
     int grid; int n_sm;
     int ctas;                     // 1: cta_group::1 kernel, 2: CTA-pair kernel (grid counts pairs)
+    int nkb;                      // k-blocks to contract (0 = all of the shadow's; fewer = a prefix of the dimensions)
+    int64_t row_bytes;            // bytes of one shadow row for the partition's L2 test (0 = gal->dph * 2)
     unsigned int* sync_ctr;       // optional zeroed device word: lets the pairs of a full round re-align (galleries larger than L2)
 };
 int tensor_plan(int64_t nq, int64_t n, int n_sm, int ctas, int* grid, int* n_slots, int* min_slots = nullptr, int64_t row_bytes = 0);

@@ -20,6 +20,8 @@ struct fir_gallery {
     CUtensorMap tmap_b_half;      // box 64 x 128 rows (each CTA of a pair loads half a tile)
     const float* tensor_center = nullptr;          // optional [dp] (device, owned by the creator): the shadows are of x − center
     const unsigned char* tensor_exclude = nullptr; // optional [n] (device): rows that never become tensor-path candidates
+    // prefix distances on the tensor path: row norms over the first prefix_d dimensions (shadow order), rebuilt when the prefix changes
+    float* prefix_norm2 = nullptr; int prefix_d = 0; int tensor_d_eff = 0;
     // natural-order (class-major) shadow for the per-class reductions on tensor cores (built lazily by tensor_class_min)
     bool nat_ready = false; int nat_classes = 0;
     void* tensor_buf_nat = nullptr;
@@ -51,7 +53,7 @@ namespace fir {
 int exact_topk_device(fir_gallery* g, const float* dq, int64_t nq, int k, int d_end, const int32_t* qmap,
                       const int32_t* n_active, float* part_d, int32_t* part_i, int nsplit, float* od, int32_t* oi,
                       int64_t active_offset = 0, int64_t active_cap = 0);
-int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
+int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist, int d_end = 0);
 constexpr int kApproxDeclined = -100;   // approx_search_topk: the error model does not cover this gallery — the caller takes the exact path
 int approx_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist);
 // per-class nearest neighbour (L2) through the tensor-core candidate kernel; kApproxDeclined when the gallery is not class-major

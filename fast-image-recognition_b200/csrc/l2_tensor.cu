@@ -1158,10 +1158,10 @@ static size_t cand_smem_bytes(bool a_res) {
 
 int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     CandParams p{};
-    p.part = make_partition(a.qry->rows, a.gal->rows, a.n_sm, a.ctas, (int64_t)a.gal->dph * 2);
+    p.part = make_partition(a.qry->rows, a.gal->rows, a.n_sm, a.ctas, a.row_bytes > 0 ? a.row_bytes : (int64_t)a.gal->dph * 2);
     p.nq = a.qry->rows; p.n = a.gal->rows;
     p.perm_a = a.gal->perm_a; p.perm_b = a.gal->perm_b;
-    p.nkb = a.gal->dph / BK;
+    p.nkb = a.nkb > 0 ? a.nkb : a.gal->dph / BK;
     p.n_slots = a.n_slots;
     p.gal_norm2 = a.gal->norm2; p.qry_norm2 = a.qry->norm2;
     p.gal_meta = a.gal->meta; p.qry_row_scale = a.qry->row_scale;
@@ -1461,7 +1461,12 @@ static size_t seed_plan(fir_gallery* g, int64_t nq, int k, int ctas, SeedPlan* s
     // 2 % of the gallery in whole tiles, at most 64 tiles: about m·N/S rows of the whole gallery fall under the seeded threshold
     // — a few thousand list insertions per query over tens of thousands of tiles at N = 10M, where a 2 % sample would cost
     // 2 % of the whole search (16 ms of 850 at C5)
-    const int64_t S = std::min<int64_t>(g->n / div / BN * BN, 64 * BN);
+    // ... and no more than 64·sqrt(N / 10M · 512 / D) tiles: the sample costs ~S·D per query block whatever the gallery size, the
+    // insertions it saves ~N / S, so the best S grows like sqrt(N / D) (7 tiles at 100k x 512, 23 at 1.25M x 512 — a shard of C5
+    // over 8 GPUs, where a 64-tile sample was 3 % of the step — 64 at 10M x 512 and at the 1M x 32 pivot gallery of DEM, whose
+    // 32-entry lists make insertions dear: 4.07 -> 4.40 ms per search with 21 tiles)
+    const int64_t sqrt_tiles = std::max<int64_t>(4, (int64_t)std::ceil(64.0 * std::sqrt((double)g->n / 1e7 * 512.0 / (double)std::max(g->d, 1))));
+    const int64_t S = std::min<int64_t>(g->n / div / BN * BN, std::min<int64_t>(64, sqrt_tiles) * BN);
     if (!seed_enabled() || S < 4 * BN || nq < 4 * BM) return 0;
     sp->S = S;
     // m >= k would make a too-small seed impossible, but every step down in m removes list replacements from the first
@@ -1539,7 +1544,8 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     TensorSide qs;
     const bool first = prof_kind == FIR_KERNEL_L2_CANDIDATES;
     auto* ev_pack = first ? g->prof_begin(FIR_PHASE_PACK_QUERIES) : nullptr;
-    FIR_TRY(tensor_pack_side(dq, nq, g->dp, g->d, BM, pb.qbuf, &qs, nullptr, false, true, g->stream, g->tensor_center, nullptr));
+    const int d_eff = g->tensor_d_eff > 0 ? g->tensor_d_eff : g->d;      // distances over the first d_eff dimensions (recognize_image_bf's prefix)
+    FIR_TRY(tensor_pack_side(dq, nq, g->dp, d_eff, BM, pb.qbuf, &qs, nullptr, false, true, g->stream, g->tensor_center, nullptr));
     CUtensorMap tmap_a;
     FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
     const int rt = pb.n_slots * pb.R;
@@ -1549,11 +1555,14 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     TensorSearchArgs a{};
     a.skip_if_zero = n_rows;
     a.seed_thr = seed_in;
-    a.gal = &g->tside; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = ctas == 2 ? &g->tmap_b_half : &g->tmap_b; a.ctas = ctas;
-    a.n_sm = g->n_sm; a.d = g->d; a.R = pb.R; a.n_slots = pb.n_slots; a.cand_val = pb.cand_val; a.cand_idx = pb.cand_idx; a.slot_bound = pb.slot_bound; a.grid = pb.grid;
+    TensorSide gal_side = g->tside;
+    if (d_eff < g->d) { gal_side.norm2 = g->prefix_norm2; a.nkb = round_up(d_eff, BK) / BK; }     // prefix: its own row norms, fewer k-blocks of the same shadow
+    a.row_bytes = (int64_t)g->tside.dph * 2;
+    a.gal = &gal_side; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = ctas == 2 ? &g->tmap_b_half : &g->tmap_b; a.ctas = ctas;
+    a.n_sm = g->n_sm; a.d = d_eff; a.R = pb.R; a.n_slots = pb.n_slots; a.cand_val = pb.cand_val; a.cand_idx = pb.cand_idx; a.slot_bound = pb.slot_bound; a.grid = pb.grid;
     if (sp && sp->S) {
         auto* evs = g->prof_begin(FIR_PHASE_SEED);
-        TensorSide sample = g->tside;
+        TensorSide sample = gal_side;
         sample.rows = sp->S; sample.rows_padded = sp->S;
         const int srt = sp->n_slots * sp->R;
         FIR_CUDA_TRY(cudaMemsetAsync(sp->cand_idx, 0xFF, (size_t)nq * srt * 4, g->stream));
@@ -1573,16 +1582,16 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     }
     { auto* ev = g->prof_begin(prof_kind); int st_ = launch_tensor_candidates(a, g->stream); g->prof_end(ev); FIR_TRY(st_); }
     ErrModel em{};
-    em.kind = 0; em.d = g->d; em.nkb = round_up(g->d, BK) / BK; em.q_norm2 = qs.norm2; em.q_resid = qs.resid; em.gal_stats = g->d_stats;
-    em.rel = (double)(g->d + 4) * 5.9604644775390625e-08; em.dist_scale = (double)g->d;
+    em.kind = 0; em.d = d_eff; em.nkb = round_up(d_eff, BK) / BK; em.q_norm2 = qs.norm2; em.q_resid = qs.resid; em.gal_stats = g->d_stats;
+    em.rel = (double)(d_eff + 4) * 5.9604644775390625e-08; em.dist_scale = (double)d_eff;
     auto* ev1 = first ? g->prof_begin(FIR_PHASE_PRUNE) : nullptr;
     const bool listed = (uint64_t)nq * (uint64_t)rt < 0xffffffffull;          // cells are 32-bit
     if (listed) FIR_CUDA_TRY(cudaMemsetAsync(pb.pair_count, 0, 4, g->stream));
     FIR_TRY(launch_prune(pb.cand_val, pb.cand_idx, nq, rt, k, em, g->stream, n_rows, listed ? pb.pair_cells : nullptr, pb.pair_count));
     g->prof_end(ev1);
     auto* ev2 = first ? g->prof_begin(FIR_PHASE_RERANK) : nullptr;
-    if (listed) FIR_TRY(launch_pair_list(FIR_L2, dq, g->dp, g->rows, g->dp, g->d, pb.pair_cells, pb.pair_count, (int64_t)nq * rt, rt, pb.cand_idx, pb.cand_exact, g->stream));
-    else FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, g->d, pb.cand_idx, rt, 0, pb.cand_exact, g->stream));
+    if (listed) FIR_TRY(launch_pair_list(FIR_L2, dq, g->dp, g->rows, g->dp, d_eff, pb.pair_cells, pb.pair_count, (int64_t)nq * rt, rt, pb.cand_idx, pb.cand_exact, g->stream));
+    else FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, d_eff, pb.cand_idx, rt, 0, pb.cand_exact, g->stream));
     g->prof_end(ev2);
     auto* ev3 = first ? g->prof_begin(FIR_PHASE_SELECT) : nullptr;
     FIR_TRY(launch_select(pb.cand_exact, pb.cand_idx, pb.slot_bound, nq, pb.n_slots, pb.R, k, em, index_offset, od, oi, flagged, n_flagged, fail_flags,
@@ -1593,9 +1602,38 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
 }
 }  // namespace
 
-int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist) {
+// ‖x[:d_eff]‖² per shadow row (fp64 sum → fp32, like pack_rows_kernel), +inf for padding / excluded rows
+__global__ void prefix_norm_kernel(const float* __restrict__ rows, int64_t n, int64_t rows_padded, int ld, int d_eff, int64_t perm_a, int64_t perm_b,
+                                   const unsigned char* __restrict__ exclude, float* __restrict__ norm2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows_padded) return;
+    const int64_t src = row < n ? (row * perm_a + perm_b) % n : 0;
+    if (row >= n || (exclude && exclude[src])) { if (lane == 0) norm2[row] = __int_as_float(0x7f800000); return; }
+    double n2 = 0.0;
+    for (int c = lane; c < d_eff; c += 32) { const double x = (double)rows[src * ld + c]; n2 += x * x; }
+    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    if (lane == 0) norm2[row] = (float)n2;
+}
+
+int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, int memspace, int32_t* out_idx, float* out_dist, int d_end) {
     g->dbg_cand_idx = nullptr; g->dbg_cand_val = nullptr; g->dbg_cand_exact = nullptr;      // the previous call's lists die with its workspace
     FIR_TRY(ensure_gallery_side(g));
+    // Prefix distances (recognize_image_bf(.., max_features), db_features.cpp:319-335): the same shadow, k-blocks up to the prefix,
+    // queries packed with zeros beyond it (so the dimensions the last k-block carries past the prefix contribute exactly nothing),
+    // prefix row norms; the full-length norm / residual maxima in d_stats stay valid upper bounds for the error model.
+    const int d_eff = (d_end > 0 && d_end < g->d) ? d_end : g->d;
+    g->tensor_d_eff = d_eff;
+    if (d_eff < g->d) {
+        if (g->tensor_center) return fail(FIR_ERR_UNSUPPORTED, "prefix distances are not available on a centred shadow");
+        if (!g->prefix_norm2) FIR_CUDA_TRY(cudaMalloc(&g->prefix_norm2, sizeof(float) * (size_t)g->tside.rows_padded));
+        if (g->prefix_d != d_eff) {
+            prefix_norm_kernel<<<(unsigned)ceil_div(g->tside.rows_padded, 8), 256, 0, g->stream>>>(g->rows, g->n, g->tside.rows_padded, g->dp, d_eff, g->tside.perm_a,
+                                                                                                     g->tside.perm_b, g->tensor_exclude, g->prefix_norm2);
+            FIR_CUDA_TRY(cudaGetLastError());
+            g->prefix_d = d_eff;
+        }
+    }
     const int ctas = tensor_cta_mode();
     // Pass 1: each query gets (slots x 2 column halves) short lists over disjoint, pseudo-randomly interleaved parts of the
     // gallery — cheap to maintain (cost ~ R² per list).  A list that would have needed more than R of the k best makes the
@@ -1692,9 +1730,9 @@ int tensor_search_topk(fir_gallery* g, const float* queries, int64_t nq, int k, 
     }
     // what is still uncertified: exact CUDA-core re-run (device-side count; see above)
     auto* evx = g->prof_begin(FIR_PHASE_EXACT_RERUN);
-    FIR_TRY(exact_topk_device(g, dq, nq, k, g->d, exact_list, exact_count, part_d, part_i, nsplit_fast, od, oi, 0, kFbFast));
+    FIR_TRY(exact_topk_device(g, dq, nq, k, d_eff, exact_list, exact_count, part_d, part_i, nsplit_fast, od, oi, 0, kFbFast));
     if (nq > kFbFast)
-        FIR_TRY(exact_topk_device(g, dq, nq, k, g->d, exact_list, exact_count, part_d, part_i, nsplit_slow, od, oi, kFbFast, nq - kFbFast));
+        FIR_TRY(exact_topk_device(g, dq, nq, k, d_eff, exact_list, exact_count, part_d, part_i, nsplit_slow, od, oi, kFbFast, nq - kFbFast));
     g->prof_end(evx);
     g->stats.path_used = FIR_PATH_TENSOR;
     g->stats.n_candidates = p1.n_slots * p1.R;

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(SW * 32) stream_distance_kernel(const float* _
     }
     __syncthreads();
     float* wt = tiles + (size_t)warp * 2 * 32 * SLD;
+    const float log2c = METRIC == FIR_KL ? glibc_logf(2.0f) : 0.f;
     const int nslab = (d_end + SCH - 1) / SCH;
     const int64_t ngroups = (n + 31) / 32;
     for (int64_t grp = (int64_t)blockIdx.x * SW + warp; grp < ngroups; grp += (int64_t)gridDim.x * SW) {
@@ -66,6 +67,24 @@ __global__ void __launch_bounds__(SW * 32) stream_distance_kernel(const float* _
             const float* row = wt + (sl & 1) * 32 * SLD + lane * SLD;
             const int k0 = sl * SCH;
             const int kmax = min(SCH, d_end - k0);
+            if constexpr (METRIC == FIR_KL) {
+                // the query element of a step is warp-uniform here (every lane walks its own gallery row against the same query):
+                // zero elements take the r·logf(2) shortcut (kl_step_uniform1).  One query at a time with the dimension loop
+                // rolled: the live code is one step (two logf bodies), not NQ x 4 of them.
+#pragma unroll
+                for (int qi = 0; qi < NQ; ++qi) {
+                    if (qi >= nq_live) break;                                  // uniform; spare query slots are never stored
+                    float a = acc[qi];
+                    const float* qrow = &qs[qi * dq_pad + k0];
+#pragma unroll 1
+                    for (int kk = 0; kk < kmax; ++kk) {
+                        const float r = row[kk];
+                        const bool light_ok = !__any_sync(0xffffffffu, r > 1.7014118e38f);
+                        kl_step_uniform1(a, qrow[kk], r, log2c, light_ok);
+                    }
+                    acc[qi] = a;
+                }
+            } else {
             int kk = 0;
             for (; kk + 4 <= kmax; kk += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(&row[kk]);
@@ -79,6 +98,7 @@ __global__ void __launch_bounds__(SW * 32) stream_distance_kernel(const float* _
             for (; kk < kmax; ++kk)
 #pragma unroll
                 for (int qi = 0; qi < NQ; ++qi) dist_step<METRIC>(acc[qi], qs[qi * dq_pad + k0 + kk], row[kk]);
+            }
             __syncwarp();
         }
         const int64_t myrow = r0 + lane;

@@ -104,7 +104,8 @@ int fir_normalize_rows(float* rows, int64_t n, int32_t d, int32_t metric, int32_
  * Writes, per query, the k lexicographically smallest (feature_distance, gallery index) pairs —
  * k = 1 is the reference argmin (strict '<' ⇒ lowest index on ties, -1 if nothing is < 100000).
  * max_features > 0 restricts the distance to the first max_features dimensions and divides by it
- * (recognize_image_bf's prefix mode); 0 = all D.  out_idx/out_dist: nq x k. */
+ * (recognize_image_bf's prefix mode); 0 = all D — Euclidean prefixes run on the tensor path as well (the shadow's
+ * k-blocks up to the prefix, prefix row norms).  out_idx/out_dist: nq x k. */
 int fir_search_topk(fir_gallery* g, const float* queries, int64_t nq, int32_t k, int32_t max_features,
                     int32_t path, int32_t memspace, int32_t* out_idx, float* out_dist);
 int fir_search_last_stats(const fir_gallery* g, fir_search_stats* stats);

@@ -129,6 +129,28 @@ print("OK")
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("n,nq,d", [(30000, 1500, 512), (20011, 900, 200)])
+def test_tensor_prefix_max_features(fir, port, n, nq, d):
+    """recognize_image_bf's prefix distance (db_features.cpp:319-335: the first max_features dimensions, mean over them) on the
+    tensor path: the k-blocks of the shadow up to the prefix, prefix row norms, queries packed with zeros beyond the prefix —
+    same bits as the port's prefix brute force (top-1) and as the exact kernels (top-5), for prefixes that end inside a k-block,
+    on a k-block boundary and one short of D; the cached prefix norms follow the prefix from call to call."""
+    g, gl, q, ql = make_data(port, "l2", n, nq, d, 40, seed=3)
+    g[100:104] = g[7]                                            # exact ties: lowest index wins on every path
+    gal = fir.Gallery(g, gl, "l2")
+    for mf in (64, 100, d - 1, 37, 128):
+        ti, td = gal.search(q, k=5, max_features=mf, path=fir.PATH_TENSOR)
+        assert gal.stats()["path_used"] == fir.PATH_TENSOR
+        ei, ed = gal.search(q, k=5, max_features=mf, path=fir.PATH_EXACT)
+        assert np.array_equal(ti, ei) and np.array_equal(bits(td), bits(ed)), mf
+        oi, od = port.bf("l2", g, q[:200], max_features=mf, nthreads=os.cpu_count() or 1)
+        assert np.array_equal(ti[:200, 0], oi) and np.array_equal(bits(td[:200, 0]), bits(od)), mf
+    ti, td = gal.search(q, k=5, path=fir.PATH_TENSOR)             # and back to all dimensions
+    ei, ed = gal.search(q, k=5, path=fir.PATH_EXACT)
+    assert np.array_equal(ti, ei) and np.array_equal(bits(td), bits(ed))
+    gal.close()
+
+
 @pytest.mark.parametrize("n,nq,d,c", [(30000, 700, 512, 60), (20011, 1100, 200, 333), (70000, 300, 96, 7)])
 def test_class_min_on_tensor_cores_matches_oracle(fir, port, n, nq, d, c):
     """fir_class_min (Euclidean, large batch) through the tcgen05 candidate passes: per-class approximate minima in the epilogue

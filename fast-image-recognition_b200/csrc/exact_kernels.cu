@@ -519,10 +519,11 @@ __global__ void __launch_bounds__(PW * 32) pair_list_kernel(const float* __restr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t total = *count;
-    const int64_t base = ((int64_t)blockIdx.x * PW + warp) * 32;
-    if (base >= total) return;
     float* xs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (2 * 32 * LLD);
     float* qs = xs + 32 * LLD;
+    // warps stride over the list: the grid is sized for the machine, not for the worst-case list (at C5 the list could hold
+    // 77M cells and holds 1.5M — 600k blocks that exit at once cost more than the rerank itself)
+    for (int64_t base = ((int64_t)blockIdx.x * PW + warp) * 32; base < total; base += (int64_t)gridDim.x * PW * 32) {
     const bool valid = base + lane < total;
     const uint32_t cell = valid ? cells[base + lane] : 0u;
     const int64_t my_q = valid ? (int64_t)(cell / (uint32_t)rt) : -1;
@@ -560,13 +561,15 @@ __global__ void __launch_bounds__(PW * 32) pair_list_kernel(const float* __restr
         __syncwarp();
     }
     if (valid) out[cell] = __fdiv_rn(acc, (float)d_end);
+    __syncwarp();
+    }
 }
 
 int launch_pair_list(int metric, const float* q, int ldq, const float* x, int ldx, int d_end, const uint32_t* cells, const int32_t* count,
                      int64_t max_cells, int rt, const int32_t* cand_idx, float* out, cudaStream_t s) {
     if (max_cells <= 0) return FIR_OK;
     const size_t smem = sizeof(float) * (size_t)PW * (2 * 32 * LLD);
-    const unsigned grid = (unsigned)ceil_div(max_cells, (int64_t)PW * 32);    // sized for the worst case; blocks past *count exit at once
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(max_cells, (int64_t)PW * 32), 148 * 16);   // warps stride over the device-side count
     auto go = [&](auto kern) -> int {
         FIR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, PW * 32, smem, s>>>(q, ldq, x, ldx, d_end, cells, count, rt, cand_idx, out);

@@ -1230,14 +1230,39 @@ __device__ __forceinline__ double approx_error_bound(double nq2, double rq, doub
 
 constexpr int PRUNE_STAGE_MAX = 1024;   // valid candidates per query staged in shared memory (4 warps x 8 KiB)
 
-__global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ cand_val, int32_t* __restrict__ cand_idx, int64_t nq, int rt, int k,
+// How many of a query's candidate lists can hold anything: a query block of a full round is written by ONE unit (2 lists), a
+// remainder block by one unit per tile range — but the arrays are sized for the widest block (C5: 2 x 24 lists of 16 for every
+// one of the 100k queries, of which 95 % use 2).  prune / select scan only the lists their query's block was given.
+struct SlotUse { Partition part; int q_per_block; int lists_per_slot; int on; };
+__device__ __forceinline__ int slots_used(const SlotUse& u, int64_t q, int n_slots_total) {
+    if (!u.on) return n_slots_total;
+    const Partition& P = u.part;
+    const int64_t rq = q / u.q_per_block - P.full_rounds * P.grid;
+    int slots;
+    if (rq < 0) slots = 1;
+    else if (P.n_phases > 0) {
+        slots = 1;
+        for (int j = 0; j < kMaxPhases; ++j) {
+            const PartPhase ph = part_phase(P, j);
+            if (j < P.n_phases && rq >= ph.qb0 && rq < ph.qb0 + ph.nqb) slots = ph.g;
+        }
+    } else {
+        const int64_t first = ((rq * P.ntiles + 1) * P.grid - 1) / P.rem_total;
+        const int64_t last = (((rq + 1) * P.ntiles) * P.grid - 1) / P.rem_total;
+        slots = (int)(last - first + 1);
+    }
+    return min(n_slots_total, slots * u.lists_per_slot);
+}
+
+__global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ cand_val, int32_t* __restrict__ cand_idx, int64_t nq, int rt_in, int k,
                                                            const ErrModel em, const int32_t* __restrict__ n_active,
-                                                           uint32_t* __restrict__ pair_cells, int32_t* __restrict__ pair_count) {
+                                                           uint32_t* __restrict__ pair_cells, int32_t* __restrict__ pair_count, const SlotUse su, int R) {
     extern __shared__ __align__(16) unsigned char prune_smem[];
     __shared__ int s_cnt[4];
     __shared__ int s_off;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t q = (int64_t)blockIdx.x * 4 + warp;
+    const int rt = rt_in;                                                      // row stride of the candidate arrays
     int base = 0;                                                              // survivors of this warp's query
     if (q < nq && n_active && q >= *n_active) {                                // second pass: rows past the flagged count are padding
         int32_t* ci = cand_idx + q * rt;
@@ -1245,6 +1270,7 @@ __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ c
     } else if (q < nq) {
     float* cv = cand_val + q * rt;
     int32_t* ci = cand_idx + q * rt;
+    const int rtu = su.on ? slots_used(su, q, rt / R) * R : rt;               // cells beyond it were never written (idx = -1 from the memset)
     // Stage the VALID candidates compacted into shared memory first: one round trip to global memory instead of one per
     // selection round (a warp serves one query, so nothing else hides that latency when only a few queries are active).
     // (Seeded lists are mostly empty, so the capacity is counted in valid entries; a row with more takes the global path.)
@@ -1253,10 +1279,10 @@ __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ c
     int32_t* si = reinterpret_cast<int32_t*>(sv + cap);
     int nv = 0;
 #pragma unroll 4
-    for (int c0 = 0; c0 < rt; c0 += 32) {
+    for (int c0 = 0; c0 < rtu; c0 += 32) {
         const int c = c0 + lane;
-        const int32_t idx = c < rt ? ci[c] : -1;
-        const float v = c < rt ? cv[c] : 0.f;
+        const int32_t idx = c < rtu ? ci[c] : -1;
+        const float v = c < rtu ? cv[c] : 0.f;
         const uint32_t m = __ballot_sync(0xffffffffu, idx >= 0);
         const int o = nv + __popc(m & ((1u << lane) - 1));
         if (idx >= 0 && o < cap) { sv[o] = v; si[o] = idx; }
@@ -1264,7 +1290,7 @@ __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ c
     }
     __syncwarp();
     const float* rv = sv; const int32_t* ri = si;                              // what the rounds read
-    if (nv > cap) { rv = cv; ri = ci; nv = rt; }
+    if (nv > cap) { rv = cv; ri = ci; nv = rtu; }
     // k-th smallest approx among valid candidates: k rounds of "smallest value greater than the previous" (duplicates counted)
     float kth = -__int_as_float(0x7f800000);
     int taken = 0;
@@ -1299,7 +1325,7 @@ __global__ void __launch_bounds__(128) tensor_prune_kernel(float* __restrict__ c
         base += __popc(m);
     }
     __syncwarp();
-    for (int c = base + lane; c < rt; c += 32) ci[c] = -1;
+    for (int c = base + lane; c < rtu; c += 32) ci[c] = -1;
     }
     // the survivors of all queries go on one list so that the rerank's warps are full: cell = q * rt + position.  One
     // atomic per block, not per query: ten thousand same-address atomics serialise in L2 for longer than the kernel's work.
@@ -1321,11 +1347,13 @@ __global__ void __launch_bounds__(128) tensor_select_kernel(const float* __restr
                                                             const float* __restrict__ slot_bound, int64_t nq, int n_slots, int R, int k,
                                                             const ErrModel em, int64_t index_offset, float* __restrict__ out_dist,
                                                             int32_t* __restrict__ out_idx, int32_t* flagged, int32_t* n_flagged, unsigned char* fail_flags,
-                                                            float* max_bound, const int32_t* __restrict__ n_active, float* __restrict__ seed_out) {
+                                                            float* max_bound, const int32_t* __restrict__ n_active, float* __restrict__ seed_out,
+                                                            const SlotUse su) {
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (q >= nq || (n_active && q >= *n_active)) return;
     const int rt = n_slots * R;
+    const int lists = su.on ? slots_used(su, q, n_slots) : n_slots;          // lists this query's block was given (the others hold nothing)
     const float* ce = cand_exact + q * rt;
     const int32_t* ci = cand_idx + q * rt;
     float last_d = -1.f; int last_i = -1;
@@ -1357,7 +1385,7 @@ __global__ void __launch_bounds__(128) tensor_select_kernel(const float* __restr
     }
     if (lane != 0) return;
     double B = __longlong_as_double(0x7ff0000000000000LL);
-    for (int s = 0; s < n_slots; ++s) {
+    for (int s = 0; s < lists; ++s) {
         const float b = slot_bound[q * n_slots + s];
         if (b == b && (double)b < B) B = (double)b;                            // NaN = list never written = nothing excluded there
     }
@@ -1380,21 +1408,31 @@ __global__ void __launch_bounds__(128) tensor_select_kernel(const float* __restr
         atomicMax(reinterpret_cast<unsigned int*>(max_bound), __float_as_uint((float)E));
 }
 
-int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s, const int32_t* n_active,
-                 uint32_t* pair_cells, int32_t* pair_count) {
+static int launch_prune_su(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s, const int32_t* n_active,
+                           uint32_t* pair_cells, int32_t* pair_count, const SlotUse& su, int R) {
     const size_t smem = (size_t)4 * 2 * std::min(rt, PRUNE_STAGE_MAX) * 4;
-    tensor_prune_kernel<<<(unsigned)ceil_div(nq, 4), 128, smem, s>>>(cand_val, cand_idx, nq, rt, k, em, n_active, pair_cells, pair_count);
+    tensor_prune_kernel<<<(unsigned)ceil_div(nq, 4), 128, smem, s>>>(cand_val, cand_idx, nq, rt, k, em, n_active, pair_cells, pair_count, su, R);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
+int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s, const int32_t* n_active,
+                 uint32_t* pair_cells, int32_t* pair_count) {
+    return launch_prune_su(cand_val, cand_idx, nq, rt, k, em, s, n_active, pair_cells, pair_count, SlotUse{}, 1);
+}
 
+static int launch_select_su(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots, int R, int k,
+                            const ErrModel& em, int64_t index_offset, float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged,
+                            unsigned char* fail_flags, float* max_bound, cudaStream_t s, const int32_t* n_active, float* seed_out, const SlotUse& su) {
+    tensor_select_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, em, index_offset, out_dist,
+                                                                   out_idx, flagged, n_flagged, fail_flags, max_bound, n_active, seed_out, su);
+    FIR_CUDA_TRY(cudaGetLastError());
+    return FIR_OK;
+}
 int launch_select(const float* cand_exact, const int32_t* cand_idx, const float* slot_bound, int64_t nq, int n_slots, int R, int k,
                   const ErrModel& em, int64_t index_offset, float* out_dist, int32_t* out_idx, int32_t* flagged, int32_t* n_flagged,
                   unsigned char* fail_flags, float* max_bound, cudaStream_t s, const int32_t* n_active, float* seed_out) {
-    tensor_select_kernel<<<(unsigned)ceil_div(nq, 4), 128, 0, s>>>(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, em, index_offset, out_dist,
-                                                                   out_idx, flagged, n_flagged, fail_flags, max_bound, n_active, seed_out);
-    FIR_CUDA_TRY(cudaGetLastError());
-    return FIR_OK;
+    return launch_select_su(cand_exact, cand_idx, slot_bound, nq, n_slots, R, k, em, index_offset, out_dist, out_idx, flagged, n_flagged, fail_flags,
+                            max_bound, s, n_active, seed_out, SlotUse{});
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1587,15 +1625,20 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     auto* ev1 = first ? g->prof_begin(FIR_PHASE_PRUNE) : nullptr;
     const bool listed = (uint64_t)nq * (uint64_t)rt < 0xffffffffull;          // cells are 32-bit
     if (listed) FIR_CUDA_TRY(cudaMemsetAsync(pb.pair_count, 0, 4, g->stream));
-    FIR_TRY(launch_prune(pb.cand_val, pb.cand_idx, nq, rt, k, em, g->stream, n_rows, listed ? pb.pair_cells : nullptr, pb.pair_count));
+    SlotUse su{};
+    if (first) {        // (the second pass serves a compacted query list: its few query blocks all use every list)
+        su.part = make_partition(nq, g->n, g->n_sm, ctas, (int64_t)g->tside.dph * 2);
+        su.q_per_block = BM * ctas; su.lists_per_slot = EPI_WARPS / 4; su.on = 1;
+    }
+    FIR_TRY(launch_prune_su(pb.cand_val, pb.cand_idx, nq, rt, k, em, g->stream, n_rows, listed ? pb.pair_cells : nullptr, pb.pair_count, su, pb.R));
     g->prof_end(ev1);
     auto* ev2 = first ? g->prof_begin(FIR_PHASE_RERANK) : nullptr;
     if (listed) FIR_TRY(launch_pair_list(FIR_L2, dq, g->dp, g->rows, g->dp, d_eff, pb.pair_cells, pb.pair_count, (int64_t)nq * rt, rt, pb.cand_idx, pb.cand_exact, g->stream));
     else FIR_TRY(launch_pair_distances(FIR_L2, dq, nq, g->dp, g->rows, g->dp, g->n, d_eff, pb.cand_idx, rt, 0, pb.cand_exact, g->stream));
     g->prof_end(ev2);
     auto* ev3 = first ? g->prof_begin(FIR_PHASE_SELECT) : nullptr;
-    FIR_TRY(launch_select(pb.cand_exact, pb.cand_idx, pb.slot_bound, nq, pb.n_slots, pb.R, k, em, index_offset, od, oi, flagged, n_flagged, fail_flags,
-                          max_bound, g->stream, n_rows, seed_out));
+    FIR_TRY(launch_select_su(pb.cand_exact, pb.cand_idx, pb.slot_bound, nq, pb.n_slots, pb.R, k, em, index_offset, od, oi, flagged, n_flagged, fail_flags,
+                             max_bound, g->stream, n_rows, seed_out, su));
     g->prof_end(ev3);
     g->stats.gpu_launches += 5;   // pack, candidates, prune, rerank, select
     return FIR_OK;

@@ -96,6 +96,18 @@ def test_c4_full_size_directed_enumeration(fir, port, ref_l2):
     dem = fir.Dem(gal, pivot0=12345)
     assert dem.chain_rows == 15_000 and dem.n_pivots == 32
     gh, glh = to_host(g), gl.cpu().numpy()
+    # latency mode at size, on a handle whose workspace is sized by this very call, with query counts that are not powers of two
+    # (the streaming kernel runs 4 / 8 query slots and must drop the spare ones — it once wrote them past the end of the buffer)
+    fresh = fir.Gallery(g, gl, "l2")
+    for m in (3, 5, 7):
+        si, sd = fresh.search(q[:m], k=1, path=fir.PATH_EXACT)
+        smn, sarg = fresh.class_min(q[:m])
+        ti, td = gal.search(q[:m], k=1, path=fir.PATH_TENSOR)
+        torch.cuda.synchronize()
+        assert torch.equal(si, ti) and torch.equal(sd.view(torch.int32), td.view(torch.int32))
+        best = smn.min(dim=1)
+        assert torch.equal(best.values.view(torch.int32), td[:, 0].view(torch.int32))
+    fresh.close()
     del g
     rdem = ref_l2.dem_create_injected(gh, glh, dem.pivots, dem.P, float(dem.threshold))
     sample = np.linspace(0, 4095, 48).astype(np.int64)

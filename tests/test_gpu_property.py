@@ -1,5 +1,7 @@
 """GPU: randomised parity of the CUDA path against the C restatement on ragged shapes (rows not a multiple of any tile, odd
 dimensions, duplicates, k above the gallery size, every metric), through the C-ABI with host buffers."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
@@ -7,7 +9,9 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 from util import bits
 
 pytestmark = pytest.mark.gpu
-SET = settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+# FIR_PROPERTY_EXAMPLES=N switches to a soak run: N freshly drawn problems per test instead of the 30 fixed ones
+_SOAK = int(os.environ.get("FIR_PROPERTY_EXAMPLES", "0"))
+SET = settings(max_examples=_SOAK or 30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=not _SOAK)
 
 
 def _rows(seed, n, d, metric, dup=0):
@@ -47,7 +51,7 @@ def test_latency_mode_any_shape(fir, port, seed, n, nq, d, k, metric):
     gal.close()
 
 
-@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+@settings(max_examples=_SOAK or 15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=not _SOAK)
 @given(seed=st.integers(0, 10**6), n=st.integers(6, 400), nq=st.integers(1, 90), fc=st.integers(1, 255), c=st.integers(5, 9),
        th=st.sampled_from([0.5, 0.7, 0.9, 1.3]), kind=st.sampled_from(["posteriors", "diff", "ratio"]))
 def test_twd_any_shape(fir, port, seed, n, nq, fc, c, th, kind):
@@ -68,7 +72,7 @@ def test_twd_any_shape(fir, port, seed, n, nq, fc, c, th, kind):
     gal.close()
 
 
-@settings(max_examples=14, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+@settings(max_examples=_SOAK or 14, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=not _SOAK)
 @given(seed=st.integers(0, 10**6), n=st.integers(1, 6000), nq=st.integers(1, 300), d=st.integers(16, 520), k=st.integers(1, 28),
        dup=st.integers(0, 40), scale=st.sampled_from([1.0, 1e-3, 37.0]))
 def test_tensor_path_any_shape(fir, port, seed, n, nq, d, k, dup, scale):
@@ -85,7 +89,7 @@ def test_tensor_path_any_shape(fir, port, seed, n, nq, d, k, dup, scale):
     gal.close()
 
 
-@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+@settings(max_examples=_SOAK or 12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=not _SOAK)
 @given(seed=st.integers(0, 10**6), n=st.integers(400, 3500), nq=st.integers(1, 60), d=st.integers(4, 72), c=st.integers(2, 40),
        metric=st.sampled_from(["l2", "chi2", "kl"]), thr_scale=st.sampled_from([1.0, 1.0, 0.3, 0.02]), m_frac=st.sampled_from([0.0, 0.01, 0.1, 0.5, 1.0]))
 def test_dem_build_and_search_any_shape(fir, port, seed, n, nq, d, c, metric, thr_scale, m_frac):
@@ -120,7 +124,7 @@ def test_dem_build_and_search_any_shape(fir, port, seed, n, nq, d, c, metric, th
     gal.close()
 
 
-@settings(max_examples=10, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=True)
+@settings(max_examples=_SOAK or 10, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture], derandomize=not _SOAK)
 @given(seed=st.integers(0, 10**6), d=st.integers(3, 130), c=st.integers(5, 12), per=st.integers(2, 40), nq=st.integers(1, 80),
        K=st.integers(1, 9), clusters=st.integers(1, 6))
 def test_fp64_classifiers_any_shape(fir, port, seed, d, c, per, nq, K, clusters):

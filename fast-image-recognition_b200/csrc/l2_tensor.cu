@@ -543,10 +543,10 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t taddr, const float* 
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
-            float v0 = fmaf(negc, __uint_as_float(rr[i + 0]), nx4.x);
-            float v1 = fmaf(negc, __uint_as_float(rr[i + 1]), nx4.y);
-            float v2 = fmaf(negc, __uint_as_float(rr[i + 2]), nx4.z);
-            float v3 = fmaf(negc, __uint_as_float(rr[i + 3]), nx4.w);
+            // two columns per instruction (FFMA2: fma.rn on both halves, the same bits as two fmaf)
+            const float2 v01 = __ffma2_rn(make_float2(negc, negc), make_float2(__uint_as_float(rr[i + 0]), __uint_as_float(rr[i + 1])), make_float2(nx4.x, nx4.y));
+            const float2 v23 = __ffma2_rn(make_float2(negc, negc), make_float2(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])), make_float2(nx4.z, nx4.w));
+            const float v0 = v01.x, v1 = v01.y, v2 = v23.x, v3 = v23.y;
             rr[i + 0] = __float_as_uint(v0); rr[i + 1] = __float_as_uint(v1);
             rr[i + 2] = __float_as_uint(v2); rr[i + 3] = __float_as_uint(v3);
             gm[i >> 2] = fminf(fminf(v0, v1), fminf(v2, v3));
@@ -592,8 +592,9 @@ __device__ __forceinline__ void epilogue_scan_tile_mins(uint32_t taddr, const fl
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
-            m = fminf(m, fminf(fminf(fmaf(negc, __uint_as_float(rr[i + 0]), nx4.x), fmaf(negc, __uint_as_float(rr[i + 1]), nx4.y)),
-                               fminf(fmaf(negc, __uint_as_float(rr[i + 2]), nx4.z), fmaf(negc, __uint_as_float(rr[i + 3]), nx4.w))));
+            const float2 v01 = __ffma2_rn(make_float2(negc, negc), make_float2(__uint_as_float(rr[i + 0]), __uint_as_float(rr[i + 1])), make_float2(nx4.x, nx4.y));
+            const float2 v23 = __ffma2_rn(make_float2(negc, negc), make_float2(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])), make_float2(nx4.z, nx4.w));
+            m = fminf(m, fminf(fminf(v01.x, v01.y), fminf(v23.x, v23.y)));
         }
         lv[c0 >> 5] = m;
     }
@@ -827,8 +828,9 @@ __device__ __forceinline__ void epilogue_scan_tile_cls(uint32_t taddr, const flo
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
-            const float v0 = fmaf(negc, __uint_as_float(rr[i + 0]), nx4.x), v1 = fmaf(negc, __uint_as_float(rr[i + 1]), nx4.y);
-            const float v2 = fmaf(negc, __uint_as_float(rr[i + 2]), nx4.z), v3 = fmaf(negc, __uint_as_float(rr[i + 3]), nx4.w);
+            const float2 v01 = __ffma2_rn(make_float2(negc, negc), make_float2(__uint_as_float(rr[i + 0]), __uint_as_float(rr[i + 1])), make_float2(nx4.x, nx4.y));
+            const float2 v23 = __ffma2_rn(make_float2(negc, negc), make_float2(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])), make_float2(nx4.z, nx4.w));
+            const float v0 = v01.x, v1 = v01.y, v2 = v23.x, v3 = v23.y;
             rr[i + 0] = __float_as_uint(v0); rr[i + 1] = __float_as_uint(v1); rr[i + 2] = __float_as_uint(v2); rr[i + 3] = __float_as_uint(v3);
             gm[i >> 2] = fminf(fminf(v0, v1), fminf(v2, v3));
         }

@@ -15,7 +15,7 @@ so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.
                                                         "fast-image-recognition_b200", "libfir_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 KEY = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "UCGABAR", "LDGSTS", "LDG", "STG", "LDS", "STS",
-       "ATOM", "ATOMS", "RED", "SHFL", "FFMA", "FADD", "FMUL", "MUFU", "DFMA", "DADD", "DMUL", "HMMA", "IMAD", "BAR", "BRA"]
+       "ATOM", "ATOMS", "RED", "SHFL", "FFMA", "FFMA2", "FADD", "FMUL", "MUFU", "DFMA", "DADD", "DMUL", "HMMA", "IMAD", "BAR", "BRA"]
 kern, hist, order = None, collections.defaultdict(collections.Counter), []
 for line in out.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)

@@ -462,6 +462,21 @@ def run_gpu(args):
                     "kernel_ms": k_ms / k_n, "kernel_share_of_step": (k_ms / 1e3) / t_dev, "flops_per_launch": flops,
                     "algorithmic": "2*D flop per distance evaluation x queries x this rank's gallery rows",
                     "traffic": traffic_from_profiles(args.config if world == 1 else "", "l2_candidates_kernel_2cta")}
+            try:        # DRAM floor of the launch: the fp16 shadow once per sweep of the work partition (full rounds + remainder phases / blocks)
+                import ctypes as C
+                n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+                dph = -(-d // 64) * 64
+                ph, sl = C.c_int32(0), C.c_int32(0)
+                fir.lib().fir_debug_partition_check(nq, min(hi - lo, 40_000), n_sm, 2, 1 << 40 if (hi - lo) * dph * 2 > (48 << 20) else 0, C.byref(ph), C.byref(sl))
+                units = max(1, n_sm // 2)
+                nqb = -(-nq // 256)
+                full, rem = divmod(nqb, units)
+                sweeps = (full + (ph.value if ph.value > 0 else rem)) if full > 0 else 1        # no full round: the shadow is (re)used out of L2
+                roof["traffic_floor"] = float(sweeps) * (hi - lo) * dph * 2
+                roof["traffic_floor_is"] = "%d sweeps (%d full rounds + %d remainder %s) x %.2f GB fp16 shadow" % (
+                    sweeps, full, sweeps - full, "phases" if ph.value > 0 else "blocks", (hi - lo) * dph * 2 / 1e9)
+            except Exception:
+                pass
         # k = 1 on the same data (the reference's own operation)
         idx1 = torch.empty((nq, 1), dtype=torch.int32, device=dev)
         d1 = torch.empty((nq, 1), dtype=torch.float32, device=dev)

@@ -144,7 +144,7 @@ def test_c5_full_size_topk(fir, port, ref_l2):
     and a phased remainder: 100 query blocks on 74 pairs).  The unmodified reference's BruteForce::recognize (top-1) and the
     pinned port (top-10) over the whole gallery on a query sample; on all queries: k = 1 is the head of k = 10, distances
     ascend, ties ascend by index, the call is idempotent, and nothing needed the CUDA-core re-run."""
-    need_host_ram(72)
+    need_host_ram(52)
     n, d, C, nq = 10_000_000, 512, 1000, 25_600
     g, gl, q, ql = make(fir, n, nq, d, C, "l2")
     gal = fir.Gallery(g, gl, "l2")

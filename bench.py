@@ -717,7 +717,14 @@ def parity_and_cpu(env, synth, cfg, args, q_host, res_host, gal, k, dem):
                                                          and np.array_equal(np.asarray(rb).astype(np.uint8), gb[sample]) and np.array_equal(np.asarray(re_).astype(np.int32), ge[sample]))})
             par["ratio_sweep"] = sweep
             rdem.close()
-        bi, _ = gal.search(env.torch.from_numpy(q_host).to(env.dev), k=1)
+        qd_all = env.torch.from_numpy(q_host).to(env.dev)
+        bi, _ = gal.search(qd_all, k=1)
+        try:        # the exact GPU brute force over the same gallery, timed beside the approximate search (speed-up vs GPU BF)
+            ea, eb = env.torch.cuda.Event(enable_timing=True), env.torch.cuda.Event(enable_timing=True)
+            ea.record(); gal.search(qd_all, k=1); eb.record(); env.torch.cuda.synchronize()
+            par["gpu_brute_force_ms"] = float(ea.elapsed_time(eb))
+        except Exception:
+            pass
         par["recall_at_1_vs_bf"] = float((bi.cpu().numpy()[:, 0] == idx).mean())
         par["below_threshold_frac"] = float(below.mean())
         par["checked_percent"] = float(100.0 * evals.mean() / n)

@@ -97,9 +97,11 @@ struct TensorSide {              // fp16 shadow of a set of fp32 rows
     int64_t rows = 0, rows_padded = 0;
     int64_t perm_a = 1, perm_b = 0;   // shadow row p = original row (p*perm_a + perm_b) mod rows
     int dph = 0;
+    bool folded = false;         // gallery side: columns d, d+1 hold ‖x‖²·scale·2^a as an fp16 hi/lo pair, meta[2] = a (see fold_norm_kernel)
 };
 
 size_t tensor_side_bytes(int64_t rows, int d, int row_tile);
+int tensor_fold_norms(TensorSide* side, int d, const float* d_stats, cudaStream_t s);     // gallery side, after tensor_pack_side
 int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out,
                      float* d_stats /*[2]: max ||x||, max resid (device)*/, bool permute, bool per_row_scale, cudaStream_t s,
                      const float* center = nullptr /*[d] device: shadow of x - center*/, const unsigned char* exclude = nullptr /*[n] device*/);
@@ -115,6 +117,7 @@ struct TensorSearchArgs {
     int mins_only;                        // seed pass: per-slot column-group minima instead of top-R lists (R must be 4)
     int grid; int n_sm;
     int ctas;                     // 1: cta_group::1 kernel, 2: CTA-pair kernel (grid counts pairs)
+    int nf;                       // the gallery shadow carries its row norms as two extra columns and the queries are packed to match (see fold_norm_kernel)
     int nkb;                      // k-blocks to contract (0 = all of the shadow's; fewer = a prefix of the dimensions)
     int64_t row_bytes;            // bytes of one shadow row for the partition's L2 test (0 = gal->dph * 2)
     unsigned int* sync_ctr;       // optional zeroed device word: lets the pairs of a full round re-align (galleries larger than L2)
@@ -137,6 +140,7 @@ struct ErrModel {
     double abs_coef;          // kind 2: E = abs_coef · (‖q‖₁ + max‖x‖₁)
     const float* q_l1; const float* x_l1_max;                               // kind 2, 3 (device)
     double lam_coef; const float* q_minpos; const float* x_minpos;          // kind 3 (device)
+    double extra_nx2;         // kind 0: added to E as extra_nx2 · (max ‖x‖)² (the folded-norm representation error)
     double dist_scale;        // approx units per reference-distance unit: D on the tensor path (squared distance), 1 otherwise
 };
 int launch_prune(float* cand_val, int32_t* cand_idx, int64_t nq, int rt, int k, const ErrModel& em, cudaStream_t s, const int32_t* n_active = nullptr,

@@ -149,7 +149,8 @@ __global__ void absmax_kernel(const float* __restrict__ rows, int64_t n, int ld,
 __global__ void pack_rows_kernel(const float* __restrict__ rows, int64_t n, int64_t rows_padded, int ld, int d, int dph,
                                  __half* __restrict__ h, float* __restrict__ norm2, float* __restrict__ resid,
                                  unsigned int* meta, unsigned int* stats_bits, int64_t perm_a, int64_t perm_b, float* __restrict__ row_scale,
-                                 const float* __restrict__ center, const unsigned char* __restrict__ exclude) {
+                                 const float* __restrict__ center, const unsigned char* __restrict__ exclude,
+                                 const unsigned int* __restrict__ fold_meta) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows_padded) return;
@@ -183,7 +184,7 @@ __global__ void pack_rows_kernel(const float* __restrict__ rows, int64_t n, int6
         float xs = (float)x * scale;
         __half hv = __float2half_rn(xs);
         if (fabsf(__half2float(hv)) < 6.103515625e-05f) hv = __float2half_rn(0.f);
-        hr[c] = hv;
+        hr[c] = fold_meta ? __hneg(hv) : hv;         // folded norms: the query side is stored negated (exact), see fold_norm_kernel
         float back = __half2float(hv) * inv;
         double df = x - (double)back;
         n2 += x * x;
@@ -192,6 +193,18 @@ __global__ void pack_rows_kernel(const float* __restrict__ rows, int64_t n, int6
     for (int o = 16; o > 0; o >>= 1) {
         n2 += __shfl_xor_sync(0xffffffffu, n2, o);
         r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
+    if (fold_meta) {
+        // query side of the folded norms: columns d, d + 1 both hold U = scale · 2^(−a−1), so that the contraction adds
+        // (T_hi + T_lo)·U = ‖x‖²·s_g·s_q / 2 to −q̂·x̂.  U is a power of two; a row whose U leaves the fp16 normal range cannot be
+        // folded: it gets U = 0 and an infinite residual, i.e. an infinite error bound — its certificate fails and it is re-run exactly
+        __syncwarp();
+        if (lane == 0) {
+            const float U = ldexpf(scale, -(int)fold_meta[2] - 1);
+            const bool ok = U >= 6.103515625e-05f && U <= 32768.f;
+            hr[d] = hr[d + 1] = __float2half_rn(ok ? U : 0.f);
+            if (!ok) r2 = __longlong_as_double(0x7ff0000000000000LL);
+        }
     }
     if (lane == 0) {
         float nf = __double2float_ru(n2);
@@ -213,10 +226,53 @@ size_t tensor_side_bytes(int64_t rows, int d, int row_tile) {
     return al256((size_t)rp * dph * 2) + 3 * al256((size_t)rp * 4) + 256 + 1024;
 }
 
+// Folded norms.  When the k-blocks of the shadow have at least two spare columns (D mod 64 <= 62: the 32-dimensional pivot
+// space of directed enumeration, 200-, 96-dimensional features ...), the row norm rides in them: columns d, d + 1 hold
+// T = ‖x‖²·s_g·2^a as an fp16 hi/lo pair (a brings the largest T into [64, 128): hi/lo then carry T to 2⁻²⁰ of that maximum,
+// values under 2⁻¹⁴ flushed like everywhere else), the query rows are stored NEGATED with U = s_q·2^(−a−1) in the same two
+// columns, and the tensor core delivers  acc'' = ‖x‖²·s_g·s_q/2 − q̂·x̂ = v·(s_g·s_q/2)  directly: the epilogue compares raw
+// accumulators (no FFMA, no norm loads — the pass over a K = 32 pivot space is bound by exactly those instructions) and
+// multiplies by the power of two 2/(s_g·s_q) only when it flushes a list.  Padding / excluded rows have T = +inf.
+__global__ void fold_norm_kernel(__half* __restrict__ h, const float* __restrict__ norm2, int64_t rows_padded, int dph, int d,
+                                 unsigned int* __restrict__ meta, const float* __restrict__ stats) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows_padded) return;
+    const float sg = __uint_as_float(meta[1]);
+    const float tmax = stats[0] * stats[0] * sg;          // stats[0] = max ‖x‖, rounded up
+    int e = 0;
+    if (tmax > 0.f && isfinite(tmax)) frexpf(tmax, &e);   // tmax = m·2^e, m in [0.5, 1)
+    const int a = 7 - e;                                  // largest T in [64, 128)
+    if (row == 0) meta[2] = (unsigned int)a;
+    const float T = ldexpf(norm2[row] * sg, a);           // exact: powers of two
+    __half hi = __float2half_rn(T);
+    if (fabsf(__half2float(hi)) < 6.103515625e-05f) hi = __float2half_rn(0.f);
+    float lof = isfinite(T) ? T - __half2float(hi) : 0.f;
+    __half lo = __float2half_rn(lof);
+    if (fabsf(__half2float(lo)) < 6.103515625e-05f) lo = __float2half_rn(0.f);
+    h[row * dph + d] = hi;
+    h[row * dph + d + 1] = lo;
+}
+
+int tensor_fold_norms(TensorSide* side, int d, const float* d_stats, cudaStream_t s) {
+    if (side->dph - d < 2 || !d_stats) return FIR_OK;
+    fold_norm_kernel<<<(unsigned)ceil_div(side->rows_padded, 256), 256, 0, s>>>(side->h, side->norm2, side->rows_padded, side->dph, d, side->meta, d_stats);
+    FIR_CUDA_TRY(cudaGetLastError());
+    side->folded = true;
+    return FIR_OK;
+}
+
 static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
+static int tensor_pack_side_ex(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out, float* d_stats,
+                               bool permute, bool per_row_scale, cudaStream_t s, const float* center, const unsigned char* exclude,
+                               const unsigned int* fold_meta);
 int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out, float* d_stats,
                      bool permute, bool per_row_scale, cudaStream_t s, const float* center, const unsigned char* exclude) {
+    return tensor_pack_side_ex(rows, n, ld, d, row_tile, buf, out, d_stats, permute, per_row_scale, s, center, exclude, nullptr);
+}
+static int tensor_pack_side_ex(const float* rows, int64_t n, int ld, int d, int row_tile, void* buf, TensorSide* out, float* d_stats,
+                               bool permute, bool per_row_scale, cudaStream_t s, const float* center, const unsigned char* exclude,
+                               const unsigned int* fold_meta) {
     int64_t rp = ceil_div(n, row_tile) * row_tile;
     int dph = round_up(d, BK);
     char* p = (char*)(((uintptr_t)buf + 1023) & ~(uintptr_t)1023);     // TMA global address alignment (>=16B); keep 1 KiB
@@ -243,7 +299,7 @@ int tensor_pack_side(const float* rows, int64_t n, int ld, int d, int row_tile, 
     }
     pack_rows_kernel<<<(unsigned)ceil_div(rp, 8), 256, 0, s>>>(rows, n, rp, ld, d, dph, out->h, out->norm2, out->resid, out->meta,
                                                               (unsigned int*)d_stats, out->perm_a, out->perm_b, per_row_scale ? out->row_scale : nullptr,
-                                                              center, exclude);
+                                                              center, exclude, (fold_meta && per_row_scale && dph - d >= 2) ? fold_meta : nullptr);
     FIR_CUDA_TRY(cudaGetLastError());
     return FIR_OK;
 }
@@ -497,6 +553,7 @@ struct CandParams {
     const float* cls_E;         // [nq] approximation error bound of the query
     double cls_rho;             // relative error of the reference's sequential sum
     // full rounds of a gallery larger than L2: the pairs re-align every kSyncTiles tiles (see the TMA producer)
+    int nf;                     // folded norms: accumulators ARE v·(s_g·s_q/2) (fold_norm_kernel); CTA-pair kernel only
     int sync_tiles;             // tiles between two re-alignments (a power of two, > kSyncLag)
     unsigned int* sync_ctr;     // [1 + kMaxPhases * kMaxRanges] zeroed before the launch ([0]: full rounds, then one per (phase, range)); nullptr = off
 };
@@ -531,7 +588,7 @@ constexpr int EPI_COLS = BN / (EPI_WARPS / 4);   // 128 columns per epilogue war
 constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
 
 // One accumulator tile (this warp's 32 rows x EPI_COLS columns): v = ‖x‖² − 2·s·acc, keep each row's R smallest.
-template <int R>
+template <int R, bool NF = false>
 __device__ __forceinline__ void epilogue_scan_tile(uint32_t taddr, const float* __restrict__ nxs, int jbase, float negc,
                                                    float (&lv)[R], int (&li)[R], float& mx, float& thr, float tau) {
 #pragma unroll 1
@@ -542,6 +599,9 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t taddr, const float* 
         float gm[8];                                    // minimum of each group of 4 columns
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
+            if constexpr (NF) {                         // folded norms: the accumulator is the value (in units of s_g·s_q / 2)
+                gm[i >> 2] = fminf(fminf(__uint_as_float(rr[i + 0]), __uint_as_float(rr[i + 1])), fminf(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])));
+            } else {
             const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
             // two columns per instruction (FFMA2: fma.rn on both halves, the same bits as two fmaf)
             const float2 v01 = __ffma2_rn(make_float2(negc, negc), make_float2(__uint_as_float(rr[i + 0]), __uint_as_float(rr[i + 1])), make_float2(nx4.x, nx4.y));
@@ -550,6 +610,7 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t taddr, const float* 
             rr[i + 0] = __float_as_uint(v0); rr[i + 1] = __float_as_uint(v1);
             rr[i + 2] = __float_as_uint(v2); rr[i + 3] = __float_as_uint(v3);
             gm[i >> 2] = fminf(fminf(v0, v1), fminf(v2, v3));
+            }
         }
         const float vmin = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
         if (__any_sync(0xffffffffu, vmin < thr)) {
@@ -582,6 +643,7 @@ __device__ __forceinline__ void epilogue_scan_tile(uint32_t taddr, const float* 
 
 // Seed pass: no lists, no indices — slot g of the row keeps the minimum over column group g (32 columns) of every tile this
 // thread sees.  Branch-free, so a short scan is not dominated by list warm-up the way a top-R scan of a few tiles is.
+template <bool NF = false>
 __device__ __forceinline__ void epilogue_scan_tile_mins(uint32_t taddr, const float* __restrict__ nxs, float negc, float (&lv)[4]) {
 #pragma unroll
     for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
@@ -591,24 +653,30 @@ __device__ __forceinline__ void epilogue_scan_tile_mins(uint32_t taddr, const fl
         float m = lv[c0 >> 5];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
+            if constexpr (NF) {
+                m = fminf(m, fminf(fminf(__uint_as_float(rr[i + 0]), __uint_as_float(rr[i + 1])), fminf(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]))));
+            } else {
             const float4 nx4 = *reinterpret_cast<const float4*>(&nxs[c0 + i]);
             const float2 v01 = __ffma2_rn(make_float2(negc, negc), make_float2(__uint_as_float(rr[i + 0]), __uint_as_float(rr[i + 1])), make_float2(nx4.x, nx4.y));
             const float2 v23 = __ffma2_rn(make_float2(negc, negc), make_float2(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])), make_float2(nx4.z, nx4.w));
             m = fminf(m, fminf(fminf(v01.x, v01.y), fminf(v23.x, v23.y)));
+            }
         }
         lv[c0 >> 5] = m;
     }
 }
 
 // write one row's list: cand_val/cand_idx [(qrow * n_slots + slot) * R ..], slot_bound = the list's maximum if it is full
+// (vscale: 1, or with folded norms the power of two 2 / (s_g·s_q) that turns a raw accumulator into v — an exact product)
 template <int R>
-__device__ __forceinline__ void epilogue_flush(const CandParams& p, int64_t qrow, int slot, const float (&lv)[R], const int (&li)[R], float thr) {
+__device__ __forceinline__ void epilogue_flush(const CandParams& p, int64_t qrow, int slot, const float (&lv)[R], const int (&li)[R], float thr, float vscale = 1.f) {
     if (qrow >= p.nq) return;
     const float nqv = p.qry_norm2[qrow];
     const int64_t o = (qrow * p.n_slots + slot) * R;
+    thr = __fmul_rn(thr, vscale);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        p.cand_val[o + r] = lv[r] + nqv;
+        p.cand_val[o + r] = __fmul_rn(lv[r], vscale) + nqv;
         // shadow position -> original gallery row (the fp16 copy is stored in a strided permutation)
         p.cand_idx[o + r] = li[r] < 0 ? -1 : (int32_t)(((int64_t)li[r] * p.perm_a + p.perm_b) % p.n);
     }
@@ -1095,6 +1163,7 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
         const int row = lg * 32 + lane;
         const float sg = __uint_as_float(p.gal_meta[1]);
         float negc = 0.f;                              // −2 / (gallery scale · this row's query scale), set per query block
+        float vscale = 1.f;                            // folded norms: 2 / (s_g·s_q), a power of two (raw accumulator → v); else 1
         float lv[R]; int li[R]; float thr = __int_as_float(0x7f800000), mx = thr, tau = thr;
         ClsState cst; cst.cls = -1; cst.end = 0; cst.bv = thr; cst.bi = -1; cst.thr = -thr;
         int64_t cur_qb = -1;
@@ -1106,13 +1175,16 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
                     if (CLS == 1 && cur_qb >= 0) cls_flush_min(p, cur_qb * (2 * BM) + rank * BM + row, cst);
                     cst.cls = -1; cst.end = 0; cst.bv = __int_as_float(0x7f800000); cst.bi = -1; cst.thr = -__int_as_float(0x7f800000);
                 } else
-                if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
+                if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr, vscale);
 #pragma unroll
                 for (int r = 0; r < R; ++r) { lv[r] = __int_as_float(0x7f800000); li[r] = p.mins_only ? 0 : -1; }
                 mx = __int_as_float(0x7f800000);
                 cur_qb = qb;
-                { const int64_t qr = qb * (2 * BM) + rank * BM + row; negc = -2.0f / (sg * (qr < p.nq ? p.qry_row_scale[qr] : 1.f));
+                { const int64_t qr = qb * (2 * BM) + rank * BM + row;
+                  const float sq = qr < p.nq ? p.qry_row_scale[qr] : 1.f;
+                  negc = -2.0f / (sg * sq);
                   tau = (p.seed_thr && qr < p.nq) ? p.seed_thr[qr] - p.qry_norm2[qr] : mx;
+                  if (p.nf) { vscale = -negc; tau = __fmul_rn(tau, 0.5f * sg * sq); }        // thresholds live in accumulator units (exact: powers of two)
 #ifdef FIR_MEASURE
                   if (p.debug_nolist) tau = -mx;
 #endif
@@ -1126,10 +1198,12 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
                 epilogue_scan_tile_cls<CLS>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, p,
                                             cur_qb * (2 * BM) + rank * BM + row, cst);
             } else if constexpr (R == 4) {
-                if (p.mins_only) epilogue_scan_tile_mins(taddr, nx_s + as * BN + half * EPI_COLS, negc, lv);
+                if (p.mins_only) { if (p.nf) epilogue_scan_tile_mins<true>(taddr, nullptr, negc, lv); else epilogue_scan_tile_mins<false>(taddr, nx_s + as * BN + half * EPI_COLS, negc, lv); }
+                else if (p.nf) epilogue_scan_tile<R, true>(taddr, nullptr, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, mx, thr, tau);
                 else epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, mx, thr, tau);
             } else {
-                epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, mx, thr, tau);
+                if (p.nf) epilogue_scan_tile<R, true>(taddr, nullptr, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, mx, thr, tau);
+                else epilogue_scan_tile<R>(taddr, nx_s + as * BN + half * EPI_COLS, (int)(tile * BN) + half * EPI_COLS, negc, lv, li, mx, thr, tau);
             }
             tc_fence_before();
             __syncwarp();
@@ -1137,7 +1211,7 @@ l2_candidates_kernel_2cta(const __grid_constant__ CUtensorMap tmap_a, const __gr
             as ^= 1; if (as == 0) aphase ^= 1;
         }
         if constexpr (CLS != 0) { if (CLS == 1 && cur_qb >= 0) cls_flush_min(p, cur_qb * (2 * BM) + rank * BM + row, cst); }
-        else if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr);
+        else if (cur_qb >= 0) epilogue_flush<R>(p, (cur_qb * (2 * BM) + rank * BM + row), part_slot(P, unit, cur_qb) * 2 + half, lv, li, thr, vscale);
     }
 
     tc_fence_before();
@@ -1164,6 +1238,7 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
     p.nq = a.qry->rows; p.n = a.gal->rows;
     p.perm_a = a.gal->perm_a; p.perm_b = a.gal->perm_b;
     p.nkb = a.nkb > 0 ? a.nkb : a.gal->dph / BK;
+    p.nf = (a.nf && a.ctas == 2) ? 1 : 0;
     p.n_slots = a.n_slots;
     p.gal_norm2 = a.gal->norm2; p.qry_norm2 = a.qry->norm2;
     p.gal_meta = a.gal->meta; p.qry_row_scale = a.qry->row_scale;
@@ -1215,7 +1290,8 @@ int launch_tensor_candidates(const TensorSearchArgs& a, cudaStream_t s) {
 __device__ __forceinline__ double approx_error_bound(double nq2, double rq, double NX, double RX, int nkb);
 __device__ __forceinline__ void err_bounds(const ErrModel& m, int64_t q, double& E, double& rho) {
     rho = m.rel;
-    if (m.kind == 0) E = approx_error_bound((double)m.q_norm2[q], (double)m.q_resid[q], (double)m.gal_stats[0], (double)m.gal_stats[1], m.nkb);
+    if (m.kind == 0) E = approx_error_bound((double)m.q_norm2[q], (double)m.q_resid[q], (double)m.gal_stats[0], (double)m.gal_stats[1], m.nkb) +
+                         m.extra_nx2 * (double)m.gal_stats[0] * (double)m.gal_stats[0];
     else if (m.kind == 2) E = m.abs_coef * ((double)m.q_l1[q] + (double)*m.x_l1_max);
     else if (m.kind == 3) {
         const double mp = fmin((double)m.q_minpos[q], (double)*m.x_minpos);      // +inf when a side has no positive element
@@ -1448,6 +1524,10 @@ static int ensure_gallery_side(fir_gallery* g) {
     if (!g->d_stats) FIR_CUDA_TRY(cudaMalloc(&g->d_stats, 64));
     FIR_CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, 64, g->stream));
     FIR_TRY(tensor_pack_side(g->rows, g->n, g->dp, g->d, BN, g->tensor_buf, &g->tside, g->d_stats, true, false, g->stream, g->tensor_center, g->tensor_exclude));
+    {   // spare columns in the last k-block: the row norms ride in them (fold_norm_kernel); FIR_TENSOR_FOLD=0 keeps the norm loads
+        static const int fold_on = [] { const char* e = getenv("FIR_TENSOR_FOLD"); return e ? atoi(e) : 1; }();
+        if (fold_on && tensor_cta_mode() == 2) FIR_TRY(tensor_fold_norms(&g->tside, g->d, g->d_stats, g->stream));
+    }
     FIR_TRY(tensor_encode_map(&g->tmap_b, g->tside.h, g->tside.rows_padded, g->tside.dph, BN));
     FIR_TRY(tensor_encode_map(&g->tmap_b_half, g->tside.h, g->tside.rows_padded, g->tside.dph, BN / 2));
     g->tensor_ready = true;
@@ -1585,7 +1665,8 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     const bool first = prof_kind == FIR_KERNEL_L2_CANDIDATES;
     auto* ev_pack = first ? g->prof_begin(FIR_PHASE_PACK_QUERIES) : nullptr;
     const int d_eff = g->tensor_d_eff > 0 ? g->tensor_d_eff : g->d;      // distances over the first d_eff dimensions (recognize_image_bf's prefix)
-    FIR_TRY(tensor_pack_side(dq, nq, g->dp, d_eff, BM, pb.qbuf, &qs, nullptr, false, true, g->stream, g->tensor_center, nullptr));
+    const bool nf = g->tside.folded && d_eff == g->d && ctas == 2;          // (a prefix call leaves the norm columns to the zero padding of its queries)
+    FIR_TRY(tensor_pack_side_ex(dq, nq, g->dp, d_eff, BM, pb.qbuf, &qs, nullptr, false, true, g->stream, g->tensor_center, nullptr, nf ? g->tside.meta : nullptr));
     CUtensorMap tmap_a;
     FIR_TRY(tensor_encode_map(&tmap_a, qs.h, qs.rows_padded, qs.dph, BM));
     const int rt = pb.n_slots * pb.R;
@@ -1598,6 +1679,7 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     TensorSide gal_side = g->tside;
     if (d_eff < g->d) { gal_side.norm2 = g->prefix_norm2; a.nkb = round_up(d_eff, BK) / BK; }     // prefix: its own row norms, fewer k-blocks of the same shadow
     a.row_bytes = (int64_t)g->tside.dph * 2;
+    a.nf = nf ? 1 : 0;
     a.gal = &gal_side; a.qry = &qs; a.tmap_a = &tmap_a; a.tmap_b = ctas == 2 ? &g->tmap_b_half : &g->tmap_b; a.ctas = ctas;
     a.n_sm = g->n_sm; a.d = d_eff; a.R = pb.R; a.n_slots = pb.n_slots; a.cand_val = pb.cand_val; a.cand_idx = pb.cand_idx; a.slot_bound = pb.slot_bound; a.grid = pb.grid;
     if (sp && sp->S) {
@@ -1624,6 +1706,9 @@ int run_pass(fir_gallery* g, const float* dq, int64_t nq, int k, int ctas, const
     ErrModel em{};
     em.kind = 0; em.d = d_eff; em.nkb = round_up(d_eff, BK) / BK; em.q_norm2 = qs.norm2; em.q_resid = qs.resid; em.gal_stats = g->d_stats;
     em.rel = (double)(d_eff + 4) * 5.9604644775390625e-08; em.dist_scale = (double)d_eff;
+    // folded norms: the hi/lo pair carries ‖x‖²·s_g to 2⁻²⁰ of the largest (1e-6), and the two extra products pass through the
+    // tensor core's fp32 accumulation like the others ((4·nkb + 8)·2⁻²² of a term of size ≤ max‖x‖² / 2 — 3e-6 at nkb = 1)
+    em.extra_nx2 = nf ? 1e-6 + (double)(4 * em.nkb + 8) * 2.384185791015625e-07 : 0.0;
     auto* ev1 = first ? g->prof_begin(FIR_PHASE_PRUNE) : nullptr;
     const bool listed = (uint64_t)nq * (uint64_t)rt < 0xffffffffull;          // cells are 32-bit
     if (listed) FIR_CUDA_TRY(cudaMemsetAsync(pb.pair_count, 0, 4, g->stream));

@@ -129,6 +129,26 @@ print("OK")
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("n,nq,d", [(20000, 1300, 200), (9000, 700, 33), (12000, 500, 62), (12000, 500, 63)])
+def test_tensor_folded_norms(fir, port, n, nq, d):
+    """With at least two spare columns in the last k-block (D mod 64 <= 62) the gallery's row norms ride in the shadow and the
+    epilogue compares raw accumulators (fold_norm_kernel): same bits as the port for un-normalised rows of mixed magnitude; queries
+    whose scale cannot be folded (1e-8 x and 1e+7 x the gallery's magnitude: U leaves the fp16 range) come back exact through the
+    fallback; D = 63 has one spare column and keeps the norm loads."""
+    rng = np.random.default_rng(d)
+    g = (rng.standard_normal((n, d)) * rng.uniform(0.2, 3.0, (n, 1))).astype(np.float32)       # row norms spread over a decade
+    q = (rng.standard_normal((nq, d)) * rng.uniform(0.2, 3.0, (nq, 1))).astype(np.float32)
+    q[5] *= np.float32(1e-8); q[6] *= np.float32(1e7); q[7] = 0
+    g[100:103] = g[7]
+    gal = fir.Gallery(g, None, "l2")
+    for k in (1, 10):
+        idx, dist = gal.search(q, k=k, path=fir.PATH_TENSOR)
+        assert gal.stats()["path_used"] == fir.PATH_TENSOR
+        oi, od = port.topk("l2", g, q, k, nthreads=os.cpu_count() or 1)
+        assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od)), k
+    gal.close()
+
+
 @pytest.mark.parametrize("n,nq,d", [(30000, 1500, 512), (20011, 900, 200)])
 def test_tensor_prefix_max_features(fir, port, n, nq, d):
     """recognize_image_bf's prefix distance (db_features.cpp:319-335: the first max_features dimensions, mean over them) on the

@@ -117,3 +117,21 @@ def test_tensor_work_partition_covers_every_item_once(fir):
         seen_phased += ph.value > 0
         assert ph.value <= 4 and sl.value <= 160
     assert seen_phased > 10
+
+
+def test_library_carries_the_blackwell_data_path():
+    """The shipped library is sm_100a code with the tcgen05 / TMA / TMEM data path in its candidate kernels (no PTX-only or
+    recompiled mma.sync build can pass for it): UTCHMMA.2CTA (tcgen05.mma cta_group::2), UTMALDG (TMA loads), LDTM
+    (tcgen05.ld), UTCBAR (tcgen05.commit), FFMA2 in the epilogue.  Needs cuobjdump (CUDA toolkit); skipped without it."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    so = os.path.join(ROOT, "fast-image-recognition_b200", "libfir_b200.so")
+    if not os.path.exists(exe) or not os.path.exists(so):
+        pytest.skip("cuobjdump or the built library not present")
+    lst = subprocess.run([exe, "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in lst and "sm_90" not in lst and "sm_80" not in lst          # one architecture, the target
+    sass = subprocess.run([exe, "-sass", "-fun", "_ZN3fir25l2_candidates_kernel_2ctaILi16ELb1ELi0EEEv14CUtensorMap_stS1_NS_10CandParamsE", so],
+                          capture_output=True, text=True).stdout
+    for op in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "LDTM", "UTCBAR.2CTA.MULTICAST", "FFMA2", "SYNCS"):
+        assert op in sass, op
